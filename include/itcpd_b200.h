@@ -1,0 +1,175 @@
+/* libitcpd_b200 -- B200-native (sm_100a) CP-ALS engine behind ITensorCPD.jl's algorithm hooks.
+ *
+ * Plain C ABI: opaque handle, raw pointers, 64-bit sizes, int status returns (0 = ok), no
+ * exceptions, no torch / CUDA types in any signature.  Host buffers are caller-owned and only
+ * touched during the call; every device buffer is owned by the handle.  One handle = one driver
+ * thread (like the reference's C helper it is not re-entrant).  All calls are synchronous on
+ * return unless stated otherwise.
+ *
+ * Layout conventions are the reference's: the dense target T is
+ * column-major in the user's index order (first index fastest), factor A_n is I_n x R
+ * column-major, Gram matrices R x R, lambda length R.  Sample / pivot matrices are int64,
+ * 1-based (as Julia stores them), nsamp x (N-1) column-major.
+ *
+ * Each entry point cites the reference interface (file:line under the ITensorCPD.jl tree) that
+ * it replaces.  INTEGRATION.md shows the `ccall` binding for each.
+ */
+#ifndef ITCPD_B200_H
+#define ITCPD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct itcpd_ctx itcpd_ctx;
+
+/* status codes */
+enum {
+    ITCPD_OK = 0,
+    ITCPD_ERR_CUDA = 1,        /* a CUDA runtime / driver call failed (see itcpd_last_error) */
+    ITCPD_ERR_ARG = 2,         /* bad argument / call order */
+    ITCPD_ERR_NO_DEVICE = 3,   /* no sm_100 device: the library has NO CPU fallback */
+    ITCPD_ERR_NAN = 4,         /* NaN fit (reference: throw("Error NAN"), fit_check.jl:40-42) */
+    ITCPD_ERR_COMM = 5,        /* NCCL / peer-memory failure */
+    ITCPD_ERR_UNSUPPORTED = 6
+};
+
+/* solve paths reported by itcpd_solve (ldiv_solve.jl:13-29) */
+enum { ITCPD_SOLVE_CHOLESKY = 0, ITCPD_SOLVE_QRCP = 1 };
+
+/* MTTKRP algorithms (all give the same M_n; they differ in how T is streamed) */
+enum {
+    ITCPD_MTTKRP_TREE = 0,   /* default: two-pass dimension tree, TMA + FP64 DMMA GEMM            */
+    ITCPD_MTTKRP_DIRECT = 1  /* one fused pass per mode, plain FMA kernel (debug / cross-check)   */
+};
+
+int         itcpd_version(void);
+const char *itcpd_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Replaces nothing in the reference (which has no device state); mirrors the build/load
+ * convention of deps/build.jl:1-28 + src/ITensorCPD.jl:25-36. */
+int itcpd_create(itcpd_ctx **out, int device);
+int itcpd_destroy(itcpd_ctx *ctx);
+int itcpd_device_info(itcpd_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes);
+int itcpd_synchronize(itcpd_ctx *ctx);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t itcpd_launch_count(itcpd_ctx *ctx);
+/* runtime options: "mttkrp_alg" (0/1), "swizzle" (1/0, debug), "tile_warps" (4|8) ... */
+int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);
+
+/* ---- target tensor (ALS.target, als_optimizer.jl:5-10; decompose.jl:5-7 wraps without copy) - */
+int itcpd_set_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, const double *host_colmajor);
+/* i.i.d. N(0,1) entries from a counter-based generator (Philox4x32-10 + Box-Muller); element with
+ * global column-major linear index e gets the value of counter (seed, e + elem_offset), so slabs of
+ * one big tensor can be generated independently on several GPUs. */
+int itcpd_generate_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, uint64_t seed, int64_t elem_offset);
+int itcpd_get_tensor(itcpd_ctx *ctx, double *host_colmajor);
+int itcpd_tensor_norm(itcpd_ctx *ctx, double *fro_norm);            /* norm(T), README.md:96 */
+
+/* ---- CPD state (CPD{TargetT}, cpd.jl:7-46) ------------------------------------------------- */
+int itcpd_set_rank(itcpd_ctx *ctx, int rank);
+int itcpd_set_factor(itcpd_ctx *ctx, int mode, const double *host);  /* cp[n]   cpd.jl:28 */
+int itcpd_get_factor(itcpd_ctx *ctx, int mode, double *host);
+int itcpd_set_lambda(itcpd_ctx *ctx, const double *host);            /* cp[]    cpd.jl:29 */
+int itcpd_get_lambda(itcpd_ctx *ctx, double *host);
+int itcpd_get_gram(itcpd_ctx *ctx, int mode, double *host);          /* :part_grammian[n] */
+/* random_factors (cpd.jl:48-60): randn(I_n,R) per mode from one counter-based stream, column
+ * normalised; lambda = norms of the last factor.  (Julia's MersenneTwister stream is not
+ * reproducible outside Julia; the Julia extension passes its own factors via itcpd_set_factor.) */
+int itcpd_random_cpd(itcpd_ctx *ctx, uint64_t seed);
+
+/* ---- the five per-mode hooks of optimize.jl:19-30 ------------------------------------------ */
+/* compute_als(::MttkrpAlgorithm) (optimizers/.../standard/tensor.jl:3-14): all Grams G_n = A_n'A_n */
+int itcpd_compute_grams(itcpd_ctx *ctx);
+/* compute_krp(::MttkrpAlgorithm) (MttkrpAlgorithm.jl:18-31): Gamma = hadamard_{m != mode} G_m.
+ * host_out (R x R) may be NULL. */
+int itcpd_gram_hadamard(itcpd_ctx *ctx, int mode, double *host_out);
+/* matricize_tensor(::KRPFreeNormal / ::KRPNormal) (algorithms/.../standard/tensor.jl:12-44 ->
+ * had_contract.jl:72-124): M_mode = T_(mode) * KRP(other factors).  host_out (I_mode x R) may be NULL. */
+int itcpd_mttkrp(itcpd_ctx *ctx, int mode, double *host_out);
+/* solve_ls_problem (MttkrpAlgorithm.jl:34-41) -> ldiv_solve! (ldiv_solve.jl:13-29): pivoted
+ * Cholesky (dpstrf semantics, absolute tol, upper) + permuted triangular solves; on rank
+ * deficiency the column-pivoted-QR min-norm solve (dgelsy semantics, rcond = R*eps).
+ * Operates on the device-resident Gamma and M_mode; path_out/rank_out may be NULL. */
+int itcpd_solve(itcpd_ctx *ctx, int mode, double chol_tol, int *path_out, int *rank_out);
+/* row_norm (math_tools/row_norm.jl:4-24): lambda_r = ||X[:,r]||, A_mode = X ./ lambda */
+int itcpd_normalize(itcpd_ctx *ctx, int mode);
+/* post_solve (tensor.jl:46-49): G_mode = A_mode' A_mode */
+int itcpd_post_solve(itcpd_ctx *ctx, int mode);
+/* check_converge(::FitCheck) scalars (fit_check.jl:28-29, converge_checks.jl:5-11):
+ * inner = sum(M_N .* A_N .* lambda), model_norm2 = lambda' (hadamard_n G_n) lambda.  Uses the
+ * saved last-mode MTTKRP: no extra tensor pass. */
+int itcpd_fit_terms(itcpd_ctx *ctx, double *inner, double *model_norm2);
+
+/* ---- whole sweeps (optimize.jl:15-32 body), device resident --------------------------------- */
+/* Runs `nsweeps` ALS sweeps (modes 1..N in order, Gram refresh after each mode, fit scalars after
+ * each sweep).  inner[] / model_norm2[] (length nsweeps) may be NULL.  The host keeps the
+ * FitCheck / NoCheck state machine (fit_check.jl:30-65) and decides when to stop. */
+int itcpd_sweep(itcpd_ctx *ctx, int nsweeps, double chol_tol, double *inner, double *model_norm2);
+/* same, but only enqueues the work on the handle's stream; results land in the handle's pinned
+ * staging area and are fetched by itcpd_sweep_results after itcpd_synchronize. */
+int itcpd_sweep_async(itcpd_ctx *ctx, int nsweeps, double chol_tol);
+int itcpd_sweep_results(itcpd_ctx *ctx, int nsweeps, double *inner, double *model_norm2, int *qrcp_fallbacks);
+/* als_optimize (als_optimizer.jl:15-25) end to end from HOST buffers: upload T and the N initial
+ * factors, run nsweeps sweeps, download factors + lambda + per-sweep fit scalars. */
+int itcpd_als_from_host(itcpd_ctx *ctx, int order, const int64_t *dims, const double *host_T, int rank,
+                        const double *const *host_factors_in, int nsweeps, double chol_tol,
+                        double *const *host_factors_out, double *host_lambda_out,
+                        double *inner, double *model_norm2);
+
+/* ---- reconstruct (algebra/reconstruct.jl:2-9) and residual ------------------------------------ */
+int itcpd_reconstruct(itcpd_ctx *ctx, double *host_colmajor);
+/* ||T - [[lambda; A_1..A_N]]||_F without materialising the reconstruction */
+int itcpd_residual_norm(itcpd_ctx *ctx, double *fro_norm);
+
+/* ---- sampled / randomized path ---------------------------------------------------------------- */
+/* compute_leverage_score_probabilitiy (math_tools/probability.jl:3-10): p_i = ||Q[i,:]||^2/min(I,R) */
+int itcpd_leverage_scores(itcpd_ctx *ctx, int mode, double *host_out);
+/* sample_factor_matrices (probability.jl:23-33): nsamp i.i.d. weighted draws with replacement for
+ * every mode != skip_mode from the current device-side leverage scores. out: int64 1-based,
+ * nsamp x (N-1) column-major. */
+int itcpd_sample_factor_matrices(itcpd_ctx *ctx, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *host_out);
+/* pivot_hadamard (algebra/had_contract.jl:277-295): K[s,r] = prod_{m != mode} A_m[piv[s,m], r] */
+int itcpd_pivot_hadamard(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double *host_out);
+/* fused_flatten_sample (algebra/pivot_mapping.jl:59-85): out[:, s] = mode fibre of T at piv[s,:] */
+int itcpd_gather_fibers(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double *host_out);
+/* column_to_multi_coords / multi_coords_to_column (pivot_mapping.jl:17-47), host-side integer maps */
+int itcpd_column_to_multi_coords(int64_t ncols, const int64_t *cols, int ndims, const int64_t *dims, int64_t *out);
+int itcpd_multi_coords_to_column(int64_t ncols, const int64_t *coords, int ndims, const int64_t *dims, int64_t *out);
+/* sparse-sign embeddings: same signature and libc-rand() stream as the reference's C helper
+ * (algebra/sparse_sign.c:25-70, algebra/sparsestack.c:24-79; bound at SEQRCS.jl:41-60). */
+void itcpd_sparse_sign(int l, int n, int s, double *vals, int *rows, int *colstarts);
+void itcpd_sparsestack(int l, int n, int s, double *vals, int *rows, int *colstarts);
+/* sketched_matricization (pivot_mapping.jl:111-140): A_sk = T_(mode) * Omega' (I_mode x l) from the
+ * (rows 0-based, vals) arrays the generators above fill; s non-zeros per column. */
+int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *rows0, const double *vals, double *host_out);
+/* one sampled ALS mode update (ProjectionAlgorithm.jl:57-68 with normal=true): given 1-based pivots
+ * for `mode`, gathers T_s and K on the device, solves (K'K) \ (T_s K)', normalises, refreshes the
+ * Gram and the leverage scores of `mode`. */
+int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol);
+
+/* ---- multi-GPU (slab sharding along the last mode; one process per GPU) ------------------------ */
+/* The handle's tensor is the local slab T[..., slab]; factor N holds only the slab's rows.
+ * After itcpd_comm_init every MTTKRP of a non-sharded mode is all-reduced, and the norms / Gram /
+ * fit scalars of the sharded mode are all-reduced. */
+int itcpd_comm_unique_id(void *out128);                       /* rank 0: ncclGetUniqueId */
+int itcpd_comm_init(itcpd_ctx *ctx, int nranks, int rank, const void *id128);
+int itcpd_comm_destroy(itcpd_ctx *ctx);
+int itcpd_allgather_factor(itcpd_ctx *ctx, int mode, int64_t rows_total, double *host_out);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+/* average device time (ms, CUDA events on the handle's stream) of the dominant GEMM kernel over
+ * the launches since the last reset, and how many launches that was */
+int itcpd_gemm_timing(itcpd_ctx *ctx, int reset, double *avg_ms, int64_t *launches);
+/* FP64 tensor-pipe peak probe: register-resident DMMA.8x8x4 issue loop on every SM; returns
+ * achieved TFLOP/s (2*8*8*4 flops per instruction) -- a roofline denominator for this box. */
+int itcpd_probe_dmma_peak(itcpd_ctx *ctx, double *tflops);
+int itcpd_probe_dfma_peak(itcpd_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITCPD_B200_H */

@@ -1,0 +1,802 @@
+// extern "C" entry points of libitcpd_b200 (see include/itcpd_b200.h for the contract and the
+// reference interfaces each one replaces).
+#include "common.cuh"
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <algorithm>
+
+namespace itcpd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t n) {
+    if (n <= bytes && p) return ITCPD_OK;
+    release();
+    if (n == 0) n = 256;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+        p = nullptr;
+        bytes = 0;
+        return ITCPD_ERR_CUDA;
+    }
+    bytes = n;
+    return ITCPD_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+int64_t mode_rows(const itcpd_ctx *c, int mode) { return c->dims[mode]; }
+
+static int ensure_pinned(itcpd_ctx *c, size_t doubles) {
+    if (doubles <= c->pinned_doubles) return ITCPD_OK;
+    if (c->pinned) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->pinned); c->pinned = nullptr; }
+    size_t n = std::max<size_t>(doubles, 4096);
+    CUDA_TRY(cudaHostAlloc((void **)&c->pinned, n * 8, cudaHostAllocDefault));
+    c->pinned_doubles = n;
+    return ITCPD_OK;
+}
+
+// Split points of the dimension tree (DESIGN.md "dimension tree"): pass A keeps modes [0,sa) free,
+// pass B keeps modes [sb,N) free, sb <= sa; both GEMM outputs should have >= 16384 rows when possible.
+void choose_splits(itcpd_ctx *c) {
+    const int N = c->order;
+    const int64_t want = 16384;
+    int sa = N - 1;
+    {
+        int64_t rows = 1;
+        for (int s = 1; s <= N - 1; ++s) {
+            rows *= c->dims[s - 1];
+            if (rows >= want) { sa = s; break; }
+        }
+    }
+    int sb = 1;
+    {
+        for (int s = sa; s >= 1; --s) {
+            int64_t rows = 1;
+            for (int n = s; n < N; ++n) rows *= c->dims[n];
+            if (rows >= want) { sb = s; break; }
+        }
+    }
+    if (c->force_split_a >= 1 && c->force_split_a <= N - 1) sa = c->force_split_a;
+    if (c->force_split_b >= 1 && c->force_split_b <= sa) sb = c->force_split_b;
+    if (sb > sa) sb = sa;
+    c->split_a = sa;
+    c->split_b = sb;
+    c->PA.valid = c->PB.valid = false;
+}
+
+int ensure_cpd_buffers(itcpd_ctx *c) {
+    ARG_CHECK(c->has_tensor && c->rank > 0, "set the tensor and the rank first");
+    const int R = c->rank;
+    int64_t maxrows = 0;
+    for (int n = 0; n < c->order; ++n) {
+        const int64_t rows = c->dims[n];
+        maxrows = std::max(maxrows, rows);
+        TRY(c->A[n].reserve((size_t)rows * R * 8));
+        TRY(c->M[n].reserve((size_t)rows * R * 8));
+        TRY(c->G[n].reserve((size_t)R * R * 8));
+        TRY(c->lev[n].reserve((size_t)rows * 8));
+    }
+    TRY(c->X.reserve((size_t)maxrows * R * 8));
+    TRY(c->lambda.reserve((size_t)R * 8));
+    TRY(c->Gamma.reserve((size_t)R * R * 8));
+    TRY(c->status.reserve(256));
+    TRY(c->fit2.reserve(64));
+    return ITCPD_OK;
+}
+
+static void invalidate_all(itcpd_ctx *c) {
+    c->PA.valid = c->PB.valid = false;
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->m_valid[n] = false; c->fver[n]++; }
+}
+
+static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
+    ARG_CHECK(order >= 2 && order <= ITCPD_MAX_ORDER, "tensor order must be in [2,8]");
+    int64_t n = 1;
+    for (int i = 0; i < order; ++i) {
+        ARG_CHECK(dims[i] >= 1, "tensor dimensions must be positive");
+        n *= dims[i];
+    }
+    c->order = order;
+    for (int i = 0; i < order; ++i) c->dims[i] = dims[i];
+    c->ld0 = dims[0] + (dims[0] & 1);
+    c->nelem = n;
+    c->nstore = n / dims[0] * c->ld0;
+    TRY(c->T.reserve((size_t)c->nstore * 8 + 256));
+    c->has_tensor = true;
+    choose_splits(c);
+    invalidate_all(c);
+    if (c->rank > 0) TRY(ensure_cpd_buffers(c));
+    return ITCPD_OK;
+}
+
+// the partial contraction feeding `mode`, recomputed only when a contracted factor changed
+static int ensure_partial(itcpd_ctx *c, int kind) {
+    Partial &P = (kind == 0) ? c->PA : c->PB;
+    const int split = (kind == 0) ? c->split_a : c->split_b;
+    const int d0 = (kind == 0) ? split : 0, d1 = (kind == 0) ? c->order : split;
+    bool ok = P.valid && P.split == split;
+    for (int n = d0; ok && n < d1; ++n) ok = (P.dep_version[n] == c->fver[n]);
+    if (ok) return ITCPD_OK;
+    int64_t rows = 1;
+    if (kind == 0) { rows = c->ld0; for (int n = 1; n < split; ++n) rows *= c->dims[n]; }
+    else { for (int n = split; n < c->order; ++n) rows *= c->dims[n]; }
+    TRY(P.buf.reserve((size_t)rows * c->rank * 8));
+    TRY(launch_partial_gemm(c, kind, split, P.buf.as<double>()));
+    P.valid = true;
+    P.split = split;
+    for (int n = d0; n < d1; ++n) P.dep_version[n] = c->fver[n];
+    return ITCPD_OK;
+}
+
+static int mttkrp_device(itcpd_ctx *c, int mode) {
+    double *out = c->M[mode].as<double>();
+    if (c->mttkrp_alg == ITCPD_MTTKRP_DIRECT) {
+        TRY(k_direct_mttkrp(c, mode, out));
+    } else if (mode < c->split_a) {
+        TRY(ensure_partial(c, 0));
+        TRY(k_partial_mttkrp(c, c->PA.buf.as<double>(), 0, c->split_a - 1, c->ld0, mode, out));
+    } else {
+        TRY(ensure_partial(c, 1));
+        TRY(k_partial_mttkrp(c, c->PB.buf.as<double>(), c->split_b, c->order - 1, c->dims[c->split_b], mode, out));
+    }
+    // slab sharding: T is a slab of the last mode, so every other mode's MTTKRP is a partial sum
+    if (comm_active(c) && mode != c->order - 1) TRY(comm_allreduce_sum(c, out, c->dims[mode] * c->rank));
+    c->m_valid[mode] = true;
+    c->last_mttkrp_mode = mode;
+    return ITCPD_OK;
+}
+
+static int gram_device(itcpd_ctx *c, int mode) {
+    TRY(k_gram(c, c->A[mode].as<double>(), c->dims[mode], c->rank, c->G[mode].as<double>()));
+    if (comm_active(c) && mode == c->order - 1) TRY(comm_allreduce_sum(c, c->G[mode].as<double>(), (int64_t)c->rank * c->rank));
+    return ITCPD_OK;
+}
+
+static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_dev) {
+    TRY(k_gram_hadamard(c, mode, c->Gamma.as<double>()));
+    TRY(mttkrp_device(c, mode));
+    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, tol, c->X.as<double>(), status_dev));
+    TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
+    c->fver[mode]++;
+    TRY(gram_device(c, mode));
+    return ITCPD_OK;
+}
+
+}  // namespace itcpd
+
+using namespace itcpd;
+
+#define CHECK_CTX(c) ARG_CHECK((c) != nullptr, "null context")
+#define CHECK_MODE(c, m) ARG_CHECK((m) >= 0 && (m) < (c)->order, "mode out of range (0-based)")
+#define USE_DEVICE(c) CUDA_TRY(cudaSetDevice((c)->device))
+
+extern "C" {
+
+int itcpd_version(void) { return 100; }
+const char *itcpd_last_error(void) { return g_err; }
+
+int itcpd_create(itcpd_ctx **out, int device) {
+    ARG_CHECK(out != nullptr, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device visible (%s); libitcpd_b200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return ITCPD_ERR_NO_DEVICE;
+    }
+    ARG_CHECK(device >= 0 && device < ndev, "device index out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libitcpd_b200 is built for sm_100a only and has no fallback path", device, prop.major, prop.minor);
+        return ITCPD_ERR_NO_DEVICE;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    itcpd_ctx *c = new itcpd_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->hbm_bytes = prop.totalGlobalMem;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
+    int st = ensure_pinned(c, 4096);
+    if (st != ITCPD_OK) { delete c; return st; }
+    *out = c;
+    return ITCPD_OK;
+}
+
+int itcpd_destroy(itcpd_ctx *c) {
+    if (!c) return ITCPD_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    itcpd_comm_destroy(c);
+    DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
+                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T};
+    for (DevBuf *b : bufs) b->release();
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); }
+    for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ITCPD_OK;
+}
+
+int itcpd_device_info(itcpd_ctx *c, int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes) {
+    CHECK_CTX(c);
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)c->hbm_bytes;
+    return ITCPD_OK;
+}
+
+int itcpd_synchronize(itcpd_ctx *c) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int64_t itcpd_launch_count(itcpd_ctx *c) { return c ? c->launches : -1; }
+
+int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
+    CHECK_CTX(c);
+    ARG_CHECK(name != nullptr, "null option name");
+    std::string n(name);
+    if (n == "mttkrp_alg") { ARG_CHECK(value == 0 || value == 1, "mttkrp_alg must be 0 or 1"); c->mttkrp_alg = (int)value; }
+    else if (n == "swizzle") c->swizzle = value != 0;
+    else if (n == "tile_warps") { ARG_CHECK(value == 4 || value == 8, "tile_warps must be 4 or 8"); c->tile_warps = (int)value; }
+    else if (n == "split_a") { c->force_split_a = (int)value; if (c->has_tensor) choose_splits(c); }
+    else if (n == "split_b") { c->force_split_b = (int)value; if (c->has_tensor) choose_splits(c); }
+    else if (n == "time_gemm") c->time_gemm = value != 0;
+    else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
+    return ITCPD_OK;
+}
+
+// ---- tensor -----------------------------------------------------------------------------------
+int itcpd_set_tensor(itcpd_ctx *c, int order, const int64_t *dims, const double *host) {
+    CHECK_CTX(c);
+    ARG_CHECK(dims && host, "null argument");
+    USE_DEVICE(c);
+    TRY(set_shape(c, order, dims));
+    if (c->ld0 == c->dims[0]) {
+        CUDA_TRY(cudaMemcpyAsync(c->T.p, host, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        TRY(c->work.reserve((size_t)c->nelem * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->work.p, host, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(k_pad_copy_in(c, c->work.as<double>(), c->T.as<double>()));
+    }
+    CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_generate_tensor(itcpd_ctx *c, int order, const int64_t *dims, uint64_t seed, int64_t elem_offset) {
+    CHECK_CTX(c);
+    ARG_CHECK(dims != nullptr, "null dims");
+    USE_DEVICE(c);
+    TRY(set_shape(c, order, dims));
+    TRY(k_generate(c, seed, elem_offset));
+    CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_get_tensor(itcpd_ctx *c, double *host) {
+    CHECK_CTX(c);
+    ARG_CHECK(c->has_tensor && host, "no tensor / null host pointer");
+    USE_DEVICE(c);
+    if (c->ld0 == c->dims[0]) {
+        CUDA_TRY(cudaMemcpyAsync(host, c->T.p, (size_t)c->nelem * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        TRY(c->work.reserve((size_t)c->nelem * 8));
+        TRY(k_pad_copy_out(c, c->T.as<double>(), c->work.as<double>()));
+        CUDA_TRY(cudaMemcpyAsync(host, c->work.p, (size_t)c->nelem * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_tensor_norm(itcpd_ctx *c, double *fro) {
+    CHECK_CTX(c);
+    ARG_CHECK(c->has_tensor && fro, "no tensor / null out pointer");
+    USE_DEVICE(c);
+    TRY(c->fit2.reserve(64));
+    TRY(k_sumsq(c, c->T.as<double>(), c->nstore, c->fit2.as<double>()));
+    if (comm_active(c)) TRY(comm_allreduce_sum(c, c->fit2.as<double>(), 1));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *fro = std::sqrt(c->pinned[0]);
+    return ITCPD_OK;
+}
+
+// ---- CPD state --------------------------------------------------------------------------------
+int itcpd_set_rank(itcpd_ctx *c, int rank) {
+    CHECK_CTX(c);
+    ARG_CHECK(rank >= 1, "rank must be positive");
+    USE_DEVICE(c);
+    c->rank = rank;
+    invalidate_all(c);
+    if (c->has_tensor) TRY(ensure_cpd_buffers(c));
+    return ITCPD_OK;
+}
+
+int itcpd_set_factor(itcpd_ctx *c, int mode, const double *host) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(host && c->rank > 0, "null host pointer / rank not set");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    CUDA_TRY(cudaMemcpyAsync(c->A[mode].p, host, (size_t)c->dims[mode] * c->rank * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->fver[mode]++;
+    return ITCPD_OK;
+}
+
+static int d2h(itcpd_ctx *c, double *host, const void *dev, size_t bytes) {
+    CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_get_factor(itcpd_ctx *c, int mode, double *host) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(host && c->A[mode].p, "null host pointer / factor not set");
+    USE_DEVICE(c);
+    return d2h(c, host, c->A[mode].p, (size_t)c->dims[mode] * c->rank * 8);
+}
+
+int itcpd_set_lambda(itcpd_ctx *c, const double *host) {
+    CHECK_CTX(c);
+    ARG_CHECK(host && c->rank > 0, "null host pointer / rank not set");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    CUDA_TRY(cudaMemcpyAsync(c->lambda.p, host, (size_t)c->rank * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_get_lambda(itcpd_ctx *c, double *host) {
+    CHECK_CTX(c);
+    ARG_CHECK(host && c->lambda.p, "null host pointer / lambda not set");
+    USE_DEVICE(c);
+    return d2h(c, host, c->lambda.p, (size_t)c->rank * 8);
+}
+
+int itcpd_get_gram(itcpd_ctx *c, int mode, double *host) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(host && c->G[mode].p, "null host pointer / gram not computed");
+    USE_DEVICE(c);
+    return d2h(c, host, c->G[mode].p, (size_t)c->rank * c->rank * 8);
+}
+
+int itcpd_random_cpd(itcpd_ctx *c, uint64_t seed) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    ARG_CHECK(!comm_active(c), "random_cpd is single-GPU; set the factor slabs explicitly when sharded");
+    uint64_t off = 0;
+    for (int n = 0; n < c->order; ++n) {
+        const int64_t cnt = c->dims[n] * c->rank;
+        TRY(k_randn_matrix(c, c->X.as<double>(), cnt, seed, off));
+        off += (uint64_t)cnt + (cnt & 1);
+        TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[n], c->rank, c->A[n].as<double>(), c->lambda.as<double>(), false));
+        c->fver[n]++;
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+// ---- per-mode hooks ---------------------------------------------------------------------------
+int itcpd_compute_grams(itcpd_ctx *c) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    for (int n = 0; n < c->order; ++n) TRY(gram_device(c, n));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_gram_hadamard(itcpd_ctx *c, int mode, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    TRY(k_gram_hadamard(c, mode, c->Gamma.as<double>()));
+    if (host_out) return d2h(c, host_out, c->Gamma.p, (size_t)c->rank * c->rank * 8);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_mttkrp(itcpd_ctx *c, int mode, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    TRY(mttkrp_device(c, mode));
+    if (host_out) return d2h(c, host_out, c->M[mode].p, (size_t)c->dims[mode] * c->rank * 8);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_solve(itcpd_ctx *c, int mode, double chol_tol, int *path_out, int *rank_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    ARG_CHECK(c->m_valid[mode], "call itcpd_mttkrp(mode) before itcpd_solve(mode)");
+    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, chol_tol, c->X.as<double>(), c->status.as<int>()));
+    int *h = reinterpret_cast<int *>(c->pinned);
+    CUDA_TRY(cudaMemcpyAsync(h, c->status.p, 12, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (path_out) *path_out = h[0];
+    if (rank_out) *rank_out = h[1];
+    return ITCPD_OK;
+}
+
+int itcpd_normalize(itcpd_ctx *c, int mode) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
+    c->fver[mode]++;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_post_solve(itcpd_ctx *c, int mode) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    TRY(gram_device(c, mode));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_fit_terms(itcpd_ctx *c, double *inner, double *model_norm2) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    ARG_CHECK(c->m_valid[c->order - 1], "the last mode's MTTKRP has not been computed");
+    TRY(k_fit_terms(c, c->fit2.as<double>()));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (inner) *inner = c->pinned[0];
+    if (model_norm2) *model_norm2 = c->pinned[1];
+    return ITCPD_OK;
+}
+
+// ---- whole sweeps -----------------------------------------------------------------------------
+// pinned staging layout: [0, 2*nsweeps) fit scalars; then 3 ints per (sweep, mode) of solve status
+int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
+    CHECK_CTX(c);
+    ARG_CHECK(nsweeps >= 1, "nsweeps must be positive");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    const int N = c->order;
+    const size_t need = 2 * (size_t)nsweeps + ((size_t)nsweeps * N * 3 * 4 + 7) / 8 + 8;
+    TRY(ensure_pinned(c, need));
+    TRY(c->status.reserve((size_t)N * 3 * 4 + 64));
+    int *hstat = reinterpret_cast<int *>(c->pinned + 2 * (size_t)nsweeps);
+    for (int s = 0; s < nsweeps; ++s) {
+        for (int mode = 0; mode < N; ++mode) {
+            int *st = c->status.as<int>() + 3 * mode;
+            TRY(mode_update_device(c, mode, chol_tol, st));
+            CUDA_TRY(cudaMemcpyAsync(hstat + ((size_t)s * N + mode) * 3, st, 12, cudaMemcpyDeviceToHost, c->stream));
+        }
+        TRY(k_fit_terms(c, c->fit2.as<double>()));
+        CUDA_TRY(cudaMemcpyAsync(c->pinned + 2 * (size_t)s, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return ITCPD_OK;
+}
+
+int itcpd_sweep_results(itcpd_ctx *c, int nsweeps, double *inner, double *model_norm2, int *qrcp_fallbacks) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ARG_CHECK(2 * (size_t)nsweeps <= c->pinned_doubles, "no results staged for that many sweeps");
+    const int *hstat = reinterpret_cast<const int *>(c->pinned + 2 * (size_t)nsweeps);
+    int fb = 0;
+    for (int s = 0; s < nsweeps; ++s) {
+        if (inner) inner[s] = c->pinned[2 * s];
+        if (model_norm2) model_norm2[s] = c->pinned[2 * s + 1];
+        for (int m = 0; m < c->order; ++m) fb += (hstat[((size_t)s * c->order + m) * 3] == ITCPD_SOLVE_QRCP);
+    }
+    if (qrcp_fallbacks) *qrcp_fallbacks = fb;
+    return ITCPD_OK;
+}
+
+int itcpd_sweep(itcpd_ctx *c, int nsweeps, double chol_tol, double *inner, double *model_norm2) {
+    TRY(itcpd_sweep_async(c, nsweeps, chol_tol));
+    return itcpd_sweep_results(c, nsweeps, inner, model_norm2, nullptr);
+}
+
+int itcpd_als_from_host(itcpd_ctx *c, int order, const int64_t *dims, const double *host_T, int rank,
+                        const double *const *fin, int nsweeps, double chol_tol, double *const *fout, double *lambda_out,
+                        double *inner, double *model_norm2) {
+    CHECK_CTX(c);
+    ARG_CHECK(dims && host_T && fin && fout, "null argument");
+    USE_DEVICE(c);
+    TRY(set_shape(c, order, dims));
+    if (c->rank != rank) { c->rank = rank; invalidate_all(c); }
+    TRY(ensure_cpd_buffers(c));
+    // uploads are enqueued back to back on the handle's stream; no host sync until the results are read
+    if (c->ld0 == c->dims[0]) {
+        CUDA_TRY(cudaMemcpyAsync(c->T.p, host_T, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        TRY(c->work.reserve((size_t)c->nelem * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->work.p, host_T, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(k_pad_copy_in(c, c->work.as<double>(), c->T.as<double>()));
+    }
+    CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
+    for (int n = 0; n < order; ++n) {
+        CUDA_TRY(cudaMemcpyAsync(c->A[n].p, fin[n], (size_t)dims[n] * rank * 8, cudaMemcpyHostToDevice, c->stream));
+        c->fver[n]++;
+    }
+    for (int n = 0; n < order; ++n) TRY(gram_device(c, n));
+    TRY(itcpd_sweep_async(c, nsweeps, chol_tol));
+    for (int n = 0; n < order; ++n)
+        CUDA_TRY(cudaMemcpyAsync(fout[n], c->A[n].p, (size_t)dims[n] * rank * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (lambda_out) CUDA_TRY(cudaMemcpyAsync(lambda_out, c->lambda.p, (size_t)rank * 8, cudaMemcpyDeviceToHost, c->stream));
+    return itcpd_sweep_results(c, nsweeps, inner, model_norm2, nullptr);
+}
+
+// ---- reconstruct / residual ---------------------------------------------------------------------
+int itcpd_reconstruct(itcpd_ctx *c, double *host) {
+    CHECK_CTX(c);
+    ARG_CHECK(host && c->has_tensor && c->rank > 0, "null host pointer / no state");
+    USE_DEVICE(c);
+    TRY(c->work.reserve((size_t)c->nelem * 8));
+    TRY(k_reconstruct(c, c->work.as<double>(), nullptr));
+    return d2h(c, host, c->work.p, (size_t)c->nelem * 8);
+}
+
+int itcpd_residual_norm(itcpd_ctx *c, double *fro) {
+    CHECK_CTX(c);
+    ARG_CHECK(fro && c->has_tensor && c->rank > 0, "null out pointer / no state");
+    USE_DEVICE(c);
+    TRY(k_reconstruct(c, nullptr, c->fit2.as<double>()));
+    if (comm_active(c)) TRY(comm_allreduce_sum(c, c->fit2.as<double>(), 1));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *fro = std::sqrt(c->pinned[0]);
+    return ITCPD_OK;
+}
+
+// ---- sampled path -------------------------------------------------------------------------------
+static int ensure_leverage(itcpd_ctx *c, int mode) {
+    if (c->lev_ver[mode] == c->fver[mode] && c->lev_ver[mode] != 0) return ITCPD_OK;
+    TRY(k_gram(c, c->A[mode].as<double>(), c->dims[mode], c->rank, c->G[mode].as<double>()));
+    TRY(k_leverage(c, c->A[mode].as<double>(), c->G[mode].as<double>(), c->dims[mode], c->rank, c->lev[mode].as<double>()));
+    c->lev_ver[mode] = c->fver[mode];
+    return ITCPD_OK;
+}
+
+int itcpd_leverage_scores(itcpd_ctx *c, int mode, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    TRY(ensure_leverage(c, mode));
+    if (host_out) return d2h(c, host_out, c->lev[mode].p, (size_t)c->dims[mode] * 8);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_sample_factor_matrices(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, skip_mode);
+    ARG_CHECK(nsamp >= 1 && host_out, "bad nsamp / null out pointer");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    for (int m = 0; m < c->order; ++m)
+        if (m != skip_mode) TRY(ensure_leverage(c, m));
+    const size_t bytes = (size_t)nsamp * (c->order - 1) * 8;
+    TRY(c->samp_piv.reserve(bytes));
+    TRY(k_sample_rows(c, skip_mode, nsamp, seed, c->samp_piv.as<int64_t>()));
+    CUDA_TRY(cudaMemcpyAsync(host_out, c->samp_piv.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+static int check_pivots(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv) {
+    int col = 0;
+    for (int m = 0; m < c->order; ++m) {
+        if (m == mode) continue;
+        for (int64_t s = 0; s < nsamp; ++s) {
+            const int64_t v = piv[s + nsamp * col];
+            if (v < 1 || v > c->dims[m]) { set_error("pivot (%lld,%d) = %lld out of range [1,%lld]", (long long)s, col, (long long)v, (long long)c->dims[m]); return ITCPD_ERR_ARG; }
+        }
+        ++col;
+    }
+    return ITCPD_OK;
+}
+
+static int upload_pivots(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots) {
+    TRY(check_pivots(c, mode, nsamp, host_pivots));
+    const size_t bytes = (size_t)nsamp * (c->order - 1) * 8;
+    TRY(c->samp_piv.reserve(bytes));
+    CUDA_TRY(cudaMemcpyAsync(c->samp_piv.p, host_pivots, bytes, cudaMemcpyHostToDevice, c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(nsamp >= 1 && host_pivots && host_out, "bad nsamp / null pointer");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    TRY(upload_pivots(c, mode, nsamp, host_pivots));
+    TRY(c->samp_K.reserve((size_t)nsamp * c->rank * 8));
+    TRY(k_pivot_hadamard(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_K.as<double>()));
+    return d2h(c, host_out, c->samp_K.p, (size_t)nsamp * c->rank * 8);
+}
+
+int itcpd_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(nsamp >= 1 && host_pivots && host_out && c->has_tensor, "bad nsamp / null pointer / no tensor");
+    USE_DEVICE(c);
+    TRY(upload_pivots(c, mode, nsamp, host_pivots));
+    TRY(c->samp_T.reserve((size_t)nsamp * c->dims[mode] * 8));
+    TRY(k_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
+    return d2h(c, host_out, c->samp_T.p, (size_t)nsamp * c->dims[mode] * 8);
+}
+
+int itcpd_column_to_multi_coords(int64_t ncols, const int64_t *cols, int ndims, const int64_t *dims, int64_t *out) {
+    ARG_CHECK(cols && dims && out && ndims >= 1, "null argument");
+    for (int64_t s = 0; s < ncols; ++s) {
+        int64_t rem = cols[s] - 1;
+        for (int d = 0; d < ndims; ++d) {
+            out[s + ncols * d] = rem % dims[d] + 1;
+            rem /= dims[d];
+        }
+    }
+    return ITCPD_OK;
+}
+
+int itcpd_multi_coords_to_column(int64_t ncols, const int64_t *coords, int ndims, const int64_t *dims, int64_t *out) {
+    ARG_CHECK(coords && dims && out && ndims >= 1, "null argument");
+    for (int64_t s = 0; s < ncols; ++s) {
+        int64_t col = 0, stride = 1;
+        for (int d = 0; d < ndims; ++d) {
+            col += (coords[s + ncols * d] - 1) * stride;
+            stride *= dims[d];
+        }
+        out[s] = col + 1;
+    }
+    return ITCPD_OK;
+}
+
+int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows0, const double *vals, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(l >= 1 && s >= 1 && rows0 && vals && host_out && c->has_tensor, "bad argument");
+    USE_DEVICE(c);
+    const int s_eff = std::min(s, l);
+    const int64_t ncols = c->nelem / c->dims[mode];
+    const int64_t nnz = ncols * s_eff;
+    // CSR by sketch row with a stable counting sort: entries of a row stay in increasing nz order
+    std::vector<int64_t> row_ptr((size_t)l + 1, 0), col((size_t)nnz);
+    std::vector<double> val((size_t)nnz);
+    for (int64_t q = 0; q < nnz; ++q) {
+        ARG_CHECK(rows0[q] >= 0 && rows0[q] < l, "sketch row index out of range");
+        row_ptr[(size_t)rows0[q] + 1]++;
+    }
+    for (int j = 0; j < l; ++j) row_ptr[(size_t)j + 1] += row_ptr[j];
+    {
+        std::vector<int64_t> fill(row_ptr.begin(), row_ptr.end() - 1);
+        for (int64_t q = 0; q < nnz; ++q) {
+            const int64_t pos = fill[rows0[q]]++;
+            col[(size_t)pos] = q / s_eff;
+            val[(size_t)pos] = vals[q];
+        }
+    }
+    const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)nnz * 8;
+    TRY(c->work.reserve(b_ptr + 2 * b_col + 64));
+    char *base = (char *)c->work.p;
+    CUDA_TRY(cudaMemcpyAsync(base, row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    TRY(c->samp_T.reserve((size_t)l * c->dims[mode] * 8));
+    TRY(k_sketch_csr(c, mode, l, (const int64_t *)base, (const int64_t *)(base + b_ptr), (const double *)(base + b_ptr + b_col),
+                     c->samp_T.as<double>()));
+    return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+}
+
+int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(nsamp >= 1 && host_pivots && c->has_tensor, "bad nsamp / null pointer / no tensor");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    ARG_CHECK(!comm_active(c), "the sampled path is single-GPU in this build");
+    const int R = c->rank;
+    const int64_t I = c->dims[mode];
+    TRY(upload_pivots(c, mode, nsamp, host_pivots));
+    TRY(c->samp_K.reserve((size_t)nsamp * R * 8));
+    TRY(c->samp_T.reserve((size_t)nsamp * I * 8));
+    TRY(k_pivot_hadamard(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_K.as<double>()));
+    TRY(k_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
+    // normal equations of the sampled problem (ProjectionAlgorithm.jl:61-62): (K'K) X' = (T_s K)'
+    TRY(k_gram(c, c->samp_K.as<double>(), nsamp, R, c->Gamma.as<double>()));
+    TRY(k_small_gemm_nn(c, c->samp_T.as<double>(), c->samp_K.as<double>(), I, nsamp, R, c->M[mode].as<double>()));
+    c->m_valid[mode] = false;  // M[mode] now holds the *sampled* MTTKRP
+    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>()));
+    TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
+    c->fver[mode]++;
+    TRY(ensure_leverage(c, mode));  // also refreshes G[mode] (post_solve of LevScoreSampled, krp_lev...:55-58)
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_allgather_factor(itcpd_ctx *c, int mode, int64_t rows_total, double *host_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(host_out != nullptr, "null out pointer");
+    USE_DEVICE(c);
+    const int R = c->rank;
+    if (!comm_active(c) || mode != c->order - 1) {
+        ARG_CHECK(rows_total == c->dims[mode], "rows_total must equal the local row count for a replicated factor");
+        return d2h(c, host_out, c->A[mode].p, (size_t)rows_total * R * 8);
+    }
+    const int nr = comm_size(c);
+    const int64_t loc = c->dims[mode];
+    ARG_CHECK(loc * nr == rows_total, "slabs must be equal-sized for the all-gather");
+    // gather rank-major [rank][loc x R] then interleave into the rows_total x R column-major factor on the host
+    TRY(c->work.reserve((size_t)rows_total * R * 8));
+    TRY(comm_allgather(c, c->A[mode].as<double>(), c->work.as<double>(), loc * R));
+    std::vector<double> tmp((size_t)rows_total * R);
+    TRY(d2h(c, tmp.data(), c->work.p, (size_t)rows_total * R * 8));
+    for (int g = 0; g < nr; ++g)
+        for (int r = 0; r < R; ++r)
+            memcpy(host_out + (size_t)g * loc + (size_t)rows_total * r, tmp.data() + ((size_t)g * R + r) * loc, (size_t)loc * 8);
+    return ITCPD_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------------------
+int itcpd_gemm_timing(itcpd_ctx *c, int reset, double *avg_ms, int64_t *launches) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i < c->gemm_events_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->gemm_events[i].first, c->gemm_events[i].second));
+        tot += ms;
+    }
+    if (avg_ms) *avg_ms = c->gemm_events_used ? tot / (double)c->gemm_events_used : 0.0;
+    if (launches) *launches = (int64_t)c->gemm_events_used;
+    if (reset) c->gemm_events_used = 0;
+    return ITCPD_OK;
+}
+
+int itcpd_probe_dmma_peak(itcpd_ctx *c, double *tflops) {
+    CHECK_CTX(c);
+    ARG_CHECK(tflops != nullptr, "null out pointer");
+    USE_DEVICE(c);
+    return probe_dmma(c, tflops);
+}
+
+int itcpd_probe_dfma_peak(itcpd_ctx *c, double *tflops) {
+    CHECK_CTX(c);
+    ARG_CHECK(tflops != nullptr, "null out pointer");
+    USE_DEVICE(c);
+    return probe_dfma(c, tflops);
+}
+
+}  // extern "C"

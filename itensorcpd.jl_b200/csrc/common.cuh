@@ -1,0 +1,168 @@
+// Shared declarations of libitcpd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/itcpd_b200.h"
+
+#define ITCPD_MAX_ORDER 8
+
+namespace itcpd {
+
+void set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            itcpd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return ITCPD_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+#define ARG_CHECK(cond, msg)                                         \
+    do {                                                             \
+        if (!(cond)) {                                               \
+            itcpd::set_error("%s:%d %s", __FILE__, __LINE__, msg);   \
+            return ITCPD_ERR_ARG;                                    \
+        }                                                            \
+    } while (0)
+
+#define TRY(expr)                    \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != ITCPD_OK) return _s; \
+    } while (0)
+
+// A device buffer that grows on demand (never shrinks): all scratch lives behind the handle.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// One cached partial contraction of the dimension tree.
+//   kind A: P[(i_0..i_{s-1}), r] = sum_{i_s..i_{N-1}} T * prod_{m>=s} A_m   (modes [0,s) stay free)
+//   kind B: Q[(i_s..i_{N-1}), r] = sum_{i_0..i_{s-1}} T * prod_{m<s}  A_m   (modes [s,N) stay free)
+struct Partial {
+    DevBuf buf;
+    bool valid = false;
+    int split = 0;
+    uint64_t dep_version[ITCPD_MAX_ORDER];  // versions of the contracted factors when computed
+};
+
+struct Comm;  // comm.cu
+
+}  // namespace itcpd
+
+struct itcpd_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // options
+    int mttkrp_alg = ITCPD_MTTKRP_TREE;
+    int swizzle = 1;
+    int tile_warps = 8;
+    int force_split_a = 0, force_split_b = 0;
+
+    // tensor
+    int order = 0;
+    int64_t dims[ITCPD_MAX_ORDER] = {0};
+    int64_t ld0 = 0;    // leading dimension of mode 0 in device storage (dims[0] rounded up to even)
+    int64_t nelem = 0;  // logical element count
+    int64_t nstore = 0; // stored element count (ld0 * prod(dims[1:]))
+    itcpd::DevBuf T;
+    bool has_tensor = false;
+
+    // CPD
+    int rank = 0;
+    itcpd::DevBuf A[ITCPD_MAX_ORDER];   // I_n x R col-major
+    itcpd::DevBuf G[ITCPD_MAX_ORDER];   // R x R
+    itcpd::DevBuf M[ITCPD_MAX_ORDER];   // last MTTKRP of each mode, I_n x R
+    itcpd::DevBuf X;                    // solve output (max I x R)
+    itcpd::DevBuf lambda, Gamma, lev[ITCPD_MAX_ORDER];
+    uint64_t lev_ver[ITCPD_MAX_ORDER] = {0};  // fver value the leverage scores were computed for (0 = never)
+    uint64_t fver[ITCPD_MAX_ORDER] = {0};  // factor versions (bumped on every change)
+    bool m_valid[ITCPD_MAX_ORDER] = {false};
+    int last_mttkrp_mode = -1;
+
+    // dimension tree
+    itcpd::Partial PA, PB;
+    int split_a = 0, split_b = 0;
+
+    // scratch
+    itcpd::DevBuf packK, krp_scratch[2], work, work2, redux, solve_ws, ipiv, status, fit2, samp_piv, samp_K, samp_T;
+    double *pinned = nullptr;   // pinned host staging (fit scalars, status words)
+    size_t pinned_doubles = 0;
+
+    // GEMM timing (CUDA events on `stream`)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    size_t gemm_events_used = 0;
+    bool time_gemm = false;
+
+    // multi-GPU
+    itcpd::Comm *comm = nullptr;
+};
+
+namespace itcpd {
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- gemm_dmma.cu -------------------------------------------------------------------------
+// Partial contraction of the dimension tree (the dominant kernel).
+//  kind 0 ("A"): out[m, r] = sum_k T[m + M*k] K[k, r]; m in [0,M) = stored modes [0,split), k = modes [split,N)
+//  kind 1 ("B"): out[n, r] = sum_m T[m + Mc*n] K[m, r]; m = stored modes [0,split), n = modes [split,N)
+int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out);
+int probe_dmma(itcpd_ctx *c, double *tflops);
+int probe_dfma(itcpd_ctx *c, double *tflops);
+
+// ---- kernels.cu ---------------------------------------------------------------------------
+int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G);
+int k_gram_hadamard(itcpd_ctx *c, int skip_mode, double *Gamma);
+int k_colnorm_scale(itcpd_ctx *c, const double *X, int64_t rows, int R, double *A, double *lambda, bool rows_are_slab);
+int k_fit_terms(itcpd_ctx *c, double *out2 /*device: inner, norm2*/);
+int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64_t ld_first, int mode, double *out);
+int k_direct_mttkrp(itcpd_ctx *c, int mode, double *out);
+int k_generate(itcpd_ctx *c, uint64_t seed, int64_t elem_offset);
+int k_randn_matrix(itcpd_ctx *c, double *dst, int64_t n, uint64_t seed, uint64_t stream_offset);
+int k_sumsq(itcpd_ctx *c, const double *x, int64_t n, double *out_dev);
+int k_pad_copy_in(itcpd_ctx *c, const double *src_dense, double *dst_padded);   // dims[0] -> ld0
+int k_pad_copy_out(itcpd_ctx *c, const double *src_padded, double *dst_dense);
+int k_reconstruct(itcpd_ctx *c, double *out_dense_or_null, double *resid_sumsq_dev_or_null);
+
+// ---- solve.cu -----------------------------------------------------------------------------
+// X (rows x R) = (Gamma \ M^T)^T with the ldiv_solve.jl semantics. status_dev[0]=path, [1]=rank.
+int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev);
+int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out);
+
+// ---- sampled.cu ---------------------------------------------------------------------------
+int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev);
+int k_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *K_dev);
+int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
+int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
+int k_small_gemm_nn(itcpd_ctx *c, const double *A, const double *B, int64_t m, int64_t k, int n, double *C); // C = A B
+
+// ---- comm.cu ------------------------------------------------------------------------------
+int comm_allreduce_sum(itcpd_ctx *c, double *buf, int64_t n);
+int comm_allgather(itcpd_ctx *c, const double *send, double *recv, int64_t n_per_rank);
+bool comm_active(const itcpd_ctx *c);
+int comm_rank(const itcpd_ctx *c);
+int comm_size(const itcpd_ctx *c);
+
+// ---- api.cu helpers -----------------------------------------------------------------------
+int ensure_cpd_buffers(itcpd_ctx *c);
+int64_t mode_rows(const itcpd_ctx *c, int mode);
+void choose_splits(itcpd_ctx *c);
+
+}  // namespace itcpd

@@ -1,0 +1,499 @@
+// The dominant kernel: partial contraction of the dimension tree as a TMA-staged FP64 DMMA GEMM.
+//
+// Replaces the R-pass per-rank contraction loop of the reference's MTTKRP
+// (src/algebra/had_contract.jl:72-124, reached from algorithms/.../standard/tensor.jl:32-44) and the
+// permute+GEMM of KRPNormal (tensor.jl:12-20).  The dense tensor is never permuted or copied: it is
+// viewed as a column-major matrix (modes [0,split) x modes [split,N)) and streamed from HBM once per
+// pass through 2-D TMA boxes (cp.async.bulk.tensor, 128B swizzle) into a 4-stage mbarrier ring; the
+// Khatri-Rao operand is pre-packed in MMA fragment order and staged with 1-D bulk copies.  Eight
+// consumer warps issue mma.sync m8n8k4 f64 (SASS DMMA.8x8x4; FP64 has no tcgen05 kind) on 32 x 8*NB
+// register tiles; the TMA refill duty rotates over the warps (one elected lane).  Persistent CTAs.
+//
+//  kind 0 ("A"): out[m, r] = sum_k T[m + M*k]  * K[k, r]   (free index m contiguous in memory)
+//  kind 1 ("B"): out[n, r] = sum_m T[m + Mc*n] * K[m, r]   (contraction index m contiguous in memory)
+#include "common.cuh"
+
+namespace itcpd {
+
+constexpr int BK = 16;      // contraction tile: 16 doubles = one 128-byte swizzle row
+constexpr int STAGES = 4;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// row permutation of kind-1 A fragments: makes the 8 lanes of a quarter warp hit 8 distinct
+// 16-byte bank groups under the 128B swizzle (see DESIGN.md "fragment maps")
+__device__ __forceinline__ int sigma_b(int g) { return (g >> 1) + ((g & 1) << 2); }
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------------
+template <int NB, int WARPS>
+struct GemmSmem {
+    static constexpr int BM = 32 * WARPS;
+    static constexpr int T_BYTES = BM * BK * 8;
+    static constexpr int K_BYTES = BK * 8 * NB * 8;
+    static constexpr int STAGE_BYTES = T_BYTES + K_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024 /*alignment slack*/;
+};
+
+template <int NB, int WARPS, int KIND>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 2 : 1))
+partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restrict__ Kp, double *__restrict__ out,
+                    int64_t rows_out, int R, int num_row_tiles, int num_rblocks, int kt_count, int swz_mask) {
+    using S = GemmSmem<NB, WARPS>;
+    constexpr int BM = S::BM;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sT0 = smem_base;
+    const uint32_t sK0 = smem_base + STAGES * S::T_BYTES;
+    const uint32_t bar0 = sK0 + STAGES * S::K_BYTES;  // full[STAGES], empty[STAGES]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 8 * (STAGES + s), WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int num_tiles = num_row_tiles * num_rblocks;
+    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_iters = my_tiles * kt_count;
+
+    // Stage refill for pipeline iteration j (one elected lane; the duty rotates over the warps so that
+    // no warp's DMMA stream carries the whole TMA-issue overhead).
+    auto issue = [&](int j) {
+        const int sj = j % STAGES;
+        if (j >= STAGES) mbar_wait(bar0 + 8 * (STAGES + sj), (uint32_t)((j / STAGES - 1) & 1));
+        const int jt = j / kt_count;
+        const int kt = j - jt * kt_count;
+        const int tile = (int)blockIdx.x + jt * (int)gridDim.x;
+        const int row_tile = tile / num_rblocks;
+        const int rb = tile - row_tile * num_rblocks;
+        const int row0 = row_tile * BM;
+        const uint32_t full = bar0 + 8 * sj;
+        mbar_expect_tx(full, S::STAGE_BYTES);
+        const uint32_t dT = sT0 + sj * S::T_BYTES;
+        if (KIND == 0) {
+#pragma unroll 1
+            for (int gg = 0; gg < BM / 16; ++gg) tma_load_2d(dT + gg * (BK * 128), &tmap, row0 + 16 * gg, kt * BK, full);
+        } else {
+            tma_load_2d(dT, &tmap, kt * BK, row0, full);
+        }
+        const double *src = Kp + ((size_t)kt * num_rblocks + rb) * (size_t)(BK * 8 * NB);
+        bulk_load_1d(sK0 + sj * S::K_BYTES, src, S::K_BYTES, full);
+    };
+
+    if (warp == 0 && lane == 0) {
+        for (int j = 0; j < STAGES - 1 && j < total_iters; ++j) issue(j);
+    }
+    __syncwarp();
+
+    const int g = lane >> 2;   // MMA groupID
+    const int t = lane & 3;    // MMA threadID_in_group
+    int it = 0;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row_tile = tile / num_rblocks;
+        const int rb = tile - row_tile * num_rblocks;
+        const int64_t row0 = (int64_t)row_tile * BM;
+
+        double acc[4][NB][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kt = 0; kt < kt_count; ++kt, ++it) {
+            {
+                const int j = it + STAGES - 1;
+                if (j < total_iters && warp == (it % WARPS)) {
+                    if (lane == 0) issue(j);
+                    __syncwarp();
+                }
+            }
+            const int stage = it % STAGES;
+            mbar_wait(bar0 + 8 * stage, (uint32_t)((it / STAGES) & 1));
+            const uint32_t sT = sT0 + stage * S::T_BYTES;
+            const uint32_t sK = sK0 + stage * S::K_BYTES;
+#pragma unroll
+            for (int pair = 0; pair < 2; ++pair) {
+                double2 b[NB];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) b[nb] = lds128(sK + (((pair * NB + nb) * 32 + lane) << 4));
+                double a[4][2];  // [row block][k-step of the pair]
+                if (KIND == 0) {
+                    // smem box = [k row (128 B)][16 m]; one LDS.128 = rows m=2g,2g+1 of a 16-row group at one k
+#pragma unroll
+                    for (int gq = 0; gq < 2; ++gq) {
+                        const uint32_t base = sT + (2 * warp + gq) * (BK * 128);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int rho = 8 * pair + 2 * t + e;
+                            const double2 v = lds128(base + rho * 128 + ((g ^ (rho & swz_mask)) << 4));
+                            a[2 * gq + 0][e] = v.x;
+                            a[2 * gq + 1][e] = v.y;
+                        }
+                    }
+                } else {
+                    // smem box = [n row (128 B)][16 m]; one LDS.128 = k = 2c, 2c+1 of one output row
+#pragma unroll
+                    for (int rbk = 0; rbk < 4; ++rbk) {
+                        const int nl = 32 * warp + 8 * rbk + sigma_b(g);
+                        const int c = 4 * pair + t;
+                        const double2 v = lds128(sT + nl * 128 + ((c ^ (nl & swz_mask)) << 4));
+                        a[rbk][0] = v.x;
+                        a[rbk][1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int rbk = 0; rbk < 4; ++rbk)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+                            dmma884(acc[rbk][nb][0], acc[rbk][nb][1], a[rbk][e], e == 0 ? b[nb].x : b[nb].y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + stage));
+        }
+
+        // ---- epilogue: registers -> global (column-major rows_out x R) ----
+        if (KIND == 0) {
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+                const int64_t m = row0 + 32 * warp + 16 * gq + 2 * g;
+                if (m < rows_out) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int r = 8 * (rb * NB + nb) + 2 * t + j;
+                            if (r < R) {
+                                double *dst = out + m + rows_out * (int64_t)r;
+                                if (m + 1 < rows_out) {
+                                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[2 * gq][nb][j], acc[2 * gq + 1][nb][j]);
+                                } else {
+                                    dst[0] = acc[2 * gq][nb][j];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int rbk = 0; rbk < 4; ++rbk) {
+                const int64_t n = row0 + 32 * warp + 8 * rbk + sigma_b(g);
+                if (n < rows_out) {
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int r = 8 * (rb * NB + nb) + 2 * t + j;
+                            if (r < R) out[n + rows_out * (int64_t)r] = acc[rbk][nb][j];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Khatri-Rao operand packing: K[k, r] = prod_f A_f[i_f(k), r] written in DMMA B-fragment order
+//   Kp[kt][rb][pair][nb][lane][e],  k = 16 kt + 8 pair + 2 (lane&3) + e,  r = 8 (rb NB + nb) + (lane>>2)
+// zero for k >= K extent, padded rows of mode 0 and r >= R.
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+    const double *fac[ITCPD_MAX_ORDER];
+    int64_t ext[ITCPD_MAX_ORDER];   // extent used to decode the linear k (ld0 for a padded mode 0)
+    int64_t dim[ITCPD_MAX_ORDER];   // logical rows of the factor
+    int nf;
+    int64_t kext;                   // product of ext
+    int R, NB, num_rblocks, kt_count;
+};
+
+__global__ void pack_krp_kernel(PackArgs a, double *__restrict__ Kp, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = idx & 1;
+        const int lane = (idx >> 1) & 31;
+        int64_t q = idx >> 6;
+        const int nb = q % a.NB; q /= a.NB;
+        const int pair = q & 1; q >>= 1;
+        const int rb = q % a.num_rblocks; q /= a.num_rblocks;
+        const int64_t kt = q;
+        const int64_t k = 16 * kt + 8 * pair + 2 * (lane & 3) + e;
+        const int r = 8 * (rb * a.NB + nb) + (lane >> 2);
+        double v = 0.0;
+        if (k < a.kext && r < a.R) {
+            v = 1.0;
+            int64_t rem = k;
+            for (int f = 0; f < a.nf; ++f) {
+                const int64_t i = rem % a.ext[f];
+                rem /= a.ext[f];
+                v = (i < a.dim[f]) ? v * a.fac[f][i + a.dim[f] * (int64_t)r] : 0.0;
+            }
+        }
+        Kp[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+static int make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint64_t d1, uint32_t box0, uint32_t box1, bool swz) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return ITCPD_ERR_CUDA; }
+    cuuint64_t gdim[2] = {d0, d1};
+    cuuint64_t gstr[1] = {d0 * 8};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=(%llu,%llu) box=(%u,%u)", (int)r, (unsigned long long)d0,
+                  (unsigned long long)d1, box0, box1);
+        return ITCPD_ERR_CUDA;
+    }
+    return ITCPD_OK;
+}
+
+template <int NB, int WARPS, int KIND>
+static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, double *out, int64_t rows_out, int R,
+                      int num_row_tiles, int num_rblocks, int kt_count) {
+    using S = GemmSmem<NB, WARPS>;
+    auto kern = partial_gemm_kernel<NB, WARPS, KIND>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    const int per_sm = (WARPS <= 4) ? 2 : 1;
+    int64_t tiles = (int64_t)num_row_tiles * num_rblocks;
+    int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    kern<<<grid, WARPS * 32, S::TOTAL, c->stream>>>(map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count,
+                                                          c->swizzle ? 7 : 0);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+template <int WARPS, int KIND>
+static int launch_nb(itcpd_ctx *c, int NB, const CUtensorMap &map, const double *Kp, double *out, int64_t rows_out, int R,
+                     int nrt, int nrb, int ktc) {
+    switch (NB) {
+        case 1: return launch_cfg<1, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 2: return launch_cfg<2, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 3: return launch_cfg<3, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 4: return launch_cfg<4, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 5: return launch_cfg<5, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 6: return launch_cfg<6, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 7: return launch_cfg<7, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        default: return launch_cfg<8, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+    }
+}
+
+int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out) {
+    const int N = c->order, R = c->rank;
+    ARG_CHECK(split >= 1 && split < N, "bad dimension-tree split");
+    // matrix view of the stored tensor: rows = modes [0,split) (mode 0 with leading dim ld0), cols = modes [split,N)
+    int64_t Mrows = c->ld0, Ncols = 1;
+    for (int n = 1; n < split; ++n) Mrows *= c->dims[n];
+    for (int n = split; n < N; ++n) Ncols *= c->dims[n];
+
+    // choose the r blocking: NB n-blocks of 8 columns per CTA pass, as balanced as possible
+    const int nblk = (int)ceil_div(R, 8);
+    const int num_rblocks = (int)ceil_div(nblk, 8);
+    const int NB = (int)ceil_div(nblk, num_rblocks);
+
+    const int64_t kext = (kind == 0) ? Ncols : Mrows;
+    const int64_t rows_out = (kind == 0) ? Mrows : Ncols;
+    const int kt_count = (int)ceil_div(kext, BK);
+
+    // ---- pack the Khatri-Rao operand ----
+    PackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.R = R; pa.NB = NB; pa.num_rblocks = num_rblocks; pa.kt_count = kt_count; pa.kext = kext;
+    if (kind == 0) {
+        for (int n = split; n < N; ++n) {
+            pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++;
+        }
+    } else {
+        for (int n = 0; n < split; ++n) {
+            pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = (n == 0) ? c->ld0 : c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++;
+        }
+    }
+    const int64_t total = (int64_t)kt_count * num_rblocks * 2 * NB * 64;
+    TRY(c->packK.reserve((size_t)total * 8));
+    {
+        int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)c->sm_count * 8);
+        pack_krp_kernel<<<blocks, 256, 0, c->stream>>>(pa, c->packK.as<double>(), total);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+
+    // ---- tile shape ----
+    int warps = c->tile_warps;
+    if (warps != 4 && warps != 8) warps = 8;
+    // small problems: prefer the 128-row tile so that more SMs get work
+    if (ceil_div(rows_out, 256) * num_rblocks < c->sm_count) warps = 4;
+    const int BM = 32 * warps;
+    const int num_row_tiles = (int)ceil_div(rows_out, BM);
+
+    CUtensorMap map;
+    if (kind == 0) TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, 16, BK, c->swizzle != 0));
+    else TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, BK, (uint32_t)BM, c->swizzle != 0));
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_gemm) {
+        if (c->gemm_events_used == c->gemm_events.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            c->gemm_events.push_back({a, b});
+        }
+        e0 = c->gemm_events[c->gemm_events_used].first;
+        e1 = c->gemm_events[c->gemm_events_used].second;
+        c->gemm_events_used++;
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+    int st;
+    const double *Kp = c->packK.as<double>();
+    if (kind == 0) st = (warps == 8) ? launch_nb<8, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count)
+                                     : launch_nb<4, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count);
+    else st = (warps == 8) ? launch_nb<8, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count)
+                           : launch_nb<4, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count);
+    if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probes (roofline denominators measured on the box the bench runs on)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double *sink, int iters) {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = 0.5, b0 = 1e-3, b1 = 2e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], (i & 1) ? a1 : a0, (i & 2) ? b1 : b0);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double *sink, int iters) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-6 + i;
+    const double a = 1.0000001, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+static int run_probe(itcpd_ctx *c, bool dmma, double *tflops) {
+    TRY(c->work.reserve(64));
+    const int iters = 4096, blocks = c->sm_count * 4, threads = 256;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        if (dmma) probe_dmma_kernel<<<blocks, threads, 0, c->stream>>>(c->work.as<double>(), iters);
+        else probe_dfma_kernel<<<blocks, threads, 0, c->stream>>>(c->work.as<double>(), iters);
+        c->launches++;
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double warps = (double)blocks * threads / 32.0;
+    const double flops = dmma ? warps * iters * 16.0 * (2.0 * 8 * 8 * 4) : (double)blocks * threads * iters * 16.0 * 2.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return ITCPD_OK;
+}
+
+int probe_dmma(itcpd_ctx *c, double *tflops) { return run_probe(c, true, tflops); }
+int probe_dfma(itcpd_ctx *c, double *tflops) { return run_probe(c, false, tflops); }
+
+}  // namespace itcpd

@@ -1,0 +1,475 @@
+"""Host-side mirror of ITensorCPD.jl's public API for the decomposition path, driving the C-ABI.
+
+Same names, argument meaning and error behaviour as the reference (file:line into the reference):
+`decompose` (src/decompose.jl:1-69), `als_optimize` / `ALS` / `compute_als`
+(src/optimizers/als_optimizers/als_optimizer.jl:5-69), `optimize` (optimize.jl:6-35), `random_CPD`
+(src/cpd.jl:63-82), `CPD` with `cp[n]` / `cp[()]` (cpd.jl:7-46), `reconstruct`
+(src/algebra/reconstruct.jl:2-9), `FitCheck` / `NoCheck` / `CPDiffCheck` / `CPAngleCheck`
+(src/converge_checks/*.jl), algorithm objects `KRPFreeNormal`, `KRPNormal`, `LevScoreSampled`.
+
+This is what the Julia package extension does (julia/ext/ITCPDB200Ext.jl): Julia is not installed in
+this image, so the same control flow is written in Python.  Everything numeric happens in
+libitcpd_b200.so on the GPU; the only host arithmetic is the scalar convergence state machine,
+exactly as in the reference.  Python indices are 0-based (modes 0..N-1); sample / pivot matrices
+keep the reference's 1-based int64 convention.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+
+from .engine import Engine
+
+CHOLESKY_EPSILON = 1e-6  # src/ITensorCPD.jl:2
+
+
+# ------------------------------------------------------------------------------------------
+# CPD container  (cpd.jl:7-46)
+# ------------------------------------------------------------------------------------------
+class CPD:
+    def __init__(self, factors: List[np.ndarray], lam: np.ndarray):
+        self.factors = [np.asfortranarray(f, dtype=np.float64) for f in factors]
+        self.lam = np.ascontiguousarray(lam, dtype=np.float64)
+
+    def __getitem__(self, i):
+        if i == () or i is None:  # cp[] in Julia
+            return self.lam
+        return self.factors[i]
+
+    def __len__(self):
+        return len(self.factors)
+
+    def __iter__(self):
+        return iter(self.factors)
+
+    @property
+    def rank(self) -> int:
+        return int(self.lam.shape[0])
+
+    @property
+    def dims(self):
+        return tuple(int(f.shape[0]) for f in self.factors)
+
+    def copy(self):
+        return CPD([f.copy(order="F") for f in self.factors], self.lam.copy())
+
+    def __eq__(self, other):
+        return all(np.array_equal(a, b) for a, b in zip(self.factors, other.factors)) and np.array_equal(self.lam, other.lam)
+
+
+def cp_rank(cp: CPD) -> int:
+    return cp.rank
+
+
+def random_factors(dims, rank: int, rng=None):
+    """cpd.jl:48-60: randn(I_n, R) per mode from ONE generator, column-normalised; lambda = norms of
+    the last factor.  (Default stream: numpy default_rng(3) stands in for MersenneTwister(3).)"""
+    rng = np.random.default_rng(3) if rng is None else rng
+    facs, lam = [], None
+    for I in dims:
+        X = np.asfortranarray(rng.standard_normal((int(I), int(rank))))
+        lam = np.sqrt(np.sum(X * X, axis=0))
+        facs.append(np.asfortranarray(X / lam[None, :]))
+    return facs, lam
+
+
+def random_CPD(target, rank: int, rng=None) -> CPD:
+    dims = target.shape if hasattr(target, "shape") else tuple(target)
+    f, l = random_factors(dims, rank, rng)
+    return CPD(f, l)
+
+
+# ------------------------------------------------------------------------------------------
+# convergence checks (host state machines, src/converge_checks/*.jl)
+# ------------------------------------------------------------------------------------------
+class ConvergeAlg:
+    iter = 0
+    max_counter = 0
+
+
+class NoCheck(ConvergeAlg):  # no_check.jl:1-20
+    def __init__(self, maxiter: int):
+        self.iter = 0
+        self.max_counter = int(maxiter)
+        self.lastfit = -1
+
+    def check_converge(self, als, factors_lam, verbose=False) -> bool:
+        self.iter += 1
+        if verbose:
+            print(f"{als.engine.rank}\t {self.iter}")
+        if self.iter == self.max_counter:
+            self.iter = 0
+            return True
+        return False
+
+
+class FitCheck(ConvergeAlg):  # fit_check.jl:5-68
+    def __init__(self, tol, maxiter, ref_norm):
+        self.iter = 0
+        self.counter = 0
+        self.tolerance = tol
+        self.max_counter = int(maxiter)
+        self.ref_norm = float(ref_norm)
+        self.lastfit = 1.0
+        self.final_fit = 0.0
+        self.total_iter = 0
+        self.history: List[float] = []
+
+    def update(self, inner: float, fact_square: float, R: int, verbose=False) -> bool:
+        """fit_check.jl:25-65 given <T,That> and ||That||^2 from the device (itcpd_fit_terms)."""
+        self.iter += 1
+        resid = math.sqrt(abs(self.ref_norm * self.ref_norm + fact_square - 2 * abs(inner)))
+        curr = 1.0 - resid / self.ref_norm
+        dfit = abs(self.lastfit - curr)
+        self.lastfit = curr
+        self.history.append(curr)
+        if verbose:
+            print(f"{R}\t {self.iter} \t {curr} \t {dfit}")
+        if math.isnan(curr):
+            raise RuntimeError("Error NAN")
+        if dfit < self.tolerance:
+            self.counter += 1
+            if self.counter >= 2:
+                self.total_iter = self.iter
+                self.iter = 0
+                self.counter = 0
+                self.final_fit = self.lastfit
+                self.lastfit = 0
+                return True
+        else:
+            self.counter = 0
+        if self.iter >= self.max_counter:
+            self.total_iter = self.iter
+            self.iter = 0
+            self.counter = 0
+            self.final_fit = self.lastfit
+            self.lastfit = 0
+        return False
+
+    def check_converge(self, als, factors_lam, verbose=False) -> bool:
+        inner, norm2 = als.engine.fit_terms()
+        return self.update(inner, norm2, als.engine.rank, verbose)
+
+
+def CPDFit(check) -> float:
+    return check.final_fit
+
+
+def _cp_cp_inner(f1, f2):
+    inner = np.ones((f1[0].shape[1], f2[0].shape[1]))
+    for a, b in zip(f1, f2):
+        inner = inner * (a.T @ b)
+    return inner
+
+
+def _norm2(factors, lam):
+    had = np.ones((lam.shape[0], lam.shape[0]))
+    for f in factors:
+        had = had * (f.T @ f)
+    return float(lam @ had @ lam)
+
+
+class _PrevCheck(ConvergeAlg):
+    """CPDiffCheck / CPAngleCheck work on the factor matrices only (R x R algebra on host copies,
+    cp_diff_check.jl:20-71, cp_angle_check.jl:20-73); they are the stopping rules of the sampled solvers."""
+
+    def __init__(self, tol, maxiter):
+        self.iter, self.counter, self.tolerance, self.max_counter = 0, 0, tol, int(maxiter)
+        self.norm_prev_iter, self.prev, self.final_fit, self.total_iter = 0.0, None, 0, 0
+        self._lastv = 1
+
+    def _finish(self):
+        self.total_iter = self.iter
+        self.iter = 0
+        self.counter = 0
+        self.final_fit = self._lastv
+        self._lastv = 0
+        self.prev = None
+
+    def check_converge(self, als, factors_lam, verbose=False) -> bool:
+        factors, lam = factors_lam()
+        self.iter += 1
+        if self.prev is None:
+            self.prev = (factors, lam)
+            self.norm_prev_iter = self._first_norm(factors, lam)
+            return False
+        val = self._measure(factors, lam)
+        d = abs(self._lastv - val)
+        self._lastv = val
+        self.prev = (factors, lam)
+        if verbose:
+            print(f"{lam.shape[0]}\t {self.iter} \t {val} \t {d}")
+        if d < self.tolerance:
+            self.counter += 1
+            if self.counter >= 2:
+                self._finish()
+                return True
+        else:
+            self.counter = 0
+        if self.iter >= self.max_counter:
+            self._finish()
+        return False
+
+
+class CPDiffCheck(_PrevCheck):
+    @property
+    def lastfit(self):
+        return self._lastv
+
+    def _first_norm(self, f, l):
+        return _norm2(f, l)
+
+    def _measure(self, factors, lam):
+        pf, pl = self.prev
+        inner = float(pl @ _cp_cp_inner(pf, factors) @ lam)
+        sq = _norm2(factors, lam)
+        resid = math.sqrt(abs(self.norm_prev_iter + sq - 2 * abs(inner)))
+        fit = 1.0 - resid / math.sqrt(abs(self.norm_prev_iter))
+        self.norm_prev_iter = sq
+        return fit
+
+
+class CPAngleCheck(_PrevCheck):
+    @property
+    def lastangle(self):
+        return self._lastv
+
+    def _first_norm(self, f, l):
+        return math.sqrt(_norm2(f, l))
+
+    def _measure(self, factors, lam):
+        pf, pl = self.prev
+        numer = float(pl @ _cp_cp_inner(pf, factors) @ lam)
+        nc = math.sqrt(_norm2(factors, lam))
+        theta = min(1.0, numer / (nc * self.norm_prev_iter))
+        self.norm_prev_iter = nc
+        return math.acos(theta)
+
+
+# ------------------------------------------------------------------------------------------
+# algorithm objects: the 5-hook contract of optimize.jl:19-30, each hook one C-ABI call
+# ------------------------------------------------------------------------------------------
+class MttkrpAlgorithm:
+    """Normal-equation solvers (algorithms/.../standard/MttkrpAlgorithm.jl)."""
+
+    mttkrp_alg = 0  # ITCPD_MTTKRP_TREE
+
+    def compute_krp(self, als, fact):  # MttkrpAlgorithm.jl:18-31
+        als.engine.gram_hadamard(fact, fetch=False)
+
+    def matricize_tensor(self, als, fact):  # tensor.jl:12-44
+        als.engine.mttkrp(fact, fetch=False)
+
+    def solve_ls_problem(self, als, fact):  # MttkrpAlgorithm.jl:34-41 -> ldiv_solve.jl:13-29
+        als.solve_paths.append(als.engine.solve(fact, CHOLESKY_EPSILON))
+
+    def post_solve(self, als, fact):  # tensor.jl:46-49
+        als.engine.post_solve(fact)
+
+    def check_converge(self, als, verbose=False) -> bool:  # MttkrpAlgorithm.jl:5-14
+        return als.check.check_converge(als, als.fetch_cpd_arrays, verbose=verbose)
+
+
+class KRPFreeNormal(MttkrpAlgorithm):
+    """The reference default (als_optimizer.jl:45).  On the device both reference MTTKRP
+    formulations are served by the same dimension-tree GEMM: identical M, one tensor pass per half sweep."""
+
+
+class KRPNormal(MttkrpAlgorithm):
+    pass
+
+
+class DirectNormal(MttkrpAlgorithm):
+    """Cross-check variant: one plain-FMA pass over T per mode (ITCPD_MTTKRP_DIRECT)."""
+
+    mttkrp_alg = 1
+
+
+class ProjectionAlgorithm:
+    pass
+
+
+class LevScoreSampled(ProjectionAlgorithm):
+    """algorithms/.../randomized/krp_lev_score_sampled.jl:9-58 with the device doing the leverage
+    scores, the weighted sampling, both gathers and the sampled normal-equation solve."""
+
+    def __init__(self, nsamples=1):
+        self.NSamples = tuple(nsamples) if isinstance(nsamples, (tuple, list)) else (int(nsamples),)
+
+    def nsamples(self, fact):
+        return self.NSamples[0] if len(self.NSamples) == 1 else self.NSamples[fact]
+
+    def compute_krp(self, als, fact):
+        ai = als.additional_items
+        stop = ai["stop_resample"]
+        if stop < 0 or stop > als.check.iter or ai["projects_tensors"][fact] is None:
+            ai["seed"] += 1
+            ai["projects_tensors"][fact] = als.engine.sample_factor_matrices(fact, self.nsamples(fact), ai["seed"])
+
+    def matricize_tensor(self, als, fact):
+        pass  # gathered inside sampled_update together with the sampled KRP
+
+    def solve_ls_problem(self, als, fact):
+        if not als.additional_items["normal"]:
+            raise NotImplementedError("normal=false (QRCP of the sampled KRP) is not in this build; use normal=True")
+        als.engine.sampled_update(fact, als.additional_items["projects_tensors"][fact], CHOLESKY_EPSILON)
+
+    def post_solve(self, als, fact):
+        pass  # leverage refresh is part of sampled_update (krp_lev...:55-58)
+
+    def check_converge(self, als, verbose=False) -> bool:  # ProjectionAlgorithm.jl:15-54
+        if isinstance(als.check, FitCheck):
+            if als.check.iter == 0:
+                print(f"Warning: FitCheck is not enabled for {type(self).__name__} will run {als.check.max_counter} iterations.")
+            als.check.iter += 1
+            if als.check.iter >= als.check.max_counter:
+                als.check.iter = 0
+            return False
+        return als.check.check_converge(als, als.fetch_cpd_arrays, verbose=verbose)
+
+
+# ------------------------------------------------------------------------------------------
+# ALS driver
+# ------------------------------------------------------------------------------------------
+class ALS:  # als_optimizer.jl:5-10, with the device handle as `target`
+    def __init__(self, engine: Engine, alg, additional_items: dict, check: ConvergeAlg):
+        self.engine = engine
+        self.target = engine
+        self.mttkrp_alg = alg
+        self.additional_items = additional_items
+        self.check = check
+        self.solve_paths = []
+
+    def fetch_cpd_arrays(self):
+        e = self.engine
+        return [e.get_factor(n) for n in range(len(e.dims))], e.get_lambda()
+
+
+_default_engines = {}
+
+
+def _engine_for(target, device=0) -> Engine:
+    """`target` is a host array (uploaded) or an Engine that already holds the tensor."""
+    if isinstance(target, Engine):
+        return target
+    eng = _default_engines.get(device)
+    if eng is None:
+        eng = _default_engines[device] = Engine(device)
+    eng.set_tensor(target)
+    return eng
+
+
+def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None, stop_resample=-1, device=0, seed=0, **_) -> ALS:
+    """als_optimizer.jl:37-69 + standard/tensor.jl:3-14 + randomized/krp_lev_score_sampled.jl:1-40."""
+    alg = KRPFreeNormal() if alg is None else alg
+    check = NoCheck(100 if maxiter is None else maxiter) if check is None else check
+    eng = _engine_for(target, device)
+    assert tuple(eng.dims) == tuple(cp.dims), (eng.dims, cp.dims)
+    eng.set_cpd(cp.factors, cp.lam)
+    extra = {}
+    if isinstance(alg, MttkrpAlgorithm):
+        eng.set_option("mttkrp_alg", alg.mttkrp_alg)
+        eng.compute_grams()  # :part_grammian
+    elif isinstance(alg, LevScoreSampled):
+        extra.update(normal=False if normal is None else normal, stop_resample=stop_resample, seed=int(seed) * 1000003,
+                     projects_tensors=[None] * len(cp))
+        for n in range(len(cp)):
+            eng.leverage_scores(n)  # :factor_weights
+    else:
+        raise TypeError(f"unsupported algorithm {type(alg).__name__}")
+    return ALS(eng, alg, extra, check)
+
+
+def optimize(cp: CPD, als: ALS, verbose=False) -> CPD:
+    """optimize.jl:6-35 hook by hook; the state lives on the device between hooks."""
+    it = als.check.iter
+    alg = als.mttkrp_alg
+    N = len(cp)
+    eng = als.engine
+    fused = isinstance(alg, MttkrpAlgorithm) and isinstance(als.check, (NoCheck, FitCheck)) and not als.additional_items.get("per_hook")
+    while it < als.check.max_counter:
+        if fused:
+            # one device-resident sweep (itcpd_sweep == the five hooks for every mode + fit scalars)
+            inner, norm2 = eng.sweep(1, CHOLESKY_EPSILON)
+            if isinstance(als.check, FitCheck):
+                done = als.check.update(float(inner[0]), float(norm2[0]), eng.rank, verbose)
+            else:
+                done = als.check.check_converge(als, None, verbose=verbose)
+        else:
+            for fact in range(N):
+                alg.compute_krp(als, fact)
+                alg.matricize_tensor(als, fact)
+                alg.solve_ls_problem(als, fact)
+                if isinstance(alg, MttkrpAlgorithm):
+                    eng.normalize(fact)  # row_norm, optimize.jl:25
+                alg.post_solve(als, fact)
+            done = alg.check_converge(als, verbose)
+        if done:
+            break
+        it += 1
+    f, l = als.fetch_cpd_arrays()
+    return CPD(f, l)
+
+
+def als_optimize(target, cp: CPD, alg=None, check=None, maxiter=None, verbose=False, **kwargs) -> CPD:
+    als = compute_als(target, cp, alg=alg, check=check, maxiter=maxiter, **kwargs)
+    return optimize(cp, als, verbose=verbose)
+
+
+def decompose(A, rank, *args, solver=None, rng=None, alg=None, check=None, maxiter=None, verbose=False, **kwargs) -> CPD:
+    """decompose.jl:1-30 (fixed rank) and :32-69 (rank adaptive: decompose(A, epsilon, max_rank; ...))."""
+    if args:
+        return _decompose_adaptive(A, rank, args[0], rng=rng, alg=alg, check=check, maxiter=maxiter, verbose=verbose, **kwargs)
+    if solver is not None:
+        if not isinstance(solver, CPDOptimizer):
+            raise TypeError("solver must be a CPDOptimizer or nothing")  # test/cp_als.jl:15
+        raise RuntimeError("OptimizerError")  # decompose.jl:27-29
+    dims = A.dims if isinstance(A, Engine) else A.shape
+    cp = random_CPD(dims, rank, rng)
+    return als_optimize(A, cp, alg=alg, check=check, maxiter=maxiter, verbose=verbose, **kwargs)
+
+
+class CPDOptimizer:  # cpd_optimizers.jl:1
+    pass
+
+
+def increase_cpd_rank(cp: CPD, new_rank: int, rng=None) -> CPD:  # decompose.jl:71-82
+    rng = np.random.default_rng(3) if rng is None else rng
+    assert new_rank >= cp.rank
+    newf, lam = random_factors(cp.dims, new_rank, rng)
+    for old, new in zip(cp.factors, newf):
+        new[:, : cp.rank] = old
+    return CPD(newf, lam)
+
+
+def _decompose_adaptive(A, epsilon, max_rank, rng=None, alg=None, check=None, maxiter=None, verbose=False,
+                        start_rank=1, rank_step=1, device=0, **kw) -> CPD:
+    eng = _engine_for(A, device)  # the tensor is uploaded once and stays resident across rank steps
+    if verbose:
+        print(f"Starting with rank: {start_rank}")
+    current = start_rank
+    cp = random_CPD(eng.dims, start_rank, rng)
+    check = FitCheck(1e-3, 100, eng.tensor_norm()) if check is None else check
+    while True:
+        cp = als_optimize(eng, cp, alg=alg, check=check, maxiter=maxiter, verbose=verbose, **kw)
+        check.iter = 0
+        if 1.0 - CPDFit(check) < epsilon:
+            return cp
+        current += rank_step
+        if verbose:
+            print(f"\nIncreasing rank to: {current}")
+        if current > max_rank:
+            print(f"Optimization Failed to converge within rank {max_rank}")
+            return cp
+        cp = increase_cpd_rank(cp, current, rng)
+
+
+def reconstruct(cp: CPD, device=0) -> np.ndarray:
+    """reconstruct.jl:2-9 on the device (no P x R intermediate)."""
+    eng = _default_engines.get(device) or _default_engines.setdefault(device, Engine(device))
+    if tuple(eng.dims) != tuple(cp.dims):
+        eng.generate_tensor(cp.dims, seed=0)  # shape carrier only
+    eng.set_cpd(cp.factors, cp.lam)
+    return eng.reconstruct()
