@@ -168,6 +168,14 @@ int itcpd_gemm_timing(itcpd_ctx *ctx, int reset, double *avg_ms, int64_t *launch
  * achieved TFLOP/s (2*8*8*4 flops per instruction) -- a roofline denominator for this box. */
 int itcpd_probe_dmma_peak(itcpd_ctx *ctx, double *tflops);
 int itcpd_probe_dfma_peak(itcpd_ctx *ctx, double *tflops);
+/* CUDA events on the handle's stream (slots 0..15): bench.py times exactly K sweeps on the device */
+int itcpd_event_record(itcpd_ctx *ctx, int slot);
+int itcpd_event_elapsed_ms(itcpd_ctx *ctx, int slot_start, int slot_stop, double *ms);
+/* pinned (page-locked) host memory for the end-to-end path: host buffers the caller owns */
+int itcpd_host_alloc(int64_t bytes, void **out);
+int itcpd_host_free(void *p);
+/* write `bytes` of a device scratch buffer (L2 flush between timed iterations of small problems) */
+int itcpd_flush_l2(itcpd_ctx *ctx, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ The directory name contains a dot, so import it through the `itcpd` shim at the 
     cp = itcpd.decompose(T, 50, check=itcpd.FitCheck(1e-3, 100, norm_T))
 """
 from ._lib import ItcpdError, LIB_PATH, DECLARED_SYMBOLS, load  # noqa: F401
-from .engine import Engine, column_to_multi_coords, multi_coords_to_column, sparse_sign_matrix  # noqa: F401
+from .engine import Engine, PinnedBuffer, column_to_multi_coords, multi_coords_to_column, sparse_sign_matrix  # noqa: F401
 from .host import (  # noqa: F401
     ALS, CPD, CPAngleCheck, CPDFit, CPDiffCheck, CPDOptimizer, DirectNormal, FitCheck, KRPFreeNormal, KRPNormal,
     LevScoreSampled, MttkrpAlgorithm, NoCheck, ProjectionAlgorithm, als_optimize, compute_als, cp_rank, decompose,

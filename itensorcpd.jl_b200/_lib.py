@@ -75,6 +75,11 @@ _SIGS = {
     "itcpd_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "itcpd_probe_dmma_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "itcpd_probe_dfma_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "itcpd_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "itcpd_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "itcpd_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "itcpd_host_free": (C.c_int, [C.c_void_p]),
+    "itcpd_flush_l2": (C.c_int, [C.c_void_p, C.c_int64]),
 }
 
 DECLARED_SYMBOLS = tuple(_SIGS)

@@ -225,10 +225,11 @@ int itcpd_destroy(itcpd_ctx *c) {
     cudaStreamSynchronize(c->stream);
     itcpd_comm_destroy(c);
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
-                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T};
+                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush};
     for (DevBuf *b : bufs) b->release();
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); }
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -797,6 +798,47 @@ int itcpd_probe_dfma_peak(itcpd_ctx *c, double *tflops) {
     ARG_CHECK(tflops != nullptr, "null out pointer");
     USE_DEVICE(c);
     return probe_dfma(c, tflops);
+}
+
+int itcpd_event_record(itcpd_ctx *c, int slot) {
+    CHECK_CTX(c);
+    ARG_CHECK(slot >= 0 && slot < 16, "event slot must be in [0,16)");
+    USE_DEVICE(c);
+    if (!c->user_events[slot]) CUDA_TRY(cudaEventCreate(&c->user_events[slot]));
+    CUDA_TRY(cudaEventRecord(c->user_events[slot], c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_event_elapsed_ms(itcpd_ctx *c, int s0, int s1, double *ms) {
+    CHECK_CTX(c);
+    ARG_CHECK(s0 >= 0 && s0 < 16 && s1 >= 0 && s1 < 16 && ms && c->user_events[s0] && c->user_events[s1], "bad event slots");
+    USE_DEVICE(c);
+    CUDA_TRY(cudaEventSynchronize(c->user_events[s1]));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, c->user_events[s0], c->user_events[s1]));
+    *ms = f;
+    return ITCPD_OK;
+}
+
+int itcpd_host_alloc(int64_t bytes, void **out) {
+    ARG_CHECK(bytes > 0 && out, "bad host_alloc arguments");
+    CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return ITCPD_OK;
+}
+
+int itcpd_host_free(void *p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return ITCPD_OK;
+}
+
+int itcpd_flush_l2(itcpd_ctx *c, int64_t bytes) {
+    CHECK_CTX(c);
+    ARG_CHECK(bytes > 0, "bytes must be positive");
+    USE_DEVICE(c);
+    TRY(c->flush.reserve((size_t)bytes));
+    CUDA_TRY(cudaMemsetAsync(c->flush.p, 1, (size_t)bytes, c->stream));
+    c->launches++;
+    return ITCPD_OK;
 }
 
 }  // extern "C"

@@ -102,7 +102,8 @@ struct itcpd_ctx {
     int split_a = 0, split_b = 0;
 
     // scratch
-    itcpd::DevBuf packK, krp_scratch[2], work, work2, redux, solve_ws, ipiv, status, fit2, samp_piv, samp_K, samp_T;
+    itcpd::DevBuf packK, krp_scratch[2], work, work2, redux, solve_ws, ipiv, status, fit2, samp_piv, samp_K, samp_T, flush;
+    cudaEvent_t user_events[16] = {nullptr};
     double *pinned = nullptr;   // pinned host staging (fit scalars, status words)
     size_t pinned_doubles = 0;
 

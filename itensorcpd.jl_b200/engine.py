@@ -87,8 +87,9 @@ class Engine:
         self.dims = tuple(int(d) for d in dims)
         check(self._L.itcpd_generate_tensor(self._h, len(self.dims), self._dims_arg(self.dims), int(seed), int(elem_offset)))
 
-    def get_tensor(self) -> np.ndarray:
-        out = np.empty(self.dims, dtype=np.float64, order="F")
+    def get_tensor(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.dims, dtype=np.float64, order="F")
         check(self._L.itcpd_get_tensor(self._h, _addr(out)))
         return out
 
@@ -281,6 +282,40 @@ class Engine:
         v = C.c_double()
         check(self._L.itcpd_probe_dfma_peak(self._h, C.byref(v)))
         return v.value
+
+
+    def event_record(self, slot: int):
+        check(self._L.itcpd_event_record(self._h, int(slot)))
+
+    def event_elapsed_ms(self, s0: int, s1: int) -> float:
+        v = C.c_double()
+        check(self._L.itcpd_event_elapsed_ms(self._h, int(s0), int(s1), C.byref(v)))
+        return v.value
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        check(self._L.itcpd_flush_l2(self._h, int(nbytes)))
+
+
+class PinnedBuffer:
+    """Page-locked host memory (cudaHostAlloc) viewed as a numpy float64 array."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self.shape))
+        p = C.c_void_p()
+        check(_lib.load().itcpd_host_alloc(n * 8, C.byref(p)))
+        self._p = p
+        buf = (C.c_double * n).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64).reshape(self.shape, order="F")
+
+    def data_ptr(self) -> int:
+        return int(self._p.value)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            _lib.load().itcpd_host_free(self._p)
+            self._p = None
 
 
 # host-side integer maps and generators (no handle needed)
