@@ -166,9 +166,22 @@ static int gram_device(itcpd_ctx *c, int mode) {
 }
 
 static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_dev) {
-    TRY(k_gram_hadamard(c, mode, c->Gamma.as<double>()));
+    // fork: Gram-Hadamard + pivoted Cholesky depend only on the Grams, so they run on the side stream
+    // underneath the MTTKRP (the persistent GEMM leaves room for one small CTA); join before the row solves
+    cudaStream_t main_stream = c->stream;
+    if (c->overlap_factor) {
+        CUDA_TRY(cudaEventRecord(c->ev_fork, main_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        c->stream = c->side_stream;
+    }
+    int st = k_gram_hadamard(c, mode, c->Gamma.as<double>());
+    if (st == ITCPD_OK) st = k_solve_factor(c, c->Gamma.as<double>(), c->rank, tol, status_dev);
+    c->stream = main_stream;
+    TRY(st);
+    if (c->overlap_factor) CUDA_TRY(cudaEventRecord(c->ev_join, c->side_stream));
     TRY(mttkrp_device(c, mode));
-    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, tol, c->X.as<double>(), status_dev));
+    if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+    TRY(k_solve_apply(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, c->X.as<double>(), status_dev));
     TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
     c->fver[mode]++;
     TRY(gram_device(c, mode));
@@ -212,6 +225,9 @@ int itcpd_create(itcpd_ctx **out, int device) {
     c->cc_minor = prop.minor;
     c->hbm_bytes = prop.totalGlobalMem;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     int st = ensure_pinned(c, 4096);
     if (st != ITCPD_OK) { delete c; return st; }
@@ -231,6 +247,10 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    cudaStreamSynchronize(c->side_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->side_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return ITCPD_OK;
@@ -264,6 +284,8 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "split_a") { c->force_split_a = (int)value; if (c->has_tensor) choose_splits(c); }
     else if (n == "split_b") { c->force_split_b = (int)value; if (c->has_tensor) choose_splits(c); }
     else if (n == "time_gemm") c->time_gemm = value != 0;
+    else if (n == "tma3d") c->tma3d = value != 0;
+    else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     return ITCPD_OK;
 }

@@ -68,12 +68,16 @@ struct itcpd_ctx {
     int cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // Gram-Hadamard + factorisation run here underneath the MTTKRP
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap_factor = 1;
     int64_t launches = 0;
 
     // options
     int mttkrp_alg = ITCPD_MTTKRP_TREE;
     int swizzle = 1;
     int tile_warps = 8;
+    int tma3d = 1;  // kind-0 tiles as one 3-D TMA box when the row count is a multiple of 16
     int force_split_a = 0, force_split_b = 0;
 
     // tensor
@@ -145,6 +149,8 @@ int k_reconstruct(itcpd_ctx *c, double *out_dense_or_null, double *resid_sumsq_d
 // ---- solve.cu -----------------------------------------------------------------------------
 // X (rows x R) = (Gamma \ M^T)^T with the ldiv_solve.jl semantics. status_dev[0]=path, [1]=rank.
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev);
+int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev);
+int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev);
 int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out);
 
 // ---- sampled.cu ---------------------------------------------------------------------------

@@ -50,6 +50,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -85,7 +91,7 @@ struct GemmSmem {
 template <int NB, int WARPS, int KIND>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 2 : 1))
 partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restrict__ Kp, double *__restrict__ out,
-                    int64_t rows_out, int R, int num_row_tiles, int num_rblocks, int kt_count, int swz_mask) {
+                    int64_t rows_out, int R, int num_row_tiles, int num_rblocks, int kt_count, int swz_mask, int map3d) {
     using S = GemmSmem<NB, WARPS>;
     constexpr int BM = S::BM;
     extern __shared__ uint8_t smem_raw[];
@@ -125,8 +131,13 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
         mbar_expect_tx(full, S::STAGE_BYTES);
         const uint32_t dT = sT0 + sj * S::T_BYTES;
         if (KIND == 0) {
+            if (map3d) {
+                // one box (16 m, 16 k, BM/16 row groups): lands as [row group][k][16 m], same image as the 2-D loop
+                tma_load_3d(dT, &tmap, 0, kt * BK, row0 >> 4, full);
+            } else {
 #pragma unroll 1
-            for (int gg = 0; gg < BM / 16; ++gg) tma_load_2d(dT + gg * (BK * 128), &tmap, row0 + 16 * gg, kt * BK, full);
+                for (int gg = 0; gg < BM / 16; ++gg) tma_load_2d(dT + gg * (BK * 128), &tmap, row0 + 16 * gg, kt * BK, full);
+            }
         } else {
             tma_load_2d(dT, &tmap, kt * BK, row0, full);
         }
@@ -306,6 +317,20 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// kind-0 tile as ONE 3-D box: the M x K matrix viewed as (16, K, M/16) with strides (8, 8M, 128) bytes
+static int make_tmap_3d(CUtensorMap *map, const double *base, uint64_t M, uint64_t K, uint32_t groups, bool swz) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return ITCPD_ERR_CUDA;
+    cuuint64_t gdim[3] = {16, K, M / 16};
+    cuuint64_t gstr[2] = {M * 8, 128};
+    cuuint32_t box[3] = {16, (cuuint32_t)BK, groups};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ITCPD_OK : ITCPD_ERR_CUDA;
+}
+
 static int make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint64_t d1, uint32_t box0, uint32_t box1, bool swz) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return ITCPD_ERR_CUDA; }
@@ -326,7 +351,7 @@ static int make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint64_t
 
 template <int NB, int WARPS, int KIND>
 static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, double *out, int64_t rows_out, int R,
-                      int num_row_tiles, int num_rblocks, int kt_count) {
+                      int num_row_tiles, int num_rblocks, int kt_count, int map3d) {
     using S = GemmSmem<NB, WARPS>;
     auto kern = partial_gemm_kernel<NB, WARPS, KIND>;
     static bool attr_set = false;
@@ -339,7 +364,7 @@ static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, do
     int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * per_sm);
     if (grid < 1) grid = 1;
     kern<<<grid, WARPS * 32, S::TOTAL, c->stream>>>(map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count,
-                                                          c->swizzle ? 7 : 0);
+                                                c->swizzle ? 7 : 0, map3d);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
@@ -347,16 +372,16 @@ static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, do
 
 template <int WARPS, int KIND>
 static int launch_nb(itcpd_ctx *c, int NB, const CUtensorMap &map, const double *Kp, double *out, int64_t rows_out, int R,
-                     int nrt, int nrb, int ktc) {
+                     int nrt, int nrb, int ktc, int map3d) {
     switch (NB) {
-        case 1: return launch_cfg<1, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 2: return launch_cfg<2, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 3: return launch_cfg<3, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 4: return launch_cfg<4, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 5: return launch_cfg<5, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 6: return launch_cfg<6, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        case 7: return launch_cfg<7, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
-        default: return launch_cfg<8, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc);
+        case 1: return launch_cfg<1, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 2: return launch_cfg<2, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 3: return launch_cfg<3, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 4: return launch_cfg<4, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 5: return launch_cfg<5, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 6: return launch_cfg<6, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        case 7: return launch_cfg<7, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
+        default: return launch_cfg<8, WARPS, KIND>(c, map, Kp, out, rows_out, R, nrt, nrb, ktc, map3d);
     }
 }
 
@@ -408,8 +433,13 @@ int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out) {
     const int num_row_tiles = (int)ceil_div(rows_out, BM);
 
     CUtensorMap map;
-    if (kind == 0) TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, 16, BK, c->swizzle != 0));
-    else TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, BK, (uint32_t)BM, c->swizzle != 0));
+    int map3d = 0;
+    if (kind == 0) {
+        if (c->tma3d && Mrows % 16 == 0 && make_tmap_3d(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, BM / 16, c->swizzle != 0) == ITCPD_OK)
+            map3d = 1;
+        else
+            TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, 16, BK, c->swizzle != 0));
+    } else TRY(make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, BK, (uint32_t)BM, c->swizzle != 0));
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->time_gemm) {
@@ -426,10 +456,10 @@ int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out) {
     }
     int st;
     const double *Kp = c->packK.as<double>();
-    if (kind == 0) st = (warps == 8) ? launch_nb<8, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count)
-                                     : launch_nb<4, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count);
-    else st = (warps == 8) ? launch_nb<8, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count)
-                           : launch_nb<4, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count);
+    if (kind == 0) st = (warps == 8) ? launch_nb<8, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count, map3d)
+                                     : launch_nb<4, 0>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count, map3d);
+    else st = (warps == 8) ? launch_nb<8, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count, 0)
+                           : launch_nb<4, 1>(c, NB, map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count, 0);
     if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));
     return st;
 }

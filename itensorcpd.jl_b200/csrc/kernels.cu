@@ -38,7 +38,7 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
 // ------------------------------------------------------------------------------------------------
 constexpr int GT = 16;       // output tile
 constexpr int GCHUNK = 64;   // rows per smem chunk
-constexpr int GSLICE = 2048; // rows per CTA slice
+constexpr int GSLICE = 256;  // rows per CTA slice
 
 __global__ void __launch_bounds__(GT *GT) gram_partial_kernel(const double *__restrict__ A, int64_t rows, int R, double *__restrict__ part) {
     __shared__ double sa[GT][GCHUNK + 1], sb[GT][GCHUNK + 1];
@@ -271,24 +271,40 @@ __global__ void __launch_bounds__(256) partial_first_kernel(const double *__rest
     }
 }
 
-// front non-empty: one CTA per (i, r), threads run over the contiguous front index
+// front non-empty: one WARP per (i, r), lanes run over the contiguous front index with 16-byte loads
 __global__ void __launch_bounds__(256) partial_general_kernel(const double *__restrict__ P, const double *__restrict__ wf,
                                                               const double *__restrict__ wb, int64_t F, int64_t I, int64_t B,
                                                               double *__restrict__ out) {
-    __shared__ double sh[8];
-    const int64_t i = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5);
     const int r = blockIdx.y;
+    if (i >= I) return;
     const double *p = P + F * i + F * I * B * (int64_t)r;
     const double *f = wf + F * (int64_t)r;
     double acc = 0.0;
-    for (int64_t b = 0; b < B; ++b) {
-        double inner = 0.0;
-        const double *pb = p + F * I * b;
-        for (int64_t q = threadIdx.x; q < F; q += 256) inner = fma(pb[q], f[q], inner);
-        acc = wb ? fma(inner, wb[b + B * (int64_t)r], acc) : acc + inner;
+    if ((F & 1) == 0) {
+        for (int64_t b = 0; b < B; ++b) {
+            const double2 *pb = reinterpret_cast<const double2 *>(p + F * I * b);
+            const double2 *f2 = reinterpret_cast<const double2 *>(f);
+            double in0 = 0.0, in1 = 0.0;
+            for (int64_t q = lane; q < F / 2; q += 32) {
+                const double2 pv = pb[q], fv = f2[q];
+                in0 = fma(pv.x, fv.x, in0);
+                in1 = fma(pv.y, fv.y, in1);
+            }
+            const double inner = in0 + in1;
+            acc = wb ? fma(inner, wb[b + B * (int64_t)r], acc) : acc + inner;
+        }
+    } else {
+        for (int64_t b = 0; b < B; ++b) {
+            double inner = 0.0;
+            const double *pb = p + F * I * b;
+            for (int64_t q = lane; q < F; q += 32) inner = fma(pb[q], f[q], inner);
+            acc = wb ? fma(inner, wb[b + B * (int64_t)r], acc) : acc + inner;
+        }
     }
-    acc = block_sum<256>(acc, sh);
-    if (threadIdx.x == 0) out[i + I * (int64_t)r] = acc;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[i + I * (int64_t)r] = acc;
 }
 
 int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64_t ld_first, int mode, double *out) {
@@ -309,7 +325,7 @@ int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64
         dim3 grid((unsigned)ceil_div(Ilog, 32), (unsigned)R);
         partial_first_kernel<<<grid, 256, 0, c->stream>>>(P, wb, I, Ilog, B, out);
     } else {
-        dim3 grid((unsigned)Ilog, (unsigned)R);
+        dim3 grid((unsigned)ceil_div(Ilog, 8), (unsigned)R);
         partial_general_kernel<<<grid, 256, 0, c->stream>>>(P, wf, wb, F, Ilog, B, out);
     }
     c->launches++;

@@ -285,10 +285,9 @@ __global__ void __launch_bounds__(64) qrcp_solve_rows_kernel(const double *__res
 }
 
 int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
-    const size_t ws_doubles = (size_t)R * R + 8 * (size_t)R;
-    // reuse the second half of solve_ws for the QR workspace (first half holds the Cholesky factor)
-    TRY(c->solve_ws.reserve(((size_t)R * R + ws_doubles) * 8 + 1024));
-    double *ws = c->solve_ws.as<double>() + (size_t)R * R;
+    // workspace: behind the Cholesky factor (ldw*R + R doubles) inside solve_ws (sized by run_cholesky)
+    const size_t chol_doubles = (size_t)(R | 1) * R + R;
+    double *ws = c->solve_ws.as<double>() + chol_doubles;
     int *jp = c->ipiv.as<int>() + R;
     TRY(c->work.reserve((size_t)rows * R * 8));
     qrcp_factor_kernel<<<1, QT, 0, c->stream>>>(Gamma, R, ws, jp, status_dev);

@@ -1,198 +1,260 @@
 // R x R normal-equation solve (src/algebra/ldiv_solve.jl:13-29):
 //   cholesky(Hermitian(Gamma), RowMaximum(), check=true, tol) \ B      -> LAPACK dpstrf + permuted dpotrs
-//   on failure: qr(Gamma, ColumnNorm()) \ B                            -> xGELSY min-norm (see qrcp below)
-// Latency-bound block-level kernels: one CTA factorises (matrix resident in shared memory when it
-// fits), then one thread per right-hand side runs the two triangular solves against the factor.
+//   on failure: qr(Gamma, ColumnNorm()) \ B                            -> xGELSY min-norm (qrcp.cu)
+// Latency-bound block/warp-level kernels:
+//   * pivoted_cholesky_kernel: one CTA, matrix resident in shared memory (odd leading dimension, no bank
+//     conflicts), left-looking dpstf2 order: 3 block barriers per column.
+//   * chol_solve_warp_kernel: one WARP per right-hand side (a row of M); the vector lives in registers
+//     (lane l owns entries l, l+32, ...), each substitution step is one shuffle broadcast + E FMAs.
 #include "common.cuh"
 #include <cfloat>
 
 namespace itcpd {
 
-constexpr int CH_THREADS = 512;
+constexpr int CH_THREADS = 256;
 
 // status words written by the factorisation: [0] path (0 chol / 1 qrcp), [1] rank, [2] info
+// Wg receives the factor with leading dimension ldw = n | 1.
 __global__ void __launch_bounds__(CH_THREADS) pivoted_cholesky_kernel(const double *__restrict__ Gin, int n, double tol,
                                                                       double *__restrict__ Wg, int *__restrict__ piv,
                                                                       int *__restrict__ status, int use_smem) {
     extern __shared__ double sm_dyn[];
-    __shared__ double red_v[CH_THREADS / 32];
-    __shared__ int red_i[CH_THREADS / 32];
-    __shared__ int s_p;
+    __shared__ int s_p, s_fail;
     __shared__ double s_ajj, s_stop;
-    __shared__ int s_fail;
-    double *W = use_smem ? sm_dyn : Wg;
+    __shared__ int s_piv[1024];
+    const int ldw = n | 1;
+    const int NT = blockDim.x;
+    double *W = use_smem ? sm_dyn : Wg;                       // full symmetric copy; rows < j become the factor
+    double *dd = use_smem ? sm_dyn + (size_t)ldw * n : Wg + (size_t)ldw * n;  // running diagonal (dpstf2 "work")
     const int tid = threadIdx.x;
-    for (int e = tid; e < n * n; e += CH_THREADS) W[e] = Gin[e];
-    for (int e = tid; e < n; e += CH_THREADS) piv[e] = e;
+    for (int e = tid; e < n * n; e += NT) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
+    for (int e = tid; e < n; e += NT) { s_piv[e] = e; dd[e] = Gin[e + (size_t)n * e]; }
     if (tid == 0) s_fail = 0;
     __syncthreads();
 
     int rank = n;
     for (int j = 0; j < n; ++j) {
-        // ---- pivot: first maximum of the remaining (updated) diagonal, dpstf2 semantics ----
-        double bv = -DBL_MAX;
-        int bi = n;
-        bool has_nan = false;
-        for (int i = j + tid; i < n; i += CH_THREADS) {
-            const double d = W[i + n * i];
-            if (d != d) has_nan = true;
-            if (d > bv) { bv = d; bi = i; }
-        }
-        if (has_nan) { bv = DBL_MAX; bi = -1; }  // NaN poisons the factorisation (LAPACK: disnan(ajj) -> fail)
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            double v = red_v[0];
-            int ix = red_i[0];
-            for (int w = 1; w < CH_THREADS / 32; ++w)
-                if (red_v[w] > v || (red_v[w] == v && red_i[w] < ix)) { v = red_v[w]; ix = red_i[w]; }
-            s_p = ix;
-            s_ajj = v;
-            if (j == 0) {
-                s_stop = (tol < 0.0) ? n * DBL_EPSILON * v : tol;
-                if (ix < 0 || !(v > 0.0)) s_fail = 1;            // dpstf2: ajj <= 0 or NaN at the start
-            } else if (ix < 0 || !(v > s_stop)) {
-                s_fail = 1;                                       // pivot <= tol: rank deficient
+        // ---- pivot: first maximum of the running diagonal (warp 0 only) ----
+        if (tid < 32) {
+            double bv = -DBL_MAX;
+            int bi = n;
+            bool bad = false;
+            for (int i = j + tid; i < n; i += 32) {
+                const double d = dd[i];
+                if (d != d) bad = true;
+                if (d > bv) { bv = d; bi = i; }
+            }
+            if (bad) { bv = DBL_MAX; bi = -1; }  // NaN poisons the factorisation (LAPACK: disnan -> fail)
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (tid == 0) {
+                s_p = bi;
+                s_ajj = bv;
+                if (j == 0) {
+                    s_stop = (tol < 0.0) ? n * DBL_EPSILON * bv : tol;
+                    if (bi < 0 || !(bv > 0.0)) s_fail = 1;   // dpstf2: ajj <= 0 or NaN at the start
+                } else if (bi < 0 || !(bv > s_stop)) {
+                    s_fail = 1;                               // pivot <= tol: rank deficient
+                }
             }
         }
         __syncthreads();
         if (s_fail) { rank = j; break; }
         const int p = s_p;
-        // ---- symmetric interchange j <-> p on the full square ----
+        // ---- symmetric interchange j <-> p (single phase: off-diagonal rows and columns, then the 2x2 block) ----
         if (p != j) {
-            for (int k = tid; k < n; k += CH_THREADS) {  // rows
-                const double a = W[j + n * k], b = W[p + n * k];
-                W[j + n * k] = b; W[p + n * k] = a;
+            for (int t = tid; t < n; t += NT) {
+                if (t != j && t != p) {
+                    double a = W[j + (size_t)ldw * t], b = W[p + (size_t)ldw * t];
+                    W[j + (size_t)ldw * t] = b; W[p + (size_t)ldw * t] = a;
+                    a = W[t + (size_t)ldw * j]; b = W[t + (size_t)ldw * p];
+                    W[t + (size_t)ldw * j] = b; W[t + (size_t)ldw * p] = a;
+                }
             }
-            __syncthreads();
-            for (int k = tid; k < n; k += CH_THREADS) {  // columns
-                const double a = W[k + n * j], b = W[k + n * p];
-                W[k + n * j] = b; W[k + n * p] = a;
+            if (tid == 0) {
+                const double a = W[j + (size_t)ldw * j];
+                W[j + (size_t)ldw * j] = W[p + (size_t)ldw * p];
+                W[p + (size_t)ldw * p] = a;
+                const double b = W[j + (size_t)ldw * p];
+                W[j + (size_t)ldw * p] = W[p + (size_t)ldw * j];
+                W[p + (size_t)ldw * j] = b;
+                const double d = dd[j]; dd[j] = dd[p]; dd[p] = d;
+                const int q = s_piv[j]; s_piv[j] = s_piv[p]; s_piv[p] = q;
             }
-            if (tid == 0) { const int q = piv[j]; piv[j] = piv[p]; piv[p] = q; }
             __syncthreads();
         }
+        // ---- row j of the factor: U[j,k] = (A[j,k] - sum_{l<j} U[l,j] U[l,k]) / U[j,j]; diagonal down-date ----
         const double d = sqrt(s_ajj);
-        // ---- scale row j of the factor ----
-        for (int k = j + 1 + tid; k < n; k += CH_THREADS) W[j + n * k] = W[j + n * k] / d;
-        if (tid == 0) W[j + n * j] = d;
-        __syncthreads();
-        // ---- trailing update on the full square (keeps both triangles so interchanges stay trivial) ----
-        const int m = n - j - 1;
-        for (int e = tid; e < m * m; e += CH_THREADS) {
-            const int i = j + 1 + e % m, k = j + 1 + e / m;
-            W[i + n * k] = fma(-W[j + n * i], W[j + n * k], W[i + n * k]);
+        for (int k = j + 1 + tid; k < n; k += NT) {
+            const double *cj = W + (size_t)ldw * j, *ck = W + (size_t)ldw * k;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int l = 0;
+            for (; l + 3 < j; l += 4) {
+                s0 = fma(cj[l], ck[l], s0); s1 = fma(cj[l + 1], ck[l + 1], s1);
+                s2 = fma(cj[l + 2], ck[l + 2], s2); s3 = fma(cj[l + 3], ck[l + 3], s3);
+            }
+            for (; l < j; ++l) s0 = fma(cj[l], ck[l], s0);
+            const double u = (ck[j] - ((s0 + s1) + (s2 + s3))) / d;
+            W[j + (size_t)ldw * k] = u;
+            dd[k] = fma(-u, u, dd[k]);
         }
+        if (tid == 0) W[j + (size_t)ldw * j] = d;
         __syncthreads();
     }
     if (use_smem)
-        for (int e = tid; e < n * n; e += CH_THREADS) Wg[e] = W[e];
+        for (int e = tid; e < ldw * n; e += NT) Wg[e] = W[e];
+    for (int e = tid; e < n; e += NT) piv[e] = s_piv[e];
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
-// One thread per right-hand side (a row of M): x = P (U^T U)^{-1} P^T b, written to row `i` of X.
-// U (upper triangle of Wg, column-major) is staged in shared memory when it fits.
-constexpr int TS_THREADS = 64;
+// One warp per right-hand side: x = P (U^T U)^{-1} P^T b with b = row i of M, result to row i of X.
+// Lane l keeps entries k = l + 32 e (e < E) in registers.  mode: 0 full solve, 1 forward only and
+// return ||y[0:nn]||^2 (leverage scores).
+constexpr int TSW_WARPS = 8;
 
-__global__ void __launch_bounds__(TS_THREADS) chol_solve_rows_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
-                                                                     const int *__restrict__ status, const double *__restrict__ M,
-                                                                     int64_t rows, int n, double *__restrict__ X, int u_in_smem,
-                                                                     int b_in_smem, double *__restrict__ bglob, int fwd_only_rank) {
+template <int E>
+__global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
+                                                                         const int *__restrict__ status, const double *__restrict__ M,
+                                                                         int64_t rows, int n, double *__restrict__ X, int u_in_smem,
+                                                                         int fwd_only, int nn_dev_slot) {
     extern __shared__ double sm_dyn[];
-    if (fwd_only_rank < 0 && status[0] != ITCPD_SOLVE_CHOLESKY) return;  // the QRCP path handles this system
+    if (!fwd_only && status[0] != ITCPD_SOLVE_CHOLESKY) return;  // the QRCP path handles this system
+    const int ldw = n | 1;
     const double *U = Wg;
-    double *sb = sm_dyn;
+    __shared__ double s_rd[1024];  // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
+    for (int e = threadIdx.x; e < n; e += TSW_WARPS * 32) s_rd[e] = 1.0 / Wg[e + (size_t)ldw * e];
     if (u_in_smem) {
-        for (int e = threadIdx.x; e < n * n; e += TS_THREADS) sm_dyn[e] = Wg[e];
+        for (int e = threadIdx.x; e < ldw * n; e += TSW_WARPS * 32) sm_dyn[e] = Wg[e];
         U = sm_dyn;
-        sb = sm_dyn + (size_t)n * n;
-        __syncthreads();
     }
-    const int64_t i = blockIdx.x * (int64_t)TS_THREADS + threadIdx.x;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t i = blockIdx.x * (int64_t)TSW_WARPS + (threadIdx.x >> 5);
     if (i >= rows) return;
-    // element k of this thread's vector
-    double *bp;
-    int64_t bs;
-    if (b_in_smem) { bp = sb + threadIdx.x; bs = TS_THREADS; }
-    else { bp = bglob + i; bs = rows; }
-#define BV(k) bp[(int64_t)(k) * bs]
-    const int nn = (fwd_only_rank >= 0) ? fwd_only_rank : n;
-    for (int k = 0; k < n; ++k) BV(k) = M[i + rows * (int64_t)piv[k]];
-    // forward: U^T y = P^T b
-    for (int k = 0; k < nn; ++k) {
-        double s0 = BV(k), s1 = 0.0;
-        const double *uk = U + (size_t)n * k;
-        int l = 0;
-        for (; l + 1 < k; l += 2) { s0 = fma(-uk[l], BV(l), s0); s1 = fma(-uk[l + 1], BV(l + 1), s1); }
-        if (l < k) s0 = fma(-uk[l], BV(l), s0);
-        BV(k) = (s0 + s1) / uk[k];
+    const int nn = fwd_only ? status[nn_dev_slot] : n;
+    double b[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = lane + 32 * e;
+        b[e] = (k < n) ? M[i + rows * (int64_t)piv[k]] : 0.0;
     }
-    if (fwd_only_rank >= 0) {  // leverage score: ||y||^2 (k_leverage)
+    // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
+    for (int k = 0; k < nn; ++k) {
+        const int owner = k & 31, eo = k >> 5;
+        double yk = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (e == eo) yk = b[e];
+        yk = __shfl_sync(0xffffffffu, yk, owner) * s_rd[k];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = lane + 32 * e;
+            if (l == k) b[e] = yk;
+            else if (l > k && l < nn) b[e] = fma(-U[k + (size_t)ldw * l], yk, b[e]);
+        }
+    }
+    if (fwd_only) {
         double s = 0.0;
-        for (int k = 0; k < nn; ++k) s = fma(BV(k), BV(k), s);
-        X[i] = s;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (lane + 32 * e < nn) s = fma(b[e], b[e], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) X[i] = s;
         return;
     }
-    // backward: U x = y
+    // backward: U x = y  (after x_k is known, y_l -= U[l,k] x_k for l < k)
     for (int k = n - 1; k >= 0; --k) {
-        double s0 = BV(k), s1 = 0.0;
-        int l = k + 1;
-        for (; l + 1 < n; l += 2) { s0 = fma(-U[k + (size_t)n * l], BV(l), s0); s1 = fma(-U[k + (size_t)n * (l + 1)], BV(l + 1), s1); }
-        if (l < n) s0 = fma(-U[k + (size_t)n * l], BV(l), s0);
-        BV(k) = (s0 + s1) / U[k + (size_t)n * k];
+        const int owner = k & 31, eo = k >> 5;
+        double xk = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (e == eo) xk = b[e];
+        xk = __shfl_sync(0xffffffffu, xk, owner) * s_rd[k];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = lane + 32 * e;
+            if (l == k) b[e] = xk;
+            else if (l < k) b[e] = fma(-U[l + (size_t)ldw * k], xk, b[e]);
+        }
     }
-    for (int k = 0; k < n; ++k) X[i + rows * (int64_t)piv[k]] = BV(k);
-#undef BV
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int k = lane + 32 * e;
+        if (k < n) X[i + rows * (int64_t)piv[k]] = b[e];
+    }
 }
 
-static int smem_limit(itcpd_ctx *) { return 227 * 1024 - 2048; }
+// dynamic shared memory budget: 227 KB per CTA minus the static arrays of these kernels (pivots, reciprocal diagonal)
+static int smem_limit(itcpd_ctx *) { return 208 * 1024; }
 
 static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
-    TRY(c->solve_ws.reserve((size_t)R * R * 8 * 2 + 1024));
+    const int ldw = R | 1;
+    TRY(c->solve_ws.reserve(((size_t)ldw * R + R) * 8 + ((size_t)R * R + 8 * (size_t)R) * 8 + 1024));
     TRY(c->ipiv.reserve((size_t)R * 4 * 2));
-    const size_t need = (size_t)R * R * 8;
+    const size_t need = ((size_t)ldw * R + R) * 8;
     const int use_smem = need <= (size_t)smem_limit(c);
     static bool attr = false;
     if (!attr) {
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
-        CUDA_TRY(cudaFuncSetAttribute(chol_solve_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr = true;
     }
-    pivoted_cholesky_kernel<<<1, CH_THREADS, use_smem ? need : 0, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(),
+    const int threads = R <= 64 ? 64 : (R <= 128 ? 128 : CH_THREADS);
+    pivoted_cholesky_kernel<<<1, threads, use_smem ? need : 0, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(),
                                                                                  status_dev, use_smem);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }
 
-static int run_tri_solves(itcpd_ctx *c, const double *M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only_rank) {
-    const size_t u_bytes = (size_t)R * R * 8, b_bytes = (size_t)R * TS_THREADS * 8;
-    int u_in = 0, b_in = 0;
-    size_t smem = 0;
-    if (u_bytes + b_bytes <= (size_t)smem_limit(c)) { u_in = 1; b_in = 1; smem = u_bytes + b_bytes; }
-    else if (b_bytes <= (size_t)smem_limit(c)) { b_in = 1; smem = b_bytes; }
-    double *bglob = nullptr;
-    if (!b_in) {
-        TRY(c->work.reserve((size_t)rows * R * 8));
-        bglob = c->work.as<double>();
+template <int E>
+static int launch_tsw(itcpd_ctx *c, const double *M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
+    const size_t u_bytes = (size_t)(R | 1) * R * 8;
+    const int u_in = u_bytes <= (size_t)smem_limit(c);
+    auto kern = chol_solve_warp_kernel<E>;
+    static bool attr = false;
+    if (!attr) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
+        attr = true;
     }
-    chol_solve_rows_kernel<<<(unsigned)ceil_div(rows, TS_THREADS), TS_THREADS, smem, c->stream>>>(
-        c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, u_in, b_in, bglob, fwd_only_rank);
+    kern<<<(unsigned)ceil_div(rows, TSW_WARPS), TSW_WARPS * 32, u_in ? u_bytes : 0, c->stream>>>(
+        c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, u_in, fwd_only, slot);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }
 
+static int run_tri_solves(itcpd_ctx *c, const double *M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
+    const int E = (int)ceil_div(R, 32);
+    if (E <= 1) return launch_tsw<1>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    if (E <= 2) return launch_tsw<2>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    if (E <= 4) return launch_tsw<4>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    if (E <= 8) return launch_tsw<8>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    if (E <= 16) return launch_tsw<16>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    if (E <= 32) return launch_tsw<32>(c, M, rows, R, X, status_dev, fwd_only, slot);
+    set_error("rank %d is above the 1024 limit of the solve kernels", R);
+    return ITCPD_ERR_UNSUPPORTED;
+}
+
 int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev);  // qrcp.cu
+
+// The factorisation only needs Gamma (the Gram-Hadamard), not the MTTKRP, so the sweep driver runs it on a
+// side stream underneath the GEMM pass; k_solve_apply then joins and applies it to the rows of M.
+int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
+    return run_cholesky(c, Gamma, R, tol, status_dev);
+}
+
+int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
+    TRY(run_tri_solves(c, M, rows, R, X, status_dev, 0, 1));
+    TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
+    return ITCPD_OK;
+}
 
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev) {
     TRY(run_cholesky(c, Gamma, R, tol, status_dev));
-    TRY(run_tri_solves(c, M, rows, R, X, status_dev, -1));
+    TRY(run_tri_solves(c, M, rows, R, X, status_dev, 0, 1));
     // rank-deficient systems are re-solved by the pivoted-QR min-norm path; it is a no-op (device-side
     // early exit on status[0]) when the Cholesky succeeded, so no host round trip is needed here.
     TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
@@ -200,7 +262,8 @@ int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, in
 }
 
 // leverage scores (math_tools/probability.jl:3-10): p_i = ||Q[i,:]||^2 / min(I,R) with A = QR.
-// Q = A U^{-1} for the Cholesky factor of the Gram matrix, so ||Q[i,:]||^2 = ||U^{-T} a_i||^2.
+// Q = A U^{-1} for the Cholesky factor of the Gram matrix, so ||Q[i,:]||^2 = ||U^{-T} a_i||^2
+// (restricted to the numerical rank found by the pivoted factorisation).
 __global__ void fill_kernel(double *x, int64_t n, double v) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
@@ -216,13 +279,10 @@ int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int
         c->launches++;
         return ITCPD_OK;
     }
-    TRY(c->status.reserve(64));
-    int *st = c->status.as<int>() + 8;
+    TRY(c->status.reserve(256));
+    int *st = c->status.as<int>() + 32;
     TRY(run_cholesky(c, G, R, -1.0, st));
-    int h[3];
-    CUDA_TRY(cudaMemcpyAsync(h, st, 12, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    TRY(run_tri_solves(c, A, rows, R, lev_out, st, h[1]));
+    TRY(run_tri_solves(c, A, rows, R, lev_out, st, 1, 1));
     scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)std::min<int64_t>(rows, R));
     c->launches++;
     CUDA_TRY(cudaGetLastError());
