@@ -241,7 +241,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     cudaStreamSynchronize(c->stream);
     itcpd_comm_destroy(c);
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
-                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush};
+                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev};
     for (DevBuf *b : bufs) b->release();
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); }
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -286,6 +286,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "time_gemm") c->time_gemm = value != 0;
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
+    else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     return ITCPD_OK;
 }

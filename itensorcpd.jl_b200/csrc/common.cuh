@@ -60,6 +60,13 @@ struct Partial {
 
 struct Comm;  // comm.cu
 
+// stream-K split description of one GEMM shape (host-built, cached per kind)
+struct StreamKTable {
+    int64_t key[6] = {-1, -1, -1, -1, -1, -1};
+    int nsplit = 0, off_ptr = 0, off_list = 0;
+    DevBuf dev;
+};
+
 }  // namespace itcpd
 
 struct itcpd_ctx {
@@ -77,6 +84,7 @@ struct itcpd_ctx {
     int mttkrp_alg = ITCPD_MTTKRP_TREE;
     int swizzle = 1;
     int tile_warps = 8;
+    int stream_k = 1;  // split the tiles of the last partial wave along k (hybrid stream-K)
     int tma3d = 1;  // kind-0 tiles as one 3-D TMA box when the row count is a multiple of 16
     int force_split_a = 0, force_split_b = 0;
 
@@ -103,6 +111,8 @@ struct itcpd_ctx {
 
     // dimension tree
     itcpd::Partial PA, PB;
+    itcpd::StreamKTable sk_table[2];
+    itcpd::DevBuf sk_slots;
     int split_a = 0, split_b = 0;
 
     // scratch

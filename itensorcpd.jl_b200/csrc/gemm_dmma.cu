@@ -91,9 +91,11 @@ struct GemmSmem {
 template <int NB, int WARPS, int KIND>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS <= 4 ? 2 : 1))
 partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__restrict__ Kp, double *__restrict__ out,
-                    int64_t rows_out, int R, int num_row_tiles, int num_rblocks, int kt_count, int swz_mask, int map3d) {
+                    int64_t rows_out, int R, int num_row_tiles, int num_rblocks, int kt_count, int swz_mask, int map3d,
+                    int full_waves, double *__restrict__ slots) {
     using S = GemmSmem<NB, WARPS>;
     constexpr int BM = S::BM;
+    constexpr int BN = 8 * NB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sT0 = smem_base;
@@ -112,18 +114,36 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
     }
     __syncthreads();
 
-    const int num_tiles = num_row_tiles * num_rblocks;
-    const int my_tiles = (num_tiles > (int)blockIdx.x) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int total_iters = my_tiles * kt_count;
+    // Hybrid stream-K work split.  The first `full_waves` rounds are data parallel (tile = cta + w * grid: the CTAs
+    // of a round stream neighbouring rows of the same k columns, which keeps DRAM pages / TLB entries shared);
+    // the tiles of the last, partial round are cut along k into gridDim.x equal ranges so that every SM runs the
+    // same number of DMMA iterations whatever the tile count.  A range that begins or ends inside a tile leaves a
+    // partial tile in `slots`; streamk_fixup_kernel adds the parts in ascending-k order (deterministic).
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int dp_iters = full_waves * kt_count;
+    const int rem_units = max(0, num_row_tiles * num_rblocks - full_waves * G) * kt_count;
+    const int r0 = (int)((int64_t)rem_units * cta / G), r1 = (int)((int64_t)rem_units * (cta + 1) / G);
+    const int total_iters = dp_iters + (r1 - r0);
+    auto locate = [&](int j, int &tile, int &kt) {
+        if (j < dp_iters) {
+            const int w = j / kt_count;
+            kt = j - w * kt_count;
+            tile = cta + w * G;
+        } else {
+            const int u = r0 + (j - dp_iters);
+            const int q = u / kt_count;
+            kt = u - q * kt_count;
+            tile = full_waves * G + q;
+        }
+    };
 
     // Stage refill for pipeline iteration j (one elected lane; the duty rotates over the warps so that
     // no warp's DMMA stream carries the whole TMA-issue overhead).
     auto issue = [&](int j) {
         const int sj = j % STAGES;
         if (j >= STAGES) mbar_wait(bar0 + 8 * (STAGES + sj), (uint32_t)((j / STAGES - 1) & 1));
-        const int jt = j / kt_count;
-        const int kt = j - jt * kt_count;
-        const int tile = (int)blockIdx.x + jt * (int)gridDim.x;
+        int tile, kt;
+        locate(j, tile, kt);
         const int row_tile = tile / num_rblocks;
         const int rb = tile - row_tile * num_rblocks;
         const int row0 = row_tile * BM;
@@ -154,7 +174,10 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
     const int t = lane & 3;    // MMA threadID_in_group
     int it = 0;
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    while (it < total_iters) {
+        int tile, kt_begin;
+        locate(it, tile, kt_begin);
+        const int kt_end = min(kt_count, kt_begin + (total_iters - it));
         const int row_tile = tile / num_rblocks;
         const int rb = tile - row_tile * num_rblocks;
         const int64_t row0 = (int64_t)row_tile * BM;
@@ -165,7 +188,7 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
 #pragma unroll
             for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        for (int kt = 0; kt < kt_count; ++kt, ++it) {
+        for (int kt = kt_begin; kt < kt_end; ++kt, ++it) {
             {
                 const int j = it + STAGES - 1;
                 if (j < total_iters && warp == (it % WARPS)) {
@@ -219,20 +242,38 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
             if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + stage));
         }
 
-        // ---- epilogue: registers -> global (column-major rows_out x R) ----
+        // ---- epilogue: registers -> global.  Full tile: column-major rows_out x R output.  Partial tile (the
+        // range started or stopped inside it): dense BM x BN slot, 2*cta (+1 when it holds the head of the tile).
+        const bool full_tile = (kt_begin == 0 && kt_end == kt_count);
+        double *dst_base;
+        int64_t ldo, row_lim;
+        int col0, col_lim;
+        if (full_tile) {
+            dst_base = out + row0;
+            ldo = rows_out;
+            row_lim = rows_out - row0;
+            col0 = BN * rb;
+            col_lim = R;
+        } else {
+            dst_base = slots + (size_t)(2 * cta + (kt_begin == 0 ? 1 : 0)) * (size_t)(BM * BN);
+            ldo = BM;
+            row_lim = BM;
+            col0 = 0;
+            col_lim = BN;
+        }
         if (KIND == 0) {
 #pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
-                const int64_t m = row0 + 32 * warp + 16 * gq + 2 * g;
-                if (m < rows_out) {
+                const int m = 32 * warp + 16 * gq + 2 * g;
+                if (m < row_lim) {
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const int r = 8 * (rb * NB + nb) + 2 * t + j;
-                            if (r < R) {
-                                double *dst = out + m + rows_out * (int64_t)r;
-                                if (m + 1 < rows_out) {
+                            const int r = col0 + 8 * nb + 2 * t + j;
+                            if (r < col_lim) {
+                                double *dst = dst_base + m + ldo * (int64_t)r;
+                                if (m + 1 < row_lim) {
                                     *reinterpret_cast<double2 *>(dst) = make_double2(acc[2 * gq][nb][j], acc[2 * gq + 1][nb][j]);
                                 } else {
                                     dst[0] = acc[2 * gq][nb][j];
@@ -245,18 +286,41 @@ partial_gemm_kernel(const __grid_constant__ CUtensorMap tmap, const double *__re
         } else {
 #pragma unroll
             for (int rbk = 0; rbk < 4; ++rbk) {
-                const int64_t n = row0 + 32 * warp + 8 * rbk + sigma_b(g);
-                if (n < rows_out) {
+                const int n = 32 * warp + 8 * rbk + sigma_b(g);
+                if (n < row_lim) {
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const int r = 8 * (rb * NB + nb) + 2 * t + j;
-                            if (r < R) out[n + rows_out * (int64_t)r] = acc[rbk][nb][j];
+                            const int r = col0 + 8 * nb + 2 * t + j;
+                            if (r < col_lim) dst_base[n + ldo * (int64_t)r] = acc[rbk][nb][j];
                         }
                     }
                 }
             }
+        }
+    }
+}
+
+// Adds the partial tiles left by the stream-K split, in ascending-k order, and writes the finished tile.
+__global__ void __launch_bounds__(256) streamk_fixup_kernel(const int *__restrict__ tile_ids, const int *__restrict__ slot_ptr,
+                                                            const int *__restrict__ slot_list, const double *__restrict__ slots,
+                                                            double *__restrict__ out, int64_t rows_out, int R, int num_rblocks,
+                                                            int BM, int BN) {
+    const int s = blockIdx.x;
+    const int tile = tile_ids[s];
+    const int row_tile = tile / num_rblocks;
+    const int rb = tile - row_tile * num_rblocks;
+    const int64_t row0 = (int64_t)row_tile * BM;
+    const int p0 = slot_ptr[s], p1 = slot_ptr[s + 1];
+    for (int e = blockIdx.y * 256 + threadIdx.x; e < BM * BN; e += 256 * gridDim.y) {
+        const int lc = e / BM, lr = e - lc * BM;
+        const int64_t row = row0 + lr;
+        const int r = rb * BN + lc;
+        if (row < rows_out && r < R) {
+            double v = 0.0;
+            for (int p = p0; p < p1; ++p) v += slots[(size_t)slot_list[p] * (size_t)(BM * BN) + e];
+            out[row + rows_out * (int64_t)r] = v;
         }
     }
 }
@@ -353,6 +417,7 @@ template <int NB, int WARPS, int KIND>
 static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, double *out, int64_t rows_out, int R,
                       int num_row_tiles, int num_rblocks, int kt_count, int map3d) {
     using S = GemmSmem<NB, WARPS>;
+    constexpr int BM = S::BM, BN = 8 * NB;
     auto kern = partial_gemm_kernel<NB, WARPS, KIND>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -360,13 +425,67 @@ static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, do
         attr_set = true;
     }
     const int per_sm = (WARPS <= 4) ? 2 : 1;
-    int64_t tiles = (int64_t)num_row_tiles * num_rblocks;
-    int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * per_sm);
+    const int64_t tiles = (int64_t)num_row_tiles * num_rblocks;
+    int grid = (int)std::min<int64_t>(tiles * kt_count, (int64_t)c->sm_count * per_sm);
     if (grid < 1) grid = 1;
+    // stream_k: 0 never, 1 adaptive (only when the last data-parallel wave would idle >= 4 % of the SM-time), 2 always
+    const double waves_exact = (double)tiles / grid, waves_dp = (double)ceil_div(tiles, grid);
+    const bool use_sk = c->stream_k == 2 || (c->stream_k == 1 && tiles % grid != 0 && 1.0 - waves_exact / waves_dp >= 0.04);
+    const int full_waves = use_sk ? (int)(tiles / grid) : (int)ceil_div(tiles, grid);
+    if (!use_sk) grid = (int)std::min<int64_t>(tiles, grid);
+    const int64_t rem_tiles = std::max<int64_t>(0, tiles - (int64_t)full_waves * grid);
+    const int64_t rem_units = rem_tiles * kt_count;
+
+    // ---- stream-K bookkeeping (host): which tiles of the last round are split, and which slots hold their parts ----
+    StreamKTable &tb = c->sk_table[KIND];
+    const int64_t key[6] = {tiles, kt_count, grid, BM, BN, full_waves};
+    if (memcmp(key, tb.key, sizeof(key)) != 0) {
+        std::vector<int> tile_ids, slot_ptr(1, 0), slot_list;
+        int cur_tile = -1;
+        for (int cta = 0; cta < grid && rem_units > 0; ++cta) {
+            const int64_t a0 = rem_units * cta / grid, a1 = rem_units * (cta + 1) / grid;
+            int64_t u = a0;
+            while (u < a1) {
+                const int64_t q = u / kt_count, kb = u - q * kt_count;
+                const int64_t ke = std::min<int64_t>(kt_count, kb + (a1 - u));
+                const int tile = (int)((int64_t)full_waves * grid + q);
+                if (!(kb == 0 && ke == kt_count)) {
+                    if (tile != cur_tile) {
+                        if (cur_tile >= 0) slot_ptr.push_back((int)slot_list.size());
+                        tile_ids.push_back(tile);
+                        cur_tile = tile;
+                    }
+                    slot_list.push_back(2 * cta + (kb == 0 ? 1 : 0));
+                }
+                u += ke - kb;
+            }
+        }
+        if (cur_tile >= 0) slot_ptr.push_back((int)slot_list.size());
+        tb.nsplit = (int)tile_ids.size();
+        const size_t n1 = tile_ids.size(), n2 = slot_ptr.size(), n3 = slot_list.size();
+        TRY(tb.dev.reserve((n1 + n2 + n3 + 4) * sizeof(int)));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // table rebuilds are rare (shape change); keep the copy simple
+        if (tb.nsplit > 0) {
+            CUDA_TRY(cudaMemcpy(tb.dev.as<int>(), tile_ids.data(), n1 * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(tb.dev.as<int>() + n1, slot_ptr.data(), n2 * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(tb.dev.as<int>() + n1 + n2, slot_list.data(), n3 * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        tb.off_ptr = (int)n1;
+        tb.off_list = (int)(n1 + n2);
+        memcpy(tb.key, key, sizeof(key));
+    }
+    if (tb.nsplit > 0) TRY(c->sk_slots.reserve((size_t)2 * grid * BM * BN * 8));
+
     kern<<<grid, WARPS * 32, S::TOTAL, c->stream>>>(map, Kp, out, rows_out, R, num_row_tiles, num_rblocks, kt_count,
-                                                c->swizzle ? 7 : 0, map3d);
+                                                c->swizzle ? 7 : 0, map3d, full_waves, c->sk_slots.as<double>());
     c->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (tb.nsplit > 0) {
+        streamk_fixup_kernel<<<dim3((unsigned)tb.nsplit, (unsigned)std::max(1, std::min(BM * BN / 1024, 4 * c->sm_count / tb.nsplit))), 256, 0, c->stream>>>(tb.dev.as<int>(), tb.dev.as<int>() + tb.off_ptr, tb.dev.as<int>() + tb.off_list,
+                                                              c->sk_slots.as<double>(), out, rows_out, R, num_rblocks, BM, BN);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     return ITCPD_OK;
 }
 

@@ -79,6 +79,21 @@ def test_mttkrp_all_splits_and_tiles(engine, warps, splits):
         engine.set_option("split_b", 0)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_mttkrp_stream_k_modes(engine, mode):
+    """stream-K off / forced on: partial tiles + ordered fix-up give the same MTTKRP (to rounding)."""
+    engine.set_option("stream_k", mode)
+    try:
+        for dims, R in [((40, 36, 300), 24), ((300, 20, 24), 70), ((64, 64, 64), 64)]:
+            T, cp = make_problem(dims, R, seed=8)
+            engine.set_tensor(T)
+            engine.set_cpd(cp.factors, cp.lam)
+            for n in range(3):
+                assert relerr(engine.mttkrp(n), cpals.mttkrp_krp_normal(T, cp.factors, n)) < 1e-12, (mode, dims, n)
+    finally:
+        engine.set_option("stream_k", 1)
+
+
 def test_mttkrp_no_swizzle_debug_mode(engine):
     dims, R = (32, 32, 32), 16
     T, cp = make_problem(dims, R, seed=6)
