@@ -151,6 +151,26 @@ int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *ro
  * Gram and the leverage scores of `mode`. */
 int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol);
 
+/* qr(T_(mode), ColumnNorm()) of the pivot-projected setup (optimizers/.../randomized/qr_lev_score_sampled.jl:22-23,126-127):
+ * column-pivoted Householder QR of the mode unfolding on the device.  piv_out: the full pivot order, n = P / I_mode
+ * int64 entries, 1-based; rdiag_out: diag(R), min(I_mode, n) doubles. */
+int itcpd_qrcp_unfolding(itcpd_ctx *ctx, int mode, int64_t *piv_out, double *rdiag_out);
+/* the same factorisation for a caller-supplied column-major m x n host matrix; `steps` eliminations (<= min(m,n)) */
+int itcpd_qrcp_matrix(itcpd_ctx *ctx, int64_t m, int64_t n, const double *host_A, int64_t steps, int64_t *piv_out, double *rdiag_out);
+/* SEQRCS, matrix-free variant with compute_r = false (algebra/SEQRCS.jl:139-182): sparse-sign sketch of the unfolding
+ * (libc rand() stream of the reference's generators), QRCP of the sketch, first t sketch pivots -> candidate columns,
+ * QRCP of the gathered candidate columns, p = [candidates[p_subset]; remaining columns].  piv_out: n int64 1-based;
+ * rdiag_out: diag(R) of the candidate QR (nrdiag_out values, caller provides I_mode doubles). */
+int itcpd_seqrcs(itcpd_ctx *ctx, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
+                 int64_t *nrdiag_out, int64_t *ncand_out);
+/* pivot-projected solvers: cache the projector of `mode` and its sampled target T_s = fused_flatten_sample(T, mode, piv)
+ * on the device (qr_lev_score_sampled.jl:64-65, 162-163); then one mode update per call
+ * (ProjectionAlgorithm.jl:57-68, normal = true; post_solve is a no-op for these solvers). */
+int itcpd_set_projector(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots);
+int itcpd_projected_update(itcpd_ctx *ctx, int mode, double chol_tol);
+/* after the setup only the samples are touched: release the dense tensor (ALS(ITensor(inds(target)), ...), :77,175) */
+int itcpd_drop_tensor(itcpd_ctx *ctx);
+
 /* ---- multi-GPU (slab sharding along the last mode; one process per GPU) ------------------------ */
 /* The handle's tensor is the local slab T[..., slab]; factor N holds only the slab's rows.
  * After itcpd_comm_init every MTTKRP of a non-sharded mode is all-reduced, and the norms / Gram /

@@ -11,8 +11,9 @@ from ._lib import ItcpdError, LIB_PATH, DECLARED_SYMBOLS, load  # noqa: F401
 from .engine import Engine, PinnedBuffer, column_to_multi_coords, multi_coords_to_column, sparse_sign_matrix  # noqa: F401
 from .host import (  # noqa: F401
     ALS, CPD, CPAngleCheck, CPDFit, CPDiffCheck, CPDOptimizer, DirectNormal, FitCheck, KRPFreeNormal, KRPNormal,
-    LevScoreSampled, MttkrpAlgorithm, NoCheck, ProjectionAlgorithm, als_optimize, compute_als, cp_rank, decompose,
-    increase_cpd_rank, optimize, random_CPD, random_factors, reconstruct,
+    LevScoreSampled, MttkrpAlgorithm, NoCheck, ProjectionAlgorithm, QRPivProjected, SEQRCSPivProjected, als_optimize,
+    compute_als, cp_rank, decompose, increase_cpd_rank, optimize, random_CPD, random_factors, reconstruct, start, stop,
+    update_samples,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -116,6 +116,7 @@ static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
     c->nstore = n / dims[0] * c->ld0;
     TRY(c->T.reserve((size_t)c->nstore * 8 + 256));
     c->has_tensor = true;
+    c->has_tensor_data = true;
     choose_splits(c);
     invalidate_all(c);
     if (c->rank > 0) TRY(ensure_cpd_buffers(c));
@@ -195,6 +196,7 @@ using namespace itcpd;
 #define CHECK_CTX(c) ARG_CHECK((c) != nullptr, "null context")
 #define CHECK_MODE(c, m) ARG_CHECK((m) >= 0 && (m) < (c)->order, "mode out of range (0-based)")
 #define USE_DEVICE(c) CUDA_TRY(cudaSetDevice((c)->device))
+#define NEED_T(c) ARG_CHECK((c)->has_tensor && (c)->has_tensor_data, "the dense tensor is not resident (never set, or released by itcpd_drop_tensor)")
 
 extern "C" {
 
@@ -241,9 +243,9 @@ int itcpd_destroy(itcpd_ctx *c) {
     cudaStreamSynchronize(c->stream);
     itcpd_comm_destroy(c);
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
-                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev};
+                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev, &c->qr_A, &c->qr_piv, &c->qr_rdiag};
     for (DevBuf *b : bufs) b->release();
-    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); }
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); }
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -322,6 +324,7 @@ int itcpd_generate_tensor(itcpd_ctx *c, int order, const int64_t *dims, uint64_t
 
 int itcpd_get_tensor(itcpd_ctx *c, double *host) {
     CHECK_CTX(c);
+    NEED_T(c);
     ARG_CHECK(c->has_tensor && host, "no tensor / null host pointer");
     USE_DEVICE(c);
     if (c->ld0 == c->dims[0]) {
@@ -337,6 +340,7 @@ int itcpd_get_tensor(itcpd_ctx *c, double *host) {
 
 int itcpd_tensor_norm(itcpd_ctx *c, double *fro) {
     CHECK_CTX(c);
+    NEED_T(c);
     ARG_CHECK(c->has_tensor && fro, "no tensor / null out pointer");
     USE_DEVICE(c);
     TRY(c->fit2.reserve(64));
@@ -450,6 +454,7 @@ int itcpd_gram_hadamard(itcpd_ctx *c, int mode, double *host_out) {
 
 int itcpd_mttkrp(itcpd_ctx *c, int mode, double *host_out) {
     CHECK_CTX(c);
+    NEED_T(c);
     CHECK_MODE(c, mode);
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
@@ -508,6 +513,7 @@ int itcpd_fit_terms(itcpd_ctx *c, double *inner, double *model_norm2) {
 // pinned staging layout: [0, 2*nsweeps) fit scalars; then 3 ints per (sweep, mode) of solve status
 int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
     CHECK_CTX(c);
+    NEED_T(c);
     ARG_CHECK(nsweeps >= 1, "nsweeps must be positive");
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
@@ -591,6 +597,7 @@ int itcpd_reconstruct(itcpd_ctx *c, double *host) {
 
 int itcpd_residual_norm(itcpd_ctx *c, double *fro) {
     CHECK_CTX(c);
+    NEED_T(c);
     ARG_CHECK(fro && c->has_tensor && c->rank > 0, "null out pointer / no state");
     USE_DEVICE(c);
     TRY(k_reconstruct(c, nullptr, c->fit2.as<double>()));
@@ -672,6 +679,7 @@ int itcpd_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *h
 
 int itcpd_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double *host_out) {
     CHECK_CTX(c);
+    NEED_T(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(nsamp >= 1 && host_pivots && host_out && c->has_tensor, "bad nsamp / null pointer / no tensor");
     USE_DEVICE(c);
@@ -706,44 +714,222 @@ int itcpd_multi_coords_to_column(int64_t ncols, const int64_t *coords, int ndims
     return ITCPD_OK;
 }
 
-int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows0, const double *vals, double *host_out) {
-    CHECK_CTX(c);
-    CHECK_MODE(c, mode);
-    ARG_CHECK(l >= 1 && s >= 1 && rows0 && vals && host_out && c->has_tensor, "bad argument");
-    USE_DEVICE(c);
-    const int s_eff = std::min(s, l);
-    const int64_t ncols = c->nelem / c->dims[mode];
+// CSR by sketch row with a stable counting sort: entries of a row stay in increasing non-zero order
+// (the order the reference's dict_rows visits them, pivot_mapping.jl:127-137); uploaded into c->work.
+struct SketchCsr {
+    std::vector<int64_t> row_ptr, col;
+    std::vector<double> val;
+    const int64_t *d_ptr = nullptr, *d_col = nullptr;
+    const double *d_val = nullptr;
+};
+
+static int build_sketch_csr(itcpd_ctx *c, int l, int s_eff, int64_t ncols, const int *rows0, const double *vals, SketchCsr &k) {
     const int64_t nnz = ncols * s_eff;
-    // CSR by sketch row with a stable counting sort: entries of a row stay in increasing nz order
-    std::vector<int64_t> row_ptr((size_t)l + 1, 0), col((size_t)nnz);
-    std::vector<double> val((size_t)nnz);
+    k.row_ptr.assign((size_t)l + 1, 0);
+    k.col.resize((size_t)nnz);
+    k.val.resize((size_t)nnz);
     for (int64_t q = 0; q < nnz; ++q) {
         ARG_CHECK(rows0[q] >= 0 && rows0[q] < l, "sketch row index out of range");
-        row_ptr[(size_t)rows0[q] + 1]++;
+        k.row_ptr[(size_t)rows0[q] + 1]++;
     }
-    for (int j = 0; j < l; ++j) row_ptr[(size_t)j + 1] += row_ptr[j];
+    for (int j = 0; j < l; ++j) k.row_ptr[(size_t)j + 1] += k.row_ptr[j];
     {
-        std::vector<int64_t> fill(row_ptr.begin(), row_ptr.end() - 1);
+        std::vector<int64_t> fill(k.row_ptr.begin(), k.row_ptr.end() - 1);
         for (int64_t q = 0; q < nnz; ++q) {
             const int64_t pos = fill[rows0[q]]++;
-            col[(size_t)pos] = q / s_eff;
-            val[(size_t)pos] = vals[q];
+            k.col[(size_t)pos] = q / s_eff;
+            k.val[(size_t)pos] = vals[q];
         }
     }
     const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)nnz * 8;
     TRY(c->work.reserve(b_ptr + 2 * b_col + 64));
     char *base = (char *)c->work.p;
-    CUDA_TRY(cudaMemcpyAsync(base, row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base, k.row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, k.col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, k.val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    k.d_ptr = (const int64_t *)base;
+    k.d_col = (const int64_t *)(base + b_ptr);
+    k.d_val = (const double *)(base + b_ptr + b_col);
+    return ITCPD_OK;
+}
+
+int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows0, const double *vals, double *host_out) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(l >= 1 && s >= 1 && rows0 && vals && host_out && c->has_tensor, "bad argument");
+    USE_DEVICE(c);
+    const int s_eff = std::min(s, l);
+    const int64_t ncols = c->nelem / c->dims[mode];
+    SketchCsr k;
+    TRY(build_sketch_csr(c, l, s_eff, ncols, rows0, vals, k));
     TRY(c->samp_T.reserve((size_t)l * c->dims[mode] * 8));
-    TRY(k_sketch_csr(c, mode, l, (const int64_t *)base, (const int64_t *)(base + b_ptr), (const double *)(base + b_ptr + b_col),
-                     c->samp_T.as<double>()));
+    TRY(k_sketch_csr(c, mode, l, k.d_ptr, k.d_col, k.d_val, c->samp_T.as<double>()));
     return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+}
+
+// ---- column-pivoted QR on the device (pivot-projected setup) ----------------------------------------
+static int qrcp_fetch(itcpd_ctx *c, int64_t n, int64_t nr, int64_t *piv_out, double *rdiag_out) {
+    std::vector<int64_t> tmp((size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->qr_piv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (rdiag_out) CUDA_TRY(cudaMemcpyAsync(rdiag_out, c->qr_rdiag.p, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < n; ++i) piv_out[i] = tmp[(size_t)i] + 1;  // 1-based, like LinearAlgebra's QRPivoted.p
+    return ITCPD_OK;
+}
+
+int itcpd_qrcp_matrix(itcpd_ctx *c, int64_t m, int64_t n, const double *host_A, int64_t steps, int64_t *piv_out, double *rdiag_out) {
+    CHECK_CTX(c);
+    ARG_CHECK(m >= 1 && n >= 1 && host_A && piv_out && steps >= 1, "bad argument");
+    USE_DEVICE(c);
+    const int64_t nr = std::min<int64_t>(std::min(m, n), steps);
+    TRY(c->qr_A.reserve((size_t)m * n * 8));
+    TRY(c->qr_piv.reserve((size_t)n * 8));
+    TRY(c->qr_rdiag.reserve((size_t)std::min(m, n) * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->qr_A.p, host_A, (size_t)m * n * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), m, n, nr, c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    return qrcp_fetch(c, n, nr, piv_out, rdiag_out);
+}
+
+int itcpd_qrcp_unfolding(itcpd_ctx *c, int mode, int64_t *piv_out, double *rdiag_out) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(piv_out && c->has_tensor, "null out pointer / no tensor");
+    USE_DEVICE(c);
+    const int64_t m = c->dims[mode], n = c->nelem / m, nr = std::min(m, n);
+    TRY(c->qr_A.reserve((size_t)m * n * 8));
+    TRY(c->qr_piv.reserve((size_t)n * 8));
+    TRY(c->qr_rdiag.reserve((size_t)nr * 8));
+    TRY(k_unfold(c, mode, c->qr_A.as<double>()));
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), m, n, nr, c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    return qrcp_fetch(c, n, nr, piv_out, rdiag_out);
+}
+
+int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
+                 int64_t *nrdiag_out, int64_t *ncand_out) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(l >= 1 && s >= 1 && t >= 1 && t <= l && piv_out && c->has_tensor, "bad argument (need 1 <= t <= l)");
+    USE_DEVICE(c);
+    const int N = c->order;
+    const int64_t m = c->dims[mode], n = c->nelem / m;
+    ARG_CHECK(n < (int64_t)1 << 31 && (int64_t)n * std::min(s, l) < (int64_t)1 << 31, "the reference's C generators index with 32-bit ints");
+    const int s_eff = std::min(s, l);
+    // 1. sparse-sign embedding (SEQRCS.jl:144-146) -- same libc rand() stream as the reference's generators
+    std::vector<double> vals((size_t)n * s_eff);
+    std::vector<int> rows((size_t)n * s_eff), colstarts((size_t)n + 1);
+    if (injective) itcpd_sparsestack(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
+    else itcpd_sparse_sign(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
+    // 2. sketch A_sk = T_(mode) Omega^T (I x l) (SEQRCS.jl:149)
+    SketchCsr k;
+    TRY(build_sketch_csr(c, l, s_eff, n, rows.data(), vals.data(), k));
+    TRY(c->qr_A.reserve((size_t)m * std::max<int64_t>(l, 1) * 8));
+    TRY(k_sketch_csr(c, mode, l, k.d_ptr, k.d_col, k.d_val, c->qr_A.as<double>()));
+    // 3. QRCP of the sketch, first t pivots (SEQRCS.jl:152-158)
+    TRY(c->qr_piv.reserve((size_t)std::max<int64_t>(n, l) * 8));
+    TRY(c->qr_rdiag.reserve((size_t)std::max<int64_t>(m, 1) * 8 + (size_t)std::min<int64_t>(m, l) * 8));
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), m, l, std::min<int64_t>(t, std::min<int64_t>(m, l)), c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    std::vector<int64_t> p_sk((size_t)t);
+    CUDA_TRY(cudaMemcpyAsync(p_sk.data(), c->qr_piv.p, (size_t)t * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // 4. candidate columns: for each selected sketch row (pivot order) the columns hashed to it, unique'd (SEQRCS.jl:159)
+    std::vector<char> seen((size_t)n, 0);
+    std::vector<int64_t> cand;
+    for (int64_t q = 0; q < t; ++q) {
+        const int64_t r = p_sk[(size_t)q];
+        for (int64_t e = k.row_ptr[(size_t)r]; e < k.row_ptr[(size_t)r + 1]; ++e) {
+            const int64_t col = k.col[(size_t)e];
+            if (!seen[(size_t)col]) { seen[(size_t)col] = 1; cand.push_back(col); }
+        }
+    }
+    const int64_t nc = (int64_t)cand.size();
+    ARG_CHECK(nc >= 1, "SE-QRCS selected no candidate column");
+    // 5. gather the candidate columns (fused_flatten_sample, SEQRCS.jl:166) and QRCP them
+    std::vector<int64_t> coords((size_t)nc * (N - 1));
+    {
+        int col = 0;
+        std::vector<int64_t> rem(cand);
+        for (int q = 0; q < N; ++q) {
+            if (q == mode) continue;
+            for (int64_t i = 0; i < nc; ++i) { coords[(size_t)(i + nc * col)] = rem[(size_t)i] % c->dims[q] + 1; rem[(size_t)i] /= c->dims[q]; }
+            ++col;
+        }
+    }
+    TRY(c->samp_piv.reserve((size_t)nc * (N - 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->samp_piv.p, coords.data(), (size_t)nc * (N - 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(c->qr_A.reserve((size_t)m * nc * 8));
+    TRY(k_gather_fibers(c, mode, nc, c->samp_piv.as<int64_t>(), c->qr_A.as<double>()));
+    const int64_t nr = std::min(m, nc);
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), m, nc, nr, c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    std::vector<int64_t> p_sub((size_t)nc);
+    CUDA_TRY(cudaMemcpyAsync(p_sub.data(), c->qr_piv.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (rdiag_out) CUDA_TRY(cudaMemcpyAsync(rdiag_out, c->qr_rdiag.p, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // 6. p = [candidates[p_subset]; setdiff(1:n, candidates)] (SEQRCS.jl:167-168), 1-based
+    int64_t w = 0;
+    for (int64_t i = 0; i < nc; ++i) piv_out[w++] = cand[(size_t)p_sub[(size_t)i]] + 1;
+    for (int64_t col = 0; col < n; ++col)
+        if (!seen[(size_t)col]) piv_out[w++] = col + 1;
+    if (nrdiag_out) *nrdiag_out = nr;
+    if (ncand_out) *ncand_out = nc;
+    return ITCPD_OK;
+}
+
+int itcpd_set_projector(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(nsamp >= 1 && host_pivots && c->has_tensor, "bad nsamp / null pointer / no tensor");
+    USE_DEVICE(c);
+    TRY(check_pivots(c, mode, nsamp, host_pivots));
+    const size_t pb = (size_t)nsamp * (c->order - 1) * 8;
+    TRY(c->proj_piv[mode].reserve(pb));
+    TRY(c->proj_T[mode].reserve((size_t)nsamp * c->dims[mode] * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->proj_piv[mode].p, host_pivots, pb, cudaMemcpyHostToDevice, c->stream));
+    TRY(k_gather_fibers(c, mode, nsamp, c->proj_piv[mode].as<int64_t>(), c->proj_T[mode].as<double>()));
+    c->proj_n[mode] = nsamp;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    USE_DEVICE(c);
+    ARG_CHECK(c->proj_n[mode] > 0, "call itcpd_set_projector(mode) first");
+    ARG_CHECK(c->rank > 0 && c->A[mode].p, "CPD state not set");
+    const int R = c->rank;
+    const int64_t I = c->dims[mode], ns = c->proj_n[mode];
+    TRY(c->samp_K.reserve((size_t)ns * R * 8));
+    TRY(k_pivot_hadamard(c, mode, ns, c->proj_piv[mode].as<int64_t>(), c->samp_K.as<double>()));
+    TRY(k_gram(c, c->samp_K.as<double>(), ns, R, c->Gamma.as<double>()));
+    TRY(k_small_gemm_nn(c, c->proj_T[mode].as<double>(), c->samp_K.as<double>(), I, ns, R, c->M[mode].as<double>()));
+    c->m_valid[mode] = false;
+    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>()));
+    TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
+    c->fver[mode]++;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+int itcpd_drop_tensor(itcpd_ctx *c) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->T.release();
+    c->PA.buf.release();
+    c->PB.buf.release();
+    c->qr_A.release();
+    c->PA.valid = c->PB.valid = false;
+    c->has_tensor_data = false;
+    return ITCPD_OK;
 }
 
 int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol) {
     CHECK_CTX(c);
+    NEED_T(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(nsamp >= 1 && host_pivots && c->has_tensor, "bad nsamp / null pointer / no tensor");
     USE_DEVICE(c);

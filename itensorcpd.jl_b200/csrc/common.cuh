@@ -95,7 +95,8 @@ struct itcpd_ctx {
     int64_t nelem = 0;  // logical element count
     int64_t nstore = 0; // stored element count (ld0 * prod(dims[1:]))
     itcpd::DevBuf T;
-    bool has_tensor = false;
+    bool has_tensor = false;        // shape known (dims valid)
+    bool has_tensor_data = false;   // dense data resident (false after itcpd_drop_tensor)
 
     // CPD
     int rank = 0;
@@ -118,6 +119,9 @@ struct itcpd_ctx {
     // scratch
     itcpd::DevBuf packK, krp_scratch[2], work, work2, redux, solve_ws, ipiv, status, fit2, samp_piv, samp_K, samp_T, flush;
     cudaEvent_t user_events[16] = {nullptr};
+    // pivot-projected solvers: cached projector (1-based int64, nsamp x (N-1)) and sampled target (I_n x nsamp) per mode
+    itcpd::DevBuf proj_piv[ITCPD_MAX_ORDER], proj_T[ITCPD_MAX_ORDER], qr_A, qr_piv, qr_rdiag;
+    int64_t proj_n[ITCPD_MAX_ORDER] = {0};
     double *pinned = nullptr;   // pinned host staging (fit scalars, status words)
     size_t pinned_doubles = 0;
 
@@ -168,6 +172,8 @@ int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int
 int k_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *K_dev);
 int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
 int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
+int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, int64_t *jpvt_dev, double *rdiag_dev);  // qrcp_wide.cu
+int k_unfold(itcpd_ctx *c, int mode, double *out);
 int k_small_gemm_nn(itcpd_ctx *c, const double *A, const double *B, int64_t m, int64_t k, int n, double *C); // C = A B
 
 // ---- comm.cu ------------------------------------------------------------------------------

@@ -251,6 +251,48 @@ class Engine:
         p = self._piv(pivots)
         check(self._L.itcpd_sampled_update(self._h, mode, p.shape[0], _addr(p), float(chol_tol)))
 
+    # -- pivot-projected solvers ------------------------------------------------------------
+    def qrcp_unfolding(self, mode: int):
+        """qr(T_(mode), ColumnNorm()): (p 1-based int64 over all unfolding columns, diag(R))."""
+        m = self.dims[mode]
+        n = int(np.prod(self.dims)) // m
+        piv = np.empty(n, dtype=np.int64)
+        rd = np.empty(min(m, n))
+        check(self._L.itcpd_qrcp_unfolding(self._h, mode, _addr(piv), _addr(rd)))
+        return piv, rd
+
+    def qrcp_matrix(self, A, steps: Optional[int] = None):
+        A = _f64(A)
+        m, n = A.shape
+        steps = min(m, n) if steps is None else int(steps)
+        piv = np.empty(n, dtype=np.int64)
+        rd = np.empty(min(m, n, steps))
+        check(self._L.itcpd_qrcp_matrix(self._h, m, n, _addr(A), steps, _addr(piv), _addr(rd)))
+        return piv, rd
+
+    def seqrcs(self, mode: int, l: int, s: int, t: int, injective: bool = False, seed: Optional[int] = None):
+        """SEQRCS (SEQRCS.jl:139-182, compute_r=false): (p 1-based, diag(R) of the candidate QR, #candidates)."""
+        m = self.dims[mode]
+        n = int(np.prod(self.dims)) // m
+        piv = np.empty(n, dtype=np.int64)
+        rd = np.empty(m)
+        nr, nc = C.c_int64(), C.c_int64()
+        if seed is not None:
+            C.CDLL(None).srand(C.c_uint(seed))
+        check(self._L.itcpd_seqrcs(self._h, mode, int(l), int(s), int(t), int(bool(injective)), _addr(piv), _addr(rd),
+                                   C.byref(nr), C.byref(nc)))
+        return piv, rd[: nr.value].copy(), nc.value
+
+    def set_projector(self, mode: int, pivots):
+        p = self._piv(pivots)
+        check(self._L.itcpd_set_projector(self._h, mode, p.shape[0], _addr(p)))
+
+    def projected_update(self, mode: int, chol_tol: float = 1e-6):
+        check(self._L.itcpd_projected_update(self._h, mode, float(chol_tol)))
+
+    def drop_tensor(self):
+        check(self._L.itcpd_drop_tensor(self._h))
+
     # -- multi-GPU --------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -330,6 +330,144 @@ class LevScoreSampled(ProjectionAlgorithm):
         return als.check.check_converge(als, als.fetch_cpd_arrays, verbose=verbose)
 
 
+def _pick(v, fact):
+    if isinstance(v, (tuple, list)):
+        return v[0] if len(v) == 1 else v[fact]
+    return v
+
+
+class _PivotBased(ProjectionAlgorithm):
+    """QRPivProjected / SEQRCSPivProjected (algorithms/.../randomized/qr_lev_score_sampled.jl:10-168): the projector
+    of every mode is fixed at setup (column-pivoted QR / SE-QRCS of the unfolding, run on the device), the sampled
+    target T_s is gathered once and cached on the device; each sweep only forms the sampled KRP and solves."""
+
+    def __init__(self, start=1, end=0, random_modes=None, rank_vect=None):
+        self.Start, self.End = start, end
+        self.random_modes = None if random_modes is None else tuple(random_modes)  # 1-based mode numbers, as in Julia
+        if rank_vect is not None and not isinstance(rank_vect, dict):
+            rv = rank_vect if isinstance(rank_vect, (tuple, list)) else (rank_vect,) * len(self.random_modes)
+            rank_vect = dict(zip(self.random_modes, rv))
+        self.rank_vect = rank_vect
+
+    def compute_krp(self, als, fact):
+        pass  # pivot_hadamard happens inside projected_update (qr_lev...:151-160)
+
+    def matricize_tensor(self, als, fact):
+        pass  # cached target_transform[fact] (qr_lev...:162-166)
+
+    def solve_ls_problem(self, als, fact):
+        if not als.additional_items["normal"]:
+            raise NotImplementedError("normal=false (QRCP of the sampled KRP) is not in this build; use normal=True")
+        als.engine.projected_update(fact, CHOLESKY_EPSILON)
+
+    def post_solve(self, als, fact):
+        pass  # qr_lev...:168
+
+    check_converge = LevScoreSampled.check_converge
+
+
+class QRPivProjected(_PivotBased):
+    def __init__(self, start_or_n=None, end=None):
+        if start_or_n is None:
+            super().__init__(1, 0)
+        elif end is None:
+            n = start_or_n
+            super().__init__(tuple([1] * len(n)) if isinstance(n, (tuple, list)) else 1, n)
+        else:
+            super().__init__(start_or_n, end)
+
+
+class SEQRCSPivProjected(_PivotBased):
+    pass
+
+
+def start(alg):
+    return alg.Start
+
+
+def stop(alg):
+    return alg.End
+
+
+def _proj_range(alg, n, dRis):
+    int_end = _pick(alg.End, n)
+    int_end = dRis if int_end == 0 else int_end
+    int_end = min(dRis, int_end)
+    int_start = _pick(alg.Start, n)
+    assert 0 < int_start <= int_end
+    return int_start, int_end
+
+
+def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed) -> "ALS":
+    """optimizers/.../randomized/qr_lev_score_sampled.jl:1-78 (QRPivProjected) and :80-176 (SEQRCSPivProjected)."""
+    from .engine import column_to_multi_coords
+
+    rng = np.random.default_rng(7) if rng is None else rng
+    dims = eng.dims
+    N = len(dims)
+    lst = () if alg.random_modes is None else alg.random_modes
+    ref_pivs, pivots, projectors, eff = [], [], [], []
+    for n in range(N):
+        rdims = [dims[m] for m in range(N) if m != n]
+        dRis = int(np.prod(rdims))
+        int_start, int_end = _proj_range(alg, n, dRis)
+        m = dims[n]
+        if (n + 1) in lst and isinstance(alg, SEQRCSPivProjected):
+            k_sk = int_end if alg.rank_vect is None else alg.rank_vect[n + 1]
+            l = int(round(3 * m * math.log(m)))   # qr_lev...:122
+            s = int(round(math.log(m)))           # :123
+            p, dr, _ = eng.seqrcs(n, l, s, min(k_sk, l), injective=injective, seed=None if seed is None else seed + n)
+        else:
+            p, dr = eng.qrcp_unfolding(n)
+        ref_pivs.append(p.copy())
+        meff = int(np.sum(np.abs(dr) / np.max(np.abs(dr)) > trunc_tol))   # :28 / :137
+        eff.append(meff)
+        rest = p[meff:]
+        p = np.concatenate([p[:meff], rest[rng.permutation(len(rest))] if shuffle_pivots else rest])
+        coords = column_to_multi_coords(p, rdims)
+        pivots.append(coords)
+        proj = np.asfortranarray(coords[int_start - 1: int_end, :])
+        projectors.append(proj)
+        eng.set_projector(n, proj)   # gathers + caches target_transform[n] on the device
+    extra = dict(ref_projectors=ref_pivs, projects=pivots, projects_tensors=projectors, effective_ranks=eff,
+                 normal=True if normal is None else normal, dims=tuple(dims))
+    eng.drop_tensor()  # ALS(ITensor(inds(target)), ...): only the samples are needed from here on (:77, :175)
+    return ALS(eng, alg, extra, check)
+
+
+def update_samples(target, als: "ALS", new_num_end, reshuffle=False, new_num_start=0, rng=None) -> "ALS":
+    """algorithms/.../qr_lev_score_sampled.jl:95-149: new sample range without redoing the QR (re-gathers T_s)."""
+    from .engine import column_to_multi_coords
+
+    rng = np.random.default_rng(11) if rng is None else rng
+    old = als.mttkrp_alg
+    assert isinstance(old, _PivotBased)
+    alg = type(old).__new__(type(old))
+    _PivotBased.__init__(alg, old.Start if new_num_start == 0 else new_num_start, old.End if new_num_end == 0 else new_num_end,
+                         old.random_modes, old.rank_vect)
+    eng = als.engine
+    eng.set_tensor(target)  # the setup dropped the dense tensor; the reference also re-reads `target` here (:135)
+    ai = als.additional_items
+    dims = eng.dims
+    N = len(dims)
+    pivots = [p.copy() for p in ai["projects"]]
+    projectors = []
+    for pos in range(N):
+        rdims = [dims[m] for m in range(N) if m != pos]
+        if reshuffle:
+            p, meff = ai["ref_projectors"][pos], ai["effective_ranks"][pos]
+            rest = p[meff:]
+            pivots[pos] = column_to_multi_coords(np.concatenate([p[:meff], rest[rng.permutation(len(rest))]]), rdims)
+        int_start, int_end = _proj_range(alg, pos, int(np.prod(rdims)))
+        proj = np.asfortranarray(pivots[pos][int_start - 1: int_end, :])
+        projectors.append(proj)
+        eng.set_projector(pos, proj)
+    eng.drop_tensor()
+    extra = dict(ai)
+    extra.update(projects=pivots, projects_tensors=projectors)
+    return ALS(eng, alg, extra, als.check)
+
+
 # ------------------------------------------------------------------------------------------
 # ALS driver
 # ------------------------------------------------------------------------------------------
@@ -361,7 +499,8 @@ def _engine_for(target, device=0) -> Engine:
     return eng
 
 
-def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None, stop_resample=-1, device=0, seed=0, **_) -> ALS:
+def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None, stop_resample=-1, device=0, seed=0,
+                shuffle_pivots=True, trunc_tol=0.01, injective=False, rng=None, **_) -> ALS:
     """als_optimizer.jl:37-69 + standard/tensor.jl:3-14 + randomized/krp_lev_score_sampled.jl:1-40."""
     alg = KRPFreeNormal() if alg is None else alg
     check = NoCheck(100 if maxiter is None else maxiter) if check is None else check
@@ -377,6 +516,8 @@ def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None
                      projects_tensors=[None] * len(cp))
         for n in range(len(cp)):
             eng.leverage_scores(n)  # :factor_weights
+    elif isinstance(alg, _PivotBased):
+        return _setup_pivot_based(alg, eng, cp, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed)
     else:
         raise TypeError(f"unsupported algorithm {type(alg).__name__}")
     return ALS(eng, alg, extra, check)
@@ -388,6 +529,8 @@ def optimize(cp: CPD, als: ALS, verbose=False) -> CPD:
     alg = als.mttkrp_alg
     N = len(cp)
     eng = als.engine
+    if isinstance(alg, _PivotBased):
+        eng.set_cpd(cp.factors, cp.lam)  # an ALS object can be re-used with another starting CPD (update_samples)
     fused = isinstance(alg, MttkrpAlgorithm) and isinstance(als.check, (NoCheck, FitCheck)) and not als.additional_items.get("per_hook")
     while it < als.check.max_counter:
         if fused:

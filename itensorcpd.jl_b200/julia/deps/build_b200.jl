@@ -4,7 +4,7 @@
 csrc = joinpath(@__DIR__, "..", "..", "csrc")
 out  = joinpath(@__DIR__, "..", "..", "lib")
 mkpath(out)
-srcs = [joinpath(csrc, f) for f in ("api.cu", "gemm_dmma.cu", "kernels.cu", "solve.cu", "qrcp.cu",
+srcs = [joinpath(csrc, f) for f in ("api.cu", "gemm_dmma.cu", "kernels.cu", "solve.cu", "qrcp.cu", "qrcp_wide.cu",
                                      "sampled.cu", "comm.cu", "sparse_sign.cu")]
 lib_file = joinpath(out, "libitcpd_b200.so")
 compile = `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared

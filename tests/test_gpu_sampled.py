@@ -163,3 +163,111 @@ def test_angle_check_and_fitcheck_warning_for_sampled(engine, capsys):
     itcpd.als_optimize(A, itcpd.CPD(cp0.factors, cp0.lam), alg=itcpd.LevScoreSampled(100), normal=True, check=chk)
     assert "FitCheck is not enabled" in capsys.readouterr().out  # ProjectionAlgorithm.jl:30-36
     assert chk.iter == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pivot-projected solvers: device QRCP, SE-QRCS, cached projectors
+# ---------------------------------------------------------------------------------------------------------
+def _rank_k_error(A, p, k):
+    """|| A[:,p] - Q_k R_k || / ||A|| for the QR of the pivoted matrix truncated to k columns."""
+    Ap = A[:, p - 1]
+    Q, R = np.linalg.qr(Ap[:, :k])
+    return np.linalg.norm(Ap - Q @ (Q.T @ Ap), 2) / np.linalg.norm(A, 2)
+
+
+@pytest.mark.parametrize("m,n", [(12, 40), (50, 3000), (40, 25), (64, 64)])
+def test_device_qrcp_matches_lapack(engine, m, n):
+    """qr(A, ColumnNorm()): same pivot order and |diag(R)| as LAPACK dgeqp3 on generic matrices."""
+    rng = np.random.default_rng(20)
+    A = np.asfortranarray(rng.standard_normal((m, n)) * np.exp(rng.standard_normal(n))[None, :])
+    piv, rd = engine.qrcp_matrix(A)
+    _, R, p = sampled.qrcp(A)
+    k = min(m, n)
+    assert sorted(piv.tolist()) == list(range(1, n + 1))
+    assert np.array_equal(piv[:k], p[:k])
+    assert np.max(np.abs(np.abs(rd) - np.abs(np.diag(R)))) < 1e-10 * np.abs(R[0, 0])
+
+
+def test_device_qrcp_unfolding_all_modes(engine):
+    rng = np.random.default_rng(21)
+    T = np.asfortranarray(rng.standard_normal((9, 10, 11)) * np.exp(rng.standard_normal((1, 10, 1))))
+    engine.set_tensor(T)
+    for mode in range(3):
+        piv, rd = engine.qrcp_unfolding(mode)
+        _, R, p = sampled.qrcp(cpals.unfold(T, mode))
+        k = T.shape[mode]
+        assert np.array_equal(piv[:k], p[:k]) and sorted(piv.tolist()) == list(range(1, T.size // k + 1))
+        assert np.max(np.abs(np.abs(rd) - np.abs(np.diag(R)))) < 1e-10 * np.abs(R[0, 0])
+
+
+@pytest.mark.parametrize("inj", [False, True])
+def test_device_seqrcs_matches_oracle_and_qrcp_quality(engine, inj):
+    """test/SEQRCS_test.jl:32-47 scaled: with the same libc rand() stream the device SE-QRCS must select the same
+    candidate set as the oracle, and its rank-k approximation error must be within 1e-2 of plain QRCP."""
+    rng = np.random.default_rng(22)
+    A = np.asfortranarray(rng.standard_normal((50, 3000)))
+    k, l, s, t = 40, 750, 1, 40
+    engine.set_tensor(A)
+    piv, rd, ncand = engine.seqrcs(0, l, s, t, injective=inj, seed=17)
+    info = {}
+    Q, R, p = sampled.seqrcs_tensor(A, 0, l, s, t, use_omega=False, injective=inj, which="ref", seed=17, info=info)
+    assert ncand == info["subset"]
+    assert sorted(piv.tolist()) == list(range(1, 3001))
+    assert set(piv[:ncand].tolist()) == set(p[:ncand].tolist())      # same candidate columns
+    assert np.array_equal(piv[ncand:], p[ncand:])                     # same remainder order
+    assert np.array_equal(piv[:k], p[:k])                             # same leading pivots
+    _, _, p_act = sampled.qrcp(A)
+    assert abs(_rank_k_error(A, piv, k) - _rank_k_error(A, p_act, k)) <= 1e-2
+
+
+def test_projected_update_matches_oracle(engine):
+    T, cp, rng = problem((14, 12, 10), 5, 23)
+    engine.set_tensor(T)
+    engine.set_cpd(cp.factors, cp.lam)
+    mode = 2
+    piv = np.asfortranarray(np.stack([rng.integers(1, 15, size=90), rng.integers(1, 13, size=90)], axis=1).astype(np.int64))
+    engine.set_projector(mode, piv)
+    engine.drop_tensor()
+    import itcpd
+    with pytest.raises(itcpd.ItcpdError):
+        engine.mttkrp(0)  # the dense tensor is gone, exactly like ALS(ITensor(inds(target)), ...)
+    engine.projected_update(mode)
+    K = sampled.pivot_hadamard([cp.factors[0], cp.factors[1]], piv)
+    Ts = sampled.fused_flatten_sample(T, mode, piv)
+    X = cpals.ldiv_solve(K.T @ K, np.asfortranarray((Ts @ K).T)).T
+    Ao, lo = cpals.row_norm(X)
+    assert np.linalg.norm(engine.get_factor(mode) - Ao) / np.linalg.norm(Ao) < 1e-10
+    assert np.linalg.norm(engine.get_lambda() - lo) / np.linalg.norm(lo) < 1e-10
+
+
+def test_pivot_projected_als_like_reference_tests(engine):
+    """test/rand_cp_als.jl:28-96 scaled: QRPivProjected / SEQRCSPivProjected + update_samples bookkeeping; on an exactly
+    low-rank tensor the projected solvers come within 10 % of the exact-ALS error."""
+    import itcpd
+
+    rng = np.random.default_rng(24)
+    A = cpals.reconstruct(cpals.random_CPD((12, 13, 11), 4, rng))
+    nA = np.linalg.norm(A)
+    cp0 = cpals.random_CPD(A, 3, rng)
+    start_cp = itcpd.CPD(cp0.factors, cp0.lam)
+    exact = itcpd.als_optimize(A, start_cp, check=itcpd.CPDiffCheck(1e-5, 100), alg=itcpd.KRPNormal())
+    e_exact = np.linalg.norm(A - itcpd.reconstruct(exact)) / nA
+
+    als = itcpd.compute_als(A, start_cp, alg=itcpd.QRPivProjected(100), check=itcpd.CPDiffCheck(1e-5, 100), trunc_tol=4)
+    als = itcpd.update_samples(A, als, 120, reshuffle=False)
+    assert itcpd.stop(als.mttkrp_alg) == 120 and itcpd.start(als.mttkrp_alg) == 1
+    assert type(als.mttkrp_alg) is itcpd.QRPivProjected
+    assert als.additional_items["effective_ranks"][0] < 12
+    itcpd.optimize(start_cp, als)
+
+    for alg, kw in [(itcpd.QRPivProjected(140), {}),
+                    (itcpd.SEQRCSPivProjected(1, 140, (1, 2, 3), (10, 10, 10)), dict(seed=3)),
+                    (itcpd.SEQRCSPivProjected((1,), (140,), (1, 2, 3), (10, 10, 10)), dict(seed=4, injective=True, shuffle_pivots=False))]:
+        ok = False
+        for attempt in range(5):
+            o = itcpd.als_optimize(A, start_cp, alg=alg, check=itcpd.CPDiffCheck(1e-5, 100), rng=np.random.default_rng(100 + attempt), **kw)
+            e = np.linalg.norm(A - itcpd.reconstruct(o)) / nA
+            if abs(e_exact - e) / e_exact < 0.1:
+                ok = True
+                break
+        assert ok, (type(alg).__name__, e_exact, e)
