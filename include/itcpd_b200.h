@@ -66,6 +66,10 @@ int itcpd_set_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, const doubl
  * global column-major linear index e gets the value of counter (seed, e + elem_offset), so slabs of
  * one big tensor can be generated independently on several GPUs. */
 int itcpd_generate_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, uint64_t seed, int64_t elem_offset);
+/* synthetic low-rank + noise target generated on the device: T = sum_r prod_n A_n[i_n, r] + noise * N(0,1) with
+ * A_n = column-normalised randn(I_n, rank) from the counter-based stream `seed` (accuracy studies at sizes where
+ * a host tensor is impractical).  Leaves the handle's CPD state at the planted factors. */
+int itcpd_generate_lowrank_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, int rank, uint64_t seed, double noise);
 int itcpd_get_tensor(itcpd_ctx *ctx, double *host_colmajor);
 int itcpd_tensor_norm(itcpd_ctx *ctx, double *fro_norm);            /* norm(T), README.md:96 */
 

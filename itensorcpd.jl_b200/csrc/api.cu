@@ -322,6 +322,32 @@ int itcpd_generate_tensor(itcpd_ctx *c, int order, const int64_t *dims, uint64_t
     return ITCPD_OK;
 }
 
+int itcpd_generate_lowrank_tensor(itcpd_ctx *c, int order, const int64_t *dims, int rank, uint64_t seed, double noise) {
+    CHECK_CTX(c);
+    ARG_CHECK(dims != nullptr && rank >= 1, "null dims / bad rank");
+    USE_DEVICE(c);
+    TRY(set_shape(c, order, dims));
+    c->rank = rank;
+    TRY(ensure_cpd_buffers(c));
+    TRY(itcpd_random_cpd(c, seed));
+    {   // lambda = 1: the planted tensor is the plain sum of the rank-one terms
+        std::vector<double> ones((size_t)rank, 1.0);
+        CUDA_TRY(cudaMemcpyAsync(c->lambda.p, ones.data(), (size_t)rank * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (c->ld0 == c->dims[0]) {
+        TRY(k_reconstruct(c, c->T.as<double>(), nullptr));
+    } else {
+        TRY(c->work.reserve((size_t)c->nelem * 8));
+        TRY(k_reconstruct(c, c->work.as<double>(), nullptr));
+        TRY(k_pad_copy_in(c, c->work.as<double>(), c->T.as<double>()));
+    }
+    if (noise != 0.0) TRY(k_add_noise(c, seed ^ 0x9E3779B97F4A7C15ull, noise));
+    CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
 int itcpd_get_tensor(itcpd_ctx *c, double *host) {
     CHECK_CTX(c);
     NEED_T(c);

@@ -154,6 +154,7 @@ int k_fit_terms(itcpd_ctx *c, double *out2 /*device: inner, norm2*/);
 int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64_t ld_first, int mode, double *out);
 int k_direct_mttkrp(itcpd_ctx *c, int mode, double *out);
 int k_generate(itcpd_ctx *c, uint64_t seed, int64_t elem_offset);
+int k_add_noise(itcpd_ctx *c, uint64_t seed, double sigma);
 int k_randn_matrix(itcpd_ctx *c, double *dst, int64_t n, uint64_t seed, uint64_t stream_offset);
 int k_sumsq(itcpd_ctx *c, const double *x, int64_t n, double *out_dev);
 int k_pad_copy_in(itcpd_ctx *c, const double *src_dense, double *dst_padded);   // dims[0] -> ld0

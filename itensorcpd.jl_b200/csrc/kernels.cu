@@ -437,6 +437,20 @@ __global__ void randn_kernel(double *__restrict__ dst, int64_t n, uint64_t seed,
         dst[s] = normal_at(seed, (uint64_t)s + off);
 }
 
+__global__ void add_noise_kernel(double *__restrict__ T, int64_t ld0, int64_t dim0, int64_t nstore, uint64_t seed, double sigma) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nstore; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = s % ld0, rest = s / ld0;
+        if (i0 < dim0) T[s] += sigma * normal_at(seed, (uint64_t)(i0 + dim0 * rest));
+    }
+}
+
+int k_add_noise(itcpd_ctx *c, uint64_t seed, double sigma) {
+    add_noise_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(c->T.as<double>(), c->ld0, c->dims[0], c->nstore, seed, sigma);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
 int k_randn_matrix(itcpd_ctx *c, double *dst, int64_t n, uint64_t seed, uint64_t stream_offset) {
     randn_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 8), 256, 0, c->stream>>>(dst, n, seed, stream_offset);
     c->launches++;

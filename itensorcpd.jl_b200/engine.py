@@ -87,6 +87,11 @@ class Engine:
         self.dims = tuple(int(d) for d in dims)
         check(self._L.itcpd_generate_tensor(self._h, len(self.dims), self._dims_arg(self.dims), int(seed), int(elem_offset)))
 
+    def generate_lowrank_tensor(self, dims, rank: int, seed: int = 0, noise: float = 0.0):
+        self.dims = tuple(int(d) for d in dims)
+        self.rank = int(rank)
+        check(self._L.itcpd_generate_lowrank_tensor(self._h, len(self.dims), self._dims_arg(self.dims), int(rank), int(seed), float(noise)))
+
     def get_tensor(self, out=None) -> np.ndarray:
         if out is None:
             out = np.empty(self.dims, dtype=np.float64, order="F")
