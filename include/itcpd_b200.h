@@ -150,10 +150,11 @@ void itcpd_sparsestack(int l, int n, int s, double *vals, int *rows, int *colsta
 /* sketched_matricization (pivot_mapping.jl:111-140): A_sk = T_(mode) * Omega' (I_mode x l) from the
  * (rows 0-based, vals) arrays the generators above fill; s non-zeros per column. */
 int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *rows0, const double *vals, double *host_out);
-/* one sampled ALS mode update (ProjectionAlgorithm.jl:57-68 with normal=true): given 1-based pivots
- * for `mode`, gathers T_s and K on the device, solves (K'K) \ (T_s K)', normalises, refreshes the
- * Gram and the leverage scores of `mode`. */
-int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol);
+/* one sampled ALS mode update (ProjectionAlgorithm.jl:57-68): given 1-based pivots for `mode`, gathers T_s and K on
+ * the device and solves  normal != 0: (K'K) \ (T_s K)'  (pivoted Cholesky, QRCP fallback)
+ *                        normal == 0: qr(K, ColumnNorm()) \ T_s'  (pivoted-QR min-norm least squares, nsamp >= R);
+ * then normalises and refreshes the Gram and the leverage scores of `mode` (post_solve of LevScoreSampled). */
+int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol, int normal);
 
 /* qr(T_(mode), ColumnNorm()) of the pivot-projected setup (optimizers/.../randomized/qr_lev_score_sampled.jl:22-23,126-127):
  * column-pivoted Householder QR of the mode unfolding on the device.  piv_out: the full pivot order, n = P / I_mode
@@ -169,9 +170,9 @@ int itcpd_seqrcs(itcpd_ctx *ctx, int mode, int l, int s, int t, int injective, i
                  int64_t *nrdiag_out, int64_t *ncand_out);
 /* pivot-projected solvers: cache the projector of `mode` and its sampled target T_s = fused_flatten_sample(T, mode, piv)
  * on the device (qr_lev_score_sampled.jl:64-65, 162-163); then one mode update per call
- * (ProjectionAlgorithm.jl:57-68, normal = true; post_solve is a no-op for these solvers). */
+ * (ProjectionAlgorithm.jl:57-68, `normal` as in itcpd_sampled_update; post_solve is a no-op for these solvers). */
 int itcpd_set_projector(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots);
-int itcpd_projected_update(itcpd_ctx *ctx, int mode, double chol_tol);
+int itcpd_projected_update(itcpd_ctx *ctx, int mode, double chol_tol, int normal);
 /* after the setup only the samples are touched: release the dense tensor (ALS(ITensor(inds(target)), ...), :77,175) */
 int itcpd_drop_tensor(itcpd_ctx *ctx);
 

@@ -68,12 +68,12 @@ _SIGS = {
     "itcpd_sparse_sign": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itcpd_sparsestack": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itcpd_sketch_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_dp]),
-    "itcpd_sampled_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double]),
+    "itcpd_sampled_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int]),
     "itcpd_qrcp_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_dp]),
     "itcpd_qrcp_matrix": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp, C.c_int64, C.c_void_p, c_dp]),
     "itcpd_seqrcs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "itcpd_set_projector": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
-    "itcpd_projected_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "itcpd_projected_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "itcpd_drop_tensor": (C.c_int, [C.c_void_p]),
     "itcpd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itcpd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

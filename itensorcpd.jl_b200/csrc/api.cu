@@ -670,6 +670,21 @@ int itcpd_sample_factor_matrices(itcpd_ctx *c, int skip_mode, int64_t nsamp, uin
     return ITCPD_OK;
 }
 
+// the sampled least-squares problem of one mode (ProjectionAlgorithm.jl:57-68): K is nsamp x R, Ts is I x nsamp
+static int sampled_ls(itcpd_ctx *c, int mode, const double *K, const double *Ts, int64_t nsamp, double chol_tol, int normal) {
+    const int R = c->rank;
+    const int64_t I = c->dims[mode];
+    c->m_valid[mode] = false;  // M[mode] is reused for the *sampled* MTTKRP
+    if (normal) {
+        // (K'K) X' = (T_s K)'
+        TRY(k_gram(c, K, nsamp, R, c->Gamma.as<double>()));
+        TRY(k_small_gemm_nn(c, Ts, K, I, nsamp, R, c->M[mode].as<double>()));
+        return k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>());
+    }
+    ARG_CHECK(nsamp >= R && nsamp < ((int64_t)1 << 31), "normal=false needs at least R samples");
+    return qrcp_ls_solve(c, K, (int)nsamp, R, Ts, I, c->X.as<double>(), c->status.as<int>(), 1);
+}
+
 static int check_pivots(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv) {
     int col = 0;
     for (int m = 0; m < c->order; ++m) {
@@ -920,7 +935,7 @@ int itcpd_set_projector(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *ho
     return ITCPD_OK;
 }
 
-int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol) {
+int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol, int normal) {
     CHECK_CTX(c);
     CHECK_MODE(c, mode);
     USE_DEVICE(c);
@@ -930,10 +945,7 @@ int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol) {
     const int64_t I = c->dims[mode], ns = c->proj_n[mode];
     TRY(c->samp_K.reserve((size_t)ns * R * 8));
     TRY(k_pivot_hadamard(c, mode, ns, c->proj_piv[mode].as<int64_t>(), c->samp_K.as<double>()));
-    TRY(k_gram(c, c->samp_K.as<double>(), ns, R, c->Gamma.as<double>()));
-    TRY(k_small_gemm_nn(c, c->proj_T[mode].as<double>(), c->samp_K.as<double>(), I, ns, R, c->M[mode].as<double>()));
-    c->m_valid[mode] = false;
-    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>()));
+    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->proj_T[mode].as<double>(), ns, chol_tol, normal));
     TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
     c->fver[mode]++;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -953,7 +965,7 @@ int itcpd_drop_tensor(itcpd_ctx *c) {
     return ITCPD_OK;
 }
 
-int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol) {
+int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol, int normal) {
     CHECK_CTX(c);
     NEED_T(c);
     CHECK_MODE(c, mode);
@@ -968,11 +980,7 @@ int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *h
     TRY(c->samp_T.reserve((size_t)nsamp * I * 8));
     TRY(k_pivot_hadamard(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_K.as<double>()));
     TRY(k_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
-    // normal equations of the sampled problem (ProjectionAlgorithm.jl:61-62): (K'K) X' = (T_s K)'
-    TRY(k_gram(c, c->samp_K.as<double>(), nsamp, R, c->Gamma.as<double>()));
-    TRY(k_small_gemm_nn(c, c->samp_T.as<double>(), c->samp_K.as<double>(), I, nsamp, R, c->M[mode].as<double>()));
-    c->m_valid[mode] = false;  // M[mode] now holds the *sampled* MTTKRP
-    TRY(k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>()));
+    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->samp_T.as<double>(), nsamp, chol_tol, normal));
     TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
     c->fver[mode]++;
     TRY(ensure_leverage(c, mode));  // also refreshes G[mode] (post_solve of LevScoreSampled, krp_lev...:55-58)

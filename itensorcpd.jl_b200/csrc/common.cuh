@@ -166,6 +166,7 @@ int k_reconstruct(itcpd_ctx *c, double *out_dense_or_null, double *resid_sumsq_d
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev);
 int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev);
 int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev);
+int qrcp_ls_solve(itcpd_ctx *c, const double *A, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force);  // qrcp.cu
 int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out);
 
 // ---- sampled.cu ---------------------------------------------------------------------------

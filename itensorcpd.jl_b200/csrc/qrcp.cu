@@ -114,24 +114,24 @@ __device__ void larfg_block(int m, double *alpha, double *x, int incx, double *t
 }
 
 // workspace layout (doubles): A[n*n] | tau[n] | tauz[n] | vn1[n] | vn2[n] | wmin[n] | wmax[n] | wv[n]
-__global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restrict__ Gin, int n, double *__restrict__ ws, int *__restrict__ jpvt,
-                                                         int *__restrict__ status) {
-    if (status[0] != ITCPD_SOLVE_QRCP) return;
+__global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restrict__ Gin, int m, int n, double *__restrict__ ws, int *__restrict__ jpvt,
+                                                         int *__restrict__ status, int force) {
+    if (!force && status[0] != ITCPD_SOLVE_QRCP) return;
     __shared__ double sh[QT / 32];
     __shared__ double s_v[QT / 32];
     __shared__ int s_i[QT / 32];
     __shared__ int s_p;
     __shared__ int s_rank;
-    double *A = ws, *tau = A + (size_t)n * n, *tauz = tau + n, *vn1 = tauz + n, *vn2 = vn1 + n, *wmin = vn2 + n, *wmax = wmin + n,
+    double *A = ws, *tau = A + (size_t)m * n, *tauz = tau + n, *vn1 = tauz + n, *vn2 = vn1 + n, *wmin = vn2 + n, *wmax = wmin + n,
            *wv = wmax + n;
     const int tid = threadIdx.x;
-    for (int e = tid; e < n * n; e += QT) A[e] = Gin[e];
+    for (int64_t e = tid; e < (int64_t)m * n; e += QT) A[e] = Gin[e];
     for (int e = tid; e < n; e += QT) jpvt[e] = e;
     __syncthreads();
     // initial column norms
     for (int k = 0; k < n; ++k) {
         double ss = 0.0;
-        for (int i = tid; i < n; i += QT) ss = fma(A[i + (size_t)n * k], A[i + (size_t)n * k], ss);
+        for (int i = tid; i < m; i += QT) ss = fma(A[i + (size_t)m * k], A[i + (size_t)m * k], ss);
         const double nr = sqrt(blk_sum(ss, sh));
         if (tid == 0) { vn1[k] = nr; vn2[k] = nr; }
     }
@@ -156,32 +156,32 @@ __global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restric
         __syncthreads();
         const int p = s_p;
         if (p != j && p < n) {
-            for (int i = tid; i < n; i += QT) { const double a = A[i + (size_t)n * j]; A[i + (size_t)n * j] = A[i + (size_t)n * p]; A[i + (size_t)n * p] = a; }
+            for (int i = tid; i < m; i += QT) { const double a = A[i + (size_t)m * j]; A[i + (size_t)m * j] = A[i + (size_t)m * p]; A[i + (size_t)m * p] = a; }
             if (tid == 0) { const int q = jpvt[j]; jpvt[j] = jpvt[p]; jpvt[p] = q; vn1[p] = vn1[j]; vn2[p] = vn2[j]; }
             __syncthreads();
         }
         // Householder on A[j:, j]
-        if (j < n - 1) larfg_block(n - j, &A[j + (size_t)n * j], &A[j + 1 + (size_t)n * j], 1, &tau[j], sh);
+        if (j < m - 1) larfg_block(m - j, &A[j + (size_t)m * j], &A[j + 1 + (size_t)m * j], 1, &tau[j], sh);
         else { if (tid == 0) tau[j] = 0.0; __syncthreads(); }
         const double tj = tau[j];
         // apply H to the trailing columns and down-date the norms (dlaqp2)
         for (int k = j + 1; k < n; ++k) {
             double dot = 0.0;
-            for (int i = j + 1 + tid; i < n; i += QT) dot = fma(A[i + (size_t)n * j], A[i + (size_t)n * k], dot);
-            dot = blk_sum(dot, sh) + A[j + (size_t)n * k];
+            for (int i = j + 1 + tid; i < m; i += QT) dot = fma(A[i + (size_t)m * j], A[i + (size_t)m * k], dot);
+            dot = blk_sum(dot, sh) + A[j + (size_t)m * k];
             const double f = tj * dot;
             __syncthreads();
-            if (tid == 0) A[j + (size_t)n * k] -= f;
-            for (int i = j + 1 + tid; i < n; i += QT) A[i + (size_t)n * k] = fma(-f, A[i + (size_t)n * j], A[i + (size_t)n * k]);
+            if (tid == 0) A[j + (size_t)m * k] -= f;
+            for (int i = j + 1 + tid; i < m; i += QT) A[i + (size_t)m * k] = fma(-f, A[i + (size_t)m * j], A[i + (size_t)m * k]);
             __syncthreads();
             if (vn1[k] != 0.0) {
-                double temp = fabs(A[j + (size_t)n * k]) / vn1[k];
+                double temp = fabs(A[j + (size_t)m * k]) / vn1[k];
                 temp = fmax(0.0, 1.0 - temp * temp);
                 const double r = vn1[k] / vn2[k];
                 const double temp2 = temp * r * r;
                 if (temp2 <= tol3z) {
                     double ss = 0.0;
-                    for (int i = j + 1 + tid; i < n; i += QT) ss = fma(A[i + (size_t)n * k], A[i + (size_t)n * k], ss);
+                    for (int i = j + 1 + tid; i < m; i += QT) ss = fma(A[i + (size_t)m * k], A[i + (size_t)m * k], ss);
                     const double nr = sqrt(blk_sum(ss, sh));
                     __syncthreads();
                     if (tid == 0) { vn1[k] = nr; vn2[k] = nr; }
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restric
             while (rnk < n) {
                 const int i = rnk;
                 double sminpr, s1, c1, smaxpr, s2, c2;
-                laic1(2, rnk, wmin, smin, &A[(size_t)n * i], A[i + (size_t)n * i], &sminpr, &s1, &c1);
-                laic1(1, rnk, wmax, smax, &A[(size_t)n * i], A[i + (size_t)n * i], &smaxpr, &s2, &c2);
+                laic1(2, rnk, wmin, smin, &A[(size_t)m * i], A[i + (size_t)m * i], &sminpr, &s1, &c1);
+                laic1(1, rnk, wmax, smax, &A[(size_t)m * i], A[i + (size_t)m * i], &smaxpr, &s2, &c2);
                 if (smaxpr * rcond > sminpr) break;
                 for (int q = 0; q < rnk; ++q) { wmin[q] *= s1; wmax[q] *= s2; }
                 wmin[rnk] = c1; wmax[rnk] = c2;
@@ -223,19 +223,19 @@ __global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restric
     if (l > 0) {
         for (int i = rnk - 1; i >= 0; --i) {
             // generate reflector from [A(i,i), A(i, rnk:n)]
-            larfg_block(l + 1, &A[i + (size_t)n * i], &A[i + (size_t)n * rnk], n, &tauz[i], sh);
+            larfg_block(l + 1, &A[i + (size_t)m * i], &A[i + (size_t)m * rnk], m, &tauz[i], sh);
             const double tz = tauz[i];
             // apply to rows 0..i-1 from the right: w = A(0:i,i) + A(0:i, rnk:n) v ; A(:,i) -= tz w ; A(:,rnk:n) -= tz w v^T
             for (int r0 = tid; r0 < i; r0 += QT) {
-                double w = A[r0 + (size_t)n * i];
-                for (int q = 0; q < l; ++q) w = fma(A[r0 + (size_t)n * (rnk + q)], A[i + (size_t)n * (rnk + q)], w);
+                double w = A[r0 + (size_t)m * i];
+                for (int q = 0; q < l; ++q) w = fma(A[r0 + (size_t)m * (rnk + q)], A[i + (size_t)m * (rnk + q)], w);
                 wv[r0] = w;
             }
             __syncthreads();
             for (int r0 = tid; r0 < i; r0 += QT) {
                 const double w = tz * wv[r0];
-                A[r0 + (size_t)n * i] -= w;
-                for (int q = 0; q < l; ++q) A[r0 + (size_t)n * (rnk + q)] = fma(-w, A[i + (size_t)n * (rnk + q)], A[r0 + (size_t)n * (rnk + q)]);
+                A[r0 + (size_t)m * i] -= w;
+                for (int q = 0; q < l; ++q) A[r0 + (size_t)m * (rnk + q)] = fma(-w, A[i + (size_t)m * (rnk + q)], A[r0 + (size_t)m * (rnk + q)]);
             }
             __syncthreads();
         }
@@ -245,28 +245,28 @@ __global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restric
 // one thread per right-hand side: b <- Q^T b; solve T11; zero tail; apply Z^T; scatter through jpvt
 __global__ void __launch_bounds__(64) qrcp_solve_rows_kernel(const double *__restrict__ ws, const int *__restrict__ jpvt,
                                                              const int *__restrict__ status, const double *__restrict__ M, int64_t rows,
-                                                             int n, double *__restrict__ X, double *__restrict__ bglob) {
-    if (status[0] != ITCPD_SOLVE_QRCP) return;
+                                                             int m, int n, double *__restrict__ X, double *__restrict__ bglob, int force) {
+    if (!force && status[0] != ITCPD_SOLVE_QRCP) return;
     const int64_t i = blockIdx.x * 64ll + threadIdx.x;
     if (i >= rows) return;
-    const double *A = ws, *tau = A + (size_t)n * n, *tauz = tau + n;
+    const double *A = ws, *tau = A + (size_t)m * n, *tauz = tau + n;
     const int rnk = status[1];
     double *b = bglob + i;
 #define BV(k) b[(int64_t)(k) * rows]
-    for (int k = 0; k < n; ++k) BV(k) = M[i + rows * (int64_t)k];
+    for (int k = 0; k < m; ++k) BV(k) = M[i + rows * (int64_t)k];
     // Q^T b = H_{n-1} ... H_0 b applied in order 0..n-1
     for (int j = 0; j < n; ++j) {
         double dot = BV(j);
-        for (int q = j + 1; q < n; ++q) dot = fma(A[q + (size_t)n * j], BV(q), dot);
+        for (int q = j + 1; q < m; ++q) dot = fma(A[q + (size_t)m * j], BV(q), dot);
         const double f = tau[j] * dot;
         BV(j) -= f;
-        for (int q = j + 1; q < n; ++q) BV(q) = fma(-f, A[q + (size_t)n * j], BV(q));
+        for (int q = j + 1; q < m; ++q) BV(q) = fma(-f, A[q + (size_t)m * j], BV(q));
     }
     // T11 y = (Q^T b)(0:rnk)
     for (int k = rnk - 1; k >= 0; --k) {
         double s = BV(k);
-        for (int q = k + 1; q < rnk; ++q) s = fma(-A[k + (size_t)n * q], BV(q), s);
-        BV(k) = s / A[k + (size_t)n * k];
+        for (int q = k + 1; q < rnk; ++q) s = fma(-A[k + (size_t)m * q], BV(q), s);
+        BV(k) = s / A[k + (size_t)m * k];
     }
     for (int k = rnk; k < n; ++k) BV(k) = 0.0;
     // Z^T y: Z = Z_0 Z_1 ... Z_{rnk-1}; Z^T y applies Z_{rnk-1}^T first ... LAPACK dormrz('L','T') loops i = 0..rnk-1
@@ -274,27 +274,36 @@ __global__ void __launch_bounds__(64) qrcp_solve_rows_kernel(const double *__res
     if (l > 0) {
         for (int j = 0; j < rnk; ++j) {
             double dot = BV(j);
-            for (int q = 0; q < l; ++q) dot = fma(A[j + (size_t)n * (rnk + q)], BV(rnk + q), dot);
+            for (int q = 0; q < l; ++q) dot = fma(A[j + (size_t)m * (rnk + q)], BV(rnk + q), dot);
             const double f = tauz[j] * dot;
             BV(j) -= f;
-            for (int q = 0; q < l; ++q) BV(rnk + q) = fma(-f, A[j + (size_t)n * (rnk + q)], BV(rnk + q));
+            for (int q = 0; q < l; ++q) BV(rnk + q) = fma(-f, A[j + (size_t)m * (rnk + q)], BV(rnk + q));
         }
     }
     for (int k = 0; k < n; ++k) X[i + rows * (int64_t)jpvt[k]] = BV(k);
 #undef BV
 }
 
-int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
-    // workspace: behind the Cholesky factor (ldw*R + R doubles) inside solve_ws (sized by run_cholesky)
-    const size_t chol_doubles = (size_t)(R | 1) * R + R;
+// min-norm least squares  X (rows x n) = (A \\ B^T)^T  for a tall column-major A (m x n, m >= n) and the rows x m
+// matrix Bt whose row i is right-hand side i.  `force` = 0: run only when status[0] says the Cholesky failed.
+int qrcp_ls_solve(itcpd_ctx *c, const double *A, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force) {
+    ARG_CHECK(m >= n && n >= 1, "pivoted-QR least squares needs a tall (m >= n) matrix");
+    const size_t chol_doubles = (size_t)(n | 1) * n + n;            // the Cholesky factor lives in front (solve.cu)
+    const size_t ws_doubles = (size_t)m * n + 8 * (size_t)n;
+    TRY(c->solve_ws.reserve((chol_doubles + ws_doubles) * 8 + 1024));
+    TRY(c->ipiv.reserve((size_t)n * 4 * 2));
     double *ws = c->solve_ws.as<double>() + chol_doubles;
-    int *jp = c->ipiv.as<int>() + R;
-    TRY(c->work.reserve((size_t)rows * R * 8));
-    qrcp_factor_kernel<<<1, QT, 0, c->stream>>>(Gamma, R, ws, jp, status_dev);
-    qrcp_solve_rows_kernel<<<(unsigned)ceil_div(rows, 64), 64, 0, c->stream>>>(ws, jp, status_dev, M, rows, R, X, c->work.as<double>());
+    int *jp = c->ipiv.as<int>() + n;
+    TRY(c->work.reserve((size_t)rows * m * 8));
+    qrcp_factor_kernel<<<1, QT, 0, c->stream>>>(A, m, n, ws, jp, status_dev, force);
+    qrcp_solve_rows_kernel<<<(unsigned)ceil_div(rows, 64), 64, 0, c->stream>>>(ws, jp, status_dev, Bt, rows, m, n, X, c->work.as<double>(), force);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
+}
+
+int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
+    return qrcp_ls_solve(c, Gamma, R, R, M, rows, X, status_dev, 0);
 }
 
 }  // namespace itcpd

@@ -252,9 +252,9 @@ class Engine:
         check(self._L.itcpd_sketch_unfolding(self._h, mode, int(l), int(s), _addr(rows0), _addr(vals), _addr(out)))
         return out
 
-    def sampled_update(self, mode: int, pivots, chol_tol: float = 1e-6):
+    def sampled_update(self, mode: int, pivots, chol_tol: float = 1e-6, normal: bool = True):
         p = self._piv(pivots)
-        check(self._L.itcpd_sampled_update(self._h, mode, p.shape[0], _addr(p), float(chol_tol)))
+        check(self._L.itcpd_sampled_update(self._h, mode, p.shape[0], _addr(p), float(chol_tol), int(bool(normal))))
 
     # -- pivot-projected solvers ------------------------------------------------------------
     def qrcp_unfolding(self, mode: int):
@@ -292,8 +292,8 @@ class Engine:
         p = self._piv(pivots)
         check(self._L.itcpd_set_projector(self._h, mode, p.shape[0], _addr(p)))
 
-    def projected_update(self, mode: int, chol_tol: float = 1e-6):
-        check(self._L.itcpd_projected_update(self._h, mode, float(chol_tol)))
+    def projected_update(self, mode: int, chol_tol: float = 1e-6, normal: bool = True):
+        check(self._L.itcpd_projected_update(self._h, mode, float(chol_tol), int(bool(normal))))
 
     def drop_tensor(self):
         check(self._L.itcpd_drop_tensor(self._h))

@@ -312,9 +312,8 @@ class LevScoreSampled(ProjectionAlgorithm):
         pass  # gathered inside sampled_update together with the sampled KRP
 
     def solve_ls_problem(self, als, fact):
-        if not als.additional_items["normal"]:
-            raise NotImplementedError("normal=false (QRCP of the sampled KRP) is not in this build; use normal=True")
-        als.engine.sampled_update(fact, als.additional_items["projects_tensors"][fact], CHOLESKY_EPSILON)
+        als.engine.sampled_update(fact, als.additional_items["projects_tensors"][fact], CHOLESKY_EPSILON,
+                                  normal=als.additional_items["normal"])
 
     def post_solve(self, als, fact):
         pass  # leverage refresh is part of sampled_update (krp_lev...:55-58)
@@ -356,9 +355,7 @@ class _PivotBased(ProjectionAlgorithm):
         pass  # cached target_transform[fact] (qr_lev...:162-166)
 
     def solve_ls_problem(self, als, fact):
-        if not als.additional_items["normal"]:
-            raise NotImplementedError("normal=false (QRCP of the sampled KRP) is not in this build; use normal=True")
-        als.engine.projected_update(fact, CHOLESKY_EPSILON)
+        als.engine.projected_update(fact, CHOLESKY_EPSILON, normal=als.additional_items["normal"])
 
     def post_solve(self, als, fact):
         pass  # qr_lev...:168

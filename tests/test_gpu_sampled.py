@@ -271,3 +271,39 @@ def test_pivot_projected_als_like_reference_tests(engine):
                 ok = True
                 break
         assert ok, (type(alg).__name__, e_exact, e)
+
+
+@pytest.mark.parametrize("rankdef", [False, True])
+def test_sampled_update_normal_false_matches_oracle_lstsq(engine, rankdef):
+    """ProjectionAlgorithm.jl:63-64: qr(K, ColumnNorm()) \\ T_s' (pivoted-QR min-norm least squares on the tall sampled KRP)."""
+    T, cp, rng = problem((14, 12, 10), 5, 25)
+    f = [x.copy() for x in cp.factors]
+    if rankdef:  # duplicate a column in both other factors -> K has two identical columns -> rank R-1
+        f[0][:, 4] = f[0][:, 1]
+        f[2][:, 4] = f[2][:, 1]
+    engine.set_tensor(T)
+    engine.set_cpd(f, cp.lam)
+    mode = 1
+    piv = np.asfortranarray(np.stack([rng.integers(1, 15, size=120), rng.integers(1, 11, size=120)], axis=1).astype(np.int64))
+    engine.sampled_update(mode, piv, normal=False)
+    K = sampled.pivot_hadamard([f[0], f[2]], piv)
+    Ts = sampled.fused_flatten_sample(T, mode, piv)
+    X = cpals.ldiv_solve(K, np.asfortranarray(Ts.T)).T      # oracle: LAPACK dgelsy, rcond = R * eps
+    Ao, lo = cpals.row_norm(X)
+    assert np.linalg.norm(engine.get_factor(mode) - Ao) / np.linalg.norm(Ao) < 1e-9
+    assert np.linalg.norm(engine.get_lambda() - lo) / np.linalg.norm(lo) < 1e-9
+
+
+def test_default_levscore_uses_normal_false_like_reference(engine):
+    """optimizers/.../krp_lev_score_sampled.jl:7: LevScoreSampled defaults to normal=false."""
+    import itcpd
+
+    rng = np.random.default_rng(26)
+    A = cpals.reconstruct(cpals.random_CPD((20, 18, 16), 3, rng))
+    cp0 = cpals.random_CPD(A, 3, rng)
+    als = itcpd.compute_als(A, itcpd.CPD(cp0.factors, cp0.lam), alg=itcpd.LevScoreSampled(300), check=itcpd.CPDiffCheck(1e-6, 60))
+    assert als.additional_items["normal"] is False
+    o = itcpd.optimize(itcpd.CPD(cp0.factors, cp0.lam), als)
+    assert np.linalg.norm(A - itcpd.reconstruct(o)) / np.linalg.norm(A) < 5e-2
+    o = itcpd.als_optimize(A, itcpd.CPD(cp0.factors, cp0.lam), alg=itcpd.QRPivProjected(200), normal=False, check=itcpd.CPDiffCheck(1e-6, 60))
+    assert np.linalg.norm(A - itcpd.reconstruct(o)) / np.linalg.norm(A) < 5e-2
