@@ -51,22 +51,31 @@ static int ensure_pinned(itcpd_ctx *c, size_t doubles) {
 // Split points of the dimension tree (DESIGN.md "dimension tree"): pass A keeps modes [0,sa) free,
 // pass B keeps modes [sb,N) free, sb <= sa; both GEMM outputs should have >= 16384 rows when possible.
 void choose_splits(itcpd_ctx *c) {
+    // Every (sa, sb) costs the same two tensor passes (2*R*P flops, 8*P bytes each); what differs is the HBM
+    // traffic of the intermediates, in units of R doubles:
+    //   pass-A operand (Khatri-Rao of modes >= sa, written by the pack kernel and read back): 2 * prod_{n>=sa} I_n
+    //   partial P_A (written once, read once per mode updated from it):                       rows_A * (1 + sa)
+    //   pass-B operand / partial P_B likewise with the modes < sb contracted and N - sa modes served.
+    // A group of one mode needs no second level (its partial IS the MTTKRP): 2 * rows.  Ties go to the larger sa,
+    // then the smaller sb.  With slab sharding the LOCAL extents are used, which is what moves an order-3 tensor
+    // from (2,1) on one GPU to (1,1) once the last mode is split over several GPUs.
     const int N = c->order;
-    const int64_t want = 16384;
-    int sa = N - 1;
-    {
-        int64_t rows = 1;
-        for (int s = 1; s <= N - 1; ++s) {
-            rows *= c->dims[s - 1];
-            if (rows >= want) { sa = s; break; }
-        }
-    }
-    int sb = 1;
-    {
-        for (int s = sa; s >= 1; --s) {
-            int64_t rows = 1;
-            for (int n = s; n < N; ++n) rows *= c->dims[n];
-            if (rows >= want) { sb = s; break; }
+    double best = -1.0;
+    int sa = N - 1, sb = 1;
+    for (int a = 1; a <= N - 1; ++a) {
+        for (int b = 1; b <= a; ++b) {
+            double rowsA = (double)c->ld0, kA = 1.0, rowsB = 1.0, kB = (double)c->ld0;
+            for (int n = 1; n < a; ++n) rowsA *= (double)c->dims[n];
+            for (int n = a; n < N; ++n) kA *= (double)c->dims[n];
+            for (int n = b; n < N; ++n) rowsB *= (double)c->dims[n];
+            for (int n = 1; n < b; ++n) kB *= (double)c->dims[n];
+            const double costA = 2.0 * kA + rowsA * (a == 1 ? 2.0 : 1.0 + a);
+            const int servedB = N - a;
+            const double costB = 2.0 * kB + rowsB * ((N - b) == 1 ? 2.0 : 1.0 + servedB);
+            const double cost = costA + costB;
+            if (best < 0.0 || cost < best * (1.0 - 1e-9) || (cost <= best * (1.0 + 1e-9) && (a > sa || (a == sa && b < sb)))) {
+                best = cost; sa = a; sb = b;
+            }
         }
     }
     if (c->force_split_a >= 1 && c->force_split_a <= N - 1) sa = c->force_split_a;
@@ -98,6 +107,7 @@ int ensure_cpd_buffers(itcpd_ctx *c) {
 }
 
 static void invalidate_all(itcpd_ctx *c) {
+    c->graph_epoch++;
     c->PA.valid = c->PB.valid = false;
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->m_valid[n] = false; c->fver[n]++; }
 }
@@ -243,12 +253,13 @@ int itcpd_destroy(itcpd_ctx *c) {
     cudaStreamSynchronize(c->stream);
     itcpd_comm_destroy(c);
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
-                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev, &c->qr_A, &c->qr_piv, &c->qr_rdiag};
+                      &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev, &c->qr_A, &c->qr_piv, &c->qr_rdiag, &c->sweep_log};
     for (DevBuf *b : bufs) b->release();
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); }
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->sweep_graph_exec) { cudaGraphExecDestroy(c->sweep_graph_exec); c->sweep_graph_exec = nullptr; }
     cudaStreamSynchronize(c->side_stream);
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
@@ -288,8 +299,10 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "time_gemm") c->time_gemm = value != 0;
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
+    else if (n == "use_graph") c->use_graph = value != 0;
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
+    c->graph_epoch++;
     return ITCPD_OK;
 }
 
@@ -536,7 +549,49 @@ int itcpd_fit_terms(itcpd_ctx *c, double *inner, double *model_norm2) {
 }
 
 // ---- whole sweeps -----------------------------------------------------------------------------
-// pinned staging layout: [0, 2*nsweeps) fit scalars; then 3 ints per (sweep, mode) of solve status
+// Per-sweep results (inner, model_norm2, #QRCP fallbacks) are appended to a device-side log by a one-thread
+// kernel, so a sweep has no host-visible side effect until itcpd_sweep_results copies the log back.  That makes
+// the sweep body a fixed kernel sequence: after one plain sweep (which sizes every scratch buffer) it is captured
+// into a CUDA graph -- side-stream fork/join and NCCL calls included -- and the remaining sweeps are graph
+// launches (no per-kernel launch gaps; the inner loop is launch-bound once the tensor is sharded 8 ways).
+__global__ void log_sweep_kernel(const double *__restrict__ fit2, const int *__restrict__ status, int nmodes, double *__restrict__ log,
+                                 unsigned long long *__restrict__ counter, unsigned long long cap) {
+    const unsigned long long idx = *counter;
+    if (idx < cap) {
+        int fb = 0;
+        for (int m = 0; m < nmodes; ++m) fb += (status[3 * m] == ITCPD_SOLVE_QRCP);
+        log[3 * idx + 0] = fit2[0];
+        log[3 * idx + 1] = fit2[1];
+        log[3 * idx + 2] = (double)fb;
+    }
+    *counter = idx + 1;
+}
+
+static int one_sweep_device(itcpd_ctx *c, double chol_tol) {
+    const int N = c->order;
+    for (int mode = 0; mode < N; ++mode) TRY(mode_update_device(c, mode, chol_tol, c->status.as<int>() + 3 * mode));
+    TRY(k_fit_terms(c, c->fit2.as<double>()));
+    log_sweep_kernel<<<1, 1, 0, c->stream>>>(c->fit2.as<double>(), c->status.as<int>(), N, c->sweep_log.as<double>() + 1,
+                                            reinterpret_cast<unsigned long long *>(c->sweep_log.p), (unsigned long long)c->sweep_log_cap);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+static void graph_key(const itcpd_ctx *c, double tol, int64_t key[24]) {
+    int k = 0;
+    key[k++] = (int64_t)(intptr_t)c->T.p; key[k++] = (int64_t)(intptr_t)c->A[0].p; key[k++] = (int64_t)(intptr_t)c->sweep_log.p;
+    key[k++] = c->order; key[k++] = c->rank; key[k++] = c->split_a; key[k++] = c->split_b; key[k++] = c->mttkrp_alg;
+    key[k++] = c->swizzle; key[k++] = c->tile_warps; key[k++] = c->stream_k; key[k++] = c->tma3d; key[k++] = c->overlap_factor;
+    key[k++] = (int64_t)(intptr_t)c->comm; key[k++] = c->graph_epoch;
+    memcpy(&key[k++], &tol, 8);
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) key[k++] = n < c->order ? c->dims[n] : 0;
+}
+
+static void drop_graph(itcpd_ctx *c) {
+    if (c->sweep_graph_exec) { cudaGraphExecDestroy(c->sweep_graph_exec); c->sweep_graph_exec = nullptr; }
+}
+
 int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
     CHECK_CTX(c);
     NEED_T(c);
@@ -544,33 +599,68 @@ int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
     const int N = c->order;
-    const size_t need = 2 * (size_t)nsweeps + ((size_t)nsweeps * N * 3 * 4 + 7) / 8 + 8;
-    TRY(ensure_pinned(c, need));
-    TRY(c->status.reserve((size_t)N * 3 * 4 + 64));
-    int *hstat = reinterpret_cast<int *>(c->pinned + 2 * (size_t)nsweeps);
-    for (int s = 0; s < nsweeps; ++s) {
-        for (int mode = 0; mode < N; ++mode) {
-            int *st = c->status.as<int>() + 3 * mode;
-            TRY(mode_update_device(c, mode, chol_tol, st));
-            CUDA_TRY(cudaMemcpyAsync(hstat + ((size_t)s * N + mode) * 3, st, 12, cudaMemcpyDeviceToHost, c->stream));
-        }
-        TRY(k_fit_terms(c, c->fit2.as<double>()));
-        CUDA_TRY(cudaMemcpyAsync(c->pinned + 2 * (size_t)s, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    TRY(c->status.reserve(256 + (size_t)N * 12));
+    if ((int64_t)nsweeps > c->sweep_log_cap || !c->sweep_log.p) {
+        c->sweep_log_cap = std::max<int64_t>(4096, 2 * (int64_t)nsweeps);
+        TRY(c->sweep_log.reserve((size_t)(1 + 3 * c->sweep_log_cap) * 8));
     }
+    CUDA_TRY(cudaMemsetAsync(c->sweep_log.p, 0, 8, c->stream));
+    int done = 0;
+    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3;
+    if (want_graph) {
+        int64_t key[24];
+        graph_key(c, chol_tol, key);
+        if (!c->sweep_graph_exec || memcmp(key, c->sweep_graph_key, sizeof(key)) != 0) {
+            drop_graph(c);
+            TRY(one_sweep_device(c, chol_tol));  // plain sweep: sizes every buffer, sets function attributes, builds tables
+            done = 1;
+            graph_key(c, chol_tol, key);          // buffers may have been (re)allocated by the plain sweep
+            const int64_t l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            int st = one_sweep_device(c, chol_tol);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (st != ITCPD_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (st != ITCPD_OK) return st;
+                set_error("CUDA graph capture of the sweep failed: %s", cudaGetErrorString(e));
+                return ITCPD_ERR_CUDA;
+            }
+            c->launches = l0;  // nothing ran during the capture
+            c->sweep_graph_launches = 0;
+            {
+                size_t nn = 0;
+                if (cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess) c->sweep_graph_launches = (int64_t)nn;
+            }
+            e = cudaGraphInstantiate(&c->sweep_graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { c->sweep_graph_exec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return ITCPD_ERR_CUDA; }
+            memcpy(c->sweep_graph_key, key, sizeof(key));
+        }
+        for (; done < nsweeps; ++done) {
+            CUDA_TRY(cudaGraphLaunch(c->sweep_graph_exec, c->stream));
+            c->launches += c->sweep_graph_launches;
+            for (int n = 0; n < N; ++n) { c->fver[n]++; c->m_valid[n] = true; }   // what one_sweep_device does to the host state
+            c->last_mttkrp_mode = N - 1;
+        }
+    }
+    for (; done < nsweeps; ++done) TRY(one_sweep_device(c, chol_tol));
     return ITCPD_OK;
 }
 
 int itcpd_sweep_results(itcpd_ctx *c, int nsweeps, double *inner, double *model_norm2, int *qrcp_fallbacks) {
     CHECK_CTX(c);
     USE_DEVICE(c);
+    ARG_CHECK(nsweeps >= 1 && (int64_t)nsweeps <= c->sweep_log_cap && c->sweep_log.p, "no results logged for that many sweeps");
+    TRY(ensure_pinned(c, 3 * (size_t)nsweeps + 8));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->sweep_log.as<double>() + 1, (size_t)nsweeps * 24, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    ARG_CHECK(2 * (size_t)nsweeps <= c->pinned_doubles, "no results staged for that many sweeps");
-    const int *hstat = reinterpret_cast<const int *>(c->pinned + 2 * (size_t)nsweeps);
     int fb = 0;
     for (int s = 0; s < nsweeps; ++s) {
-        if (inner) inner[s] = c->pinned[2 * s];
-        if (model_norm2) model_norm2[s] = c->pinned[2 * s + 1];
-        for (int m = 0; m < c->order; ++m) fb += (hstat[((size_t)s * c->order + m) * 3] == ITCPD_SOLVE_QRCP);
+        if (inner) inner[s] = c->pinned[3 * s];
+        if (model_norm2) model_norm2[s] = c->pinned[3 * s + 1];
+        fb += (int)c->pinned[3 * s + 2];
     }
     if (qrcp_fallbacks) *qrcp_fallbacks = fb;
     return ITCPD_OK;

@@ -130,6 +130,15 @@ struct itcpd_ctx {
     size_t gemm_events_used = 0;
     bool time_gemm = false;
 
+    // whole-sweep CUDA graph + device-side result log
+    int use_graph = 1;
+    int64_t graph_epoch = 0;
+    cudaGraphExec_t sweep_graph_exec = nullptr;
+    int64_t sweep_graph_key[24] = {0};
+    int64_t sweep_graph_launches = 0;
+    itcpd::DevBuf sweep_log;      // [0] = counter (u64), then 3 doubles per sweep
+    int64_t sweep_log_cap = 0;
+
     // multi-GPU
     itcpd::Comm *comm = nullptr;
 };
