@@ -168,6 +168,11 @@ int itcpd_qrcp_matrix(itcpd_ctx *ctx, int64_t m, int64_t n, const double *host_A
  * rdiag_out: diag(R) of the candidate QR (nrdiag_out values, caller provides I_mode doubles). */
 int itcpd_seqrcs(itcpd_ctx *ctx, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
                  int64_t *nrdiag_out, int64_t *ncand_out);
+/* KRP-structured SE-QRCS (algebra/SEQRCS.jl:184-241, compute_r = false): the same procedure applied to the Khatri-Rao
+ * product of the handle's CURRENT factors of every mode != `mode` (R x n, never formed): the sketch is
+ * omega_hadamard (algebra/had_contract.jl:300-329), candidates are gathered with pivot_hadamard.  Outputs as itcpd_seqrcs. */
+int itcpd_seqrcs_krp(itcpd_ctx *ctx, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
+                     int64_t *nrdiag_out, int64_t *ncand_out);
 /* pivot-projected solvers: cache the projector of `mode` and its sampled target T_s = fused_flatten_sample(T, mode, piv)
  * on the device (qr_lev_score_sampled.jl:64-65, 162-163); then one mode update per call
  * (ProjectionAlgorithm.jl:57-68, `normal` as in itcpd_sampled_update; post_solve is a no-op for these solvers). */

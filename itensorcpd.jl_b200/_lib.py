@@ -72,6 +72,7 @@ _SIGS = {
     "itcpd_qrcp_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_dp]),
     "itcpd_qrcp_matrix": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp, C.c_int64, C.c_void_p, c_dp]),
     "itcpd_seqrcs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "itcpd_seqrcs_krp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "itcpd_set_projector": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "itcpd_projected_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "itcpd_drop_tensor": (C.c_int, [C.c_void_p]),

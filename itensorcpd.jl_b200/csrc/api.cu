@@ -540,7 +540,7 @@ int itcpd_fit_terms(itcpd_ctx *c, double *inner, double *model_norm2) {
     CHECK_CTX(c);
     USE_DEVICE(c);
     ARG_CHECK(c->m_valid[c->order - 1], "the last mode's MTTKRP has not been computed");
-    TRY(k_fit_terms(c, c->fit2.as<double>()));
+    TRY(k_fit_terms(c, c->fit2.as<double>(), true));
     CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (inner) *inner = c->pinned[0];
@@ -560,9 +560,9 @@ __global__ void log_sweep_kernel(const double *__restrict__ fit2, const int *__r
     if (idx < cap) {
         int fb = 0;
         for (int m = 0; m < nmodes; ++m) fb += (status[3 * m] == ITCPD_SOLVE_QRCP);
-        log[3 * idx + 0] = fit2[0];
-        log[3 * idx + 1] = fit2[1];
-        log[3 * idx + 2] = (double)fb;
+        log[idx] = fit2[0];              // <T, That> (slab-partial when sharded: reduced once in itcpd_sweep_results)
+        log[cap + idx] = fit2[1];        // ||That||^2
+        log[2 * cap + idx] = (double)fb;
     }
     *counter = idx + 1;
 }
@@ -570,7 +570,7 @@ __global__ void log_sweep_kernel(const double *__restrict__ fit2, const int *__r
 static int one_sweep_device(itcpd_ctx *c, double chol_tol) {
     const int N = c->order;
     for (int mode = 0; mode < N; ++mode) TRY(mode_update_device(c, mode, chol_tol, c->status.as<int>() + 3 * mode));
-    TRY(k_fit_terms(c, c->fit2.as<double>()));
+    TRY(k_fit_terms(c, c->fit2.as<double>(), false));
     log_sweep_kernel<<<1, 1, 0, c->stream>>>(c->fit2.as<double>(), c->status.as<int>(), N, c->sweep_log.as<double>() + 1,
                                             reinterpret_cast<unsigned long long *>(c->sweep_log.p), (unsigned long long)c->sweep_log_cap);
     c->launches++;
@@ -605,8 +605,10 @@ int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
         TRY(c->sweep_log.reserve((size_t)(1 + 3 * c->sweep_log_cap) * 8));
     }
     CUDA_TRY(cudaMemsetAsync(c->sweep_log.p, 0, 8, c->stream));
+    c->sweep_log_reduced = false;
     int done = 0;
-    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3;
+    // NCCL collectives are not captured: a sharded sweep is launched kernel by kernel
+    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3 && !comm_active(c);
     if (want_graph) {
         int64_t key[24];
         graph_key(c, chol_tol, key);
@@ -654,13 +656,21 @@ int itcpd_sweep_results(itcpd_ctx *c, int nsweeps, double *inner, double *model_
     USE_DEVICE(c);
     ARG_CHECK(nsweeps >= 1 && (int64_t)nsweeps <= c->sweep_log_cap && c->sweep_log.p, "no results logged for that many sweeps");
     TRY(ensure_pinned(c, 3 * (size_t)nsweeps + 8));
-    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->sweep_log.as<double>() + 1, (size_t)nsweeps * 24, cudaMemcpyDeviceToHost, c->stream));
+    double *log = c->sweep_log.as<double>() + 1;
+    const size_t cap = (size_t)c->sweep_log_cap, nb = (size_t)nsweeps * 8;
+    if (comm_active(c) && !c->sweep_log_reduced) {  // the only per-sweep collective that can wait
+        TRY(comm_allreduce_sum(c, log, nsweeps));
+        c->sweep_log_reduced = true;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, log, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned + nsweeps, log + cap, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned + 2 * (size_t)nsweeps, log + 2 * cap, nb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     int fb = 0;
     for (int s = 0; s < nsweeps; ++s) {
-        if (inner) inner[s] = c->pinned[3 * s];
-        if (model_norm2) model_norm2[s] = c->pinned[3 * s + 1];
-        fb += (int)c->pinned[3 * s + 2];
+        if (inner) inner[s] = c->pinned[s];
+        if (model_norm2) model_norm2[s] = c->pinned[nsweeps + s];
+        fb += (int)c->pinned[2 * (size_t)nsweeps + s];
     }
     if (qrcp_fallbacks) *qrcp_fallbacks = fb;
     return ITCPD_OK;
@@ -999,6 +1009,72 @@ int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int
     if (rdiag_out) CUDA_TRY(cudaMemcpyAsync(rdiag_out, c->qr_rdiag.p, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     // 6. p = [candidates[p_subset]; setdiff(1:n, candidates)] (SEQRCS.jl:167-168), 1-based
+    int64_t w = 0;
+    for (int64_t i = 0; i < nc; ++i) piv_out[w++] = cand[(size_t)p_sub[(size_t)i]] + 1;
+    for (int64_t col = 0; col < n; ++col)
+        if (!seen[(size_t)col]) piv_out[w++] = col + 1;
+    if (nrdiag_out) *nrdiag_out = nr;
+    if (ncand_out) *ncand_out = nc;
+    return ITCPD_OK;
+}
+
+int itcpd_seqrcs_krp(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
+                     int64_t *nrdiag_out, int64_t *ncand_out) {
+    CHECK_CTX(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(l >= 1 && s >= 1 && t >= 1 && t <= l && piv_out && c->has_tensor && c->rank > 0 && c->A[0].p, "bad argument (need 1 <= t <= l and a CPD state)");
+    USE_DEVICE(c);
+    const int N = c->order, R = c->rank;
+    int64_t n = 1;
+    for (int q = 0; q < N; ++q) if (q != mode) n *= c->dims[q];
+    ARG_CHECK(n < (int64_t)1 << 31 && (int64_t)n * std::min(s, l) < (int64_t)1 << 31, "the reference's C generators index with 32-bit ints");
+    const int s_eff = std::min(s, l);
+    std::vector<double> vals((size_t)n * s_eff);
+    std::vector<int> rows((size_t)n * s_eff), colstarts((size_t)n + 1);
+    if (injective) itcpd_sparsestack(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
+    else itcpd_sparse_sign(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
+    // sketch of the KRP (SEQRCS.jl:195): A_sk is l x R in the reference; we hold its transpose R x l, which is what is QR'd (:198)
+    SketchCsr k;
+    TRY(build_sketch_csr(c, l, s_eff, n, rows.data(), vals.data(), k));
+    TRY(c->qr_A.reserve((size_t)R * l * 8));
+    TRY(k_omega_hadamard(c, mode, l, k.d_ptr, k.d_col, k.d_val, c->qr_A.as<double>()));
+    TRY(c->qr_piv.reserve((size_t)std::max<int64_t>(n, l) * 8));
+    TRY(c->qr_rdiag.reserve((size_t)std::max<int64_t>(R, 1) * 8 * 2));
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), R, l, std::min<int64_t>(t, std::min<int64_t>(R, l)), c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    std::vector<int64_t> p_sk((size_t)t);
+    CUDA_TRY(cudaMemcpyAsync(p_sk.data(), c->qr_piv.p, (size_t)t * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // candidates: every column with a non-zero in one of the selected sketch rows, in ASCENDING column order
+    // (rows_sel = omega[p_sk, :]; findall over eachcol, SEQRCS.jl:205-207)
+    std::vector<char> seen((size_t)n, 0);
+    for (int64_t q = 0; q < t; ++q) {
+        const int64_t r = p_sk[(size_t)q];
+        for (int64_t e = k.row_ptr[(size_t)r]; e < k.row_ptr[(size_t)r + 1]; ++e) seen[(size_t)k.col[(size_t)e]] = 1;
+    }
+    std::vector<int64_t> cand;
+    for (int64_t col = 0; col < n; ++col) if (seen[(size_t)col]) cand.push_back(col);
+    const int64_t nc = (int64_t)cand.size();
+    ARG_CHECK(nc >= 1, "SE-QRCS selected no candidate column");
+    std::vector<int64_t> coords((size_t)nc * (N - 1));
+    {
+        int col = 0;
+        std::vector<int64_t> rem(cand);
+        for (int q = 0; q < N; ++q) {
+            if (q == mode) continue;
+            for (int64_t i = 0; i < nc; ++i) { coords[(size_t)(i + nc * col)] = rem[(size_t)i] % c->dims[q] + 1; rem[(size_t)i] /= c->dims[q]; }
+            ++col;
+        }
+    }
+    TRY(c->samp_piv.reserve((size_t)nc * (N - 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->samp_piv.p, coords.data(), (size_t)nc * (N - 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(c->qr_A.reserve((size_t)R * nc * 8));
+    TRY(k_pivot_hadamard_t(c, mode, nc, c->samp_piv.as<int64_t>(), c->qr_A.as<double>()));   // ffkrpn' (SEQRCS.jl:220-221)
+    const int64_t nr = std::min<int64_t>(R, nc);
+    TRY(k_qrcp_wide(c, c->qr_A.as<double>(), R, nc, nr, c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
+    std::vector<int64_t> p_sub((size_t)nc);
+    CUDA_TRY(cudaMemcpyAsync(p_sub.data(), c->qr_piv.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (rdiag_out) CUDA_TRY(cudaMemcpyAsync(rdiag_out, c->qr_rdiag.p, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     int64_t w = 0;
     for (int64_t i = 0; i < nc; ++i) piv_out[w++] = cand[(size_t)p_sub[(size_t)i]] + 1;
     for (int64_t col = 0; col < n; ++col)

@@ -136,8 +136,9 @@ struct itcpd_ctx {
     cudaGraphExec_t sweep_graph_exec = nullptr;
     int64_t sweep_graph_key[24] = {0};
     int64_t sweep_graph_launches = 0;
-    itcpd::DevBuf sweep_log;      // [0] = counter (u64), then 3 doubles per sweep
+    itcpd::DevBuf sweep_log;      // [0] = counter (u64), then inner[cap] | norm2[cap] | fallbacks[cap]
     int64_t sweep_log_cap = 0;
+    bool sweep_log_reduced = false;
 
     // multi-GPU
     itcpd::Comm *comm = nullptr;
@@ -159,7 +160,7 @@ int probe_dfma(itcpd_ctx *c, double *tflops);
 int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G);
 int k_gram_hadamard(itcpd_ctx *c, int skip_mode, double *Gamma);
 int k_colnorm_scale(itcpd_ctx *c, const double *X, int64_t rows, int R, double *A, double *lambda, bool rows_are_slab);
-int k_fit_terms(itcpd_ctx *c, double *out2 /*device: inner, norm2*/);
+int k_fit_terms(itcpd_ctx *c, double *out2 /*device: inner, norm2*/, bool reduce_now);
 int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64_t ld_first, int mode, double *out);
 int k_direct_mttkrp(itcpd_ctx *c, int mode, double *out);
 int k_generate(itcpd_ctx *c, uint64_t seed, int64_t elem_offset);
@@ -185,6 +186,8 @@ int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_de
 int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
 int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, int64_t *jpvt_dev, double *rdiag_dev);  // qrcp_wide.cu
 int k_unfold(itcpd_ctx *c, int mode, double *out);
+int k_omega_hadamard(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
+int k_pivot_hadamard_t(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
 int k_small_gemm_nn(itcpd_ctx *c, const double *A, const double *B, int64_t m, int64_t k, int n, double *C); // C = A B
 
 // ---- comm.cu ------------------------------------------------------------------------------

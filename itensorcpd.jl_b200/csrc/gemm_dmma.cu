@@ -339,28 +339,49 @@ struct PackArgs {
     int R, NB, num_rblocks, kt_count;
 };
 
-__global__ void pack_krp_kernel(PackArgs a, double *__restrict__ Kp, int64_t total) {
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int e = idx & 1;
-        const int lane = (idx >> 1) & 31;
-        int64_t q = idx >> 6;
-        const int nb = q % a.NB; q /= a.NB;
-        const int pair = q & 1; q >>= 1;
-        const int rb = q % a.num_rblocks; q /= a.num_rblocks;
-        const int64_t kt = q;
-        const int64_t k = 16 * kt + 8 * pair + 2 * (lane & 3) + e;
-        const int r = 8 * (rb * a.NB + nb) + (lane >> 2);
-        double v = 0.0;
-        if (k < a.kext && r < a.R) {
-            v = 1.0;
-            int64_t rem = k;
-            for (int f = 0; f < a.nf; ++f) {
-                const int64_t i = rem % a.ext[f];
-                rem /= a.ext[f];
-                v = (i < a.dim[f]) ? v * a.fac[f][i + a.dim[f] * (int64_t)r] : 0.0;
-            }
+// One thread per (k-tile, pair, lane): it owns the two contraction indices k0 = 16 kt + 8 pair + 2 t and k0 + 1,
+// decodes their mode coordinates ONCE, then walks the rank columns r = 8 (rb NB + nb) + g and writes one 16-byte
+// element per (rb, nb) -- a warp writes 512 contiguous bytes.  (The first version decoded every element separately:
+// ~10 64-bit divisions per double made the pack kernel cost more than the contraction it feeds when the operand is
+// a large Khatri-Rao product.)
+__global__ void __launch_bounds__(256) pack_krp_kernel(PackArgs a, double *__restrict__ Kp, int64_t nthreads) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (tid >= nthreads) return;
+    const int lane = (int)(tid & 31);
+    const int pair = (int)((tid >> 5) & 1);
+    const int64_t kt = tid >> 6;
+    const int t = lane & 3, g = lane >> 2;
+    const int64_t k0 = 16 * kt + 8 * pair + 2 * t;
+    const double *p0[ITCPD_MAX_ORDER], *p1[ITCPD_MAX_ORDER];  // row pointers of every factor for k0 and k0 + 1 (null = zero)
+    bool ok0 = k0 < a.kext, ok1 = k0 + 1 < a.kext;
+    {
+        int64_t r0 = k0, r1 = k0 + 1;
+        for (int f = 0; f < a.nf; ++f) {
+            const int64_t i0 = r0 % a.ext[f], i1 = r1 % a.ext[f];
+            r0 /= a.ext[f];
+            r1 /= a.ext[f];
+            ok0 = ok0 && i0 < a.dim[f];
+            ok1 = ok1 && i1 < a.dim[f];
+            p0[f] = a.fac[f] + (i0 < a.dim[f] ? i0 : 0);
+            p1[f] = a.fac[f] + (i1 < a.dim[f] ? i1 : 0);
         }
-        Kp[idx] = v;
+    }
+    double2 *dst = reinterpret_cast<double2 *>(Kp) + ((kt * a.num_rblocks * 2 + pair) * (int64_t)a.NB) * 32 + lane;
+    for (int rb = 0; rb < a.num_rblocks; ++rb) {
+        for (int nb = 0; nb < a.NB; ++nb) {
+            const int r = 8 * (rb * a.NB + nb) + g;
+            double v0 = 0.0, v1 = 0.0;
+            if (r < a.R) {
+                v0 = ok0 ? 1.0 : 0.0;
+                v1 = ok1 ? 1.0 : 0.0;
+                for (int f = 0; f < a.nf; ++f) {
+                    const int64_t off = a.dim[f] * (int64_t)r;
+                    if (ok0) v0 *= p0[f][off];
+                    if (ok1) v1 *= p1[f][off];
+                }
+            }
+            dst[((int64_t)rb * 2 * a.NB + nb) * 32] = make_double2(v0, v1);
+        }
     }
 }
 
@@ -537,8 +558,8 @@ int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out) {
     const int64_t total = (int64_t)kt_count * num_rblocks * 2 * NB * 64;
     TRY(c->packK.reserve((size_t)total * 8));
     {
-        int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)c->sm_count * 8);
-        pack_krp_kernel<<<blocks, 256, 0, c->stream>>>(pa, c->packK.as<double>(), total);
+        const int64_t nthreads = (int64_t)kt_count * 64;  // (k-tile, pair, lane)
+        pack_krp_kernel<<<(unsigned)ceil_div(nthreads, 256), 256, 0, c->stream>>>(pa, c->packK.as<double>(), nthreads);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) fit_final_kernel(const double *__restrict
     if (threadIdx.x == 0) { out2[0] = inner; out2[1] = q; }
 }
 
-int k_fit_terms(itcpd_ctx *c, double *out2) {
+int k_fit_terms(itcpd_ctx *c, double *out2, bool reduce_now) {
     const int N = c->order, R = c->rank;
     const int64_t rows = mode_rows(c, N - 1);
     const int nparts = (int)std::min<int64_t>(ceil_div(rows * R, 256 * 4), 256);
@@ -188,7 +188,8 @@ int k_fit_terms(itcpd_ctx *c, double *out2) {
     fit_final_kernel<<<1, 256, 0, c->stream>>>(c->redux.as<double>(), nparts, p, c->lambda.as<double>(), R, out2);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    if (comm_active(c)) TRY(comm_allreduce_sum(c, out2, 1));  // inner is a slab-partial sum; model_norm2 is replicated
+    // inner is a slab-partial sum (model_norm2 is replicated); the sweep driver defers this reduction to the result fetch
+    if (reduce_now && comm_active(c)) TRY(comm_allreduce_sum(c, out2, 1));
     return ITCPD_OK;
 }
 

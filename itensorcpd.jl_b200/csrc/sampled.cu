@@ -104,6 +104,65 @@ int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, cons
     return ITCPD_OK;
 }
 
+// ---- omega_hadamard (had_contract.jl:300-329): sparse-sign sketch of the Khatri-Rao product, transposed output ----
+// out[r, j] = sum_{e in sketch row j} val[e] * prod_{m != mode} A_m[coord_m(col[e]), r]      (R x l, column-major)
+__global__ void __launch_bounds__(128) omega_hadamard_kernel(SFac fp, SDims d, int mode, int R, const int64_t *__restrict__ row_ptr,
+                                                             const int64_t *__restrict__ col, const double *__restrict__ val,
+                                                             double *__restrict__ out) {
+    const int64_t j = blockIdx.x;
+    for (int r = threadIdx.x; r < R; r += 128) {
+        double acc = 0.0;
+        for (int64_t e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
+            int64_t rem = col[e];
+            double v = 1.0;
+            for (int m = 0; m < d.n; ++m) {
+                if (m == mode) continue;
+                v = v * fp.a[m][rem % d.dim[m] + d.dim[m] * (int64_t)r];
+                rem /= d.dim[m];
+            }
+            acc = fma(val[e], v, acc);
+        }
+        out[r + (int64_t)R * j] = acc;
+    }
+}
+
+int k_omega_hadamard(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev) {
+    SFac fp;
+    for (int m = 0; m < c->order; ++m) fp.a[m] = c->A[m].as<double>();
+    omega_hadamard_kernel<<<(unsigned)l, 128, 0, c->stream>>>(fp, sdims(c), mode, c->rank, row_ptr_dev, col_dev, val_dev, out_dev);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+// transposed sampled KRP: out[r, s] = prod_{m != mode} A_m[piv[s, col(m)], r]   (R x nsamp)
+__global__ void pivot_hadamard_t_kernel(SFac fp, SDims d, int mode, int R, int64_t nsamp, const int64_t *__restrict__ piv,
+                                        double *__restrict__ out) {
+    const int64_t total = nsamp * R;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx % R);
+        const int64_t s = idx / R;
+        double v = 1.0;
+        int col = 0;
+        for (int m = 0; m < d.n; ++m) {
+            if (m == mode) continue;
+            v = v * fp.a[m][piv[s + nsamp * col] - 1 + d.dim[m] * (int64_t)r];
+            ++col;
+        }
+        out[idx] = v;
+    }
+}
+
+int k_pivot_hadamard_t(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev) {
+    SFac fp;
+    for (int m = 0; m < c->order; ++m) fp.a[m] = c->A[m].as<double>();
+    const int64_t total = nsamp * c->rank;
+    pivot_hadamard_t_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16), 256, 0, c->stream>>>(fp, sdims(c), mode, c->rank, nsamp, piv_dev, out_dev);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
 // ---- weighted sampling with replacement: inclusive CDF + binary search ----
 __global__ void __launch_bounds__(1024) cdf_kernel(const double *__restrict__ w, int64_t n, double *__restrict__ cdf) {
     __shared__ double part[1024];

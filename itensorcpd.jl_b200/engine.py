@@ -288,6 +288,18 @@ class Engine:
                                    C.byref(nr), C.byref(nc)))
         return piv, rd[: nr.value].copy(), nc.value
 
+    def seqrcs_krp(self, mode: int, l: int, s: int, t: int, injective: bool = False, seed: Optional[int] = None):
+        """KRP-structured SE-QRCS of the handle's current factors != mode (SEQRCS.jl:184-241, compute_r=false)."""
+        n = int(np.prod([d for m, d in enumerate(self.dims) if m != mode]))
+        piv = np.empty(n, dtype=np.int64)
+        rd = np.empty(max(self.rank, 1))
+        nr, nc = C.c_int64(), C.c_int64()
+        if seed is not None:
+            C.CDLL(None).srand(C.c_uint(seed))
+        check(self._L.itcpd_seqrcs_krp(self._h, mode, int(l), int(s), int(t), int(bool(injective)), _addr(piv), _addr(rd),
+                                       C.byref(nr), C.byref(nc)))
+        return piv, rd[: nr.value].copy(), nc.value
+
     def set_projector(self, mode: int, pivots):
         p = self._piv(pivots)
         check(self._L.itcpd_set_projector(self._h, mode, p.shape[0], _addr(p)))

@@ -378,6 +378,11 @@ class SEQRCSPivProjected(_PivotBased):
     pass
 
 
+class KSEQRCSPivProjected(_PivotBased):
+    """qr_lev_score_sampled.jl:61-83: the pivots come from an SE-QRCS of the Khatri-Rao product of preliminary factors
+    (a short leverage-score sampled ALS), not of the target tensor."""
+
+
 def start(alg):
     return alg.Start
 
@@ -395,8 +400,10 @@ def _proj_range(alg, n, dRis):
     return int_start, int_end
 
 
-def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed) -> "ALS":
-    """optimizers/.../randomized/qr_lev_score_sampled.jl:1-78 (QRPivProjected) and :80-176 (SEQRCSPivProjected)."""
+def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed,
+                       guess_num_levs=None, prelim_niter=10) -> "ALS":
+    """optimizers/.../randomized/qr_lev_score_sampled.jl:1-78 (QRPivProjected), :80-176 (SEQRCSPivProjected) and
+    :178-282 (KSEQRCSPivProjected)."""
     from .engine import column_to_multi_coords
 
     rng = np.random.default_rng(7) if rng is None else rng
@@ -404,16 +411,34 @@ def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots,
     N = len(dims)
     lst = () if alg.random_modes is None else alg.random_modes
     ref_pivs, pivots, projectors, eff = [], [], [], []
+    krp_mode = isinstance(alg, KSEQRCSPivProjected)
+    if krp_mode:
+        # preliminary leverage-score sampled ALS (:193-202): its factors' KRP stands in for the tensor's unfoldings
+        prelim = 10 * cp.rank
+        start_cp = cp if guess_num_levs is None else random_CPD(dims, guess_num_levs, rng)
+        updated = als_optimize(eng, start_cp, alg=LevScoreSampled(prelim), check=NoCheck(prelim_niter), normal=True,
+                               stop_resample=0, seed=0 if seed is None else seed)
+        eng.set_cpd(updated.factors, updated.lam)  # the device holds the preliminary factors during the pivot search
     for n in range(N):
         rdims = [dims[m] for m in range(N) if m != n]
         dRis = int(np.prod(rdims))
         int_start, int_end = _proj_range(alg, n, dRis)
         m = dims[n]
-        if (n + 1) in lst and isinstance(alg, SEQRCSPivProjected):
+        if (n + 1) in lst and not isinstance(alg, QRPivProjected):
             k_sk = int_end if alg.rank_vect is None else alg.rank_vect[n + 1]
-            l = int(round(3 * m * math.log(m)))   # qr_lev...:122
-            s = int(round(math.log(m)))           # :123
-            p, dr, _ = eng.seqrcs(n, l, s, min(k_sk, l), injective=injective, seed=None if seed is None else seed + n)
+            l = int(round(3 * m * math.log(m)))   # qr_lev...:122 / :234
+            s = int(round(math.log(m)))           # :123 / :236
+            sd = None if seed is None else seed + n
+            if krp_mode:
+                p, dr, _ = eng.seqrcs_krp(n, l, s, min(k_sk, l), injective=injective, seed=sd)
+            else:
+                p, dr, _ = eng.seqrcs(n, l, s, min(k_sk, l), injective=injective, seed=sd)
+        elif krp_mode:
+            # exact QRCP of the (cprank x dRis) Khatri-Rao matrix of the preliminary factors (:241-243)
+            K = np.ones((1, updated.rank))
+            for f in (f for i, f in enumerate(updated.factors) if i != n):
+                K = (f[None, :, :] * K[:, None, :]).reshape(-1, updated.rank, order="F")
+            p, dr = eng.qrcp_matrix(np.asfortranarray(K.T))
         else:
             p, dr = eng.qrcp_unfolding(n)
         ref_pivs.append(p.copy())
@@ -497,7 +522,7 @@ def _engine_for(target, device=0) -> Engine:
 
 
 def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None, stop_resample=-1, device=0, seed=0,
-                shuffle_pivots=True, trunc_tol=0.01, injective=False, rng=None, **_) -> ALS:
+                shuffle_pivots=True, trunc_tol=0.01, injective=False, rng=None, guess_num_levs=None, prelim_niter=10, **_) -> ALS:
     """als_optimizer.jl:37-69 + standard/tensor.jl:3-14 + randomized/krp_lev_score_sampled.jl:1-40."""
     alg = KRPFreeNormal() if alg is None else alg
     check = NoCheck(100 if maxiter is None else maxiter) if check is None else check
@@ -514,7 +539,8 @@ def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None
         for n in range(len(cp)):
             eng.leverage_scores(n)  # :factor_weights
     elif isinstance(alg, _PivotBased):
-        return _setup_pivot_based(alg, eng, cp, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed)
+        return _setup_pivot_based(alg, eng, cp, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed,
+                                  guess_num_levs=guess_num_levs, prelim_niter=prelim_niter)
     else:
         raise TypeError(f"unsupported algorithm {type(alg).__name__}")
     return ALS(eng, alg, extra, check)

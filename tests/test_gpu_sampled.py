@@ -307,3 +307,44 @@ def test_default_levscore_uses_normal_false_like_reference(engine):
     assert np.linalg.norm(A - itcpd.reconstruct(o)) / np.linalg.norm(A) < 5e-2
     o = itcpd.als_optimize(A, itcpd.CPD(cp0.factors, cp0.lam), alg=itcpd.QRPivProjected(200), normal=False, check=itcpd.CPDiffCheck(1e-6, 60))
     assert np.linalg.norm(A - itcpd.reconstruct(o)) / np.linalg.norm(A) < 5e-2
+
+
+def test_device_seqrcs_krp_matches_oracle(engine):
+    """SEQRCS.jl:184-241 (KRP-structured): same candidates / pivots as the oracle under the same rand() stream
+    (test/SEQRCS_test.jl:49-83 compares it with the tensor version within 1e-2)."""
+    rng = np.random.default_rng(30)
+    dims, R = (12, 20, 25), 10
+    cp = cpals.random_CPD(dims, R, rng)
+    engine.generate_tensor(dims, seed=1)       # shape carrier: only the factors matter here
+    engine.set_cpd(cp.factors, cp.lam)
+    mode, l, s, t = 0, 120, 2, 10
+    piv, rd, ncand = engine.seqrcs_krp(mode, l, s, t, seed=41)
+    Q, Rm, p = sampled.seqrcs_krp([cp.factors[1], cp.factors[2]], l, s, t, which="ref", seed=41)
+    n = 20 * 25
+    assert sorted(piv.tolist()) == list(range(1, n + 1))
+    assert set(piv[:ncand].tolist()) == set(p[:ncand].tolist()) and np.array_equal(piv[ncand:], p[ncand:])
+    assert np.array_equal(piv[:R], p[:R])
+    assert np.max(np.abs(np.abs(rd) - np.abs(np.diag(Rm)))) < 1e-10 * abs(Rm[0, 0])
+
+
+def test_kseqrcs_projected_als(engine):
+    """test/rand_cp_als.jl:85-96 scaled: KSEQRCSPivProjected on an exactly low-rank tensor (retry loop as in the reference)."""
+    import itcpd
+
+    rng = np.random.default_rng(31)
+    A = cpals.reconstruct(cpals.random_CPD((12, 13, 11), 4, rng))
+    nA = np.linalg.norm(A)
+    cp0 = cpals.random_CPD(A, 3, rng)
+    start_cp = itcpd.CPD(cp0.factors, cp0.lam)
+    exact = itcpd.als_optimize(A, start_cp, check=itcpd.CPDiffCheck(1e-5, 100), alg=itcpd.KRPNormal())
+    e_exact = np.linalg.norm(A - itcpd.reconstruct(exact)) / nA
+    for kw in (dict(), dict(normal=False, injective=True)):
+        ok = False
+        for attempt in range(10):
+            o = itcpd.als_optimize(A, start_cp, alg=itcpd.KSEQRCSPivProjected(1, (140,), (1, 2, 3), 5), check=itcpd.CPDiffCheck(1e-5, 100),
+                                   rng=np.random.default_rng(200 + attempt), seed=attempt, **kw)
+            e = np.linalg.norm(A - itcpd.reconstruct(o)) / nA
+            if abs(e_exact - e) / e_exact < 0.1:
+                ok = True
+                break
+        assert ok, (kw, e_exact, e)

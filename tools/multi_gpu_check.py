@@ -24,6 +24,7 @@ def main():
         factors.append(np.asfortranarray(X / np.sqrt(np.sum(X * X, axis=0))[None, :]))
     slab = dims[-1] // world
     eng = itcpd.Engine(local)
+    eng.set_option("use_graph", int(os.environ.get("ITCPD_GRAPH", "1")))
     eng.generate_tensor(dims[:-1] + (slab,), seed=7, elem_offset=rank * slab * dims[0] * dims[1])
     eng.set_cpd(factors[:-1] + [np.asfortranarray(factors[-1][rank * slab:(rank + 1) * slab])], np.ones(R))
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
