@@ -243,6 +243,12 @@ def run_ours(args, cfg):
             uid.copy_(torch.frombuffer(bytearray(itcpd.Engine.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         eng.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        if os.environ.get("ITCPD_PEER", "1") == "1":
+            # fused all-reduce + solve over NVLink peer memory (CUDA IPC handles exchanged through torch.distributed)
+            mine = torch.frombuffer(bytearray(eng.peer_export()), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            eng.peer_import(world, rank, b"".join(h.cpu().numpy().tobytes() for h in allh))
     eng.compute_grams()
     ref_norm = eng.tensor_norm()
 
@@ -319,7 +325,8 @@ def run_ours(args, cfg):
                 "data": "synthetic",
                 "config": {"workload": f"dense random Float64 {'x'.join(map(str, dims))} rank {R} CP-ALS (config {args.config})",
                            "algorithm": "normal-equation ALS, two-pass dimension tree, pivoted-Cholesky solve, FitCheck scalars every sweep",
-                           "sharding": f"slab along last mode, {world} rank(s)", "l2": "flush between steps" if flush else "inputs >> L2",
+                           "sharding": f"slab along last mode, {world} rank(s)" + (", M_n all-reduce fused into the row solve over NVLink peer memory"
+                                                                                       if world > 1 and os.environ.get("ITCPD_PEER", "1") == "1" else ""), "l2": "flush between steps" if flush else "inputs >> L2",
                            "fit_after_timed_sweeps": float(fit_last), "qrcp_fallbacks": int(fallbacks)},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
 

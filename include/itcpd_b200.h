@@ -189,6 +189,14 @@ int itcpd_comm_unique_id(void *out128);                       /* rank 0: ncclGet
 int itcpd_comm_init(itcpd_ctx *ctx, int nranks, int rank, const void *id128);
 int itcpd_comm_destroy(itcpd_ctx *ctx);
 int itcpd_allgather_factor(itcpd_ctx *ctx, int mode, int64_t rows_total, double *host_out);
+/* Fused all-reduce + solve over NVLink peer memory (optional, after itcpd_comm_init; same-node ranks, CUDA IPC).
+ * export: allocates this rank's exchange buffer and returns its 64-byte IPC handle; the launcher all-gathers the
+ * handles; import: maps every peer's buffer.  From then on the M_n all-reduce of the non-sharded modes is not an NCCL
+ * call: the partial MTTKRP is published in the exchange buffer and every rank's row-solve kernel sums the peers'
+ * partials (fixed rank order, so all ranks get identical bits) while loading its right-hand sides. */
+int itcpd_peer_export(itcpd_ctx *ctx, void *handle64_out);
+int itcpd_peer_import(itcpd_ctx *ctx, int nranks, int rank, const void *handles);
+int itcpd_peer_disable(itcpd_ctx *ctx);
 
 /* ---- measurement helpers ------------------------------------------------------------------- */
 /* average device time (ms, CUDA events on the handle's stream) of the dominant GEMM kernel over

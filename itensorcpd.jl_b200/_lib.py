@@ -79,6 +79,9 @@ _SIGS = {
     "itcpd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "itcpd_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "itcpd_comm_destroy": (C.c_int, [C.c_void_p]),
+    "itcpd_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "itcpd_peer_import": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "itcpd_peer_disable": (C.c_int, [C.c_void_p]),
     "itcpd_allgather_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_dp]),
     "itcpd_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "itcpd_probe_dmma_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

@@ -152,8 +152,8 @@ static int ensure_partial(itcpd_ctx *c, int kind) {
     return ITCPD_OK;
 }
 
-static int mttkrp_device(itcpd_ctx *c, int mode) {
-    double *out = c->M[mode].as<double>();
+static int mttkrp_device(itcpd_ctx *c, int mode, double *out_override = nullptr, bool reduce = true) {
+    double *out = out_override ? out_override : c->M[mode].as<double>();
     if (c->mttkrp_alg == ITCPD_MTTKRP_DIRECT) {
         TRY(k_direct_mttkrp(c, mode, out));
     } else if (mode < c->split_a) {
@@ -164,7 +164,7 @@ static int mttkrp_device(itcpd_ctx *c, int mode) {
         TRY(k_partial_mttkrp(c, c->PB.buf.as<double>(), c->split_b, c->order - 1, c->dims[c->split_b], mode, out));
     }
     // slab sharding: T is a slab of the last mode, so every other mode's MTTKRP is a partial sum
-    if (comm_active(c) && mode != c->order - 1) TRY(comm_allreduce_sum(c, out, c->dims[mode] * c->rank));
+    if (reduce && comm_active(c) && mode != c->order - 1) TRY(comm_allreduce_sum(c, out, c->dims[mode] * c->rank));
     c->m_valid[mode] = true;
     c->last_mttkrp_mode = mode;
     return ITCPD_OK;
@@ -173,6 +173,28 @@ static int mttkrp_device(itcpd_ctx *c, int mode) {
 static int gram_device(itcpd_ctx *c, int mode) {
     TRY(k_gram(c, c->A[mode].as<double>(), c->dims[mode], c->rank, c->G[mode].as<double>()));
     if (comm_active(c) && mode == c->order - 1) TRY(comm_allreduce_sum(c, c->G[mode].as<double>(), (int64_t)c->rank * c->rank));
+    return ITCPD_OK;
+}
+
+// publish "my partial of exchange `epoch` is complete" into every peer's flag array (system scope)
+struct PeerFlags { long long *dst[ITCPD_MAX_PEERS]; int n; int rank; };
+__global__ void peer_signal_kernel(PeerFlags f, long long epoch) {
+    __threadfence_system();
+    if ((int)threadIdx.x < f.n) {
+        volatile long long *d = f.dst[threadIdx.x] + f.rank;
+        *d = epoch;
+    }
+    __threadfence_system();
+}
+static int peer_signal(itcpd_ctx *c, long long epoch) {
+    PeerFlags f;
+    memset(&f, 0, sizeof(f));
+    f.n = c->peer_n;
+    f.rank = c->peer_rank;
+    for (int q = 0; q < c->peer_n; ++q) f.dst[q] = reinterpret_cast<long long *>(c->peer_base[q]);
+    peer_signal_kernel<<<1, 32, 0, c->stream>>>(f, epoch);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }
 
@@ -190,9 +212,28 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
     c->stream = main_stream;
     TRY(st);
     if (c->overlap_factor) CUDA_TRY(cudaEventRecord(c->ev_join, c->side_stream));
-    TRY(mttkrp_device(c, mode));
-    if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
-    TRY(k_solve_apply(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, c->X.as<double>(), status_dev));
+    const bool fused_peers = c->peer_on && comm_active(c) && mode != c->order - 1;
+    if (fused_peers) {
+        // fused all-reduce + solve over NVLink peer memory: the partial MTTKRP lands in this rank's exchange slot, is
+        // published with a system-scope flag, and every rank's row-solve kernel sums the peers' slots while loading
+        const int64_t epoch = ++c->peer_epoch;
+        const size_t slot_off = 256 + (size_t)(epoch & 1) * (size_t)c->peer_slot_doubles * 8;
+        TRY(mttkrp_device(c, mode, reinterpret_cast<double *>((char *)c->xchg.p + slot_off), false));
+        TRY(peer_signal(c, epoch));
+        if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+        PeerSrc src;
+        memset(&src, 0, sizeof(src));
+        src.n = c->peer_n;
+        for (int q = 0; q < c->peer_n; ++q) src.p[q] = reinterpret_cast<const double *>((const char *)c->peer_base[q] + slot_off);
+        src.flags = reinterpret_cast<const volatile long long *>(c->xchg.p);
+        src.epoch = epoch;
+        src.reduced_out = c->M[mode].as<double>();
+        TRY(k_solve_apply_peers(c, c->Gamma.as<double>(), src, c->dims[mode], c->rank, c->X.as<double>(), status_dev));
+    } else {
+        TRY(mttkrp_device(c, mode));
+        if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+        TRY(k_solve_apply(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, c->X.as<double>(), status_dev));
+    }
     TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
     c->fver[mode]++;
     TRY(gram_device(c, mode));
@@ -251,7 +292,9 @@ int itcpd_destroy(itcpd_ctx *c) {
     if (!c) return ITCPD_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    itcpd_peer_disable(c);
     itcpd_comm_destroy(c);
+    c->xchg.release();
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
                       &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev, &c->qr_A, &c->qr_piv, &c->qr_rdiag, &c->sweep_log};
     for (DevBuf *b : bufs) b->release();
@@ -1175,6 +1218,58 @@ int itcpd_allgather_factor(itcpd_ctx *c, int mode, int64_t rows_total, double *h
     for (int g = 0; g < nr; ++g)
         for (int r = 0; r < R; ++r)
             memcpy(host_out + (size_t)g * loc + (size_t)rows_total * r, tmp.data() + ((size_t)g * R + r) * loc, (size_t)loc * 8);
+    return ITCPD_OK;
+}
+
+// ---- peer-memory exchange (CUDA IPC over NVLink) ----------------------------------------------------
+int itcpd_peer_export(itcpd_ctx *c, void *handle64_out) {
+    CHECK_CTX(c);
+    ARG_CHECK(handle64_out && c->has_tensor && c->rank > 0, "set the tensor slab and the rank before exporting");
+    USE_DEVICE(c);
+    int64_t maxrows = 0;
+    for (int n = 0; n + 1 < c->order; ++n) maxrows = std::max(maxrows, c->dims[n]);
+    c->peer_slot_doubles = maxrows * c->rank;
+    c->xchg.release();
+    TRY(c->xchg.reserve(256 + 2 * (size_t)c->peer_slot_doubles * 8));
+    CUDA_TRY(cudaMemset(c->xchg.p, 0, 256));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->xchg.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64_out, &h, 64);
+    c->peer_on = false;
+    return ITCPD_OK;
+}
+
+int itcpd_peer_import(itcpd_ctx *c, int nranks, int rank, const void *handles) {
+    CHECK_CTX(c);
+    ARG_CHECK(handles && nranks >= 2 && nranks <= ITCPD_MAX_PEERS && rank >= 0 && rank < nranks && c->xchg.p, "bad peer_import arguments (export first)");
+    USE_DEVICE(c);
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) { c->peer_base[q] = c->xchg.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)q, 64);
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_base[q] = ptr;
+    }
+    c->peer_n = nranks;
+    c->peer_rank = rank;
+    c->peer_epoch = 0;
+    c->peer_on = true;
+    c->graph_epoch++;
+    return ITCPD_OK;
+}
+
+int itcpd_peer_disable(itcpd_ctx *c) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < c->peer_n; ++q)
+        if (q != c->peer_rank && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+    for (int q = 0; q < ITCPD_MAX_PEERS; ++q) c->peer_base[q] = nullptr;
+    c->peer_on = false;
+    c->peer_n = 0;
     return ITCPD_OK;
 }
 

@@ -60,6 +60,17 @@ struct Partial {
 
 struct Comm;  // comm.cu
 
+#define ITCPD_MAX_PEERS 16
+// sources of a (possibly peer-reduced) right-hand-side matrix: n buffers summed in order; flags/epoch = the
+// system-scope publication flags to wait for (null: no wait); reduced_out = where to store the reduced matrix
+struct PeerSrc {
+    const double *p[ITCPD_MAX_PEERS];
+    int n;
+    const volatile long long *flags;
+    long long epoch;
+    double *reduced_out;
+};
+
 // stream-K split description of one GEMM shape (host-built, cached per kind)
 struct StreamKTable {
     int64_t key[6] = {-1, -1, -1, -1, -1, -1};
@@ -142,6 +153,13 @@ struct itcpd_ctx {
 
     // multi-GPU
     itcpd::Comm *comm = nullptr;
+    // peer-memory exchange (CUDA IPC): [flags: 16 x int64][pad to 256 B][partial-M buffer 0][partial-M buffer 1]
+    itcpd::DevBuf xchg;
+    void *peer_base[ITCPD_MAX_PEERS] = {nullptr};
+    int peer_n = 0, peer_rank = 0;
+    bool peer_on = false;
+    long long peer_epoch = 0;
+    int64_t peer_slot_doubles = 0;
 };
 
 namespace itcpd {
@@ -177,6 +195,7 @@ int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, in
 int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev);
 int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev);
 int qrcp_ls_solve(itcpd_ctx *c, const double *A, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force);  // qrcp.cu
+int k_solve_apply_peers(itcpd_ctx *c, const double *Gamma, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev);
 int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out);
 
 // ---- sampled.cu ---------------------------------------------------------------------------

@@ -117,11 +117,21 @@ constexpr int TSW_WARPS = 8;
 
 template <int E>
 __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
-                                                                         const int *__restrict__ status, const double *__restrict__ M,
+                                                                         const int *__restrict__ status, PeerSrc src,
                                                                          int64_t rows, int n, double *__restrict__ X, int u_in_smem,
                                                                          int fwd_only, int nn_dev_slot) {
     extern __shared__ double sm_dyn[];
-    if (!fwd_only && status[0] != ITCPD_SOLVE_CHOLESKY) return;  // the QRCP path handles this system
+    if (src.flags) {
+        // fused all-reduce: wait until every peer has published its partial M for this exchange (system-scope flags
+        // written by peer_signal_kernel into OUR memory), then sum the peers' rows in rank order while loading them
+        if (threadIdx.x < src.n) {
+            while (src.flags[threadIdx.x] < src.epoch) { }
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
+    const bool chol_ok = fwd_only || status[0] == ITCPD_SOLVE_CHOLESKY;
+    if (!chol_ok && !src.reduced_out) return;  // the QRCP path handles this system
     const int ldw = n | 1;
     const double *U = Wg;
     __shared__ double s_rd[1024];  // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
@@ -136,10 +146,29 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
     if (i >= rows) return;
     const int nn = fwd_only ? status[nn_dev_slot] : n;
     double b[E];
+    if (src.reduced_out) {
+        // materialise the reduced row (un-permuted) for the QRCP fallback / later readers
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            if (k < n) {
+                double v = 0.0;
+                for (int q = 0; q < src.n; ++q) v += src.p[q][i + rows * (int64_t)k];
+                src.reduced_out[i + rows * (int64_t)k] = v;
+            }
+        }
+        if (!chol_ok) return;
+        __syncwarp();
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int k = lane + 32 * e;
-        b[e] = (k < n) ? M[i + rows * (int64_t)piv[k]] : 0.0;
+        double v = 0.0;
+        if (k < n) {
+            const int64_t off = i + rows * (int64_t)piv[k];
+            for (int q = 0; q < src.n; ++q) v += src.p[q][off];   // fixed rank order: identical bits on every rank
+        }
+        b[e] = v;
     }
     // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
     for (int k = 0; k < nn; ++k) {
@@ -210,7 +239,7 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
 }
 
 template <int E>
-static int launch_tsw(itcpd_ctx *c, const double *M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
+static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
     const size_t u_bytes = (size_t)(R | 1) * R * 8;
     const int u_in = u_bytes <= (size_t)smem_limit(c);
     auto kern = chol_solve_warp_kernel<E>;
@@ -226,7 +255,7 @@ static int launch_tsw(itcpd_ctx *c, const double *M, int64_t rows, int R, double
     return ITCPD_OK;
 }
 
-static int run_tri_solves(itcpd_ctx *c, const double *M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
+static int run_tri_solves(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
     const int E = (int)ceil_div(R, 32);
     if (E <= 1) return launch_tsw<1>(c, M, rows, R, X, status_dev, fwd_only, slot);
     if (E <= 2) return launch_tsw<2>(c, M, rows, R, X, status_dev, fwd_only, slot);
@@ -246,15 +275,31 @@ int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *st
     return run_cholesky(c, Gamma, R, tol, status_dev);
 }
 
+static PeerSrc single_src(const double *M) {
+    PeerSrc s;
+    memset(&s, 0, sizeof(s));
+    s.p[0] = M;
+    s.n = 1;
+    return s;
+}
+
 int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
-    TRY(run_tri_solves(c, M, rows, R, X, status_dev, 0, 1));
+    TRY(run_tri_solves(c, single_src(M), rows, R, X, status_dev, 0, 1));
     TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
+    return ITCPD_OK;
+}
+
+// fused all-reduce + solve: the right-hand sides are the sum of the peers' partial MTTKRPs (read over NVLink while
+// loading); src.reduced_out (this rank's M buffer) receives the reduced matrix for the rank-deficient fallback
+int k_solve_apply_peers(itcpd_ctx *c, const double *Gamma, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev) {
+    TRY(run_tri_solves(c, src, rows, R, X, status_dev, 0, 1));
+    TRY(qrcp_minnorm_solve(c, Gamma, src.reduced_out, rows, R, X, status_dev));
     return ITCPD_OK;
 }
 
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev) {
     TRY(run_cholesky(c, Gamma, R, tol, status_dev));
-    TRY(run_tri_solves(c, M, rows, R, X, status_dev, 0, 1));
+    TRY(run_tri_solves(c, single_src(M), rows, R, X, status_dev, 0, 1));
     // rank-deficient systems are re-solved by the pivoted-QR min-norm path; it is a no-op (device-side
     // early exit on status[0]) when the Cholesky succeeded, so no host round trip is needed here.
     TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
@@ -282,7 +327,7 @@ int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int
     TRY(c->status.reserve(256));
     int *st = c->status.as<int>() + 32;
     TRY(run_cholesky(c, G, R, -1.0, st));
-    TRY(run_tri_solves(c, A, rows, R, lev_out, st, 1, 1));
+    TRY(run_tri_solves(c, single_src(A), rows, R, lev_out, st, 1, 1));
     scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)std::min<int64_t>(rows, R));
     c->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -321,6 +321,19 @@ class Engine:
         buf = C.create_string_buffer(uid, 128)
         check(self._L.itcpd_comm_init(self._h, int(nranks), int(rank), buf))
 
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._L.itcpd_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_import(self, nranks: int, rank: int, handles: bytes):
+        assert len(handles) == 64 * nranks
+        buf = C.create_string_buffer(handles, len(handles))
+        check(self._L.itcpd_peer_import(self._h, int(nranks), int(rank), buf))
+
+    def peer_disable(self):
+        check(self._L.itcpd_peer_disable(self._h))
+
     def allgather_factor(self, mode: int, rows_total: int) -> np.ndarray:
         out = np.empty((rows_total, self.rank), order="F")
         check(self._L.itcpd_allgather_factor(self._h, mode, int(rows_total), _addr(out)))

@@ -9,13 +9,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_slab_sharding_matches_single_gpu():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_gpu_slab_sharding_matches_single_gpu(peer):
+    """peer=1: the M_n all-reduce is fused into the row-solve kernel over NVLink peer memory (CUDA IPC);
+    peer=0: plain NCCL all-reduce.  Both must reproduce the single-GPU trajectory."""
     import torch
 
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29617", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    cmd = ["timeout", "120", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "2961" + ("7" if peer == "1" else "8"), os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+    env = dict(os.environ, ITCPD_PEER=peer)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

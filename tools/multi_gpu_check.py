@@ -32,6 +32,12 @@ def main():
         uid.copy_(torch.frombuffer(bytearray(itcpd.Engine.comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     eng.comm_init(world, rank, uid.cpu().numpy().tobytes())
+    if os.environ.get("ITCPD_PEER", "1") == "1":
+        # fused all-reduce + solve over NVLink peer memory: exchange the CUDA IPC handles of the exchange buffers
+        mine = torch.frombuffer(bytearray(eng.peer_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        eng.peer_import(world, rank, b"".join(h.cpu().numpy().tobytes() for h in allh))
     eng.compute_grams()
     nT = eng.tensor_norm()
     inner, norm2 = eng.sweep(nsweeps)
