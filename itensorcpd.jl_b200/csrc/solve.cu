@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
     const int ldw = n | 1;
     const double *U = Wg;
     __shared__ double s_rd[1024];  // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
+    double *s_rows = sm_dyn + (u_in_smem ? (size_t)ldw * n : 0);  // TSW_WARPS x 1024 doubles, only when src.reduced_out
     for (int e = threadIdx.x; e < n; e += TSW_WARPS * 32) s_rd[e] = 1.0 / Wg[e + (size_t)ldw * e];
     if (u_in_smem) {
         for (int e = threadIdx.x; e < ldw * n; e += TSW_WARPS * 32) sm_dyn[e] = Wg[e];
@@ -147,28 +148,34 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
     const int nn = fwd_only ? status[nn_dev_slot] : n;
     double b[E];
     if (src.reduced_out) {
-        // materialise the reduced row (un-permuted) for the QRCP fallback / later readers
+        // fused all-reduce: every peer's row is read ONCE (unpermuted, coalesced, fixed rank order: identical bits on
+        // every rank), stored as the reduced matrix (rank-deficient fallback / later readers) and permuted through a
+        // per-warp shared-memory row
+        double *rowbuf = s_rows + (size_t)(threadIdx.x >> 5) * 1024;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = lane + 32 * e;
             if (k < n) {
+                const int64_t off = i + rows * (int64_t)k;
                 double v = 0.0;
-                for (int q = 0; q < src.n; ++q) v += src.p[q][i + rows * (int64_t)k];
-                src.reduced_out[i + rows * (int64_t)k] = v;
+                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
+                src.reduced_out[off] = v;
+                rowbuf[k] = v;
             }
         }
         if (!chol_ok) return;
         __syncwarp();
-    }
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int k = lane + 32 * e;
-        double v = 0.0;
-        if (k < n) {
-            const int64_t off = i + rows * (int64_t)piv[k];
-            for (int q = 0; q < src.n; ++q) v += src.p[q][off];   // fixed rank order: identical bits on every rank
+        for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            b[e] = (k < n) ? rowbuf[piv[k]] : 0.0;
         }
-        b[e] = v;
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            b[e] = (k < n) ? src.p[0][i + rows * (int64_t)piv[k]] : 0.0;
+        }
     }
     // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
     for (int k = 0; k < nn; ++k) {
@@ -241,14 +248,15 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
 template <int E>
 static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
     const size_t u_bytes = (size_t)(R | 1) * R * 8;
-    const int u_in = u_bytes <= (size_t)smem_limit(c);
+    const int u_in = u_bytes + (size_t)TSW_WARPS * 1024 * 8 <= (size_t)smem_limit(c);
     auto kern = chol_solve_warp_kernel<E>;
     static bool attr = false;
     if (!attr) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr = true;
     }
-    kern<<<(unsigned)ceil_div(rows, TSW_WARPS), TSW_WARPS * 32, u_in ? u_bytes : 0, c->stream>>>(
+    const size_t row_bytes = M.reduced_out ? (size_t)TSW_WARPS * 1024 * 8 : 0;
+    kern<<<(unsigned)ceil_div(rows, TSW_WARPS), TSW_WARPS * 32, (u_in ? u_bytes : 0) + row_bytes, c->stream>>>(
         c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, u_in, fwd_only, slot);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
