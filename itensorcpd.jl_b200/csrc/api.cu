@@ -127,6 +127,7 @@ static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
     TRY(c->T.reserve((size_t)c->nstore * 8 + 256));
     c->has_tensor = true;
     c->has_tensor_data = true;
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) c->proj_n[n] = 0;  // cached projectors belong to the previous tensor
     choose_splits(c);
     invalidate_all(c);
     if (c->rank > 0) TRY(ensure_cpd_buffers(c));

@@ -321,8 +321,10 @@ int k_partial_mttkrp(itcpd_ctx *c, const double *P, int gfirst, int glast, int64
         wb = c->krp_scratch[1].as<double>();
     }
     const int64_t Ilog = c->dims[mode];
-    if (F == 1) {
-        const int64_t I = (mode == gfirst) ? ld_first : c->dims[mode];
+    if (wf == nullptr) {
+        // the target mode is the first of its group (no front modes; a front group of total extent 1 still carries
+        // a 1 x R weight and takes the general path)
+        const int64_t I = ld_first;
         dim3 grid((unsigned)ceil_div(Ilog, 32), (unsigned)R);
         partial_first_kernel<<<grid, 256, 0, c->stream>>>(P, wb, I, Ilog, B, out);
     } else {
