@@ -108,6 +108,12 @@ int itcpd_post_solve(itcpd_ctx *ctx, int mode);
  * saved last-mode MTTKRP: no extra tensor pass. */
 int itcpd_fit_terms(itcpd_ctx *ctx, double *inner, double *model_norm2);
 
+/* CPDiffCheck / CPAngleCheck (converge_checks/cp_diff_check.jl:20-71, cp_angle_check.jl:20-73): the checks compare the
+ * CPD of consecutive sweeps through factor matrices only.  snapshot = `check.PrevCP = CPD(factors, lambda)`;
+ * diff_terms = `(PrevCP.lambda * cp_cp_contract(PrevCP, currCP)[1] * lambda)[]` and `norm_factors(grams, lambda)`. */
+int itcpd_cpd_snapshot(itcpd_ctx *ctx);
+int itcpd_cpd_diff_terms(itcpd_ctx *ctx, double *inner_prev_curr, double *norm2_curr);
+
 /* ---- whole sweeps (optimize.jl:15-32 body), device resident --------------------------------- */
 /* Runs `nsweeps` ALS sweeps (modes 1..N in order, Gram refresh after each mode, fit scalars after
  * each sweep).  inner[] / model_norm2[] (length nsweeps) may be NULL.  The host keeps the

@@ -10,7 +10,7 @@ The directory name contains a dot, so import it through the `itcpd` shim at the 
 from ._lib import ItcpdError, LIB_PATH, DECLARED_SYMBOLS, load  # noqa: F401
 from .engine import Engine, PinnedBuffer, column_to_multi_coords, multi_coords_to_column, sparse_sign_matrix  # noqa: F401
 from .host import (  # noqa: F401
-    ALS, CPD, CPAngleCheck, CPDFit, CPDiffCheck, CPDOptimizer, DirectNormal, FitCheck, KRPFreeNormal, KRPNormal, KSEQRCSPivProjected,
+    ALS, BlockLevScoreSampled, CPD, CPAngleCheck, CPDFit, CPDiffCheck, CPDOptimizer, DirectNormal, FitCheck, KRPFreeNormal, KRPNormal, KSEQRCSPivProjected,
     LevScoreSampled, MttkrpAlgorithm, NoCheck, ProjectionAlgorithm, QRPivProjected, SEQRCSPivProjected, als_optimize,
     compute_als, cp_rank, decompose, increase_cpd_rank, optimize, random_CPD, random_factors, reconstruct, start, stop,
     update_samples,

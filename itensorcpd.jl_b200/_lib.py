@@ -52,6 +52,8 @@ _SIGS = {
     "itcpd_normalize": (C.c_int, [C.c_void_p, C.c_int]),
     "itcpd_post_solve": (C.c_int, [C.c_void_p, C.c_int]),
     "itcpd_fit_terms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "itcpd_cpd_snapshot": (C.c_int, [C.c_void_p]),
+    "itcpd_cpd_diff_terms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "itcpd_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp, c_dp]),
     "itcpd_sweep_async": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "itcpd_sweep_results": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.POINTER(C.c_int)]),

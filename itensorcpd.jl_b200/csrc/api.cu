@@ -299,7 +299,8 @@ int itcpd_destroy(itcpd_ctx *c) {
     DevBuf *bufs[] = {&c->T, &c->X, &c->lambda, &c->Gamma, &c->PA.buf, &c->PB.buf, &c->packK, &c->krp_scratch[0], &c->krp_scratch[1],
                       &c->work, &c->work2, &c->redux, &c->solve_ws, &c->ipiv, &c->status, &c->fit2, &c->samp_piv, &c->samp_K, &c->samp_T, &c->flush, &c->sk_slots, &c->sk_table[0].dev, &c->sk_table[1].dev, &c->qr_A, &c->qr_piv, &c->qr_rdiag, &c->sweep_log};
     for (DevBuf *b : bufs) b->release();
-    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); }
+    for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); c->prevA[n].release(); }
+    c->prev_lambda.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -589,6 +590,38 @@ int itcpd_fit_terms(itcpd_ctx *c, double *inner, double *model_norm2) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (inner) *inner = c->pinned[0];
     if (model_norm2) *model_norm2 = c->pinned[1];
+    return ITCPD_OK;
+}
+
+// ---- CPDiffCheck / CPAngleCheck scalars (cp_diff_check.jl:20-71, cp_angle_check.jl:20-73) -----------------------
+// PrevCP snapshot and the two scalars the host state machines need: <T_prev, T_curr> and ||T_curr||^2, from the factor
+// matrices only (cp_cp_contract + norm_factors).  The sharded last factor's cross-Grams are all-reduced.
+int itcpd_cpd_snapshot(itcpd_ctx *c) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    for (int n = 0; n < c->order; ++n) {
+        const size_t b = (size_t)c->dims[n] * c->rank * 8;
+        TRY(c->prevA[n].reserve(b));
+        CUDA_TRY(cudaMemcpyAsync(c->prevA[n].p, c->A[n].p, b, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    TRY(c->prev_lambda.reserve((size_t)c->rank * 8));
+    CUDA_TRY(cudaMemcpyAsync(c->prev_lambda.p, c->lambda.p, (size_t)c->rank * 8, cudaMemcpyDeviceToDevice, c->stream));
+    c->has_snapshot = true;
+    c->snapshot_rank = c->rank;
+    return ITCPD_OK;
+}
+
+int itcpd_cpd_diff_terms(itcpd_ctx *c, double *inner_prev_curr, double *norm2_curr) {
+    CHECK_CTX(c);
+    USE_DEVICE(c);
+    ARG_CHECK(c->has_snapshot && c->snapshot_rank == c->rank, "call itcpd_cpd_snapshot first (same rank)");
+    ARG_CHECK(!comm_active(c), "CPDiff/CPAngle scalars are single-GPU in this build");
+    TRY(k_cpd_diff_terms(c, c->fit2.as<double>()));
+    CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (inner_prev_curr) *inner_prev_curr = c->pinned[0];
+    if (norm2_curr) *norm2_curr = c->pinned[1];
     return ITCPD_OK;
 }
 

@@ -116,6 +116,9 @@ struct itcpd_ctx {
     itcpd::DevBuf M[ITCPD_MAX_ORDER];   // last MTTKRP of each mode, I_n x R
     itcpd::DevBuf X;                    // solve output (max I x R)
     itcpd::DevBuf lambda, Gamma, lev[ITCPD_MAX_ORDER];
+    itcpd::DevBuf prevA[ITCPD_MAX_ORDER], prev_lambda;   // snapshot of the CPD (CPDiffCheck / CPAngleCheck PrevCP)
+    bool has_snapshot = false;
+    int snapshot_rank = 0;
     uint64_t lev_ver[ITCPD_MAX_ORDER] = {0};  // fver value the leverage scores were computed for (0 = never)
     uint64_t fver[ITCPD_MAX_ORDER] = {0};  // factor versions (bumped on every change)
     bool m_valid[ITCPD_MAX_ORDER] = {false};
@@ -176,6 +179,8 @@ int probe_dfma(itcpd_ctx *c, double *tflops);
 
 // ---- kernels.cu ---------------------------------------------------------------------------
 int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G);
+int k_cross_gram(itcpd_ctx *c, const double *A, const double *B, int64_t rows, int R, double *C);
+int k_cpd_diff_terms(itcpd_ctx *c, double *out2);
 int k_gram_hadamard(itcpd_ctx *c, int skip_mode, double *Gamma);
 int k_colnorm_scale(itcpd_ctx *c, const double *X, int64_t rows, int R, double *A, double *lambda, bool rows_are_slab);
 int k_fit_terms(itcpd_ctx *c, double *out2 /*device: inner, norm2*/, bool reduce_now);

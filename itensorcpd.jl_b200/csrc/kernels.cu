@@ -40,7 +40,8 @@ constexpr int GT = 16;       // output tile
 constexpr int GCHUNK = 64;   // rows per smem chunk
 constexpr int GSLICE = 256;  // rows per CTA slice
 
-__global__ void __launch_bounds__(GT *GT) gram_partial_kernel(const double *__restrict__ A, int64_t rows, int R, double *__restrict__ part) {
+__global__ void __launch_bounds__(GT *GT) gram_partial_kernel(const double *__restrict__ A, const double *__restrict__ B, int64_t rows, int R,
+                                                              double *__restrict__ part) {  // part = A^T B (B == A: Gram)
     __shared__ double sa[GT][GCHUNK + 1], sb[GT][GCHUNK + 1];
     const int tx = threadIdx.x % GT, ty = threadIdx.x / GT;
     const int r1 = blockIdx.x * GT + tx, r2 = blockIdx.y * GT + ty;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(GT *GT) gram_partial_kernel(const double *__re
             const int64_t i = base + ii;
             const int ca = blockIdx.x * GT + col, cb = blockIdx.y * GT + col;
             sa[col][ii] = (i < i1 && ca < R) ? A[i + rows * (int64_t)ca] : 0.0;
-            sb[col][ii] = (i < i1 && cb < R) ? A[i + rows * (int64_t)cb] : 0.0;
+            sb[col][ii] = (i < i1 && cb < R) ? B[i + rows * (int64_t)cb] : 0.0;
         }
         __syncthreads();
 #pragma unroll 8
@@ -75,9 +76,60 @@ int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G) {
     const int slices = (int)std::max<int64_t>(1, ceil_div(rows, GSLICE));
     TRY(c->redux.reserve((size_t)slices * R * R * 8));
     dim3 grid((unsigned)ceil_div(R, GT), (unsigned)ceil_div(R, GT), (unsigned)slices);
-    gram_partial_kernel<<<grid, GT * GT, 0, c->stream>>>(A, rows, R, c->redux.as<double>());
+    gram_partial_kernel<<<grid, GT * GT, 0, c->stream>>>(A, A, rows, R, c->redux.as<double>());
     sum_slices_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, c->stream>>>(c->redux.as<double>(), (int64_t)R * R, slices, G);
     c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+// cross Gram C = A^T B of two rows x R matrices (cp_cp_contract, src/algebra/cp_contract.jl:32-52)
+int k_cross_gram(itcpd_ctx *c, const double *A, const double *B, int64_t rows, int R, double *C) {
+    const int slices = (int)std::max<int64_t>(1, ceil_div(rows, GSLICE));
+    TRY(c->redux.reserve((size_t)slices * R * R * 8));
+    dim3 grid((unsigned)ceil_div(R, GT), (unsigned)ceil_div(R, GT), (unsigned)slices);
+    gram_partial_kernel<<<grid, GT * GT, 0, c->stream>>>(A, B, rows, R, c->redux.as<double>());
+    sum_slices_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, c->stream>>>(c->redux.as<double>(), (int64_t)R * R, slices, C);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+// out2[0] = lp^T (hadamard_n X_n) lc   with X_n = A_prev,n^T A_n   (inner product of two CPDs)
+// out2[1] = lc^T (hadamard_n G_n)  lc   with G_n = A_n^T A_n        (squared norm of the current CPD)
+struct CrossPtrs { const double *x[ITCPD_MAX_ORDER]; const double *g[ITCPD_MAX_ORDER]; int n; };
+__global__ void __launch_bounds__(256) cpd_diff_final_kernel(CrossPtrs p, const double *__restrict__ lp, const double *__restrict__ lc, int R,
+                                                             double *__restrict__ out2) {
+    __shared__ double sh[8];
+    double a = 0.0, b = 0.0;
+    for (int e = threadIdx.x; e < R * R; e += 256) {
+        double hx = p.x[0][e], hg = p.g[0][e];
+        for (int m = 1; m < p.n; ++m) { hx = hx * p.x[m][e]; hg = hg * p.g[m][e]; }
+        const int r1 = e % R, r2 = e / R;
+        a = fma(hx, lp[r1] * lc[r2], a);
+        b = fma(hg, lc[r1] * lc[r2], b);
+    }
+    a = block_sum<256>(a, sh);
+    b = block_sum<256>(b, sh);
+    if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+}
+
+int k_cpd_diff_terms(itcpd_ctx *c, double *out2) {
+    const int N = c->order, R = c->rank;
+    TRY(c->work2.reserve((size_t)2 * N * R * R * 8));
+    CrossPtrs p;
+    p.n = N;
+    double *base = c->work2.as<double>();
+    // NOTE: k_cross_gram uses c->redux as scratch; results go to work2
+    for (int n = 0; n < N; ++n) {
+        double *X = base + (size_t)(2 * n) * R * R, *G = base + (size_t)(2 * n + 1) * R * R;
+        TRY(k_cross_gram(c, c->prevA[n].as<double>(), c->A[n].as<double>(), c->dims[n], R, X));
+        TRY(k_cross_gram(c, c->A[n].as<double>(), c->A[n].as<double>(), c->dims[n], R, G));
+        p.x[n] = X;
+        p.g[n] = G;
+    }
+    cpd_diff_final_kernel<<<1, 256, 0, c->stream>>>(p, c->prev_lambda.as<double>(), c->lambda.as<double>(), R, out2);
+    c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }

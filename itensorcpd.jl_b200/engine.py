@@ -172,6 +172,14 @@ class Engine:
         check(self._L.itcpd_fit_terms(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def cpd_snapshot(self):
+        check(self._L.itcpd_cpd_snapshot(self._h))
+
+    def cpd_diff_terms(self):
+        a, b = C.c_double(), C.c_double()
+        check(self._L.itcpd_cpd_diff_terms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sweep(self, nsweeps: int = 1, chol_tol: float = 1e-6):
         inner = np.empty(nsweeps)
         norm2 = np.empty(nsweeps)

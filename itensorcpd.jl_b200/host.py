@@ -157,23 +157,11 @@ def CPDFit(check) -> float:
     return check.final_fit
 
 
-def _cp_cp_inner(f1, f2):
-    inner = np.ones((f1[0].shape[1], f2[0].shape[1]))
-    for a, b in zip(f1, f2):
-        inner = inner * (a.T @ b)
-    return inner
-
-
-def _norm2(factors, lam):
-    had = np.ones((lam.shape[0], lam.shape[0]))
-    for f in factors:
-        had = had * (f.T @ f)
-    return float(lam @ had @ lam)
-
-
 class _PrevCheck(ConvergeAlg):
-    """CPDiffCheck / CPAngleCheck work on the factor matrices only (R x R algebra on host copies,
-    cp_diff_check.jl:20-71, cp_angle_check.jl:20-73); they are the stopping rules of the sampled solvers."""
+    """CPDiffCheck / CPAngleCheck compare the CPDs of consecutive sweeps through their factor matrices only
+    (cp_diff_check.jl:20-71, cp_angle_check.jl:20-73); they are the stopping rules of the sampled solvers (FitCheck is
+    disabled there).  The two scalars they need -- <That_prev, That_curr> and ||That_curr||^2 -- come from the device
+    (itcpd_cpd_snapshot / itcpd_cpd_diff_terms); the state machine below is the reference's, verbatim."""
 
     def __init__(self, tol, maxiter):
         self.iter, self.counter, self.tolerance, self.max_counter = 0, 0, tol, int(maxiter)
@@ -189,18 +177,21 @@ class _PrevCheck(ConvergeAlg):
         self.prev = None
 
     def check_converge(self, als, factors_lam, verbose=False) -> bool:
-        factors, lam = factors_lam()
+        eng = als.engine
         self.iter += 1
         if self.prev is None:
-            self.prev = (factors, lam)
-            self.norm_prev_iter = self._first_norm(factors, lam)
+            eng.cpd_snapshot()                      # check.PrevCP = CPD(factors, lambda)
+            _, sq = eng.cpd_diff_terms()
+            self.prev = True
+            self.norm_prev_iter = self._first_norm(sq)
             return False
-        val = self._measure(factors, lam)
+        inner, sq = eng.cpd_diff_terms()
+        val = self._measure(inner, sq)
         d = abs(self._lastv - val)
         self._lastv = val
-        self.prev = (factors, lam)
+        eng.cpd_snapshot()
         if verbose:
-            print(f"{lam.shape[0]}\t {self.iter} \t {val} \t {d}")
+            print(f"{eng.rank}\t {self.iter} \t {val} \t {d}")
         if d < self.tolerance:
             self.counter += 1
             if self.counter >= 2:
@@ -218,13 +209,10 @@ class CPDiffCheck(_PrevCheck):
     def lastfit(self):
         return self._lastv
 
-    def _first_norm(self, f, l):
-        return _norm2(f, l)
+    def _first_norm(self, sq):
+        return sq
 
-    def _measure(self, factors, lam):
-        pf, pl = self.prev
-        inner = float(pl @ _cp_cp_inner(pf, factors) @ lam)
-        sq = _norm2(factors, lam)
+    def _measure(self, inner, sq):
         resid = math.sqrt(abs(self.norm_prev_iter + sq - 2 * abs(inner)))
         fit = 1.0 - resid / math.sqrt(abs(self.norm_prev_iter))
         self.norm_prev_iter = sq
@@ -236,14 +224,12 @@ class CPAngleCheck(_PrevCheck):
     def lastangle(self):
         return self._lastv
 
-    def _first_norm(self, f, l):
-        return math.sqrt(_norm2(f, l))
+    def _first_norm(self, sq):
+        return math.sqrt(sq)
 
-    def _measure(self, factors, lam):
-        pf, pl = self.prev
-        numer = float(pl @ _cp_cp_inner(pf, factors) @ lam)
-        nc = math.sqrt(_norm2(factors, lam))
-        theta = min(1.0, numer / (nc * self.norm_prev_iter))
+    def _measure(self, inner, sq):
+        nc = math.sqrt(sq)
+        theta = min(1.0, inner / (nc * self.norm_prev_iter))
         self.norm_prev_iter = nc
         return math.acos(theta)
 
@@ -327,6 +313,58 @@ class LevScoreSampled(ProjectionAlgorithm):
                 als.check.iter = 0
             return False
         return als.check.check_converge(als, als.fetch_cpd_arrays, verbose=verbose)
+
+
+def block_sample_factor_matrices(nsamps, probs, block_size, skip_fact, rng):
+    """math_tools/probability.jl:61-108 (host-side integer logic, exactly as in the reference): the first non-skipped
+    mode is cut into near-equal blocks of `block_size` consecutive rows, a block is drawn with the summed leverage of its
+    rows and expanded into all its rows, the other modes get one weighted draw per block.  1-based int64 output."""
+    def draw(p):
+        w = np.abs(np.asarray(p, dtype=np.float64))
+        return int(rng.choice(len(w), p=w / w.sum())) + 1
+
+    def one_per_mode():
+        return [draw(p) for m, p in enumerate(probs) if m != skip_fact]
+
+    nf = len(probs)
+    out = np.empty((nsamps, nf - 1), dtype=np.int64, order="F")
+    blocked = np.asarray(probs[1 if skip_fact == 0 else 0])
+    nblocks, resid = len(blocked) // block_size, len(blocked) % block_size
+    edges = [1]
+    for i in range(1, nblocks + 1):
+        edges.append(edges[-1] + block_size + (1 if i <= resid else 0))
+    block_prob = [float(np.sum(blocked[edges[i] - 1: edges[i + 1] - 1])) for i in range(nblocks)]
+    m = 1
+    for _ in range(nsamps // block_size):
+        other = one_per_mode()
+        b = draw(block_prob)
+        for j in range(1, edges[b] - edges[b - 1] + 1):
+            if m > nsamps:
+                m += 1
+                break
+            out[m - 1, :] = [edges[b - 1] + j - 1] + other[1:]
+            m += 1
+    for i in range(m, nsamps + 1):
+        out[i - 1, :] = one_per_mode()
+    return out
+
+
+class BlockLevScoreSampled(LevScoreSampled):
+    """algorithms/.../randomized/krp_lev_score_sampled.jl:64-108: leverage-score sampling in blocks of consecutive rows.
+    The leverage scores come from the device; the block bookkeeping is host integer logic like in the reference; gathers,
+    the sampled solve and the leverage refresh run on the device (itcpd_sampled_update)."""
+
+    def __init__(self, nsamples=0, blocks=1):
+        super().__init__(nsamples)
+        self.Blocks = tuple(blocks) if isinstance(blocks, (tuple, list)) else (int(blocks),)
+
+    def compute_krp(self, als, fact):
+        ai = als.additional_items
+        stop = ai["stop_resample"]
+        if stop < 0 or stop > als.check.iter or ai["projects_tensors"][fact] is None:
+            probs = [als.engine.leverage_scores(n) for n in range(len(als.engine.dims))]
+            bs = self.Blocks[0] if len(self.Blocks) == 1 else self.Blocks[fact]
+            ai["projects_tensors"][fact] = block_sample_factor_matrices(self.nsamples(fact), probs, bs, fact, ai["rng"])
 
 
 def _pick(v, fact):
@@ -535,7 +573,7 @@ def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None
         eng.compute_grams()  # :part_grammian
     elif isinstance(alg, LevScoreSampled):
         extra.update(normal=False if normal is None else normal, stop_resample=stop_resample, seed=int(seed) * 1000003,
-                     projects_tensors=[None] * len(cp))
+                     projects_tensors=[None] * len(cp), rng=np.random.default_rng(seed) if rng is None else rng)
         for n in range(len(cp)):
             eng.leverage_scores(n)  # :factor_weights
     elif isinstance(alg, _PivotBased):

@@ -348,3 +348,65 @@ def test_kseqrcs_projected_als(engine):
                 ok = True
                 break
         assert ok, (kw, e_exact, e)
+
+
+def test_cpd_diff_terms_match_oracle(engine):
+    """CPDiffCheck / CPAngleCheck scalars on the device (cp_cp_contract + norm_factors, cp_diff_check.jl:31-32)."""
+    rng = np.random.default_rng(40)
+    dims, R = (14, 9, 11, 5), 6
+    prev = cpals.random_CPD(dims, R, rng)
+    curr = cpals.random_CPD(dims, R, rng)
+    prev.lam = rng.uniform(0.5, 2.0, R)
+    curr.lam = rng.uniform(0.5, 2.0, R)
+    engine.generate_tensor(dims, seed=2)
+    engine.set_cpd(prev.factors, prev.lam)
+    engine.cpd_snapshot()
+    engine.set_cpd(curr.factors, curr.lam)
+    inner, sq = engine.cpd_diff_terms()
+    inner_o = float(prev.lam @ cpals.cp_cp_inner(prev.factors, curr.factors) @ curr.lam)
+    sq_o = cpals.norm_factors([cpals.gram(f) for f in curr.factors], curr.lam)
+    assert abs(inner - inner_o) < 1e-12 * max(1.0, abs(inner_o)) and abs(sq - sq_o) < 1e-12 * sq_o
+    # explicit check against the dense tensors
+    assert abs(inner - float(np.sum(cpals.reconstruct(prev) * cpals.reconstruct(curr)))) < 1e-10 * abs(inner_o) + 1e-12
+
+
+def test_diff_check_trajectory_matches_oracle(engine):
+    """The CPDiffCheck state machine driven by device scalars stops at the same sweep, with the same value, as the oracle's."""
+    import itcpd
+
+    T, cp, rng = problem((12, 13, 11), 4, 41)
+    c1 = itcpd.CPDiffCheck(1e-4, 60)
+    itcpd.als_optimize(T, itcpd.CPD(cp.factors, cp.lam), alg=itcpd.KRPNormal(), check=c1)
+    c2 = cpals.CPDiffCheck(1e-4, 60)
+    cpals.als_optimize(T, cp, alg=cpals.KRPNormal(), check=c2)
+    assert c1.total_iter == c2.total_iter and abs(c1.final_fit - c2.final_fit) < 1e-9
+    a1 = itcpd.CPAngleCheck(1e-4, 60)
+    itcpd.als_optimize(T, itcpd.CPD(cp.factors, cp.lam), alg=itcpd.KRPNormal(), check=a1)
+    a2 = cpals.CPAngleCheck(1e-4, 60)
+    cpals.als_optimize(T, cp, alg=cpals.KRPNormal(), check=a2)
+    assert a1.total_iter == a2.total_iter and abs(a1.final_fit - a2.final_fit) < 1e-6
+
+
+def test_block_lev_score_sampled_als(engine):
+    """test/rand_cp_als.jl:126-150 scaled: BlockLevScoreSampled with CPDiffCheck on an exactly low-rank tensor."""
+    import itcpd
+
+    rng = np.random.default_rng(42)
+    A = cpals.reconstruct(cpals.random_CPD((24, 26, 22), 4, rng))
+    nA = np.linalg.norm(A)
+    cp0 = cpals.random_CPD(A, 3, rng)
+    start = itcpd.CPD(cp0.factors, cp0.lam)
+    exact = itcpd.als_optimize(A, start, check=itcpd.CPDiffCheck(1e-5, 100), alg=itcpd.KRPNormal())
+    e_exact = np.linalg.norm(A - itcpd.reconstruct(exact)) / nA
+    ok = False
+    for attempt in range(5):
+        o = itcpd.als_optimize(A, start, alg=itcpd.BlockLevScoreSampled(400, 4), normal=True, check=itcpd.CPDiffCheck(1e-5, 100), seed=attempt)
+        e = np.linalg.norm(A - itcpd.reconstruct(o)) / nA
+        if abs(e_exact - e) / e_exact < 0.1:
+            ok = True
+            break
+    assert ok, (e_exact, e)
+    piv = o and itcpd.package.host.block_sample_factor_matrices(20, [np.ones(8) / 8, np.ones(6) / 6, np.ones(5) / 5], 4, 1, np.random.default_rng(0))
+    assert piv.shape == (20, 2) and piv.min() >= 1 and piv[:, 0].max() <= 8 and piv[:, 1].max() <= 5
+    # rows of a block are consecutive in the blocked (first non-skipped) mode
+    assert np.all(np.diff(piv[:4, 0]) == 1) and len(set(piv[:4, 1].tolist())) == 1
