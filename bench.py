@@ -152,7 +152,6 @@ def slab_factors(factors, slab):
 
 
 def cpu_baseline_entry(t_normal, t_free, dims, slab, nsamples):
-    R = None
     return {
         "value": 1.0 / t_normal, "unit": "sweeps/s", "cores": blas_threads(), "kind": "port",
         "sample": f"restated oracle (numpy/OpenBLAS, not Julia), KRPNormal GEMM shape incl. permuted copies: last-mode slab "
