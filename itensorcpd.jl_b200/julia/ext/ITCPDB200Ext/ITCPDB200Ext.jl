@@ -133,6 +133,119 @@ end
 ## NoCheck never looks at the factors (no_check.jl:9-20): reuse it unchanged.
 b200_check_converge(check::NoCheck, R, _, __, verbose) = ITensorCPD.check_converge(check, nothing, itensor(zeros(R), Index(R)), nothing; verbose)
 
+## ---------------------------------------------------------------------------------------------------------------
+## Sampled path: leverage-score sampled ALS with the whole per-mode update on the device.
+## Package-side type (INTEGRATION.md patch 1b, next to LevScoreSampled in
+## src/algorithms/als_algorithms/randomized/krp_lev_score_sampled.jl:9-17):
+##     struct B200LevScoreSampled <: ProjectionAlgorithm
+##         NSamples::Tuple
+##         device::Int
+##     end
+##     B200LevScoreSampled(n::Int) = B200LevScoreSampled((n,), 0)
+## ---------------------------------------------------------------------------------------------------------------
+using ITensorCPD: B200LevScoreSampled, CPDiffCheck, CPAngleCheck
+
+struct B200SampledALS <: CPDOptimizer
+    target::ITensor
+    mttkrp_alg::B200LevScoreSampled
+    handle::Handle
+    check::ConvergeAlg
+    normal::Bool
+    stop_resample::Int
+    seed::UInt64
+end
+
+## compute_als(::LevScoreSampled) (optimizers/als_optimizers/randomized/krp_lev_score_sampled.jl:1-40): factor weights on device
+function ITensorCPD.compute_als(alg::B200LevScoreSampled, target::ITensor, cp::CPD{<:ITensor};
+                                extra_args = Dict(), check = nothing, normal = false, stop_resample = -1, seed = 0, kwargs...)
+    dense = ITensorCPD.compute_als(B200Normal(alg.device), target, cp; check)   # uploads T, factors, lambda
+    h = dense.handle
+    for n in 1:length(cp)
+        chk(ccall((:itcpd_leverage_scores, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, C_NULL))
+    end
+    return B200SampledALS(target, alg, h, check, normal, stop_resample, UInt64(seed))
+end
+
+## optimize (optimize.jl:6-35) with the ProjectionAlgorithm hooks (ProjectionAlgorithm.jl:7-68) collapsed into two calls per mode
+function ITensorCPD.optimize(cp::CPD, als::B200SampledALS; verbose = false)
+    h = als.handle.ptr
+    N = length(cp)
+    iter = als.check.iter
+    pivs = [Matrix{Int64}(undef, (length(als.mttkrp_alg.NSamples) == 1 ? als.mttkrp_alg.NSamples[1] : als.mttkrp_alg.NSamples[n]), N - 1) for n in 1:N]
+    drawn = falses(N)
+    seed = als.seed
+    while iter < als.check.max_counter
+        for fact in 1:N
+            resample = als.stop_resample < 0 || als.stop_resample > als.check.iter || !drawn[fact]   # krp_lev...:24-27
+            if resample
+                seed += 1
+                chk(ccall((:itcpd_sample_factor_matrices, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Int64, UInt64, Ptr{Int64}),
+                          h, fact - 1, size(pivs[fact], 1), seed, pivs[fact]))
+                drawn[fact] = true
+            end
+            chk(ccall((:itcpd_sampled_update, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Float64, Cint),
+                      h, fact - 1, size(pivs[fact], 1), pivs[fact], cholesky_epsilon, als.normal ? 1 : 0))
+        end
+        if b200_sampled_converged(als.check, h, verbose) && break end
+        iter += 1
+    end
+    return fetch_cpd(h, cp, als.target)
+end
+
+## CPDiffCheck from the two device scalars (cp_diff_check.jl:20-71); FitCheck is not supported for sampled solvers
+## (ProjectionAlgorithm.jl:30-51): it only counts sweeps.
+function b200_sampled_converged(check::CPDiffCheck, h, verbose)
+    check.iter += 1
+    inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
+    if isnothing(check.PrevCP)
+        chk(ccall((:itcpd_cpd_snapshot, libitcpd[]), Cint, (Ptr{Cvoid},), h))
+        chk(ccall((:itcpd_cpd_diff_terms, libitcpd[]), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
+        check.PrevCP = true
+        check.norm_prev_iter = nrm2[]
+        return false
+    end
+    chk(ccall((:itcpd_cpd_diff_terms, libitcpd[]), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
+    normResidual = sqrt(abs(check.norm_prev_iter + nrm2[] - 2 * abs(inner[])))
+    curr_fit = 1.0 - normResidual / sqrt(abs(check.norm_prev_iter))
+    Δfit = abs(check.lastfit - curr_fit)
+    check.lastfit = curr_fit
+    check.norm_prev_iter = nrm2[]
+    chk(ccall((:itcpd_cpd_snapshot, libitcpd[]), Cint, (Ptr{Cvoid},), h))
+    verbose && println("$(check.iter) \t $(curr_fit) \t $(Δfit)")
+    done = false
+    if Δfit < check.tolerance
+        check.counter += 1
+        done = check.counter >= 2
+    else
+        check.counter = 0
+    end
+    if done || check.iter >= check.max_counter
+        check.total_iter = check.iter; check.iter = 0; check.counter = 0
+        check.final_fit = check.lastfit; check.lastfit = 0; check.PrevCP = nothing
+    end
+    return done
+end
+function b200_sampled_converged(check::FitCheck, h, verbose)
+    check.iter == 0 && println("Warning: FitCheck is not enabled for B200LevScoreSampled will run $(check.max_counter) iterations.")
+    check.iter += 1
+    check.iter >= check.max_counter && (check.iter = 0)
+    return false
+end
+b200_sampled_converged(check::NoCheck, h, verbose) = b200_check_converge(check, 0, 0.0, 0.0, verbose)
+
+function fetch_cpd(h, cp::CPD, target)
+    rank = cp_rank(cp)
+    factors = Vector{ITensor}()
+    for (n, i) in enumerate(inds(cp))
+        A = Matrix{Float64}(undef, dim(i), dim(rank))
+        chk(ccall((:itcpd_get_factor, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
+        push!(factors, itensor(A, i, rank))
+    end
+    lam = Vector{Float64}(undef, dim(rank))
+    chk(ccall((:itcpd_get_lambda, libitcpd[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
+    return CPD{typeof(target)}(factors, itensor(lam, rank))
+end
+
 ## Seam 3: the sparse-sign generators keep the C ABI of libsparse_sign (SEQRCS.jl:41-60); pointing the module
 ## global `ITensorCPD.libsparse` at libitcpd_b200 and the symbols at itcpd_sparse_sign / itcpd_sparsestack
 ## yields bit-identical (vals, rows, colstarts).
