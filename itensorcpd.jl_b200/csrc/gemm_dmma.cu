@@ -440,10 +440,10 @@ static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, do
     using S = GemmSmem<NB, WARPS>;
     constexpr int BM = S::BM, BN = 8 * NB;
     auto kern = partial_gemm_kernel<NB, WARPS, KIND>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    if (!attr_set[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     const int per_sm = (WARPS <= 4) ? 2 : 1;
     const int64_t tiles = (int64_t)num_row_tiles * num_rblocks;

@@ -154,10 +154,10 @@ int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, in
     iota_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(jpvt_dev, n);
     qrw_norm_init_kernel<<<(unsigned)nb0, 256, 0, c->stream>>>(A, m, n, vn, bmax_v, bmax_i);
     c->launches += 2;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};  // function attributes are per device
+    if (!attr[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(qrw_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
+        attr[c->device & 63] = true;
     }
     ARG_CHECK((size_t)m * 8 <= 200 * 1024, "QRCP supports at most 25600 rows");
     int64_t nblocks = nb0;

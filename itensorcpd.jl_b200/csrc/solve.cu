@@ -232,10 +232,10 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
     TRY(c->ipiv.reserve((size_t)R * 4 * 2));
     const size_t need = ((size_t)ldw * R + R) * 8;
     const int use_smem = need <= (size_t)smem_limit(c);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};  // function attributes are per device
+    if (!attr[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
-        attr = true;
+        attr[c->device & 63] = true;
     }
     const int threads = R <= 64 ? 64 : (R <= 128 ? 128 : CH_THREADS);
     pivoted_cholesky_kernel<<<1, threads, use_smem ? need : 0, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(),
@@ -250,10 +250,10 @@ static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, doubl
     const size_t u_bytes = (size_t)(R | 1) * R * 8;
     const int u_in = u_bytes + (size_t)TSW_WARPS * 1024 * 8 <= (size_t)smem_limit(c);
     auto kern = chol_solve_warp_kernel<E>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};  // function attributes are per device
+    if (!attr[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
-        attr = true;
+        attr[c->device & 63] = true;
     }
     const size_t row_bytes = M.reduced_out ? (size_t)TSW_WARPS * 1024 * 8 : 0;
     kern<<<(unsigned)ceil_div(rows, TSW_WARPS), TSW_WARPS * 32, (u_in ? u_bytes : 0) + row_bytes, c->stream>>>(
