@@ -63,6 +63,7 @@ struct Comm;  // comm.cu
 #define ITCPD_MAX_PEERS 16
 // sources of a (possibly peer-reduced) right-hand-side matrix: n buffers summed in order; flags/epoch = the
 // system-scope publication flags to wait for (null: no wait); reduced_out = where to store the reduced matrix
+#define ITCPD_PEER_TIMEOUT_NS 60000000000ull  // 60 s: far above any legitimate skew between ranks of one sweep
 struct PeerSrc {
     const double *p[ITCPD_MAX_PEERS];
     int n;

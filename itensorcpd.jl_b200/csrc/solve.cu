@@ -125,7 +125,19 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
         // fused all-reduce: wait until every peer has published its partial M for this exchange (system-scope flags
         // written by peer_signal_kernel into OUR memory), then sum the peers' rows in rank order while loading them
         if (threadIdx.x < src.n) {
-            while (src.flags[threadIdx.x] < src.epoch) { }
+            // bounded: a peer that died must surface as a launch failure on this rank, not as a hung box
+            unsigned long long t0 = 0, spins = 0;
+            while (src.flags[threadIdx.x] < src.epoch) {
+                if ((++spins & 0xfffff) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > ITCPD_PEER_TIMEOUT_NS) {
+                        if (blockIdx.x == 0) printf("itcpd: peer %d never published exchange %lld\n", (int)threadIdx.x, src.epoch);
+                        __trap();
+                    }
+                }
+            }
         }
         __syncthreads();
         __threadfence_system();
