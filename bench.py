@@ -39,6 +39,7 @@ CONFIGS = {
     "C": {"dims": (256, 256, 256, 256), "rank": 32},
     "D": {"dims": (2048, 2048, 2048), "rank": 128},
     "S": {"dims": (256, 256, 256), "rank": 32},  # small smoke configuration
+    "B8": {"dims": (1024, 1024, 128), "rank": 64},  # one rank's slab of config B at 8 GPUs (per-rank chain without collectives)
 }
 
 

@@ -213,10 +213,8 @@ __global__ void __launch_bounds__(256) inner_partial_kernel(const double *__rest
 __global__ void __launch_bounds__(256) fit_final_kernel(const double *__restrict__ part, int nparts, GramPtrs p,
                                                         const double *__restrict__ lambda, int R, double *__restrict__ out2) {
     __shared__ double sh[8];
-    double s = 0.0;
-    if (threadIdx.x == 0)
-        for (int i = 0; i < nparts; ++i) s += part[i];
-    const double inner = s;
+    // nparts <= 256: one partial per thread, fixed-order tree (a serial loop in one thread costs 256 dependent L2 round trips)
+    const double inner = block_sum<256>((int)threadIdx.x < nparts ? part[threadIdx.x] : 0.0, sh);
     double q = 0.0;
     for (int e = threadIdx.x; e < R * R; e += 256) {
         double h = p.g[0][e];

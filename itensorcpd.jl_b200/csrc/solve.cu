@@ -110,6 +110,133 @@ __global__ void __launch_bounds__(CH_THREADS) pivoted_cholesky_kernel(const doub
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
+// ---- latency-tuned variant for n <= 128 ("team" kernel) --------------------------------------------------------
+// Same arithmetic, operation for operation, as pivoted_cholesky_kernel (bitwise identical factor, pivots and status),
+// but organised around the dependent chain of one column: thread k owns column k and keeps its running diagonal in
+// a register; the pivot search is three warp redux ops on an order-preserving integer key (no FP64 compares, no
+// shuffle tree) plus one named barrier across the <= 4 owning warps; the swap and the row computation share a second
+// barrier (a single warp needs only __syncwarp).  All 256 threads of the CTA take part in the load / store phases.
+constexpr int CHT_MAX_N = 128;
+constexpr int CHT_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long ordered_key(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ void team_sync(int nw, int team) {
+    if (nw == 1) __syncwarp();
+    else asm volatile("bar.sync 1, %0;" ::"r"(team) : "memory");
+}
+
+__global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_team_kernel(const double *__restrict__ Gin, int n, double tol,
+                                                                            double *__restrict__ Wg, int *__restrict__ piv,
+                                                                            int *__restrict__ status) {
+    extern __shared__ double sm_dyn[];
+    __shared__ unsigned long long s_key[4];
+    __shared__ int s_idx[4], s_bad[4];
+    __shared__ double s_swapdd;
+    __shared__ int s_piv[CHT_MAX_N];
+    __shared__ int s_rank;
+    const int ldw = n | 1;
+    const int tid = threadIdx.x;
+    const int team = (n + 31) & ~31, nw = team >> 5;
+    double *W = sm_dyn;
+    for (int e = tid; e < n * n; e += CHT_THREADS) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
+    if (tid < n) s_piv[tid] = tid;
+    if (tid == 0) s_rank = n;
+    __syncthreads();
+    if (tid < team) {
+        const int k = tid, lane = tid & 31, w = tid >> 5;
+        const bool mine = k < n;
+        double *ck = W + (size_t)ldw * (mine ? k : 0);
+        double ddk = mine ? ck[k] : 0.0;  // running diagonal (dpstf2 "work") of my column
+        double stop = 0.0;
+        int rank = n;
+        for (int j = 0; j < n; ++j) {
+            // ---- pivot: first maximum of the running diagonal over k >= j ----
+            const bool elig = mine && k >= j;
+            const unsigned long long key = elig ? ordered_key(ddk) : 0ull;
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+            const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+            const bool win = elig && hi == mh && (unsigned)key == ml;
+            const unsigned mi = __reduce_min_sync(0xffffffffu, win ? (unsigned)k : 0x7fffffffu);
+            int bb = __any_sync(0xffffffffu, elig && ddk != ddk);  // NaN poisons the factorisation
+            unsigned long long bk = ((unsigned long long)mh << 32) | ml;
+            int bi = (int)mi;
+            if (nw > 1) {
+                if (lane == 0) { s_key[w] = bk; s_idx[w] = bi; s_bad[w] = bb; }
+                team_sync(nw, team);
+                bk = s_key[0]; bi = s_idx[0]; bb = s_bad[0];
+                for (int q = 1; q < nw; ++q) {
+                    const unsigned long long kq = s_key[q];
+                    if (kq > bk) { bk = kq; bi = s_idx[q]; }  // ties keep the lower warp = the lower index
+                    bb |= s_bad[q];
+                }
+            }
+            const double bv = key_value(bk);
+            bool fail;
+            if (j == 0) {
+                stop = (tol < 0.0) ? n * DBL_EPSILON * bv : tol;
+                fail = bb || !(bv > 0.0);
+            } else {
+                fail = bb || !(bv > stop);
+            }
+            if (fail) { rank = j; break; }  // uniform over the team
+            const int p = bi;
+            const double d = sqrt(bv);
+            // ---- symmetric interchange j <-> p ----
+            if (p != j && mine) {
+                if (k != j && k != p) {
+                    double a = ck[j], b = ck[p];
+                    ck[j] = b; ck[p] = a;
+                    a = W[k + (size_t)ldw * j]; b = W[k + (size_t)ldw * p];
+                    W[k + (size_t)ldw * j] = b; W[k + (size_t)ldw * p] = a;
+                } else if (k == j) {
+                    const double a = W[j + (size_t)ldw * j];
+                    W[j + (size_t)ldw * j] = W[p + (size_t)ldw * p];
+                    W[p + (size_t)ldw * p] = a;
+                    const double b = W[j + (size_t)ldw * p];
+                    W[j + (size_t)ldw * p] = W[p + (size_t)ldw * j];
+                    W[p + (size_t)ldw * j] = b;
+                    const int q = s_piv[j]; s_piv[j] = s_piv[p]; s_piv[p] = q;
+                    s_swapdd = ddk;  // my running diagonal moves to column p
+                }
+            }
+            team_sync(nw, team);
+            if (p != j && k == p) ddk = s_swapdd;
+            // ---- row j of the factor and the diagonal down-date ----
+            if (mine && k > j) {
+                const double *cj = W + (size_t)ldw * j;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int l = 0;
+                for (; l + 3 < j; l += 4) {
+                    s0 = fma(cj[l], ck[l], s0); s1 = fma(cj[l + 1], ck[l + 1], s1);
+                    s2 = fma(cj[l + 2], ck[l + 2], s2); s3 = fma(cj[l + 3], ck[l + 3], s3);
+                }
+                for (; l < j; ++l) s0 = fma(cj[l], ck[l], s0);
+                const double u = (ck[j] - ((s0 + s1) + (s2 + s3))) / d;
+                ck[j] = u;
+                ddk = fma(-u, u, ddk);
+            } else if (k == j) {
+                ck[j] = d;
+            }
+            if (nw == 1) __syncwarp();  // (several warps: the next pivot barrier orders these writes before the next swap)
+        }
+        if (tid == 0) s_rank = rank;
+    }
+    __syncthreads();
+    const int rank = s_rank;
+    for (int e = tid; e < ldw * n; e += CHT_THREADS) Wg[e] = W[e];
+    for (int e = tid; e < n; e += CHT_THREADS) piv[e] = s_piv[e];
+    if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
+}
+
 // One warp per right-hand side: x = P (U^T U)^{-1} P^T b with b = row i of M, result to row i of X.
 // Lane l keeps entries k = l + 32 e (e < E) in registers.  mode: 0 full solve, 1 forward only and
 // return ||y[0:nn]||^2 (leverage scores).
@@ -248,6 +375,18 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
     if (!attr[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr[c->device & 63] = true;
+    }
+    if (c->chol_alg == 1 && R <= CHT_MAX_N) {
+        static bool attr_t[64] = {false};
+        if (!attr_t[c->device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
+            attr_t[c->device & 63] = true;
+        }
+        pivoted_cholesky_team_kernel<<<1, CHT_THREADS, (size_t)ldw * R * 8, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(),
+                                                                                          c->ipiv.as<int>(), status_dev);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ITCPD_OK;
     }
     const int threads = R <= 64 ? 64 : (R <= 128 ? 128 : CH_THREADS);
     pivoted_cholesky_kernel<<<1, threads, use_smem ? need : 0, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(),

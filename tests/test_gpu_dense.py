@@ -1,6 +1,8 @@
 """GPU parity tests of the dense CP-ALS path: every call goes through the C-ABI (ctypes) and is
 compared with the CPU oracle (oracle/cpals.py) on the same seeded inputs.
 Tolerances: MTTKRP 1e-12 relative Frobenius, fit trajectory 1e-9 over 100 sweeps (BASELINE.json north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -321,3 +323,64 @@ def test_graph_replay_equals_plain_sweeps(engine):
     engine.mttkrp(0)
     f = [engine.get_factor(n) for n in range(3)]
     assert relerr(engine.mttkrp(1), cpals.mttkrp_krp_normal(T, f, 1)) < 1e-12
+
+
+CHOL_DEFAULT = int(os.environ.get("ITCPD_CHOL", "1") != "0")
+
+
+@pytest.mark.parametrize("R", [1, 5, 31, 32, 33, 50, 64, 65, 100, 128])
+def test_team_cholesky_is_bitwise_the_block_kernel(engine, R):
+    """solve.cu: the latency-tuned pivoted Cholesky (chol_alg=1, n <= 128) performs the same operations in the same order
+    as the block kernel, so whole ALS trajectories -- pivots, factors, fit scalars -- must be bitwise identical."""
+    dims = (36, 40, 28)
+    T, cp = make_problem(dims, R, seed=71 + R)
+    res = {}
+    for alg in (0, 1):
+        engine.set_option("chol_alg", alg)
+        engine.set_tensor(T)
+        engine.set_cpd(cp.factors, cp.lam)
+        engine.compute_grams()
+        engine.gram_hadamard(1, fetch=False)
+        engine.mttkrp(1, fetch=False)
+        first = engine.solve(1, 1e-6)
+        inner, norm2 = engine.sweep(6)
+        res[alg] = (first, inner, norm2, [engine.get_factor(n) for n in range(3)], engine.get_lambda())
+    engine.set_option("chol_alg", CHOL_DEFAULT)
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1:3], res[1][1:3]):
+        assert np.array_equal(a, b)
+    for a, b in zip(res[0][3], res[1][3]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res[0][4], res[1][4])
+
+
+def test_team_cholesky_rank_deficient_and_nan(engine):
+    """Same stop column (rank) and QRCP hand-over as the block kernel on a singular Gamma; a NaN makes both fail at column 0."""
+    dims, R = (30, 25, 20), 12
+    T, cp = make_problem(dims, R, seed=17)
+    f = [x.copy() for x in cp.factors]
+    for m in range(3):
+        f[m][:, 7] = f[m][:, 2]
+        f[m][:, 11] = f[m][:, 5]
+    out = {}
+    for alg in (0, 1):
+        engine.set_option("chol_alg", alg)
+        engine.set_tensor(T)
+        engine.set_cpd(f, cp.lam)
+        engine.compute_grams()
+        engine.gram_hadamard(1, fetch=False)
+        engine.mttkrp(1, fetch=False)
+        pr = engine.solve(1, 1e-6)
+        engine.normalize(1)
+        out[alg] = (pr, engine.get_factor(1), engine.get_lambda())
+        fn = [x.copy() for x in cp.factors]
+        fn[0][3, 1] = np.nan
+        engine.set_cpd(fn, cp.lam)
+        engine.compute_grams()
+        engine.gram_hadamard(1, fetch=False)
+        engine.mttkrp(1, fetch=False)
+        out[alg] += (engine.solve(1, 1e-6),)
+    engine.set_option("chol_alg", CHOL_DEFAULT)
+    assert out[0][0] == out[1][0] == (1, 10)
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert out[0][3] == out[1][3] and out[0][3][0] == 1   # NaN: both kernels hand over to the QRCP path
