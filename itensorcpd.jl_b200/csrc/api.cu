@@ -285,7 +285,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
-    if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = atoi(s) != 0;
+    if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     int st = ensure_pinned(c, 4096);
     if (st != ITCPD_OK) { delete c; return st; }
@@ -349,7 +349,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
-    else if (n == "chol_alg") { ARG_CHECK(value == 0 || value == 1, "chol_alg must be 0 or 1"); c->chol_alg = (int)value; }
+    else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 2, "chol_alg must be 0, 1 or 2"); c->chol_alg = (int)value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     c->graph_epoch++;

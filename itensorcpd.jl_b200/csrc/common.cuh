@@ -90,7 +90,7 @@ struct itcpd_ctx {
     cudaStream_t side_stream = nullptr;   // Gram-Hadamard + factorisation run here underneath the MTTKRP
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_factor = 1;
-    int chol_alg = 1;  // 0: block kernel (any n), 1: latency-tuned team kernel for n <= 128 (same arithmetic, bitwise)
+    int chol_alg = 1;  // 0: block kernel (any n), 1: team kernel for n <= 128 (same arithmetic, bitwise), 2: + right-looking for n <= 64 (experimental)
     int64_t launches = 0;
 
     // options

@@ -237,6 +237,137 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_team_kernel(cons
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
+// ---- right-looking variant for n <= 64 (chol_alg = 2, EXPERIMENTAL: not the default, not yet run on hardware) -----
+// The left-looking dot is what the team kernel's dependent chain is made of (profiles/r1_cholesky_probe.txt).  Here
+// thread k owns ORIGINAL column k of the trailing matrix in registers for the whole factorisation and nothing is ever
+// swapped: a step is  pivot search -> u_k = A[q,k] / d  (q = pivot column; a uniform dynamic register index, read
+// through a jump table) -> publish u through shared memory -> rank-1 update of the register column (independent FMAs).
+// Positions follow LAPACK's interchange bookkeeping (the column at position j moves to the pivot's position), so pivots,
+// tie-breaking (first maximum in POSITION order) and the output layout equal the other kernels'; the rounding differs
+// (sequential fma down-dates instead of a 4-way split dot), so parity is by tolerance, not bitwise.
+template <int NMAX>
+__device__ __forceinline__ double rl_fetch(const double (&col)[NMAX], int q) {
+    double a = 0.0;
+#define RL_CASE(i) case i: a = col[(i) < NMAX ? (i) : 0]; break;
+    switch (q) {
+        RL_CASE(0) RL_CASE(1) RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7)
+        RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(11) RL_CASE(12) RL_CASE(13) RL_CASE(14) RL_CASE(15)
+        RL_CASE(16) RL_CASE(17) RL_CASE(18) RL_CASE(19) RL_CASE(20) RL_CASE(21) RL_CASE(22) RL_CASE(23)
+        RL_CASE(24) RL_CASE(25) RL_CASE(26) RL_CASE(27) RL_CASE(28) RL_CASE(29) RL_CASE(30) RL_CASE(31)
+        RL_CASE(32) RL_CASE(33) RL_CASE(34) RL_CASE(35) RL_CASE(36) RL_CASE(37) RL_CASE(38) RL_CASE(39)
+        RL_CASE(40) RL_CASE(41) RL_CASE(42) RL_CASE(43) RL_CASE(44) RL_CASE(45) RL_CASE(46) RL_CASE(47)
+        RL_CASE(48) RL_CASE(49) RL_CASE(50) RL_CASE(51) RL_CASE(52) RL_CASE(53) RL_CASE(54) RL_CASE(55)
+        RL_CASE(56) RL_CASE(57) RL_CASE(58) RL_CASE(59) RL_CASE(60) RL_CASE(61) RL_CASE(62) RL_CASE(63)
+        default: break;
+    }
+#undef RL_CASE
+    return a;
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const double *__restrict__ Gin, int n, double tol,
+                                                                          double *__restrict__ Wg, int *__restrict__ piv,
+                                                                          int *__restrict__ status) {
+    extern __shared__ double sm_dyn[];            // Gamma staging, then Uo[l + ldw * original column] = row l of the factor
+    __shared__ __align__(16) double s_u[NMAX];    // u of the current step by original column; 0 once a column is eliminated
+    __shared__ unsigned long long s_key[2];
+    __shared__ int s_idx[2], s_bad[2];
+    __shared__ int s_orig[NMAX];                  // position -> original column
+    __shared__ int s_rank;
+    const int ldw = n | 1;
+    const int tid = threadIdx.x;
+    constexpr int team = NMAX, nw = NMAX / 32;
+    double *W = sm_dyn;
+    for (int e = tid; e < n * n; e += CHT_THREADS) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
+    if (tid < NMAX) { s_orig[tid] = tid; s_u[tid] = 0.0; }
+    if (tid == 0) s_rank = n;
+    __syncthreads();
+    if (tid < team) {
+        const int k = tid, lane = tid & 31, w = tid >> 5;
+        const bool mine = k < n;
+        double col[NMAX];
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) col[i] = (mine && i < n) ? W[i + (size_t)ldw * k] : 0.0;
+        double ddk = mine ? W[k + (size_t)ldw * k] : 0.0;
+        bool alive = mine;
+        int posk = k;
+        double stop = 0.0;
+        int rank = n;
+        team_sync(nw, team);  // every column is in registers: the staging area becomes Uo
+        for (int j = 0; j < n; ++j) {
+            // ---- pivot: first maximum of the running diagonal in position order ----
+            const unsigned long long key = alive ? ordered_key(ddk) : 0ull;
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+            const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+            const bool win = alive && hi == mh && (unsigned)key == ml;
+            const unsigned mi = __reduce_min_sync(0xffffffffu, win ? (((unsigned)posk << 8) | (unsigned)k) : 0x7fffffffu);
+            int bb = __any_sync(0xffffffffu, alive && ddk != ddk);
+            unsigned long long bk = ((unsigned long long)mh << 32) | ml;
+            int bi = (int)mi;
+            if (nw > 1) {
+                if (lane == 0) { s_key[w] = bk; s_idx[w] = bi; s_bad[w] = bb; }
+                team_sync(nw, team);
+                const unsigned long long k0 = s_key[0], k1 = s_key[1];
+                const int i0 = s_idx[0], i1 = s_idx[1];
+                if (k1 > k0 || (k1 == k0 && i1 < i0)) { bk = k1; bi = i1; } else { bk = k0; bi = i0; }
+                bb = s_bad[0] | s_bad[1];
+            }
+            const double bv = key_value(bk);
+            bool fail;
+            if (j == 0) {
+                stop = (tol < 0.0) ? n * DBL_EPSILON * bv : tol;
+                fail = bb || !(bv > 0.0);
+            } else {
+                fail = bb || !(bv > stop);
+            }
+            if (fail) { rank = j; break; }  // uniform over the team
+            const int q = bi & 0xff, p = bi >> 8;
+            const double d = sqrt(bv);
+            // ---- interchange bookkeeping only: the pivot goes to position j, the column that sat there to position p ----
+            if (mine) {
+                if (k == q) { posk = j; s_orig[j] = k; }
+                else if (posk == j) { posk = p; s_orig[p] = k; }
+            }
+            // ---- row j of the factor ----
+            double u = 0.0;
+            if (alive) {
+                if (k == q) {
+                    W[j + (size_t)ldw * k] = d;
+                    s_u[k] = 0.0;
+                    alive = false;
+                } else {
+                    u = rl_fetch<NMAX>(col, q) / d;
+                    W[j + (size_t)ldw * k] = u;
+                    s_u[k] = u;
+                    ddk = fma(-u, u, ddk);
+                }
+            }
+            team_sync(nw, team);
+            // ---- rank-1 update of my column (rows of eliminated columns see u = 0) ----
+            if (alive) {
+#pragma unroll
+                for (int i = 0; i < NMAX; i += 2) {
+                    const double2 uu = *reinterpret_cast<const double2 *>(&s_u[i]);
+                    col[i] = fma(-uu.x, u, col[i]);
+                    col[i + 1] = fma(-uu.y, u, col[i + 1]);
+                }
+            }
+            if (nw == 1) __syncwarp();  // (two warps: the next pivot barrier orders these reads before the next s_u writes)
+        }
+        if (tid == 0) s_rank = rank;
+    }
+    __syncthreads();
+    const int rank = s_rank;
+    for (int e = tid; e < ldw * n; e += CHT_THREADS) {
+        const int c = e / ldw, l = e - c * ldw;
+        Wg[e] = (l <= c && l < rank) ? W[l + (size_t)ldw * s_orig[c]] : 0.0;
+    }
+    for (int e = tid; e < n; e += CHT_THREADS) piv[e] = s_orig[e];
+    if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
+}
+
 // One warp per right-hand side: x = P (U^T U)^{-1} P^T b with b = row i of M, result to row i of X.
 // Lane l keeps entries k = l + 32 e (e < E) in registers.  mode: 0 full solve, 1 forward only and
 // return ||y[0:nn]||^2 (leverage scores).
@@ -376,7 +507,15 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr[c->device & 63] = true;
     }
-    if (c->chol_alg == 1 && R <= CHT_MAX_N) {
+    if (c->chol_alg == 2 && R <= 64) {
+        const size_t smem = (size_t)ldw * R * 8;
+        if (R <= 32) pivoted_cholesky_rl_kernel<32><<<1, CHT_THREADS, smem, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev);
+        else pivoted_cholesky_rl_kernel<64><<<1, CHT_THREADS, smem, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ITCPD_OK;
+    }
+    if (c->chol_alg >= 1 && R <= CHT_MAX_N) {
         static bool attr_t[64] = {false};
         if (!attr_t[c->device & 63]) {
             CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));

@@ -384,3 +384,60 @@ def test_team_cholesky_rank_deficient_and_nan(engine):
     assert out[0][0] == out[1][0] == (1, 10)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
     assert out[0][3] == out[1][3] and out[0][3][0] == 1   # NaN: both kernels hand over to the QRCP path
+
+
+EXPERIMENTAL = os.environ.get("ITCPD_EXPERIMENTAL", "0") != "0"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="chol_alg=2 (right-looking Cholesky) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("R", [1, 5, 31, 32, 33, 50, 64])
+def test_right_looking_cholesky_matches_team_kernel(engine, R):
+    """solve.cu: pivoted_cholesky_rl_kernel -- same pivots/rank/status as the team kernel, values within rounding."""
+    dims = (36, 40, 28)
+    T, cp = make_problem(dims, R, seed=171 + R)
+    res = {}
+    for alg in (1, 2):
+        engine.set_option("chol_alg", alg)
+        engine.set_tensor(T)
+        engine.set_cpd(cp.factors, cp.lam)
+        engine.compute_grams()
+        Gam = engine.gram_hadamard(1)
+        engine.mttkrp(1, fetch=False)
+        first = engine.solve(1, 1e-6)
+        engine.normalize(1)
+        A1, lam1 = engine.get_factor(1), engine.get_lambda()
+        engine.set_cpd(cp.factors, cp.lam)
+        engine.compute_grams()
+        inner, norm2 = engine.sweep(20)
+        res[alg] = (first, A1, lam1, inner, norm2, np.linalg.cond(Gam))
+    engine.set_option("chol_alg", CHOL_DEFAULT)
+    assert res[1][0] == res[2][0]
+    tol = 1e-13 * max(res[1][5], 10.0)
+    assert relerr(res[2][1], res[1][1]) < tol and relerr(res[2][2], res[1][2]) < tol
+    nT2 = float(np.linalg.norm(T)) ** 2
+    assert np.max(np.abs(res[2][3] - res[1][3])) / nT2 < 1e-10 and np.max(np.abs(res[2][4] - res[1][4])) / nT2 < 1e-10
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="chol_alg=2 has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+def test_right_looking_cholesky_rank_deficient(engine):
+    dims, R = (30, 25, 20), 12
+    T, cp = make_problem(dims, R, seed=17)
+    f = [x.copy() for x in cp.factors]
+    for m in range(3):
+        f[m][:, 7] = f[m][:, 2]
+        f[m][:, 11] = f[m][:, 5]
+    out = {}
+    for alg in (1, 2):
+        engine.set_option("chol_alg", alg)
+        engine.set_tensor(T)
+        engine.set_cpd(f, cp.lam)
+        engine.compute_grams()
+        engine.gram_hadamard(1, fetch=False)
+        engine.mttkrp(1, fetch=False)
+        pr = engine.solve(1, 1e-6)
+        engine.normalize(1)
+        out[alg] = (pr, engine.get_factor(1), engine.get_lambda(), engine.leverage_scores(0))
+    engine.set_option("chol_alg", CHOL_DEFAULT)
+    assert out[1][0] == out[2][0] == (1, 10)
+    assert relerr(out[2][1], out[1][1]) < 1e-9 and relerr(out[2][2], out[1][2]) < 1e-9
+    assert relerr(out[2][3], out[1][3]) < 1e-9
