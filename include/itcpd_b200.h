@@ -159,7 +159,11 @@ int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *ro
 /* one sampled ALS mode update (ProjectionAlgorithm.jl:57-68): given 1-based pivots for `mode`, gathers T_s and K on
  * the device and solves  normal != 0: (K'K) \ (T_s K)'  (pivoted Cholesky, QRCP fallback)
  *                        normal == 0: qr(K, ColumnNorm()) \ T_s'  (pivoted-QR min-norm least squares, nsamp >= R);
- * then normalises and refreshes the Gram and the leverage scores of `mode` (post_solve of LevScoreSampled). */
+ * then normalises and refreshes the Gram and the leverage scores of `mode` (post_solve of LevScoreSampled).
+ * On a slab-sharded handle (itcpd_comm_init) the pivots are GLOBAL coordinates (the last mode spans all slabs) and must
+ * be identical on every rank: each rank contributes the samples whose last-mode coordinate lies in its slab and the
+ * sampled normal equations are all-reduced (csrc/sampled_sharded.cu); itcpd_leverage_scores then returns the scores of
+ * the LOCAL rows of the sharded factor, itcpd_sample_factor_matrices draws from the all-gathered scores. */
 int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol, int normal);
 
 /* qr(T_(mode), ColumnNorm()) of the pivot-projected setup (optimizers/.../randomized/qr_lev_score_sampled.jl:22-23,126-127):

@@ -305,6 +305,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); c->prevA[n].release(); }
     c->prev_lambda.release();
+    c->lev_gather.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -621,7 +622,6 @@ int itcpd_cpd_diff_terms(itcpd_ctx *c, double *inner_prev_curr, double *norm2_cu
     CHECK_CTX(c);
     USE_DEVICE(c);
     ARG_CHECK(c->has_snapshot && c->snapshot_rank == c->rank, "call itcpd_cpd_snapshot first (same rank)");
-    ARG_CHECK(!comm_active(c), "CPDiff/CPAngle scalars are single-GPU in this build");
     TRY(k_cpd_diff_terms(c, c->fit2.as<double>()));
     CUDA_TRY(cudaMemcpyAsync(c->pinned, c->fit2.p, 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -830,7 +830,8 @@ int itcpd_leverage_scores(itcpd_ctx *c, int mode, double *host_out) {
     CHECK_MODE(c, mode);
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
-    TRY(ensure_leverage(c, mode));
+    if (comm_active(c)) TRY(sharded_leverage(c, mode));  // the sharded factor returns the scores of the local rows
+    else TRY(ensure_leverage(c, mode));
     if (host_out) return d2h(c, host_out, c->lev[mode].p, (size_t)c->dims[mode] * 8);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ITCPD_OK;
@@ -842,11 +843,15 @@ int itcpd_sample_factor_matrices(itcpd_ctx *c, int skip_mode, int64_t nsamp, uin
     ARG_CHECK(nsamp >= 1 && host_out, "bad nsamp / null out pointer");
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
-    for (int m = 0; m < c->order; ++m)
-        if (m != skip_mode) TRY(ensure_leverage(c, m));
     const size_t bytes = (size_t)nsamp * (c->order - 1) * 8;
     TRY(c->samp_piv.reserve(bytes));
-    TRY(k_sample_rows(c, skip_mode, nsamp, seed, c->samp_piv.as<int64_t>()));
+    if (comm_active(c)) {
+        TRY(sharded_sample_rows(c, skip_mode, nsamp, seed, c->samp_piv.as<int64_t>()));
+    } else {
+        for (int m = 0; m < c->order; ++m)
+            if (m != skip_mode) TRY(ensure_leverage(c, m));
+        TRY(k_sample_rows(c, skip_mode, nsamp, seed, c->samp_piv.as<int64_t>()));
+    }
     CUDA_TRY(cudaMemcpyAsync(host_out, c->samp_piv.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ITCPD_OK;
@@ -873,7 +878,9 @@ static int check_pivots(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *pi
         if (m == mode) continue;
         for (int64_t s = 0; s < nsamp; ++s) {
             const int64_t v = piv[s + nsamp * col];
-            if (v < 1 || v > c->dims[m]) { set_error("pivot (%lld,%d) = %lld out of range [1,%lld]", (long long)s, col, (long long)v, (long long)c->dims[m]); return ITCPD_ERR_ARG; }
+            // pivots are global coordinates: on a sharded handle the last mode spans all the slabs
+            const int64_t ext = (comm_active(c) && m == c->order - 1) ? sharded_last_rows(c) : c->dims[m];
+            if (v < 1 || v > ext) { set_error("pivot (%lld,%d) = %lld out of range [1,%lld]", (long long)s, col, (long long)v, (long long)ext); return ITCPD_ERR_ARG; }
         }
         ++col;
     }
@@ -892,6 +899,7 @@ int itcpd_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *h
     CHECK_CTX(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(nsamp >= 1 && host_pivots && host_out, "bad nsamp / null pointer");
+    ARG_CHECK(!comm_active(c), "itcpd_pivot_hadamard is a single-GPU diagnostic; sharded handles go through itcpd_sampled_update");
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
     TRY(upload_pivots(c, mode, nsamp, host_pivots));
@@ -908,6 +916,10 @@ int itcpd_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *ho
     USE_DEVICE(c);
     TRY(upload_pivots(c, mode, nsamp, host_pivots));
     TRY(c->samp_T.reserve((size_t)nsamp * c->dims[mode] * 8));
+    if (comm_active(c)) {  // the rank's piece: owned fibres (zeros elsewhere), or its rows of the fibres along the sharded mode
+        TRY(sharded_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
+        return d2h(c, host_out, c->samp_T.p, (size_t)nsamp * c->dims[mode] * 8);
+    }
     TRY(k_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
     return d2h(c, host_out, c->samp_T.p, (size_t)nsamp * c->dims[mode] * 8);
 }
@@ -981,6 +993,7 @@ int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows
     NEED_T(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(l >= 1 && s >= 1 && rows0 && vals && host_out && c->has_tensor, "bad argument");
+    ARG_CHECK(!comm_active(c), "itcpd_sketch_unfolding needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
     USE_DEVICE(c);
     const int s_eff = std::min(s, l);
     const int64_t ncols = c->nelem / c->dims[mode];
@@ -1019,6 +1032,7 @@ int itcpd_qrcp_unfolding(itcpd_ctx *c, int mode, int64_t *piv_out, double *rdiag
     NEED_T(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(piv_out && c->has_tensor, "null out pointer / no tensor");
+    ARG_CHECK(!comm_active(c), "itcpd_qrcp_unfolding needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
     USE_DEVICE(c);
     const int64_t m = c->dims[mode], n = c->nelem / m, nr = std::min(m, n);
     TRY(c->qr_A.reserve((size_t)m * n * 8));
@@ -1035,6 +1049,7 @@ int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int
     NEED_T(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(l >= 1 && s >= 1 && t >= 1 && t <= l && piv_out && c->has_tensor, "bad argument (need 1 <= t <= l)");
+    ARG_CHECK(!comm_active(c), "itcpd_seqrcs needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
     USE_DEVICE(c);
     const int N = c->order;
     const int64_t m = c->dims[mode], n = c->nelem / m;
@@ -1105,6 +1120,7 @@ int itcpd_seqrcs_krp(itcpd_ctx *c, int mode, int l, int s, int t, int injective,
     CHECK_CTX(c);
     CHECK_MODE(c, mode);
     ARG_CHECK(l >= 1 && s >= 1 && t >= 1 && t <= l && piv_out && c->has_tensor && c->rank > 0 && c->A[0].p, "bad argument (need 1 <= t <= l and a CPD state)");
+    ARG_CHECK(!comm_active(c), "itcpd_seqrcs_krp needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
     USE_DEVICE(c);
     const int N = c->order, R = c->rank;
     int64_t n = 1;
@@ -1177,7 +1193,8 @@ int itcpd_set_projector(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *ho
     TRY(c->proj_piv[mode].reserve(pb));
     TRY(c->proj_T[mode].reserve((size_t)nsamp * c->dims[mode] * 8));
     CUDA_TRY(cudaMemcpyAsync(c->proj_piv[mode].p, host_pivots, pb, cudaMemcpyHostToDevice, c->stream));
-    TRY(k_gather_fibers(c, mode, nsamp, c->proj_piv[mode].as<int64_t>(), c->proj_T[mode].as<double>()));
+    if (comm_active(c)) TRY(sharded_gather_fibers(c, mode, nsamp, c->proj_piv[mode].as<int64_t>(), c->proj_T[mode].as<double>()));
+    else TRY(k_gather_fibers(c, mode, nsamp, c->proj_piv[mode].as<int64_t>(), c->proj_T[mode].as<double>()));
     c->proj_n[mode] = nsamp;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ITCPD_OK;
@@ -1191,6 +1208,11 @@ int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol, int normal) 
     ARG_CHECK(c->rank > 0 && c->A[mode].p, "CPD state not set");
     const int R = c->rank;
     const int64_t I = c->dims[mode], ns = c->proj_n[mode];
+    if (comm_active(c)) {
+        TRY(sharded_sampled_update(c, mode, ns, c->proj_piv[mode].as<int64_t>(), c->proj_T[mode].as<double>(), chol_tol, normal, false));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return ITCPD_OK;
+    }
     TRY(c->samp_K.reserve((size_t)ns * R * 8));
     TRY(k_pivot_hadamard(c, mode, ns, c->proj_piv[mode].as<int64_t>(), c->samp_K.as<double>()));
     TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->proj_T[mode].as<double>(), ns, chol_tol, normal));
@@ -1220,10 +1242,14 @@ int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *h
     ARG_CHECK(nsamp >= 1 && host_pivots && c->has_tensor, "bad nsamp / null pointer / no tensor");
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
-    ARG_CHECK(!comm_active(c), "the sampled path is single-GPU in this build");
     const int R = c->rank;
     const int64_t I = c->dims[mode];
     TRY(upload_pivots(c, mode, nsamp, host_pivots));
+    if (comm_active(c)) {
+        TRY(sharded_sampled_update(c, mode, nsamp, c->samp_piv.as<int64_t>(), nullptr, chol_tol, normal, true));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return ITCPD_OK;
+    }
     TRY(c->samp_K.reserve((size_t)nsamp * R * 8));
     TRY(c->samp_T.reserve((size_t)nsamp * I * 8));
     TRY(k_pivot_hadamard(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_K.as<double>()));

@@ -165,6 +165,7 @@ struct itcpd_ctx {
     bool peer_on = false;
     long long peer_epoch = 0;
     int64_t peer_slot_doubles = 0;
+    itcpd::DevBuf lev_gather;     // all-gathered leverage scores of the sharded factor (sampled_sharded.cu)
 };
 
 namespace itcpd {
@@ -204,6 +205,7 @@ int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t ro
 int qrcp_ls_solve(itcpd_ctx *c, const double *A, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force);  // qrcp.cu
 int k_solve_apply_peers(itcpd_ctx *c, const double *Gamma, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev);
 int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out);
+int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows_local, int64_t rows_total, int R, double *lev_out);
 
 // ---- sampled.cu ---------------------------------------------------------------------------
 int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev);
@@ -215,6 +217,16 @@ int k_unfold(itcpd_ctx *c, int mode, double *out);
 int k_omega_hadamard(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
 int k_pivot_hadamard_t(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
 int k_small_gemm_nn(itcpd_ctx *c, const double *A, const double *B, int64_t m, int64_t k, int n, double *C); // C = A B
+int k_cdf_sample(itcpd_ctx *c, const double *weights_dev, int64_t n, int64_t nsamp, uint64_t seed, uint64_t stream_id, int64_t *out_dev);
+
+// ---- sampled_sharded.cu (slab-sharded sampled path) ----------------------------------------
+int sharded_leverage(itcpd_ctx *c, int mode);
+int sharded_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev);
+int sharded_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
+int sharded_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, const double *Ts_cached, double chol_tol,
+                           int normal, bool refresh_leverage);
+int64_t sharded_last_rows(const itcpd_ctx *c);
+int64_t sharded_last_offset(const itcpd_ctx *c);
 
 // ---- comm.cu ------------------------------------------------------------------------------
 int comm_allreduce_sum(itcpd_ctx *c, double *buf, int64_t n);

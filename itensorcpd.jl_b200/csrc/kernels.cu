@@ -125,6 +125,7 @@ int k_cpd_diff_terms(itcpd_ctx *c, double *out2) {
         double *X = base + (size_t)(2 * n) * R * R, *G = base + (size_t)(2 * n + 1) * R * R;
         TRY(k_cross_gram(c, c->prevA[n].as<double>(), c->A[n].as<double>(), c->dims[n], R, X));
         TRY(k_cross_gram(c, c->A[n].as<double>(), c->A[n].as<double>(), c->dims[n], R, G));
+        if (comm_active(c) && n == N - 1) TRY(comm_allreduce_sum(c, X, (int64_t)2 * R * R));  // sharded factor: X and G are adjacent
         p.x[n] = X;
         p.g[n] = G;
     }

@@ -219,6 +219,16 @@ int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int
     return ITCPD_OK;
 }
 
+// one weighted draw of nsamp rows from an arbitrary device weight vector (the sharded path samples from gathered scores)
+int k_cdf_sample(itcpd_ctx *c, const double *weights_dev, int64_t n, int64_t nsamp, uint64_t seed, uint64_t stream_id, int64_t *out_dev) {
+    TRY(c->work.reserve((size_t)n * 8));
+    cdf_kernel<<<1, 1024, 0, c->stream>>>(weights_dev, n, c->work.as<double>());
+    sample_kernel<<<(unsigned)ceil_div(nsamp, 256), 256, 0, c->stream>>>(c->work.as<double>(), n, nsamp, seed, stream_id, out_dev);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
 // ---- small dense products for the sampled normal equations ----
 // C (m x n) = A (m x k) * B (k x n), all column-major; m = I_mode rows, k = nsamp, n = R
 __global__ void __launch_bounds__(256) gemm_nn_kernel(const double *__restrict__ A, const double *__restrict__ B, int64_t m, int64_t k, int n,

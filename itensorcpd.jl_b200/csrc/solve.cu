@@ -632,4 +632,21 @@ int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int
     return ITCPD_OK;
 }
 
+// the same for `rows` local rows of a factor with rows_total rows overall (slab-sharded factor; G is the global Gram)
+int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int64_t rows_total, int R, double *lev_out) {
+    if (rows_total <= R) {
+        fill_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)rows_total);
+        c->launches++;
+        return ITCPD_OK;
+    }
+    TRY(c->status.reserve(256));
+    int *st = c->status.as<int>() + 32;
+    TRY(run_cholesky(c, G, R, -1.0, st));
+    TRY(run_tri_solves(c, single_src(A), rows, R, lev_out, st, 1, 1));
+    scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)std::min<int64_t>(rows_total, R));
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
 }  // namespace itcpd

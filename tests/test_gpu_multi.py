@@ -23,3 +23,17 @@ def test_two_gpu_slab_sharding_matches_single_gpu(peer):
     env = dict(os.environ, ITCPD_PEER=peer)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("ITCPD_EXPERIMENTAL", "0") == "0",
+                    reason="the sharded sampled path has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+def test_two_gpu_sharded_sampled_path_matches_single_gpu():
+    """csrc/sampled_sharded.cu: owner-rank gathers + all-reduced sampled normal equations == the single-GPU sampled update."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = ["timeout", "120", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29619", os.path.join(ROOT, "tools", "multi_gpu_sampled_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "MULTI_GPU_SAMPLED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
