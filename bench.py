@@ -245,6 +245,8 @@ def run_ours(args, cfg):
         eng.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
         if os.environ.get("ITCPD_PEER", "1") == "1":
             # fused all-reduce + solve over NVLink peer memory (CUDA IPC handles exchanged through torch.distributed)
+            if os.environ.get("ITCPD_PEER_GRAPH", "0") == "1":
+                eng.set_option("peer_graph", 1)  # experimental: NCCL-free sweeps with device-side epochs, replayed from a CUDA graph
             mine = torch.frombuffer(bytearray(eng.peer_export()), dtype=torch.uint8).cuda()
             allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)

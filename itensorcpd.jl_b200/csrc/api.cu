@@ -219,16 +219,19 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         // published with a system-scope flag, and every rank's row-solve kernel sums the peers' slots while loading
         ARG_CHECK(c->dims[mode] * (int64_t)c->rank <= c->peer_slot_doubles,
                   "the peer exchange buffer was exported for a smaller shape/rank: call itcpd_peer_export/import again");
-        const int64_t epoch = ++c->peer_epoch;
-        const size_t slot_off = 256 + (size_t)(epoch & 1) * (size_t)c->peer_slot_doubles * 8;
+        const bool dev_epoch = peer_graph_active(c);  // capturable variant: epoch in device memory, slot = exchange index
+        const int64_t epoch = dev_epoch ? 0 : ++c->peer_epoch;
+        const size_t slot_off = 256 + (size_t)(dev_epoch ? mode : (epoch & 1)) * (size_t)c->peer_slot_doubles * 8;
         TRY(mttkrp_device(c, mode, reinterpret_cast<double *>((char *)c->xchg.p + slot_off), false));
-        TRY(peer_signal(c, epoch));
+        if (dev_epoch) TRY(peer_graph_signal(c));
+        else TRY(peer_signal(c, epoch));
         if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+        if (dev_epoch) TRY(peer_graph_wait(c));
         PeerSrc src;
         memset(&src, 0, sizeof(src));
         src.n = c->peer_n;
         for (int q = 0; q < c->peer_n; ++q) src.p[q] = reinterpret_cast<const double *>((const char *)c->peer_base[q] + slot_off);
-        src.flags = reinterpret_cast<const volatile long long *>(c->xchg.p);
+        src.flags = dev_epoch ? nullptr : reinterpret_cast<const volatile long long *>(c->xchg.p);  // null: the wait already happened
         src.epoch = epoch;
         src.reduced_out = c->M[mode].as<double>();
         TRY(k_solve_apply_peers(c, c->Gamma.as<double>(), src, c->dims[mode], c->rank, c->X.as<double>(), status_dev));
@@ -306,6 +309,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->A[n].release(); c->G[n].release(); c->M[n].release(); c->lev[n].release(); c->proj_piv[n].release(); c->proj_T[n].release(); c->prevA[n].release(); }
     c->prev_lambda.release();
     c->lev_gather.release();
+    c->peer_epochs.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -350,6 +354,10 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
+    else if (n == "peer_graph") {
+        ARG_CHECK(!c->peer_on, "set peer_graph before itcpd_peer_export / itcpd_peer_import");
+        c->peer_graph = value != 0;
+    }
     else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 2, "chol_alg must be 0, 1 or 2"); c->chol_alg = (int)value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
@@ -665,7 +673,7 @@ static void graph_key(const itcpd_ctx *c, double tol, int64_t key[24]) {
     key[k++] = (int64_t)(intptr_t)c->T.p; key[k++] = (int64_t)(intptr_t)c->A[0].p; key[k++] = (int64_t)(intptr_t)c->sweep_log.p;
     key[k++] = c->order; key[k++] = c->rank; key[k++] = c->split_a; key[k++] = c->split_b; key[k++] = c->mttkrp_alg;
     key[k++] = c->swizzle; key[k++] = c->tile_warps; key[k++] = c->stream_k; key[k++] = c->tma3d; key[k++] = c->overlap_factor;
-    key[k++] = (int64_t)(intptr_t)c->comm; key[k++] = c->graph_epoch;
+    key[k++] = (int64_t)(intptr_t)c->comm ^ ((int64_t)c->peer_graph << 1) ^ (int64_t)c->peer_on; key[k++] = c->graph_epoch;
     memcpy(&key[k++], &tol, 8);
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) key[k++] = n < c->order ? c->dims[n] : 0;
 }
@@ -689,8 +697,8 @@ int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
     CUDA_TRY(cudaMemsetAsync(c->sweep_log.p, 0, 8, c->stream));
     c->sweep_log_reduced = false;
     int done = 0;
-    // NCCL collectives are not captured: a sharded sweep is launched kernel by kernel
-    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3 && !comm_active(c);
+    // NCCL collectives are not captured: a sharded sweep is launched kernel by kernel unless it is NCCL-free (peer_graph)
+    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3 && (!comm_active(c) || peer_graph_active(c));
     if (want_graph) {
         int64_t key[24];
         graph_key(c, chol_tol, key);
@@ -1294,9 +1302,14 @@ int itcpd_peer_export(itcpd_ctx *c, void *handle64_out) {
     int64_t maxrows = 0;
     for (int n = 0; n + 1 < c->order; ++n) maxrows = std::max(maxrows, c->dims[n]);
     c->peer_slot_doubles = maxrows * c->rank;
+    c->peer_slots = std::max(2, c->order - 1);  // peer_graph uses one partial-M slot per exchange of a sweep
+    c->peer_small_doubles = (int64_t)c->rank * c->rank + 64;
+    c->peer_small_off = 256 + (size_t)c->peer_slots * (size_t)c->peer_slot_doubles * 8;
     c->xchg.release();
-    TRY(c->xchg.reserve(256 + 2 * (size_t)c->peer_slot_doubles * 8));
+    TRY(c->xchg.reserve(c->peer_small_off + 2 * (size_t)c->peer_small_doubles * 8));
     CUDA_TRY(cudaMemset(c->xchg.p, 0, 256));
+    TRY(c->peer_epochs.reserve(64));
+    CUDA_TRY(cudaMemset(c->peer_epochs.p, 0, 64));
     CUDA_TRY(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->xchg.p));

@@ -66,6 +66,7 @@ bool comm_active(const itcpd_ctx *c) { return c->comm != nullptr && c->comm->nra
 
 int comm_allreduce_sum(itcpd_ctx *c, double *buf, int64_t n) {
     if (!comm_active(c)) return ITCPD_OK;
+    if (peer_graph_active(c) && n <= c->peer_small_doubles) return peer_allreduce_small(c, buf, n);  // NCCL-free (capturable) sweeps
     NcclApi *a = nccl_api();
     if (!a) return ITCPD_ERR_COMM;
     NCCL_TRY(a->allreduce(buf, buf, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm->comm, c->stream));

@@ -166,6 +166,13 @@ struct itcpd_ctx {
     long long peer_epoch = 0;
     int64_t peer_slot_doubles = 0;
     itcpd::DevBuf lev_gather;     // all-gathered leverage scores of the sharded factor (sampled_sharded.cu)
+    // peer_graph.cu (option "peer_graph", off by default): device-side exchange epochs [0] partial-M, [1] small all-reduce;
+    // small slots live behind the partial-M slots of the exchange buffer
+    int peer_graph = 0;
+    itcpd::DevBuf peer_epochs;
+    size_t peer_small_off = 0;
+    int64_t peer_small_doubles = 0;
+    int peer_slots = 2;
 };
 
 namespace itcpd {
@@ -227,6 +234,12 @@ int sharded_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t 
                            int normal, bool refresh_leverage);
 int64_t sharded_last_rows(const itcpd_ctx *c);
 int64_t sharded_last_offset(const itcpd_ctx *c);
+
+// ---- peer_graph.cu ------------------------------------------------------------------------
+bool peer_graph_active(const itcpd_ctx *c);
+int peer_graph_signal(itcpd_ctx *c);
+int peer_graph_wait(itcpd_ctx *c);
+int peer_allreduce_small(itcpd_ctx *c, double *buf, int64_t n);
 
 // ---- comm.cu ------------------------------------------------------------------------------
 int comm_allreduce_sum(itcpd_ctx *c, double *buf, int64_t n);

@@ -37,3 +37,18 @@ def test_two_gpu_sharded_sampled_path_matches_single_gpu():
            "127.0.0.1", "--master-port", "29619", os.path.join(ROOT, "tools", "multi_gpu_sampled_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "MULTI_GPU_SAMPLED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("ITCPD_EXPERIMENTAL", "0") == "0",
+                    reason="peer_graph (NCCL-free, graph-replayed sharded sweeps) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+def test_two_gpu_peer_graph_matches_single_gpu():
+    """csrc/peer_graph.cu: device-side exchange epochs + peer small all-reduce, the sharded sweep replayed from a CUDA graph."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = ["timeout", "120", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29620", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+    env = dict(os.environ, ITCPD_PEER="1", ITCPD_PEER_GRAPH="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
