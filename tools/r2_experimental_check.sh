@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round-2 opener: first hardware run of everything written after round 1's GPU budget was spent.
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/r2_experimental_check.sh'
+# 1. the whole GPU suite with the opt-in tests (right-looking Cholesky chol_alg=2, sharded sampled path, peer_graph)
+# 2. A/B timings: chol_alg 1 vs 2 on the per-rank slab and config A; 2-GPU sweeps with and without peer_graph
+mkdir -p gpurun_out
+export ITCPD_EXPERIMENTAL=1
+timeout 400 python -m pytest tests -m gpu -q > gpurun_out/r2_exp_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_exp_tests.log
+tail -15 gpurun_out/r2_exp_tests.log
+B="timeout 60 python bench.py --no-cpu --no-e2e"
+for chol in 1 2; do
+  ITCPD_CHOL=$chol $B --config B8 --steps 50 > gpurun_out/r2_B8_chol$chol.json 2>> gpurun_out/r2_err.log
+  ITCPD_CHOL=$chol $B --config A --steps 50 > gpurun_out/r2_A_chol$chol.json 2>> gpurun_out/r2_err.log
+done
+for pg in 0 1; do
+  ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
+      bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/r2_N2_peergraph$pg.json 2>> gpurun_out/r2_err.log
+done
+for f in gpurun_out/r2_*.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], round(d["value"], 2), "sweeps/s", round(d["ms_per_step"], 4), "ms")
+except Exception as e:
+    print(sys.argv[1], "ERR", e)
+PY
+done
