@@ -57,7 +57,15 @@ int itcpd_device_info(itcpd_ctx *ctx, int *sm_count, int *cc_major, int *cc_mino
 int itcpd_synchronize(itcpd_ctx *ctx);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t itcpd_launch_count(itcpd_ctx *ctx);
-/* runtime options: "mttkrp_alg" (0/1), "swizzle" (1/0, debug), "tile_warps" (4|8) ... */
+/* runtime options (name, values; * = default):
+ *   "mttkrp_alg"     0* dimension tree (KRPFreeNormal / KRPNormal results), 1 direct one-pass-per-mode MTTKRP
+ *   "split_a","split_b"  force the dimension-tree split points (0* = traffic cost model)
+ *   "tile_warps"     4 | 8*  warps per GEMM CTA;  "swizzle" 1* | 0 (debug);  "tma3d" 1* | 0;  "stream_k" 0 | 1* | 2
+ *   "overlap_factor" 1* Gram-Hadamard + Cholesky on a side stream under the GEMM;  "use_graph" 1* CUDA-graph replay of sweeps
+ *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 64, experimental)
+ *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
+ *   "peer_graph"     0* | 1 (experimental) NCCL-free sharded sweeps with device-side exchange epochs; set before itcpd_peer_export
+ * environment at itcpd_create: ITCPD_CHOL=0|1|2, ITCPD_NO_GRAPH=1, ITCPD_NO_SWIZZLE=1 */
 int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);
 
 /* ---- target tensor (ALS.target, als_optimizer.jl:5-10; decompose.jl:5-7 wraps without copy) - */
