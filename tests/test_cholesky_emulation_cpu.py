@@ -22,11 +22,11 @@ double sm_dyn[129 * 128 + 256];
 inline void team_sync(int nw, int team) { if (nw == 1) __syncwarp(); else emu_named_barrier(); }
 #define ITCPD_SOLVE_CHOLESKY 0
 #define ITCPD_SOLVE_QRCP 1
-namespace itcpd {
+namespace itcpd_emu {  // not `itcpd`: libitcpd_b200.so (RTLD_GLOBAL) exports host stubs with the kernels' names
 %(kernels)s
 }
 extern "C" int run_cholesky(int which, int n, double tol, const double *G, double *W, int *piv, int *status) {
-    using namespace itcpd;
+    using namespace itcpd_emu;
     const int team = (n + 31) & ~31;
     if (which == 0) {
         const int threads = n <= 64 ? 64 : (n <= 128 ? 128 : 256);
@@ -61,7 +61,7 @@ def _build(tsan: bool, break_sync: bool = False):
     open(cpp, "w").write('#include "simt_emu.h"\n' + driver % {"kernels": body})
     flags = ["-O1", "-g", "-fsanitize=thread"] if tsan else ["-O2"]
     subprocess.run(["g++", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", os.path.join(ROOT, "tests"), *flags, "-o", so, cpp,
-                    "-lpthread"], check=True, capture_output=True)
+                    "-lpthread", "-Wl,-Bsymbolic"], check=True, capture_output=True)
     return so
 
 

@@ -56,7 +56,7 @@ def emu():
         cpp = os.path.join(td, "emu.cpp")
         so = os.path.join(td, "emu.so")
         open(cpp, "w").write(SHIM + body + DRIVER)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, cpp], check=True, capture_output=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-o", so, cpp], check=True, capture_output=True)
         lib = C.CDLL(so)
         yield lib
 
