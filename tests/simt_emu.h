@@ -100,6 +100,15 @@ inline T __shfl_down_sync(unsigned, T v, int o) {
     const int l = emu::lane();
     return emu::collective<T>(v, [l, o](T *a) { return (l + o < 32) ? a[l + o] : a[l]; });
 }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    return emu::collective<T>(v, [src](T *a) { return a[src & 31]; });
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int m) {
+    const int l = emu::lane();
+    return emu::collective<T>(v, [l, m](T *a) { return a[(l ^ m) & 31]; });
+}
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 
