@@ -295,6 +295,17 @@ def run_ours(args, cfg):
     eng.sweep_async(Kr)
     gemm_ms, gemm_n = eng.gemm_timing(True)
     eng.set_option("time_gemm", 0)
+    phases = None
+    if os.environ.get("ITCPD_BENCH_PHASES", "0") == "1":  # diagnostic: where a sweep's time goes (events after every phase, no graph)
+        try:
+            eng.set_option("time_phases", 1)
+            eng.phase_timing(True)
+            eng.sweep_async(5)
+            ph = eng.phase_timing(True)
+            eng.set_option("time_phases", 0)
+            phases = {k: v / 5.0 for k, v in ph.items() if k != "marks"}
+        except Exception as ex:
+            phases = {"error": repr(ex)}
     if dist is not None:
         import torch
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -331,6 +342,8 @@ def run_ours(args, cfg):
                                                                                        if world > 1 and os.environ.get("ITCPD_PEER", "1") == "1" else ""), "l2": "flush between steps" if flush else "inputs >> L2",
                            "fit_after_timed_sweeps": float(fit_last), "qrcp_fallbacks": int(fallbacks)},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof}
+        if phases is not None:
+            line["config"]["phase_ms_per_sweep"] = phases
 
     # ---- the README stopping rule, reported separately and outside the timed region: FitCheck(1e-3, 100, |T|)
     # from the same initial guess; on a pure-noise tensor it stops after a few sweeps (fit_check.jl:43-52) ----

@@ -64,6 +64,7 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "overlap_factor" 1* Gram-Hadamard + Cholesky on a side stream under the GEMM;  "use_graph" 1* CUDA-graph replay of sweeps
  *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 64, experimental)
  *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
+ *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph
  *   "peer_graph"     0* | 1 (experimental) NCCL-free sharded sweeps with device-side exchange epochs; set before itcpd_peer_export
  * environment at itcpd_create: ITCPD_CHOL=0|1|2, ITCPD_NO_GRAPH=1, ITCPD_NO_SWIZZLE=1 */
 int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);
@@ -220,6 +221,11 @@ int itcpd_peer_disable(itcpd_ctx *ctx);
 /* average device time (ms, CUDA events on the handle's stream) of the dominant GEMM kernel over
  * the launches since the last reset, and how many launches that was */
 int itcpd_gemm_timing(itcpd_ctx *ctx, int reset, double *avg_ms, int64_t *launches);
+/* With option "time_phases" = 1 (disables the graph) the sweep driver records a CUDA event after every phase of a mode
+ * update; this returns the accumulated milliseconds per phase id since the last reset:
+ * 0 between modes, 1 MTTKRP (pack + GEMM + second level [+ NCCL all-reduce]), 2 peer signal, 3 solve (join with the
+ * side-stream factorisation, peer wait, row solves), 4 normalise, 5 Gram refresh, 6 fit scalars.  Measurement only. */
+int itcpd_phase_timing(itcpd_ctx *ctx, int reset, int nphases, double *ms_by_phase, int64_t *marks);
 /* FP64 tensor-pipe peak probe: register-resident DMMA.8x8x4 issue loop on every SM; returns
  * achieved TFLOP/s (2*8*8*4 flops per instruction) -- a roofline denominator for this box. */
 int itcpd_probe_dmma_peak(itcpd_ctx *ctx, double *tflops);

@@ -86,6 +86,7 @@ _SIGS = {
     "itcpd_peer_disable": (C.c_int, [C.c_void_p]),
     "itcpd_allgather_factor": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_dp]),
     "itcpd_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "itcpd_phase_timing": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "itcpd_probe_dmma_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "itcpd_probe_dfma_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "itcpd_event_record": (C.c_int, [C.c_void_p, C.c_int]),

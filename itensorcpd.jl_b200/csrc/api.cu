@@ -199,7 +199,24 @@ static int peer_signal(itcpd_ctx *c, long long epoch) {
     return ITCPD_OK;
 }
 
+// phase ids of itcpd_phase_timing: time between two marks is charged to the later mark
+enum { PH_MODE_BEGIN = 0, PH_MTTKRP = 1, PH_SIGNAL = 2, PH_SOLVE = 3, PH_NORMALIZE = 4, PH_GRAM = 5, PH_FIT = 6, PH_COUNT = 7 };
+static int phase_mark(itcpd_ctx *c, int id) {
+    if (!c->time_phases) return ITCPD_OK;
+    if (c->phase_used == c->phase_events.size()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->phase_events.push_back(e);
+        c->phase_ids.push_back(0);
+    }
+    c->phase_ids[c->phase_used] = id;
+    CUDA_TRY(cudaEventRecord(c->phase_events[c->phase_used], c->stream));
+    c->phase_used++;
+    return ITCPD_OK;
+}
+
 static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_dev) {
+    TRY(phase_mark(c, PH_MODE_BEGIN));
     // fork: Gram-Hadamard + pivoted Cholesky depend only on the Grams, so they run on the side stream
     // underneath the MTTKRP (the persistent GEMM leaves room for one small CTA); join before the row solves
     cudaStream_t main_stream = c->stream;
@@ -223,8 +240,10 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         const int64_t epoch = dev_epoch ? 0 : ++c->peer_epoch;
         const size_t slot_off = 256 + (size_t)(dev_epoch ? mode : (epoch & 1)) * (size_t)c->peer_slot_doubles * 8;
         TRY(mttkrp_device(c, mode, reinterpret_cast<double *>((char *)c->xchg.p + slot_off), false));
+        TRY(phase_mark(c, PH_MTTKRP));
         if (dev_epoch) TRY(peer_graph_signal(c));
         else TRY(peer_signal(c, epoch));
+        TRY(phase_mark(c, PH_SIGNAL));
         if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
         if (dev_epoch) TRY(peer_graph_wait(c));
         PeerSrc src;
@@ -237,12 +256,16 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         TRY(k_solve_apply_peers(c, c->Gamma.as<double>(), src, c->dims[mode], c->rank, c->X.as<double>(), status_dev));
     } else {
         TRY(mttkrp_device(c, mode));
+        TRY(phase_mark(c, PH_MTTKRP));
         if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
         TRY(k_solve_apply(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, c->X.as<double>(), status_dev));
     }
+    TRY(phase_mark(c, PH_SOLVE));
     TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
+    TRY(phase_mark(c, PH_NORMALIZE));
     c->fver[mode]++;
     TRY(gram_device(c, mode));
+    TRY(phase_mark(c, PH_GRAM));
     return ITCPD_OK;
 }
 
@@ -311,6 +334,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     c->lev_gather.release();
     c->peer_epochs.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : c->phase_events) cudaEventDestroy(ev);
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->sweep_graph_exec) { cudaGraphExecDestroy(c->sweep_graph_exec); c->sweep_graph_exec = nullptr; }
@@ -351,6 +375,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "split_a") { c->force_split_a = (int)value; if (c->has_tensor) choose_splits(c); }
     else if (n == "split_b") { c->force_split_b = (int)value; if (c->has_tensor) choose_splits(c); }
     else if (n == "time_gemm") c->time_gemm = value != 0;
+    else if (n == "time_phases") { c->time_phases = value != 0; c->phase_used = 0; }
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
@@ -661,6 +686,7 @@ static int one_sweep_device(itcpd_ctx *c, double chol_tol) {
     const int N = c->order;
     for (int mode = 0; mode < N; ++mode) TRY(mode_update_device(c, mode, chol_tol, c->status.as<int>() + 3 * mode));
     TRY(k_fit_terms(c, c->fit2.as<double>(), false));
+    TRY(phase_mark(c, PH_FIT));
     log_sweep_kernel<<<1, 1, 0, c->stream>>>(c->fit2.as<double>(), c->status.as<int>(), N, c->sweep_log.as<double>() + 1,
                                             reinterpret_cast<unsigned long long *>(c->sweep_log.p), (unsigned long long)c->sweep_log_cap);
     c->launches++;
@@ -698,7 +724,7 @@ int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
     c->sweep_log_reduced = false;
     int done = 0;
     // NCCL collectives are not captured: a sharded sweep is launched kernel by kernel unless it is NCCL-free (peer_graph)
-    const bool want_graph = c->use_graph && !c->time_gemm && nsweeps >= 3 && (!comm_active(c) || peer_graph_active(c));
+    const bool want_graph = c->use_graph && !c->time_gemm && !c->time_phases && nsweeps >= 3 && (!comm_active(c) || peer_graph_active(c));
     if (want_graph) {
         int64_t key[24];
         graph_key(c, chol_tol, key);
@@ -1365,6 +1391,23 @@ int itcpd_gemm_timing(itcpd_ctx *c, int reset, double *avg_ms, int64_t *launches
     if (avg_ms) *avg_ms = c->gemm_events_used ? tot / (double)c->gemm_events_used : 0.0;
     if (launches) *launches = (int64_t)c->gemm_events_used;
     if (reset) c->gemm_events_used = 0;
+    return ITCPD_OK;
+}
+
+int itcpd_phase_timing(itcpd_ctx *c, int reset, int nphases, double *ms_by_phase, int64_t *marks) {
+    CHECK_CTX(c);
+    ARG_CHECK(nphases >= 1 && ms_by_phase, "bad phase_timing arguments");
+    USE_DEVICE(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nphases; ++i) ms_by_phase[i] = 0.0;
+    for (size_t i = 1; i < c->phase_used; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->phase_events[i - 1], c->phase_events[i]));
+        const int id = c->phase_ids[i];
+        if (id >= 0 && id < nphases) ms_by_phase[id] += ms;
+    }
+    if (marks) *marks = (int64_t)c->phase_used;
+    if (reset) c->phase_used = 0;
     return ITCPD_OK;
 }
 

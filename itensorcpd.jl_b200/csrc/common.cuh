@@ -145,6 +145,11 @@ struct itcpd_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     size_t gemm_events_used = 0;
     bool time_gemm = false;
+    // optional per-phase CUDA events of the sweep driver (option "time_phases"; itcpd_phase_timing)
+    bool time_phases = false;
+    std::vector<cudaEvent_t> phase_events;
+    std::vector<int> phase_ids;
+    size_t phase_used = 0;
 
     // whole-sweep CUDA graph + device-side result log
     int use_graph = 1;

@@ -353,6 +353,15 @@ class Engine:
         check(self._L.itcpd_gemm_timing(self._h, int(reset), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    PHASES = ("between_modes", "mttkrp", "peer_signal", "solve", "normalize", "gram", "fit")
+
+    def phase_timing(self, reset=True) -> dict:
+        """milliseconds per sweep phase since the last reset (option time_phases=1)"""
+        ms = np.zeros(len(self.PHASES))
+        n = C.c_int64()
+        check(self._L.itcpd_phase_timing(self._h, int(reset), len(self.PHASES), _addr(ms), C.byref(n)))
+        return dict(zip(self.PHASES, ms.tolist()), marks=n.value)
+
     def probe_dmma_peak(self) -> float:
         v = C.c_double()
         check(self._L.itcpd_probe_dmma_peak(self._h, C.byref(v)))

@@ -14,7 +14,7 @@ for chol in 1 2; do
   ITCPD_CHOL=$chol $B --config A --steps 50 > gpurun_out/r2_A_chol$chol.json 2>> gpurun_out/r2_err.log
 done
 for pg in 0 1; do
-  ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
+  ITCPD_BENCH_PHASES=1 ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
       bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/r2_N2_peergraph$pg.json 2>> gpurun_out/r2_err.log
 done
 for f in gpurun_out/r2_*.json; do python - "$f" <<'PY'
