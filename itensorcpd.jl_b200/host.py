@@ -16,7 +16,7 @@ keep the reference's 1-based int64 convention.
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 

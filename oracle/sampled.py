@@ -17,7 +17,6 @@ import os
 from typing import Optional, Sequence
 
 import numpy as np
-from scipy.linalg import lapack as _lapack
 from scipy.linalg import qr as _scipy_qr
 
 from . import cpals

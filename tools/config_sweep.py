@@ -1,5 +1,5 @@
 """Timing of every BASELINE.json single-GPU configuration (device resident), printed as JSON lines."""
-import json, os, sys, time
+import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import itcpd
