@@ -108,6 +108,7 @@ int ensure_cpd_buffers(itcpd_ctx *c) {
 
 static void invalidate_all(itcpd_ctx *c) {
     c->graph_epoch++;
+    c->i8_tensor_epoch++;
     c->PA.valid = c->PB.valid = false;
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->m_valid[n] = false; c->fver[n]++; }
 }
@@ -146,7 +147,12 @@ static int ensure_partial(itcpd_ctx *c, int kind) {
     if (kind == 0) { rows = c->ld0; for (int n = 1; n < split; ++n) rows *= c->dims[n]; }
     else { for (int n = split; n < c->order; ++n) rows *= c->dims[n]; }
     TRY(P.buf.reserve((size_t)rows * c->rank * 8));
-    TRY(launch_partial_gemm(c, kind, split, P.buf.as<double>()));
+    int st = ITCPD_ERR_UNSUPPORTED;
+    if (c->gemm_i8) {  // experimental INT8 tensor-core path; shapes outside its envelope fall through to the DMMA kernel
+        st = launch_partial_gemm_i8(c, kind, split, P.buf.as<double>());
+        if (st != ITCPD_OK && st != ITCPD_ERR_UNSUPPORTED) return st;
+    }
+    if (st != ITCPD_OK) TRY(launch_partial_gemm(c, kind, split, P.buf.as<double>()));
     P.valid = true;
     P.split = split;
     for (int n = d0; n < d1; ++n) P.dep_version[n] = c->fver[n];
@@ -333,6 +339,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     c->prev_lambda.release();
     c->lev_gather.release();
     c->peer_epochs.release();
+    c->i8_exp[0].buf.release(); c->i8_exp[1].buf.release(); c->i8_eb.release(); c->i8_bdig.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->phase_events) cudaEventDestroy(ev);
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
@@ -379,6 +386,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
+    else if (n == "gemm_i8") c->gemm_i8 = value != 0;
     else if (n == "peer_graph") {
         ARG_CHECK(!c->peer_on, "set peer_graph before itcpd_peer_export / itcpd_peer_import");
         c->peer_graph = value != 0;

@@ -58,6 +58,14 @@ struct Partial {
     uint64_t dep_version[ITCPD_MAX_ORDER];  // versions of the contracted factors when computed
 };
 
+// gemm_i8.cu: cached row exponents of one unfolding of the tensor
+struct I8ExpCache {
+    DevBuf buf;
+    bool valid = false;
+    int split = 0;
+    int64_t tensor_epoch = -1;
+};
+
 struct Comm;  // comm.cu
 
 #define ITCPD_MAX_PEERS 16
@@ -178,6 +186,11 @@ struct itcpd_ctx {
     size_t peer_small_off = 0;
     int64_t peer_small_doubles = 0;
     int peer_slots = 2;
+    // gemm_i8.cu (option "gemm_i8", off by default): INT8 tensor-core digit-split contraction
+    int gemm_i8 = 0;
+    int64_t i8_tensor_epoch = 0;      // bumped whenever the tensor contents change
+    itcpd::I8ExpCache i8_exp[2];
+    itcpd::DevBuf i8_eb, i8_bdig;
 };
 
 namespace itcpd {
@@ -189,6 +202,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 //  kind 0 ("A"): out[m, r] = sum_k T[m + M*k] K[k, r]; m in [0,M) = stored modes [0,split), k = modes [split,N)
 //  kind 1 ("B"): out[n, r] = sum_m T[m + Mc*n] K[m, r]; m = stored modes [0,split), n = modes [split,N)
 int launch_partial_gemm(itcpd_ctx *c, int kind, int split, double *out);
+int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out);  // gemm_i8.cu (experimental)
 int probe_dmma(itcpd_ctx *c, double *tflops);
 int probe_dfma(itcpd_ctx *c, double *tflops);
 

@@ -1,0 +1,527 @@
+// EXPERIMENTAL (option "gemm_i8", off by default; written without GPU access, not yet run on hardware):
+// the partial contraction of the dimension tree on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators)
+// with FP64-equivalent accuracy, by splitting both operands into 7 balanced base-128 digits (an Ozaki-style scheme).
+//
+//   out[m, r] = sum_k T[m, k] K[k, r]                                  (kind 0; kind 1 is the transposed view of T)
+//   T[m, k] ~= XA[m, k] 2^(ea[m] - 49),  K[k, r] ~= XB[k, r] 2^(eb[r] - 49),   X* = 49-bit signed fixed point
+//   X = sum_{p=0..6} d_p 128^(6-p),  d_p in [-64, 64]  (balanced digits: add 0x40 to every 7-bit field, extract, subtract)
+//   sum_k XA XB = sum_{p,q} 128^(12-p-q) S_pq,   S_pq = sum_k dA_p dB_q   exact in int32 (|S| <= K * 4096)
+// Only the 28 digit pairs with p + q <= 6 are formed (relative Frobenius error 5e-14 .. 1e-13 for the operands of this
+// path, tools/ozaki_numerics.py); all pairs of equal weight p + q = t share ONE int32 accumulator in TMEM, so a 128 x 64
+// tile needs 7 x 64 = 448 of the 512 TMEM columns.  Stacking the B digit planes along N turns the 28 products of a
+// k-step into 10 instructions:  A_p (128 x 32)  x  [B_0; B_1; ..; B_{6-p}] (64 (7-p) x 32)  ->  accumulators t = p .. 6.
+// At 4.5 POPS the 28 products cost what 0.3 of the FP64 DMMA pass costs; digit extraction (~30 integer ops per element)
+// and the HBM stream of T (1.33 ms at 1024^3) then bound the pass instead of the FP64 pipe (3.9 ms).
+//
+// Warp roles (10 warps, 1 CTA per SM, persistent over 128-row tiles):
+//   warps 0-7  converters: FP64 tile (TMA) -> 7 int8 digit planes in the canonical UMMA shared-memory layout
+//   warps 0-3  also the epilogue: TMEM -> registers -> sum_t acc_t 2^(-7t) in FP64 -> scale -> global
+//   warp 8     TMA producer (FP64 tiles of T, packed digit planes of the Khatri-Rao operand)
+//   warp 9     TMEM allocation + the single-thread MMA issuer
+#include "common.cuh"
+
+namespace itcpd {
+
+constexpr int I8_NDIG = 7;
+constexpr int I8_FRAC = 49;             // fixed-point bits = 7 * I8_NDIG
+constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 32;
+constexpr int I8_FSTAGES = 3, I8_DSTAGES = 2;
+constexpr int I8_F_BYTES = I8_BM * I8_BK * 8;                  // 32768: one FP64 tile
+constexpr int I8_A_PLANE = I8_BM * I8_BK;                      // 4096
+constexpr int I8_A_BYTES = I8_NDIG * I8_A_PLANE;               // 28672
+constexpr int I8_B_BYTES = I8_NDIG * I8_BN * I8_BK;            // 14336
+constexpr int I8_SMEM = I8_FSTAGES * I8_F_BYTES + I8_DSTAGES * (I8_A_BYTES + I8_B_BYTES) + 256 + 1024;
+constexpr int I8_EXP_ZERO = -100000;                           // exponent of an all-zero row / column
+
+// ------------------------------------------------------------------------------------------------------------------
+// digit arithmetic (barrier-free device code: exercised on the CPU by tests/test_i8_digits_emulation_cpu.py)
+// ------------------------------------------------------------------------------------------------------------------
+// smallest E with |x| 2^-E < 1/2
+__device__ __forceinline__ int i8_exponent(double amax) {
+    if (!(amax > 0.0)) return I8_EXP_ZERO;
+    const int biased = (int)((unsigned long long)__double_as_longlong(amax) >> 52) & 0x7ff;
+    if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(49-E) representable)
+    return biased - 1022 + 1;          // amax in [2^(b-1023), 2^(b-1022))  ->  amax 2^-(b-1021) < 1/2
+}
+// 2^(49 - E) as a double (0 for an all-zero row: every digit is then 0)
+__device__ __forceinline__ double i8_scale(int E) {
+    if (E == I8_EXP_ZERO) return 0.0;
+    return __longlong_as_double((long long)(1023 + I8_FRAC - E) << 52);
+}
+// X = rint(x scale), |X| <= 2^48; the 7 balanced digits are returned as bytes: low word = planes 0..3, high word = planes 4..6
+__device__ __forceinline__ void i8_digits(double x, double scale, unsigned &lo, unsigned &hi) {
+    const long long X = __double2ll_rn(x * scale);
+    const unsigned long long C = 0x0001020408102040ull;                  // 0x40 in every 7-bit field (bits 6,13,..,48)
+    const unsigned long long Y = (unsigned long long)(X + (long long)C);   // in [0, 2^49 + C]
+    const unsigned d6 = (unsigned)(Y) & 127u, d5 = (unsigned)(Y >> 7) & 127u, d4 = (unsigned)(Y >> 14) & 127u,
+                   d3 = (unsigned)(Y >> 21) & 127u, d2 = (unsigned)(Y >> 28) & 127u, d1 = (unsigned)(Y >> 35) & 127u,
+                   d0 = (unsigned)(Y >> 42);                               // top digit: 0 .. 128
+    // subtract 64 from every byte (two's complement int8)
+    lo = __vsub4(d0 | (d1 << 8) | (d2 << 16) | (d3 << 24), 0x40404040u);
+    hi = __vsub4(d4 | (d5 << 8) | (d6 << 16), 0x00404040u);
+}
+
+// exponents of the rows of a strided matrix view: row r, reduction index j at  base[r * sr + j * sj]
+// (a) sr == 1 (rows contiguous): one thread per row, the reduction range is split over gridDim.y (atomicMax on the exponent)
+__global__ void i8_row_exponent_strided_kernel(const double *__restrict__ base, int64_t nrows, int64_t nred, int64_t sj, int *__restrict__ E) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int64_t chunk = (nred + gridDim.y - 1) / gridDim.y;
+    const int64_t j0 = blockIdx.y * chunk, j1 = min(nred, j0 + chunk);
+    double amax = 0.0;
+    for (int64_t j = j0; j < j1; ++j) amax = fmax(amax, fabs(base[r + j * sj]));
+    atomicMax(&E[r], i8_exponent(amax));
+}
+// (b) sj == 1 (reduction index contiguous): one warp per row
+__global__ void i8_row_exponent_contig_kernel(const double *__restrict__ base, int64_t nrows, int64_t nred, int64_t sr, int *__restrict__ E) {
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    double amax = 0.0;
+    for (int64_t j = lane; j < nred; j += 32) amax = fmax(amax, fabs(base[r * sr + j]));
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) E[r] = i8_exponent(amax);
+}
+
+// Khatri-Rao operand: K[k, r] = prod_f A_f[i_f(k), r]
+struct I8Krp {
+    const double *fac[ITCPD_MAX_ORDER];
+    int64_t ext[ITCPD_MAX_ORDER], dim[ITCPD_MAX_ORDER];
+    int nf;
+    int64_t kext;
+    int R;
+};
+__device__ __forceinline__ double i8_krp_value(const I8Krp &a, int64_t k, int r) {
+    if (k >= a.kext || r >= a.R) return 0.0;
+    double v = 1.0;
+    int64_t rem = k;
+    for (int f = 0; f < a.nf; ++f) {
+        const int64_t i = rem % a.ext[f];
+        rem /= a.ext[f];
+        if (i >= a.dim[f]) return 0.0;     // padded row of a leading mode
+        v *= a.fac[f][i + a.dim[f] * (int64_t)r];
+    }
+    return v;
+}
+// column exponents eb[r] (E must be pre-set to I8_EXP_ZERO); one thread per (chunk of 256 k, r), r fastest
+__global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int r = (int)(idx % I8_BN);
+    const int64_t k0 = (idx / I8_BN) * 256;
+    if (k0 >= a.kext) return;
+    double amax = 0.0;
+    for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k) amax = fmax(amax, fabs(i8_krp_value(a, k, r)));
+    atomicMax(&E[r], i8_exponent(amax));
+}
+// digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 14336-byte block per k-tile of 32:
+//   byte(q, n, kk) = ((q*64 + n) % 8) * 16 + ((q*64 + n) / 8) * 256 + (kk / 16) * 128 + (kk % 16)
+// one thread per (k-tile, n, half): 16 consecutive k of one column -> one 16-byte store per plane
+__global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t ktiles, uint8_t *__restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= ktiles * I8_BN * 2) return;
+    const int half = (int)(idx & 1);
+    const int n = (int)((idx >> 1) % I8_BN);
+    const int64_t kt = (idx >> 1) / I8_BN;
+    const double scale = i8_scale(E[n]);
+    unsigned plane[I8_NDIG][4];
+#pragma unroll
+    for (int p = 0; p < I8_NDIG; ++p) plane[p][0] = plane[p][1] = plane[p][2] = plane[p][3] = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        unsigned lo, hi;
+        i8_digits(i8_krp_value(a, kt * I8_BK + 16 * half + j, n), scale, lo, hi);
+        const int w = j >> 2, sh = 8 * (j & 3);
+        plane[0][w] |= (lo & 0xffu) << sh;
+        plane[1][w] |= ((lo >> 8) & 0xffu) << sh;
+        plane[2][w] |= ((lo >> 16) & 0xffu) << sh;
+        plane[3][w] |= (lo >> 24) << sh;
+        plane[4][w] |= (hi & 0xffu) << sh;
+        plane[5][w] |= ((hi >> 8) & 0xffu) << sh;
+        plane[6][w] |= ((hi >> 16) & 0xffu) << sh;
+    }
+    uint8_t *blk = out + kt * (int64_t)I8_B_BYTES;
+#pragma unroll
+    for (int q = 0; q < I8_NDIG; ++q) {
+        const int row = q * I8_BN + n;
+        uint4 v = make_uint4(plane[q][0], plane[q][1], plane[q][2], plane[q][3]);
+        *reinterpret_cast<uint4 *>(blk + (row & 7) * 16 + (row >> 3) * 256 + half * 128) = v;
+    }
+}
+
+// One converter thread's share of a 128 x 32 FP64 tile -> 7 digit planes (16 elements, one 16-byte store per plane).
+//   KIND 0: F = [k (32)][m (128)] doubles; thread tid (0..255) owns row m = tid % 128 and k = 16 (tid / 128) .. +15;
+//           K-major planes   byte(m, kk) = (m % 8) * 16 + (m / 8) * 256 + (kk / 16) * 128 + (kk % 16)
+//   KIND 1: F = [n (128)][k (32)] doubles; thread (warp = tid / 32, lane) owns k = lane and rows n = 16 warp .. +15;
+//           MN-major planes  byte(n, kk) = (kk % 8) * 16 + (kk / 8) * 128 + (n / 16) * 512 + (n % 16)
+// ea_tile points at the 128 row exponents of the tile.
+template <int KIND>
+__device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, const int *__restrict__ ea_tile, uint8_t *__restrict__ A, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    unsigned plane[I8_NDIG][4];
+#pragma unroll
+    for (int p = 0; p < I8_NDIG; ++p) plane[p][0] = plane[p][1] = plane[p][2] = plane[p][3] = 0u;
+    const double scale0 = (KIND == 0) ? i8_scale(ea_tile[tid & 127]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        double x, sc;
+        if (KIND == 0) { x = F[(16 * (tid >> 7) + j) * I8_BM + (tid & 127)]; sc = scale0; }
+        else { x = F[(16 * warp + j) * I8_BK + lane]; sc = i8_scale(ea_tile[16 * warp + j]); }
+        unsigned lo, hi;
+        i8_digits(x, sc, lo, hi);
+        const int wd = j >> 2, sh = 8 * (j & 3);
+        plane[0][wd] |= (lo & 0xffu) << sh;
+        plane[1][wd] |= ((lo >> 8) & 0xffu) << sh;
+        plane[2][wd] |= ((lo >> 16) & 0xffu) << sh;
+        plane[3][wd] |= (lo >> 24) << sh;
+        plane[4][wd] |= (hi & 0xffu) << sh;
+        plane[5][wd] |= ((hi >> 8) & 0xffu) << sh;
+        plane[6][wd] |= ((hi >> 16) & 0xffu) << sh;
+    }
+    int off;
+    if (KIND == 0) { const int m = tid & 127; off = (m & 7) * 16 + (m >> 3) * 256 + (tid >> 7) * 128; }
+    else { off = (lane & 7) * 16 + (lane >> 3) * 128 + warp * 512; }
+#pragma unroll
+    for (int p = 0; p < I8_NDIG; ++p)
+        *reinterpret_cast<uint4 *>(A + p * I8_A_PLANE + off) = make_uint4(plane[p][0], plane[p][1], plane[p][2], plane[p][3]);
+}
+
+// C = 2^(ea + eb - 98 + 84) sum_t acc_t 2^(-7 t):  v = sum_t acc_t 2^(-7 t) is formed by the caller, smallest weights first
+__device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 7 * t) << 52); }
+__device__ __forceinline__ double i8_finish(double v, int em, int er) {
+    return (em == I8_EXP_ZERO || er == I8_EXP_ZERO) ? 0.0 : ldexp(v, em + er - 14);
+}
+
+#ifndef ITCPD_I8_HOST_EMULATION
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMEM / mbarrier / TMA)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t i8_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void i8_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void i8_tma_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void i8_bulk_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void i8_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void i8_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void i8_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void i8_tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void i8_tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void i8_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive int32 columns of this thread's TMEM lane
+__device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"): start address, leading / stride byte offsets in 16-byte
+// units, descriptor version 1 (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t i8_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor (UMMA::InstrDescriptor): D = S32, A = B = signed int8, M = 128, N = n, B K-major, A K- or MN-major
+__host__ __device__ constexpr uint32_t i8_idesc(int n, int a_mn_major) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+// KIND 0: T tile lands as [k (32)][m (128)] doubles (m contiguous in memory); converter thread = one row m, 16 k:
+//         K-major digit planes  byte(m, kk) = (m % 8) * 16 + (m / 8) * 256 + (kk / 16) * 128 + (kk % 16)
+// KIND 1: T tile lands as [n (128)][k (32)] doubles (k contiguous in memory); converter thread = one k, 16 rows n:
+//         MN-major digit planes byte(n, kk) = (kk % 8) * 16 + (kk / 8) * 128 + (n / 16) * 512 + (n % 16)
+template <int KIND>
+__global__ void __launch_bounds__(320, 1)
+partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea,
+                       const int *__restrict__ eb, double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count) {
+    extern __shared__ uint8_t i8_smem_raw[];
+    const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
+    const uint32_t sF = base;
+    const uint32_t sA = sF + I8_FSTAGES * I8_F_BYTES;
+    const uint32_t sB = sA + I8_DSTAGES * I8_A_BYTES;
+    const uint32_t bars = sB + I8_DSTAGES * I8_B_BYTES;
+    const uint32_t full_f = bars, empty_f = bars + 8 * I8_FSTAGES;                           // FP64 ring
+    const uint32_t full_d = empty_f + 8 * I8_FSTAGES, empty_d = full_d + 8 * I8_DSTAGES;    // digit ring
+    const uint32_t acc_full = empty_d + 8 * I8_DSTAGES, acc_empty = acc_full + 8;
+    const uint32_t tmem_slot = acc_empty + 8;
+    uint8_t *gen_base = i8_smem_raw + (base - i8_smem_u32(i8_smem_raw));                    // generic pointer to `base`
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_FSTAGES; ++s) { i8_mbar_init(full_f + 8 * s, 1); i8_mbar_init(empty_f + 8 * s, 256); }
+        for (int s = 0; s < I8_DSTAGES; ++s) { i8_mbar_init(full_d + 8 * s, 256 + 1); i8_mbar_init(empty_d + 8 * s, 1); }
+        i8_mbar_init(acc_full, 1);
+        i8_mbar_init(acc_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) i8_tmem_alloc(tmem_slot, 512);
+    i8_tc_fence_before();
+    __syncthreads();
+    i8_tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
+
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int my_tiles = (num_row_tiles - cta + G - 1) / G;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int itf = 0;
+            for (int w = 0; w < my_tiles; ++w) {
+                const int row0 = (cta + w * G) * I8_BM;
+                for (int kt = 0; kt < kt_count; ++kt, ++itf) {
+                    const int sf = itf % I8_FSTAGES, sd = itf % I8_DSTAGES;
+                    if (itf >= I8_FSTAGES) i8_mbar_wait(empty_f + 8 * sf, (uint32_t)((itf / I8_FSTAGES - 1) & 1));
+                    i8_mbar_expect_tx(full_f + 8 * sf, I8_F_BYTES);
+                    if (KIND == 0) i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, row0, kt * I8_BK, full_f + 8 * sf);
+                    else i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, kt * I8_BK, row0, full_f + 8 * sf);
+                    // digit planes of the Khatri-Rao operand for this k-tile share the digit ring slot with A
+                    if (itf >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((itf / I8_DSTAGES - 1) & 1));
+                    i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
+                    i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int it = 0;
+            for (int w = 0; w < my_tiles; ++w) {
+                if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));   // the epilogue has drained the accumulators
+                i8_tc_fence_after();
+                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                    const int sd = it % I8_DSTAGES;
+                    i8_mbar_wait(full_d + 8 * sd, (uint32_t)((it / I8_DSTAGES) & 1));
+                    i8_tc_fence_after();
+                    const uint32_t a0 = sA + sd * I8_A_BYTES, b0 = sB + sd * I8_B_BYTES;
+                    const uint64_t bdesc_lo = i8_smem_desc(b0, 128, 256);                     // B rows 0..   (K-major)
+                    const uint64_t bdesc_hi = i8_smem_desc(b0 + 256 / 8 * 256, 128, 256);     // B rows 256..
+#pragma unroll
+                    for (int p = 0; p < I8_NDIG; ++p) {
+                        const uint64_t adesc = (KIND == 0) ? i8_smem_desc(a0 + p * I8_A_PLANE, 128, 256)    // K-major: LBO = k chunk, SBO = 8-row group
+                                                           : i8_smem_desc(a0 + p * I8_A_PLANE, 128, 512);   // MN-major: LBO = k group of 8, SBO = 16-row block
+                        const int ntot = I8_BN * (I8_NDIG - p);                 // accumulators t = p .. 6
+                        const uint32_t acc = (kt > 0 || p > 0) ? 1u : 0u;       // p = 0 touches every accumulator first
+                        const uint32_t d = tmem + (uint32_t)(I8_BN * p);
+                        if (ntot > 256) {
+                            i8_mma(d, adesc, bdesc_lo, i8_idesc(256, KIND), acc);
+                            i8_mma(d + 256, adesc, bdesc_hi, i8_idesc(ntot - 256, KIND), acc);
+                        } else {
+                            i8_mma(d, adesc, bdesc_lo, i8_idesc(ntot, KIND), acc);
+                        }
+                    }
+                    i8_commit(empty_d + 8 * sd);                                // frees the digit slot when these MMAs are done
+                }
+                i8_commit(acc_full);                                            // accumulators of this tile are complete
+            }
+        }
+    } else {
+        // ===== converters (warps 0-7), epilogue (warps 0-3) =====
+        const int tid = threadIdx.x;   // 0 .. 255
+        int it = 0;
+        for (int w = 0; w < my_tiles; ++w) {
+            const int64_t row0 = (int64_t)(cta + w * G) * I8_BM;
+            for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                const int sf = it % I8_FSTAGES, sd = it % I8_DSTAGES;
+                i8_mbar_wait(full_f + 8 * sf, (uint32_t)((it / I8_FSTAGES) & 1));
+                if (it >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((it / I8_DSTAGES - 1) & 1));
+                const double *F = reinterpret_cast<const double *>(gen_base + (sF - base) + sf * I8_F_BYTES);
+                uint8_t *A = gen_base + (sA - base) + sd * I8_A_BYTES;
+                i8_convert_thread<KIND>(F, ea + row0, A, tid);
+                i8_fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
+                i8_mbar_arrive(full_d + 8 * sd);
+                i8_mbar_arrive(empty_f + 8 * sf);
+            }
+            if (warp < 4) {
+                // ---- epilogue: row m = 32 warp + lane of the tile ----
+                i8_mbar_wait(acc_full, (uint32_t)(w & 1));
+                i8_tc_fence_after();
+                const int64_t m = row0 + 32 * warp + lane;
+                const int em = (m < rows_out) ? ea[m] : I8_EXP_ZERO;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    double v[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = 0.0;
+#pragma unroll 1
+                    for (int t = I8_NDIG - 1; t >= 0; --t) {       // smallest weights first
+                        int a[32];
+                        i8_tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(I8_BN * t + 32 * half), a);
+                        const double wt = i8_weight(t);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = fma((double)a[c], wt, v[c]);
+                    }
+                    if (m < rows_out) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int r = 32 * half + c;
+                            if (r < R) out[m + rows_out * (int64_t)r] = i8_finish(v[c], em, eb[r]);
+                        }
+                    }
+                }
+                i8_tc_fence_before();
+                i8_mbar_arrive(acc_empty);
+            }
+        }
+    }
+    i8_tc_fence_before();
+    __syncthreads();
+    if (warp == 9) i8_tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*I8EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+
+static int i8_make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint64_t d1, uint32_t box0, uint32_t box1) {
+    static I8EncodeFn enc = nullptr;
+    if (!enc) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return ITCPD_ERR_CUDA;
+        enc = reinterpret_cast<I8EncodeFn>(p);
+    }
+    cuuint64_t gdim[2] = {d0, d1};
+    cuuint64_t gstr[1] = {d0 * 8};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ITCPD_OK : ITCPD_ERR_CUDA;
+}
+
+__global__ void i8_fill_int_kernel(int *x, int64_t n, int v) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+// Same contract as launch_partial_gemm (gemm_dmma.cu).  Returns ITCPD_ERR_UNSUPPORTED for shapes outside the draft's
+// envelope (R <= 64, 128-row tiles, 32-multiple contraction extent, no padded leading mode): the caller falls back to DMMA.
+int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
+    const int N = c->order, R = c->rank;
+    if (R > I8_BN || c->ld0 != c->dims[0]) return ITCPD_ERR_UNSUPPORTED;
+    int64_t Mrows = c->ld0, Ncols = 1;
+    for (int n = 1; n < split; ++n) Mrows *= c->dims[n];
+    for (int n = split; n < N; ++n) Ncols *= c->dims[n];
+    const int64_t kext = (kind == 0) ? Ncols : Mrows;
+    const int64_t rows_out = (kind == 0) ? Mrows : Ncols;
+    if (rows_out % I8_BM != 0 || kext % I8_BK != 0 || rows_out / I8_BM > INT32_MAX || kext / I8_BK > INT32_MAX) return ITCPD_ERR_UNSUPPORTED;
+    const int64_t ktiles = kext / I8_BK;
+
+    // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
+    I8ExpCache &ec = c->i8_exp[kind];
+    if (!ec.valid || ec.split != split || ec.tensor_epoch != c->i8_tensor_epoch) {
+        TRY(ec.buf.reserve((size_t)rows_out * 4));
+        i8_fill_int_kernel<<<(unsigned)ceil_div(rows_out, 256), 256, 0, c->stream>>>(ec.buf.as<int>(), rows_out, I8_EXP_ZERO);
+        if (kind == 0) {
+            const int ysplit = (int)std::max<int64_t>(1, std::min<int64_t>(kext, (int64_t)c->sm_count * 8 * 256 / std::max<int64_t>(rows_out, 1)));
+            i8_row_exponent_strided_kernel<<<dim3((unsigned)ceil_div(rows_out, 256), (unsigned)ysplit), 256, 0, c->stream>>>(
+                c->T.as<double>(), rows_out, kext, Mrows, ec.buf.as<int>());
+        } else {
+            i8_row_exponent_contig_kernel<<<(unsigned)ceil_div(rows_out * 32, 256), 256, 0, c->stream>>>(c->T.as<double>(), rows_out, kext, Mrows,
+                                                                                                         ec.buf.as<int>());
+        }
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        ec.valid = true;
+        ec.split = split;
+        ec.tensor_epoch = c->i8_tensor_epoch;
+    }
+
+    // ---- Khatri-Rao operand: column exponents, then the packed digit planes ----
+    I8Krp pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.R = R;
+    pa.kext = kext;
+    if (kind == 0) {
+        for (int n = split; n < N; ++n) { pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++; }
+    } else {
+        for (int n = 0; n < split; ++n) { pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++; }
+    }
+    TRY(c->i8_eb.reserve(I8_BN * 4));
+    TRY(c->i8_bdig.reserve((size_t)ktiles * I8_B_BYTES));
+    i8_fill_int_kernel<<<1, 64, 0, c->stream>>>(c->i8_eb.as<int>(), I8_BN, I8_EXP_ZERO);
+    i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, c->i8_eb.as<int>());
+    i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, c->i8_eb.as<int>(), ktiles, c->i8_bdig.as<uint8_t>());
+    c->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+
+    CUtensorMap map;
+    if (kind == 0) TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BM, I8_BK));
+    else TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BK, I8_BM));
+
+    const int num_row_tiles = (int)(rows_out / I8_BM);
+    const int grid = std::min(num_row_tiles, c->sm_count);
+    static bool attr[2][64] = {{false}};
+    if (!attr[kind][c->device & 63]) {
+        if (kind == 0) CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+        else CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+        attr[kind][c->device & 63] = true;
+    }
+    if (kind == 0)
+        partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, c->i8_bdig.as<uint8_t>(), ec.buf.as<int>(), c->i8_eb.as<int>(), out, rows_out, R,
+                                                                   num_row_tiles, (int)ktiles);
+    else
+        partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, c->i8_bdig.as<uint8_t>(), ec.buf.as<int>(), c->i8_eb.as<int>(), out, rows_out, R,
+                                                                   num_row_tiles, (int)ktiles);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+#endif  // ITCPD_I8_HOST_EMULATION
+
+}  // namespace itcpd

@@ -113,21 +113,21 @@ inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8)
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 
 // run `body` as one CTA of `threads` CUDA threads; `named` = participant count of `bar.sync 1, named`
-inline void emu_launch(int threads, int named, const std::function<void()> &body) {
+inline void emu_launch(int threads, int named, const std::function<void()> &body, unsigned bx = 0, unsigned by = 0, unsigned gx = 1, unsigned gy = 1) {
     blockDim = {(unsigned)threads, 1, 1};
-    gridDim = {1, 1, 1};
+    gridDim = {gx, gy, 1};
     emu::cta_bar.init(threads);
     emu::named_bar.init(named > 0 ? named : threads);
     for (int w = 0; w < (threads + 31) / 32; ++w) { emu::warp_bar[w].init(32); emu::coll_bar[w].init(); }
-    struct Arg { int t; const std::function<void()> *f; };
+    struct Arg { int t; unsigned bx, by; const std::function<void()> *f; };
     std::vector<pthread_t> th(threads);
     std::vector<Arg> args(threads);
     for (int t = 0; t < threads; ++t) {
-        args[t] = {t, &body};
+        args[t] = {t, bx, by, &body};
         pthread_create(&th[t], nullptr, [](void *p) -> void * {
             Arg *a = (Arg *)p;
             threadIdx = {(unsigned)a->t, 0, 0};
-            blockIdx = {0, 0, 0};
+            blockIdx = {a->bx, a->by, 0};
             (*a->f)();
             return nullptr;
         }, &args[t]);

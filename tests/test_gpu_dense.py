@@ -441,3 +441,19 @@ def test_right_looking_cholesky_rank_deficient(engine):
     assert out[1][0] == out[2][0] == (1, 10)
     assert relerr(out[2][1], out[1][1]) < 1e-9 and relerr(out[2][2], out[1][2]) < 1e-9
     assert relerr(out[2][3], out[1][3]) < 1e-9
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="gemm_i8 (INT8 tensor-core digit-split contraction) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dims,R", [((128, 64, 32), 48), ((256, 32, 64), 64), ((128, 32, 32, 4), 20)])
+def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R):
+    """csrc/gemm_i8.cu: tcgen05.mma kind::i8 on 7 balanced base-128 digits per operand; same 1e-12 bar as the DMMA path."""
+    T, cp = make_problem(dims, R, seed=91)
+    engine.set_option("gemm_i8", 1)
+    try:
+        engine.set_tensor(T)
+        engine.set_cpd(cp.factors, cp.lam)
+        for n in range(len(dims)):
+            M = engine.mttkrp(n)
+            assert relerr(M, cpals.mttkrp_krp_normal(T, cp.factors, n)) < 1e-12, n
+    finally:
+        engine.set_option("gemm_i8", 0)
