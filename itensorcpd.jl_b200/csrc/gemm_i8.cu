@@ -315,19 +315,26 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
     const int my_tiles = (num_row_tiles - cta + G - 1) / G;
 
     if (warp == 8) {
-        // ===== TMA producer =====
+        // ===== TMA producers: lane 0 streams the FP64 tiles of T, lane 1 the packed digit planes of the Khatri-Rao operand
+        // (two independent rings: the 3-deep FP64 prefetch must not wait for the 2-deep digit ring) =====
         if (lane == 0) {
             int itf = 0;
             for (int w = 0; w < my_tiles; ++w) {
                 const int row0 = (cta + w * G) * I8_BM;
                 for (int kt = 0; kt < kt_count; ++kt, ++itf) {
-                    const int sf = itf % I8_FSTAGES, sd = itf % I8_DSTAGES;
+                    const int sf = itf % I8_FSTAGES;
                     if (itf >= I8_FSTAGES) i8_mbar_wait(empty_f + 8 * sf, (uint32_t)((itf / I8_FSTAGES - 1) & 1));
                     i8_mbar_expect_tx(full_f + 8 * sf, I8_F_BYTES);
                     if (KIND == 0) i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, row0, kt * I8_BK, full_f + 8 * sf);
                     else i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, kt * I8_BK, row0, full_f + 8 * sf);
-                    // digit planes of the Khatri-Rao operand for this k-tile share the digit ring slot with A
-                    if (itf >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((itf / I8_DSTAGES - 1) & 1));
+                }
+            }
+        } else if (lane == 1) {
+            int itd = 0;
+            for (int w = 0; w < my_tiles; ++w) {
+                for (int kt = 0; kt < kt_count; ++kt, ++itd) {
+                    const int sd = itd % I8_DSTAGES;
+                    if (itd >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((itd / I8_DSTAGES - 1) & 1));
                     i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
                     i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
                 }
