@@ -319,6 +319,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
+    if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = atoi(s) != 0;   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
     if (st != ITCPD_OK) { delete c; return st; }
     *out = c;

@@ -13,6 +13,9 @@ for chol in 1 2; do
   ITCPD_CHOL=$chol $B --config B8 --steps 50 > gpurun_out/r2_B8_chol$chol.json 2>> gpurun_out/r2_err.log
   ITCPD_CHOL=$chol $B --config A --steps 50 > gpurun_out/r2_A_chol$chol.json 2>> gpurun_out/r2_err.log
 done
+# INT8 tensor-core contraction (draft): config B with and without it
+ITCPD_GEMM_I8=1 $B --steps 20 > gpurun_out/r2_B_gemm_i8.json 2>> gpurun_out/r2_err.log
+$B --steps 20 > gpurun_out/r2_B_dmma.json 2>> gpurun_out/r2_err.log
 for pg in 0 1; do
   ITCPD_BENCH_PHASES=1 ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
       bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/r2_N2_peergraph$pg.json 2>> gpurun_out/r2_err.log
