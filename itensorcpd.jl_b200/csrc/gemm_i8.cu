@@ -265,7 +265,7 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
 
 // shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"): start address, leading / stride byte offsets in 16-byte
 // units, descriptor version 1 (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
-__device__ __forceinline__ uint64_t i8_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__host__ __device__ __forceinline__ uint64_t i8_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
            (1ull << 46);
 }
