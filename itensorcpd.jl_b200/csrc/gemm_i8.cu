@@ -430,6 +430,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef ITCPD_I8_PROBE   // tools/i8_probe.cu includes this file for the device code only
 typedef CUresult (*I8EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                CUtensorMapFloatOOBfill);
@@ -529,6 +530,7 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }
+#endif  // ITCPD_I8_PROBE
 #endif  // ITCPD_I8_HOST_EMULATION
 
 }  // namespace itcpd

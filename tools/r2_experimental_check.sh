@@ -4,6 +4,8 @@
 # 1. the whole GPU suite with the opt-in tests (right-looking Cholesky chol_alg=2, sharded sampled path, peer_graph)
 # 2. A/B timings: chol_alg 1 vs 2 on the per-rank slab and config A; 2-GPU sweeps with and without peer_graph
 mkdir -p gpurun_out
+# 0. single-instruction probe of the INT8 tensor-core building blocks (build it first: see the header of tools/i8_probe.cu)
+[ -x tools/i8_probe ] && timeout 30 ./tools/i8_probe > gpurun_out/r2_i8_probe.txt 2>&1; tail -6 gpurun_out/r2_i8_probe.txt
 export ITCPD_EXPERIMENTAL=1
 timeout 400 python -m pytest tests -m gpu -q > gpurun_out/r2_exp_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/r2_exp_tests.log
