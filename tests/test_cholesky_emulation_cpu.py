@@ -168,4 +168,6 @@ def test_thread_sanitizer_sees_a_missing_warp_sync():
     for which in (1, 2):
         # TSAN keeps only a few recent accesses per memory cell, so one run can miss the race: several sizes, one verdict
         err = _tsan_run(so, [(20, False, False), (31, False, False), (27, False, True), (24, False, False)], (which,))
+        if "WARNING: ThreadSanitizer: data race" not in err:
+            err = _tsan_run(so, [(30, False, False), (22, False, False), (29, False, True), (32, False, False)], (which,))
         assert "WARNING: ThreadSanitizer: data race" in err, which
