@@ -1,0 +1,83 @@
+"""Is the accuracy of the 7-digit INT8 contraction (csrc/gemm_i8.cu, experimental) enough for the north-star trajectory bar?
+A vectorised numpy statement of the same arithmetic (49-bit fixed point per row / column, balanced base-128 digits by the
+add-0x40-per-field trick, the 28 digit-plane products with p + q <= 6, combination smallest weights first) replaces the
+oracle's MTTKRP inside its ALS loop; the fit trajectory over 100 sweeps must stay within 1e-9 of the plain oracle's."""
+import numpy as np
+
+from oracle import cpals
+
+C49 = sum(1 << (7 * k + 6) for k in range(7))
+
+
+def digits(X):
+    """X: int64 array, |X| <= 2^48 -> list of 7 float64 digit planes, most significant first (i8_digits in gemm_i8.cu)"""
+    Y = X + C49
+    planes = [((Y >> (7 * k)) & 127) - 64 for k in range(6)]
+    planes.append((Y >> 42) - 64)
+    return [p.astype(np.float64) for p in planes[::-1]]
+
+
+def exponents(A, axis):
+    amax = np.max(np.abs(A), axis=axis, keepdims=True)
+    _, e = np.frexp(np.where(amax > 0, amax, 1.0))        # amax = f 2^e, f in [0.5, 1)
+    return e + 1                                          # |a| 2^-E < 1/2
+
+
+def gemm_i8(A, B):
+    """A (M x K) @ B (K x N) through the digit-split scheme"""
+    ea, eb = exponents(A, 1), exponents(B, 0)
+    XA = np.rint(np.ldexp(A, 49 - ea)).astype(np.int64)
+    XB = np.rint(np.ldexp(B, 49 - eb)).astype(np.int64)
+    dA, dB = digits(XA), digits(XB)
+    v = np.zeros((A.shape[0], B.shape[1]))
+    for t in range(6, -1, -1):
+        acc = np.zeros_like(v)
+        for p in range(t + 1):
+            acc += dA[p] @ dB[t - p]                      # exact: |entries| < 2^53
+        v = acc * 2.0 ** (-7 * t) + v
+    return np.ldexp(v, ea + eb - 14)
+
+
+def mttkrp_i8(T, factors, n):
+    N = T.ndim
+    others = [m for m in range(N) if m != n]
+    Kr = factors[others[0]]
+    for m in others[1:]:
+        Kr = (factors[m][:, None, :] * Kr[None, :, :]).reshape(-1, Kr.shape[1])   # earlier modes fastest
+    Tn = np.moveaxis(T, n, 0).reshape(T.shape[n], -1, order="F")
+    return np.asfortranarray(gemm_i8(Tn, Kr))
+
+
+def test_gemm_i8_model_accuracy():
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((96, 512)) * np.exp2(rng.integers(-8, 9, size=(96, 1)))
+    B = rng.standard_normal((512, 40))
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble)).astype(np.float64)
+    assert np.linalg.norm(gemm_i8(A, B) - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_fit_trajectory_with_the_i8_contraction_stays_within_1e9():
+    rng = np.random.default_rng(5)
+    dims, R, nsweeps = (24, 20, 28), 10, 100
+    T = np.asfortranarray(rng.standard_normal(dims))
+    cp = cpals.random_CPD(T, R, np.random.default_rng(6))
+    nT = float(np.linalg.norm(T))
+    ref = cpals.FitCheck(0.0, nsweeps, nT)
+    cpals.als_optimize(T, cp, alg=cpals.KRPNormal(), check=ref)
+    # the same loop with the digit-split MTTKRP
+    f = [x.copy() for x in cp.factors]
+    grams = [cpals.gram(x) for x in f]
+    fits = []
+    lam = None
+    for _ in range(nsweeps):
+        M = None
+        for n in range(3):
+            M = mttkrp_i8(T, f, n)
+            assert np.linalg.norm(M - cpals.mttkrp_krp_normal(T, f, n)) / np.linalg.norm(M) < 1e-12
+            X = cpals.solve_ls_problem(cpals.compute_krp_gram(grams, n), M)
+            f[n], lam = cpals.row_norm(X)
+            grams[n] = cpals.gram(f[n])
+        inner = float(np.sum(M * (f[-1] * lam[None, :])))
+        norm2 = cpals.norm_factors(grams, lam)
+        fits.append(1.0 - np.sqrt(abs(nT ** 2 + norm2 - 2 * abs(inner))) / nT)
+    assert np.max(np.abs(np.array(fits) - np.array(ref.history))) < 1e-9
