@@ -205,8 +205,10 @@ __device__ __forceinline__ void i8_mbar_expect_tx(uint32_t bar, uint32_t bytes) 
 __device__ __forceinline__ void i8_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// bounded while the kernel is a draft: a protocol error must surface as a trapped launch, not as a hung GPU
 __device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
+    unsigned long long spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -215,6 +217,10 @@ __device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (!done && ++spins > (1ull << 26)) {
+            printf("itcpd gemm_i8: mbarrier 0x%x parity %u never completed (block %d thread %d)\n", bar, parity, (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
     } while (!done);
 }
 __device__ __forceinline__ void i8_tma_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
