@@ -48,17 +48,39 @@ __device__ __forceinline__ double i8_scale(int E) {
     if (E == I8_EXP_ZERO) return 0.0;
     return __longlong_as_double((long long)(1023 + I8_FRAC - E) << 52);
 }
-// X = rint(x scale), |X| <= 2^48; the 7 balanced digits are returned as bytes: low word = planes 0..3, high word = planes 4..6
-__device__ __forceinline__ void i8_digits(double x, double scale, unsigned &lo, unsigned &hi) {
+// X = rint(x scale), |X| <= 2^48.  Returns the seven 7-bit fields of Y = X + C (C = 0x40 in every field) as bytes:
+// `lo` = planes 0..3, `hi` = planes 4..6; plane 0 (the signed top digit, -64 .. 64) is already final, planes 1..6 still
+// carry the +64 offset, which i8_pack4 removes on whole words after the transposition.
+__device__ __forceinline__ void i8_fields(double x, double scale, unsigned &lo, unsigned &hi) {
     const long long X = __double2ll_rn(x * scale);
-    const unsigned long long C = 0x0001020408102040ull;                  // 0x40 in every 7-bit field (bits 6,13,..,48)
+    const unsigned long long C = 0x0001020408102040ull;                  // bits 6, 13, .., 48
     const unsigned long long Y = (unsigned long long)(X + (long long)C);   // in [0, 2^49 + C]
-    const unsigned d6 = (unsigned)(Y) & 127u, d5 = (unsigned)(Y >> 7) & 127u, d4 = (unsigned)(Y >> 14) & 127u,
-                   d3 = (unsigned)(Y >> 21) & 127u, d2 = (unsigned)(Y >> 28) & 127u, d1 = (unsigned)(Y >> 35) & 127u,
-                   d0 = (unsigned)(Y >> 42);                               // top digit: 0 .. 128
-    // subtract 64 from every byte (two's complement int8)
-    lo = __vsub4(d0 | (d1 << 8) | (d2 << 16) | (d3 << 24), 0x40404040u);
-    hi = __vsub4(d4 | (d5 << 8) | (d6 << 16), 0x00404040u);
+    const unsigned yl = (unsigned)Y, yh = (unsigned)(Y >> 32);
+    const unsigned f6 = yl & 127u, f5 = (yl >> 7) & 127u, f4 = (yl >> 14) & 127u, f3 = (yl >> 21) & 127u;
+    const unsigned f2 = ((yl >> 28) | (yh << 4)) & 127u, f1 = (yh >> 3) & 127u;
+    const unsigned f0 = ((yh >> 10) - 64u) & 255u;                         // top digit: -64 .. 64 as int8
+    lo = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
+    hi = f4 | (f5 << 8) | (f6 << 16);
+}
+// bytes of four consecutive elements -> one word per plane (byte i = element i): a 4 x 4 byte transpose with PRMT,
+// then  f - 64  on planes 1..6 without borrows:  t = f ^ 0x40;  d = t | ((t & 0x40) << 1)   (f in [0, 127])
+__device__ __forceinline__ void i8_pack4(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned (&out)[I8_NDIG]) {
+    const unsigned a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[2], lo[3], 0x5140);
+    const unsigned c = __byte_perm(lo[0], lo[1], 0x7362), d = __byte_perm(lo[2], lo[3], 0x7362);
+    const unsigned e = __byte_perm(hi[0], hi[1], 0x5140), f = __byte_perm(hi[2], hi[3], 0x5140);
+    const unsigned g = __byte_perm(hi[0], hi[1], 0x7362), h = __byte_perm(hi[2], hi[3], 0x7362);
+    out[0] = __byte_perm(a, b, 0x5410);
+    out[1] = __byte_perm(a, b, 0x7632);
+    out[2] = __byte_perm(c, d, 0x5410);
+    out[3] = __byte_perm(c, d, 0x7632);
+    out[4] = __byte_perm(e, f, 0x5410);
+    out[5] = __byte_perm(e, f, 0x7632);
+    out[6] = __byte_perm(g, h, 0x5410);
+#pragma unroll
+    for (int p = 1; p < I8_NDIG; ++p) {
+        const unsigned t = out[p] ^ 0x40404040u;
+        out[p] = t | ((t & 0x40404040u) << 1);
+    }
 }
 
 // exponents of the rows of a strided matrix view: row r, reduction index j at  base[r * sr + j * sj]
@@ -125,19 +147,13 @@ __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t k
     const double scale = i8_scale(E[n]);
     unsigned plane[I8_NDIG][4];
 #pragma unroll
-    for (int p = 0; p < I8_NDIG; ++p) plane[p][0] = plane[p][1] = plane[p][2] = plane[p][3] = 0u;
+    for (int w = 0; w < 4; ++w) {
+        unsigned lo[4], hi[4], o[I8_NDIG];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        unsigned lo, hi;
-        i8_digits(i8_krp_value(a, kt * I8_BK + 16 * half + j, n), scale, lo, hi);
-        const int w = j >> 2, sh = 8 * (j & 3);
-        plane[0][w] |= (lo & 0xffu) << sh;
-        plane[1][w] |= ((lo >> 8) & 0xffu) << sh;
-        plane[2][w] |= ((lo >> 16) & 0xffu) << sh;
-        plane[3][w] |= (lo >> 24) << sh;
-        plane[4][w] |= (hi & 0xffu) << sh;
-        plane[5][w] |= ((hi >> 8) & 0xffu) << sh;
-        plane[6][w] |= ((hi >> 16) & 0xffu) << sh;
+        for (int j = 0; j < 4; ++j) i8_fields(i8_krp_value(a, kt * I8_BK + 16 * half + 4 * w + j, n), scale, lo[j], hi[j]);
+        i8_pack4(lo, hi, o);
+#pragma unroll
+        for (int p = 0; p < I8_NDIG; ++p) plane[p][w] = o[p];
     }
     uint8_t *blk = out + kt * (int64_t)I8_B_BYTES;
 #pragma unroll
@@ -158,24 +174,21 @@ template <int KIND>
 __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, const int *__restrict__ ea_tile, uint8_t *__restrict__ A, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     unsigned plane[I8_NDIG][4];
-#pragma unroll
-    for (int p = 0; p < I8_NDIG; ++p) plane[p][0] = plane[p][1] = plane[p][2] = plane[p][3] = 0u;
     const double scale0 = (KIND == 0) ? i8_scale(ea_tile[tid & 127]) : 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        double x, sc;
-        if (KIND == 0) { x = F[(16 * (tid >> 7) + j) * I8_BM + (tid & 127)]; sc = scale0; }
-        else { x = F[(16 * warp + j) * I8_BK + lane]; sc = i8_scale(ea_tile[16 * warp + j]); }
-        unsigned lo, hi;
-        i8_digits(x, sc, lo, hi);
-        const int wd = j >> 2, sh = 8 * (j & 3);
-        plane[0][wd] |= (lo & 0xffu) << sh;
-        plane[1][wd] |= ((lo >> 8) & 0xffu) << sh;
-        plane[2][wd] |= ((lo >> 16) & 0xffu) << sh;
-        plane[3][wd] |= (lo >> 24) << sh;
-        plane[4][wd] |= (hi & 0xffu) << sh;
-        plane[5][wd] |= ((hi >> 8) & 0xffu) << sh;
-        plane[6][wd] |= ((hi >> 16) & 0xffu) << sh;
+    for (int w = 0; w < 4; ++w) {
+        unsigned lo[4], hi[4], o[I8_NDIG];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * w + jj;
+            double x, sc;
+            if (KIND == 0) { x = F[(16 * (tid >> 7) + j) * I8_BM + (tid & 127)]; sc = scale0; }
+            else { x = F[(16 * warp + j) * I8_BK + lane]; sc = i8_scale(ea_tile[16 * warp + j]); }
+            i8_fields(x, sc, lo[jj], hi[jj]);
+        }
+        i8_pack4(lo, hi, o);
+#pragma unroll
+        for (int p = 0; p < I8_NDIG; ++p) plane[p][w] = o[p];
     }
     int off;
     if (KIND == 0) { const int m = tid & 127; off = (m & 7) * 16 + (m >> 3) * 256 + (tid >> 7) * 128; }

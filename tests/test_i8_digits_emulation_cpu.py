@@ -24,9 +24,10 @@ using std::min;
 struct uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 inline long long __double2ll_rn(double x) { return llrint(x); }
-inline unsigned __vsub4(unsigned a, unsigned b) {
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long xy = ((unsigned long long)y << 32) | x;
     unsigned r = 0;
-    for (int i = 0; i < 4; ++i) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i);
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((xy >> (8 * ((s >> (4 * i)) & 7))) & 0xffu) << (8 * i);
     return r;
 }
 inline int atomicMax(int *p, int v) { static std::atomic_flag l = ATOMIC_FLAG_INIT; while (l.test_and_set()) {} int o = *p; if (v > o) *p = v; l.clear(); return o; }
@@ -121,6 +122,8 @@ def test_i8_digit_pipeline_reproduces_the_fp64_contraction(emu, kind):
     Kr = (f2[:, None, :] * f1[None, :, :]).reshape(K, R)              # k = i1 + 8 i2  (first factor fastest)
     A = rng.standard_normal((M, K)) * np.exp2(rng.integers(-6, 7, size=(M, 1)))   # rows of very different scale
     A[5, :] = 0.0                                                        # an all-zero row
+    A[9, 3] = np.nextafter(4.0, 0.0)                                     # rounds up to 2^48 in 49-bit fixed point: top digit +64
+    A[9, 4] = -np.nextafter(4.0, 0.0)
     # memory image of the tensor view: kind 0 has the output rows contiguous (T[m + M k]), kind 1 the contraction index
     if kind == 0:
         img = np.asfortranarray(A)
