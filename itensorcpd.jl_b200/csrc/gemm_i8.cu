@@ -112,8 +112,10 @@ struct I8Krp {
     int nf;
     int64_t kext;
     int R;
+    int r0;     // first rank column of this 64-column block
 };
 __device__ __forceinline__ double i8_krp_value(const I8Krp &a, int64_t k, int r) {
+    r += a.r0;
     if (k >= a.kext || r >= a.R) return 0.0;
     double v = 1.0;
     int64_t rem = k;
@@ -476,24 +478,26 @@ __global__ void i8_fill_int_kernel(int *x, int64_t n, int v) {
     if (i < n) x[i] = v;
 }
 
-// Same contract as launch_partial_gemm (gemm_dmma.cu).  Returns ITCPD_ERR_UNSUPPORTED for shapes outside the draft's
-// envelope (R <= 64, 128-row tiles, 32-multiple contraction extent, no padded leading mode): the caller falls back to DMMA.
+// Same contract as launch_partial_gemm (gemm_dmma.cu).  Ragged shapes ride on TMA's zero fill and zero digit planes; rank
+// columns are processed in blocks of 64 (one pass over T per block: 7 x 64 accumulator columns fill the TMEM).
+// Returns ITCPD_ERR_UNSUPPORTED outside the envelope (the caller then uses the DMMA kernel).
 int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     const int N = c->order, R = c->rank;
-    if (R > I8_BN || c->ld0 != c->dims[0]) return ITCPD_ERR_UNSUPPORTED;
     int64_t Mrows = c->ld0, Ncols = 1;
     for (int n = 1; n < split; ++n) Mrows *= c->dims[n];
     for (int n = split; n < N; ++n) Ncols *= c->dims[n];
     const int64_t kext = (kind == 0) ? Ncols : Mrows;
     const int64_t rows_out = (kind == 0) ? Mrows : Ncols;
-    if (rows_out % I8_BM != 0 || kext % I8_BK != 0 || rows_out / I8_BM > INT32_MAX || kext / I8_BK > INT32_MAX) return ITCPD_ERR_UNSUPPORTED;
-    const int64_t ktiles = kext / I8_BK;
+    const int64_t ktiles = ceil_div(kext, I8_BK), row_tiles = ceil_div(rows_out, I8_BM);
+    if (row_tiles > INT32_MAX / I8_BM || ktiles > INT32_MAX / I8_BK || Mrows > INT32_MAX || Ncols > INT32_MAX) return ITCPD_ERR_UNSUPPORTED;
+    const int rblocks = (int)ceil_div(R, I8_BN);
 
     // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
     I8ExpCache &ec = c->i8_exp[kind];
     if (!ec.valid || ec.split != split || ec.tensor_epoch != c->i8_tensor_epoch) {
-        TRY(ec.buf.reserve((size_t)rows_out * 4));
-        i8_fill_int_kernel<<<(unsigned)ceil_div(rows_out, 256), 256, 0, c->stream>>>(ec.buf.as<int>(), rows_out, I8_EXP_ZERO);
+        const int64_t padded = row_tiles * I8_BM;
+        TRY(ec.buf.reserve((size_t)padded * 4));
+        i8_fill_int_kernel<<<(unsigned)ceil_div(padded, 256), 256, 0, c->stream>>>(ec.buf.as<int>(), padded, I8_EXP_ZERO);
         if (kind == 0) {
             const int ysplit = (int)std::max<int64_t>(1, std::min<int64_t>(kext, (int64_t)c->sm_count * 8 * 256 / std::max<int64_t>(rows_out, 1)));
             i8_row_exponent_strided_kernel<<<dim3((unsigned)ceil_div(rows_out, 256), (unsigned)ysplit), 256, 0, c->stream>>>(
@@ -509,7 +513,17 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         ec.tensor_epoch = c->i8_tensor_epoch;
     }
 
-    // ---- Khatri-Rao operand: column exponents, then the packed digit planes ----
+    CUtensorMap map;
+    if (kind == 0) TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BM, I8_BK));
+    else TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BK, I8_BM));
+    static bool attr[2][64] = {{false}};
+    if (!attr[kind][c->device & 63]) {
+        if (kind == 0) CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+        else CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+        attr[kind][c->device & 63] = true;
+    }
+
+    // ---- Khatri-Rao operand: column exponents and packed digit planes of every 64-column block ----
     I8Krp pa;
     memset(&pa, 0, sizeof(pa));
     pa.R = R;
@@ -517,36 +531,30 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     if (kind == 0) {
         for (int n = split; n < N; ++n) { pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++; }
     } else {
-        for (int n = 0; n < split; ++n) { pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++; }
+        for (int n = 0; n < split; ++n) {
+            pa.fac[pa.nf] = c->A[n].as<double>(); pa.ext[pa.nf] = (n == 0) ? c->ld0 : c->dims[n]; pa.dim[pa.nf] = c->dims[n]; pa.nf++;
+        }
     }
-    TRY(c->i8_eb.reserve(I8_BN * 4));
-    TRY(c->i8_bdig.reserve((size_t)ktiles * I8_B_BYTES));
-    i8_fill_int_kernel<<<1, 64, 0, c->stream>>>(c->i8_eb.as<int>(), I8_BN, I8_EXP_ZERO);
-    i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, c->i8_eb.as<int>());
-    i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, c->i8_eb.as<int>(), ktiles, c->i8_bdig.as<uint8_t>());
-    c->launches += 3;
-    CUDA_TRY(cudaGetLastError());
-
-    CUtensorMap map;
-    if (kind == 0) TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BM, I8_BK));
-    else TRY(i8_make_tmap(&map, c->T.as<double>(), (uint64_t)Mrows, (uint64_t)Ncols, I8_BK, I8_BM));
-
-    const int num_row_tiles = (int)(rows_out / I8_BM);
-    const int grid = std::min(num_row_tiles, c->sm_count);
-    static bool attr[2][64] = {{false}};
-    if (!attr[kind][c->device & 63]) {
-        if (kind == 0) CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-        else CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-        attr[kind][c->device & 63] = true;
-    }
-    if (kind == 0)
-        partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, c->i8_bdig.as<uint8_t>(), ec.buf.as<int>(), c->i8_eb.as<int>(), out, rows_out, R,
-                                                                   num_row_tiles, (int)ktiles);
-    else
-        partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, c->i8_bdig.as<uint8_t>(), ec.buf.as<int>(), c->i8_eb.as<int>(), out, rows_out, R,
-                                                                   num_row_tiles, (int)ktiles);
+    TRY(c->i8_eb.reserve((size_t)rblocks * I8_BN * 4));
+    TRY(c->i8_bdig.reserve((size_t)rblocks * ktiles * I8_B_BYTES));
+    i8_fill_int_kernel<<<(unsigned)ceil_div(rblocks * I8_BN, 64), 64, 0, c->stream>>>(c->i8_eb.as<int>(), rblocks * I8_BN, I8_EXP_ZERO);
     c->launches++;
-    CUDA_TRY(cudaGetLastError());
+    const int grid = (int)std::min<int64_t>(row_tiles, c->sm_count);
+    for (int rb = 0; rb < rblocks; ++rb) {
+        pa.r0 = rb * I8_BN;
+        int *eb = c->i8_eb.as<int>() + rb * I8_BN;
+        uint8_t *bdig = c->i8_bdig.as<uint8_t>() + (size_t)rb * ktiles * I8_B_BYTES;
+        double *out_rb = out + (size_t)rb * I8_BN * rows_out;
+        const int Rb = std::min(I8_BN, R - rb * I8_BN);
+        i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, eb);
+        i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, eb, ktiles, bdig);
+        if (kind == 0)
+            partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+        else
+            partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+        c->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+    }
     return ITCPD_OK;
 }
 #endif  // ITCPD_I8_PROBE
