@@ -540,6 +540,19 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     i8_fill_int_kernel<<<(unsigned)ceil_div(rblocks * I8_BN, 64), 64, 0, c->stream>>>(c->i8_eb.as<int>(), rblocks * I8_BN, I8_EXP_ZERO);
     c->launches++;
     const int grid = (int)std::min<int64_t>(row_tiles, c->sm_count);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_gemm) {  // same bookkeeping as launch_partial_gemm: one event pair per contraction (itcpd_gemm_timing)
+        if (c->gemm_events_used == c->gemm_events.size()) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            c->gemm_events.push_back({a, b});
+        }
+        e0 = c->gemm_events[c->gemm_events_used].first;
+        e1 = c->gemm_events[c->gemm_events_used].second;
+        c->gemm_events_used++;
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
     for (int rb = 0; rb < rblocks; ++rb) {
         pa.r0 = rb * I8_BN;
         int *eb = c->i8_eb.as<int>() + rb * I8_BN;
@@ -555,6 +568,7 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         c->launches += 3;
         CUDA_TRY(cudaGetLastError());
     }
+    if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));
     return ITCPD_OK;
 }
 #endif  // ITCPD_I8_PROBE
