@@ -249,6 +249,7 @@ __device__ __forceinline__ void i8_bulk_1d(uint32_t dst, const void *src, uint32
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void i8_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void i8_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void i8_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void i8_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -324,7 +325,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         for (int s = 0; s < I8_DSTAGES; ++s) { i8_mbar_init(full_d + 8 * s, 256 + 1); i8_mbar_init(empty_d + 8 * s, 1); }
         i8_mbar_init(acc_full, 1);
         i8_mbar_init(acc_empty, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        i8_fence_mbar_init();
     }
     if (warp == 9) i8_tmem_alloc(tmem_slot, 512);
     i8_tc_fence_before();

@@ -1,0 +1,207 @@
+"""The WHOLE experimental INT8 kernel (csrc/gemm_i8.cu: partial_gemm_i8_kernel, verbatim text) executed on the host against a
+small functional model of the hardware it programs:
+  * 320 OS threads per CTA (tests/simt_emu.h), CTAs run one after the other;
+  * shared memory = one byte array, "shared addresses" = offsets into it; mbarriers = (pending arrivals, pending transaction
+    bytes, phase) records keyed by address with init / arrive / expect_tx / try_wait.parity / complete_tx;
+  * TMA 2-D tile loads (zero fill outside the tensor) and 1-D bulk copies complete synchronously and post their bytes;
+  * TMEM = 128 lanes x 512 int32 columns; tcgen05.alloc hands out column 0; tcgen05.ld 32x32b checks the warp's lane quarter;
+  * tcgen05.mma kind::i8 DECODES the 64-bit shared-memory descriptors and the instruction descriptor the kernel built
+    (start address, LBO, SBO, major-ness, N) with the canonical-layout formulas of cute/atom/mma_traits_sm100.hpp and
+    multiplies exactly; tcgen05.commit arrives on its mbarrier.
+The model is synchronous, so it says nothing about speed or about proxy-fence placement; it does execute the kernel's real
+control flow: barrier counts and parities, stage indices, descriptor arithmetic, accumulator columns, the epilogue's lane and
+column addressing, ragged tiles.  The result must match the FP64 contraction to 1e-12."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "itensorcpd.jl_b200", "csrc", "gemm_i8.cu")
+BUILD = os.path.join(ROOT, "oracle", "_build")
+
+MODEL = r"""
+#include "simt_emu.h"
+#include <algorithm>
+#include <map>
+#include <mutex>
+#define ITCPD_MAX_ORDER 8
+#define __grid_constant__
+#define __host__
+using std::min;
+struct uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline long long __double2ll_rn(double x) { return llrint(x); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long xy = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((xy >> (8 * ((s >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+    return r;
+}
+inline int atomicMax(int *p, int v) { static std::mutex m; std::lock_guard<std::mutex> g(m); int o = *p; if (v > o) *p = v; return o; }
+inline void __trap() { abort(); }
+
+// ---------------- the modelled machine ----------------
+alignas(1024) static uint8_t i8_smem_raw[232448 + 2048];
+static const uint32_t SMEM_BASE_ADDR = 0x1230;       // deliberately not 1024-aligned: the kernel must align itself
+static int32_t TMEM[128][512];
+struct CUtensorMap { const double *base; long d0, d1; int box0, box1; };
+struct MBarModel { int count = 0, pending = 0; long tx = 0; unsigned phase = 0; };
+static std::map<uint32_t, MBarModel> g_bars;
+static std::mutex g_bar_mutex;
+static long g_mma_count = 0;
+
+inline uint32_t i8_smem_u32(const void *p) { return SMEM_BASE_ADDR + (uint32_t)((const uint8_t *)p - i8_smem_raw); }
+inline uint8_t *smem_ptr(uint32_t addr) { return i8_smem_raw + (addr - SMEM_BASE_ADDR); }
+static void bar_flip(MBarModel &b) { if (b.pending == 0 && b.tx == 0) { b.phase++; b.pending = b.count; } }
+inline void i8_mbar_init(uint32_t bar, uint32_t count) { std::lock_guard<std::mutex> g(g_bar_mutex); MBarModel b; b.count = b.pending = (int)count; g_bars[bar] = b; }
+inline void bar_arrive(uint32_t bar, long tx) {
+    std::lock_guard<std::mutex> g(g_bar_mutex);
+    auto it = g_bars.find(bar);
+    if (it == g_bars.end()) { fprintf(stderr, "arrive on an uninitialised mbarrier 0x%x\n", bar); abort(); }
+    it->second.tx += tx; it->second.pending -= 1;
+    if (it->second.pending < 0) { fprintf(stderr, "too many arrivals on mbarrier 0x%x\n", bar); abort(); }
+    bar_flip(it->second);
+}
+inline void bar_complete_tx(uint32_t bar, long bytes) { std::lock_guard<std::mutex> g(g_bar_mutex); auto &b = g_bars.at(bar); b.tx -= bytes; bar_flip(b); }
+inline void i8_mbar_expect_tx(uint32_t bar, uint32_t bytes) { bar_arrive(bar, (long)bytes); }
+inline void i8_mbar_arrive(uint32_t bar) { bar_arrive(bar, 0); }
+inline void i8_mbar_wait(uint32_t bar, uint32_t parity) {
+    for (long spins = 0;; ++spins) {
+        { std::lock_guard<std::mutex> g(g_bar_mutex); if ((g_bars.at(bar).phase & 1u) != parity) return; }
+        if (spins > 40000000) { fprintf(stderr, "dead-lock: mbarrier 0x%x parity %u (thread %u)\n", bar, parity, threadIdx.x); abort(); }
+        sched_yield();
+    }
+}
+inline void i8_tma_2d(uint32_t dst, const CUtensorMap *m, int c0, int c1, uint32_t bar) {
+    double *d = (double *)smem_ptr(dst);
+    for (int j = 0; j < m->box1; ++j)
+        for (int i = 0; i < m->box0; ++i) {
+            const long g0 = c0 + i, g1 = c1 + j;
+            d[j * m->box0 + i] = (g0 < m->d0 && g1 < m->d1) ? m->base[g0 + m->d0 * g1] : 0.0;
+        }
+    bar_complete_tx(bar, (long)m->box0 * m->box1 * 8);
+}
+inline void i8_bulk_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) { memcpy(smem_ptr(dst), src, bytes); bar_complete_tx(bar, bytes); }
+inline void i8_fence_mbar_init() {}
+inline void i8_fence_proxy_async() {}
+inline void i8_tc_fence_before() {}
+inline void i8_tc_fence_after() {}
+inline void i8_tmem_alloc(uint32_t smem_dst, uint32_t cols) { if (cols != 512) abort(); if ((threadIdx.x & 31) == 0) *(uint32_t *)smem_ptr(smem_dst) = 0u; __syncwarp(); }
+inline void i8_tmem_dealloc(uint32_t, uint32_t) {}
+inline void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t a0 = (uint32_t)(adesc & 0x3fff) << 4, albo = (uint32_t)((adesc >> 16) & 0x3fff) << 4, asbo = (uint32_t)((adesc >> 32) & 0x3fff) << 4;
+    const uint32_t b0 = (uint32_t)(bdesc & 0x3fff) << 4, blbo = (uint32_t)((bdesc >> 16) & 0x3fff) << 4, bsbo = (uint32_t)((bdesc >> 32) & 0x3fff) << 4;
+    if (((adesc >> 46) & 3) != 1 || ((bdesc >> 46) & 3) != 1 || (adesc >> 61) != 0 || (bdesc >> 61) != 0) { fprintf(stderr, "bad descriptor version / layout type\n"); abort(); }
+    const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4, a_mn = (int)(idesc >> 15) & 1, b_mn = (int)(idesc >> 16) & 1;
+    if (M != 128 || b_mn != 0 || ((idesc >> 4) & 3) != 2 || ((idesc >> 7) & 7) != 1 || ((idesc >> 10) & 7) != 1 || N % 16 != 0 || N < 16 || N > 256) { fprintf(stderr, "bad instruction descriptor 0x%x\n", idesc); abort(); }
+    // the descriptor holds a 14-bit (>> 4) address: compare modulo 2^18 like the hardware
+    auto A = [&](int m, int k) -> int { const uint32_t off = a_mn ? (k % 8) * 16 + (k / 8) * albo + (m / 16) * asbo + m % 16 : (m % 8) * 16 + (m / 8) * asbo + (k / 16) * albo + k % 16; return (int8_t)*smem_ptr(a0 + off); };
+    auto B = [&](int n, int k) -> int { const uint32_t off = (n % 8) * 16 + (n / 8) * bsbo + (k / 16) * blbo + k % 16; return (int8_t)*smem_ptr(b0 + off); };
+    const int col0 = (int)(d_tmem & 0xffff);
+    if ((d_tmem >> 16) != 0 || col0 + N > 512) { fprintf(stderr, "MMA writes outside the TMEM allocation\n"); abort(); }
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            int s = 0;
+            for (int k = 0; k < 32; ++k) s += A(m, k) * B(n, k);
+            TMEM[m][col0 + n] = (accumulate ? TMEM[m][col0 + n] : 0) + s;
+        }
+    ++g_mma_count;
+}
+inline void i8_commit(uint32_t bar) { bar_arrive(bar, 0); }
+inline void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    const int lane0 = (int)(taddr >> 16), col = (int)(taddr & 0xffff), warp = (int)(threadIdx.x >> 5);
+    if (lane0 != 32 * (warp % 4) || col + 32 > 512) { fprintf(stderr, "tcgen05.ld outside the warp's lane quarter / allocation\n"); abort(); }
+    for (int c = 0; c < 32; ++c) v[c] = TMEM[lane0 + (threadIdx.x & 31)][col + c];
+}
+
+namespace itcpd_emu {
+@@NUMERICS@@
+@@DESCS@@
+@@KERNEL@@
+}
+using namespace itcpd_emu;
+
+// out (rows_out x R) = unfolding(T) * K  through the emulated kernel; exponents and digit planes by the emulated helpers
+extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, double *out) {
+    const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
+    const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
+    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
+    if (kind == 0) {
+        const unsigned gx = (unsigned)((rows_out + 63) / 64), gy = 2;
+        for (unsigned bx = 0; bx < gx; ++bx) for (unsigned by = 0; by < gy; ++by)
+            emu_launch(64, 0, [&] { i8_row_exponent_strided_kernel(T, rows_out, kext, Mrows, ea.data()); }, bx, by, gx, gy);
+    } else {
+        const unsigned gx = (unsigned)((rows_out * 32 + 63) / 64);
+        for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_row_exponent_contig_kernel(T, rows_out, kext, Mrows, ea.data()); }, bx, 0, gx, 1);
+    }
+    I8Krp a;
+    memset(&a, 0, sizeof(a));
+    a.nf = nf; a.kext = kext; a.R = R;
+    for (int f = 0; f < nf; ++f) { a.fac[f] = fac[f]; a.ext[f] = ext[f]; a.dim[f] = ext[f]; }
+    std::vector<uint8_t> bdig(ktiles * I8_B_BYTES);
+    unsigned gx = (unsigned)((((kext + 255) / 256) * I8_BN + 63) / 64);
+    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_exponent_kernel(a, eb.data()); }, bx, 0, gx, 1);
+    gx = (unsigned)((ktiles * I8_BN * 2 + 63) / 64);
+    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_pack_kernel(a, eb.data(), ktiles, bdig.data()); }, bx, 0, gx, 1);
+    CUtensorMap map;
+    map.base = T; map.d0 = Mrows; map.d1 = Ncols;
+    if (kind == 0) { map.box0 = I8_BM; map.box1 = I8_BK; } else { map.box0 = I8_BK; map.box1 = I8_BM; }
+    g_mma_count = 0;
+    for (int cta = 0; cta < grid; ++cta) {
+        g_bars.clear();
+        memset(TMEM, 0x5a, sizeof(TMEM));          // stale accumulator contents must not leak into results
+        if (kind == 0) emu_launch(320, 0, [&] { partial_gemm_i8_kernel<0>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+        else emu_launch(320, 0, [&] { partial_gemm_i8_kernel<1>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+    }
+    return g_mma_count;
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def sim():
+    text = open(SRC).read()
+    numerics = text[text.index("constexpr int I8_NDIG = 7;"):text.index("#ifndef ITCPD_I8_HOST_EMULATION")]
+    descs = text[text.index("// shared-memory matrix descriptor, SWIZZLE_NONE"):text.index("// ------------------------------------------------------------------------------------------------------------------\n// the kernel")]
+    k0 = text.index("template <int KIND>\n__global__ void __launch_bounds__(320, 1)")
+    k1 = text.index("// ------------------------------------------------------------------------------------------------------------------\n// host side")
+    kernel = text[k0:k1].replace("extern __shared__ uint8_t i8_smem_raw[];", "")
+    os.makedirs(BUILD, exist_ok=True)
+    cpp, so = os.path.join(BUILD, "i8_sim.cpp"), os.path.join(BUILD, "i8_sim.so")
+    open(cpp, "w").write(MODEL.replace("@@NUMERICS@@", numerics).replace("@@DESCS@@", descs).replace("@@KERNEL@@", kernel))
+    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-Wl,-Bsymbolic", "-I", os.path.join(ROOT, "tests"), "-o", so, cpp,
+                    "-lpthread"], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.emu_gemm_i8.restype = C.c_long
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("kind,Mrows,Ncols,R,grid", [(0, 256, 64, 48, 2), (1, 64, 256, 64, 2), (0, 200, 40, 20, 1), (1, 40, 330, 33, 3), (0, 384, 96, 64, 2)])
+def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid):
+    rng = np.random.default_rng(100 * kind + Mrows)
+    T = np.asfortranarray(rng.standard_normal((Mrows, Ncols)) * np.exp2(rng.integers(-5, 6, size=(Mrows, 1))))   # memory image T[m + Mrows n]
+    kext = Ncols if kind == 0 else Mrows
+    e1 = 8 if kext % 8 == 0 else 5 if kext % 5 == 0 else 1
+    f1 = np.asfortranarray(rng.standard_normal((e1, R)))
+    f2 = np.asfortranarray(rng.standard_normal((kext // e1, R)))
+    Kr = (f2[:, None, :] * f1[None, :, :]).reshape(kext, R)
+    rows_out = Mrows if kind == 0 else Ncols
+    out = np.full((rows_out, R), np.nan, order="F")
+    fac = (C.c_void_p * 2)(f1.ctypes.data, f2.ctypes.data)
+    ext = np.array([e1, kext // e1], dtype=np.int64)
+    nmma = sim.emu_gemm_i8(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, grid, _p(out))
+    ref = (T.astype(np.longdouble) @ Kr.astype(np.longdouble)) if kind == 0 else (T.T.astype(np.longdouble) @ Kr.astype(np.longdouble))
+    ref = ref.astype(np.float64)
+    assert np.all(np.isfinite(out)), "some outputs were never written"
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    assert err < 1e-12, err
+    ktiles, row_tiles = -(-kext // 32), -(-rows_out // 128)
+    assert nmma == 10 * ktiles * row_tiles          # 28 digit products per k-step as 10 instructions

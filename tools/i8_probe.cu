@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) i8_probe_kernel(const uint8_t *__restr
     for (int i = threadIdx.x; i < b_bytes; i += 128) gen[4096 + i] = Bg[i];
     if (threadIdx.x == 0) {
         i8_mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        i8_fence_mbar_init();
     }
     i8_fence_proxy_async();
     if (warp == 0) i8_tmem_alloc(slot, 512);
