@@ -491,6 +491,8 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     const int64_t rows_out = (kind == 0) ? Mrows : Ncols;
     const int64_t ktiles = ceil_div(kext, I8_BK), row_tiles = ceil_div(rows_out, I8_BM);
     if (row_tiles > INT32_MAX / I8_BM || ktiles > INT32_MAX / I8_BK || Mrows > INT32_MAX || Ncols > INT32_MAX) return ITCPD_ERR_UNSUPPORTED;
+    // no split-K yet: a short-and-wide contraction (few row tiles, long k) would leave most SMs idle -> DMMA + stream-K
+    if (row_tiles < c->sm_count && ktiles > 256) return ITCPD_ERR_UNSUPPORTED;
     const int rblocks = (int)ceil_div(R, I8_BN);
 
     // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
