@@ -324,7 +324,7 @@ def run_ours(args, cfg):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.config)
         except Exception:
             pass
-        i8 = os.environ.get("ITCPD_GEMM_I8", "0") == "1"   # experimental INT8 tensor-core contraction: the pass is then HBM-bound
+        i8 = os.environ.get("ITCPD_GEMM_I8", "0") in ("1", "2")   # experimental INT8 tensor-core contraction: the pass is then HBM-bound
         roof = {"bound": "tensor", "kernel": "partial_gemm_kernel (TMA + FP64 DMMA.8x8x4)", "achieved": ach, "peak": peaks["dmma_tflops"],
                 "unit": "TFLOP/s", "frac": ach / peaks["dmma_tflops"], "traffic": traffic,
                 "peak_source": "FP64 DMMA issue-rate probe measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
@@ -335,11 +335,13 @@ def run_ours(args, cfg):
                 "hbm_achieved_GBs": 8.0 * P / world / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0, "hbm_peak_GBs": mp.get("hbm_gbs"),
                 "sweep_roofline_frac": (2 * flops_per_launch / (peaks["dmma_tflops"] * 1e12)) / (ms * 1e-3 / K)}
         if i8 and gemm_ms > 0 and mp.get("hbm_gbs"):
-            gbs = 8.0 * P / world / (gemm_ms * 1e-3) / 1e9
+            bytes_per_elem = 7.0 if os.environ.get("ITCPD_GEMM_I8") == "2" else 8.0   # pre-packed digit planes stream 7 B per element
+            gbs = bytes_per_elem * P / world / (gemm_ms * 1e-3) / 1e9
             roof.update({"bound": "hbm", "kernel": "partial_gemm_i8_kernel (TMA + tcgen05.mma kind::i8 on 7 base-128 digits, TMEM accumulators)",
                          "achieved": gbs, "peak": mp["hbm_gbs"], "unit": "GB/s", "frac": gbs / mp["hbm_gbs"],
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs", "fp64_equivalent_tflops": ach,
-                         "sweep_roofline_frac": (2 * 8.0 * P / world / (mp["hbm_gbs"] * 1e9)) / (ms * 1e-3 / K)})
+                         "algorithmic_bytes_per_launch": bytes_per_elem * P / world,
+                         "sweep_roofline_frac": (2 * bytes_per_elem * P / world / (mp["hbm_gbs"] * 1e9)) / (ms * 1e-3 / K)})
         line = {"metric": "CP-ALS sweeps/sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",

@@ -319,7 +319,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
-    if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = atoi(s) != 0;   // experimental (csrc/gemm_i8.cu)
+    if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
     if (st != ITCPD_OK) { delete c; return st; }
     *out = c;
@@ -341,6 +341,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     c->lev_gather.release();
     c->peer_epochs.release();
     c->i8_exp[0].buf.release(); c->i8_exp[1].buf.release(); c->i8_eb.release(); c->i8_bdig.release();
+    c->i8_apack[0].buf.release(); c->i8_apack[1].buf.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->phase_events) cudaEventDestroy(ev);
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
@@ -387,7 +388,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
-    else if (n == "gemm_i8") c->gemm_i8 = value != 0;
+    else if (n == "gemm_i8") { ARG_CHECK(value >= 0 && value <= 2, "gemm_i8 must be 0, 1 (convert on the fly) or 2 (pre-packed digits)"); c->gemm_i8 = (int)value; }
     else if (n == "peer_graph") {
         ARG_CHECK(!c->peer_on, "set peer_graph before itcpd_peer_export / itcpd_peer_import");
         c->peer_graph = value != 0;
@@ -1273,6 +1274,8 @@ int itcpd_drop_tensor(itcpd_ctx *c) {
     c->PA.buf.release();
     c->PB.buf.release();
     c->qr_A.release();
+    c->i8_apack[0].buf.release(); c->i8_apack[1].buf.release();
+    c->i8_apack[0].valid = c->i8_apack[1].valid = false;
     c->PA.valid = c->PB.valid = false;
     c->has_tensor_data = false;
     return ITCPD_OK;

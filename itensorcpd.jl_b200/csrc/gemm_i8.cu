@@ -296,6 +296,61 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n, int a_mn_major) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Epilogue of one 128 x 64 tile by one warp: TMEM lane quarter q (= warp index mod 4, the hardware's rule for tcgen05.ld)
+// holds rows row0 + 32 q + lane.  v = sum_t acc_t 2^(-7 t) is formed smallest weights first, scaled, stored column-major.
+__device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_full, uint32_t acc_empty, int tile_seq, int64_t row0, int q, int lane,
+                                                 const int *__restrict__ ea, const int *__restrict__ eb, double *__restrict__ out,
+                                                 int64_t rows_out, int R) {
+    i8_mbar_wait(acc_full, (uint32_t)(tile_seq & 1));
+    i8_tc_fence_after();
+    const int64_t m = row0 + 32 * q + lane;
+    const int em = (m < rows_out) ? ea[m] : I8_EXP_ZERO;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        double v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = 0.0;
+#pragma unroll 1
+        for (int t = I8_NDIG - 1; t >= 0; --t) {
+            int a[32];
+            i8_tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(I8_BN * t + 32 * half), a);
+            const double wt = i8_weight(t);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = fma((double)a[c], wt, v[c]);
+        }
+        if (m < rows_out) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int r = 32 * half + c;
+                if (r < R) out[m + rows_out * (int64_t)r] = i8_finish(v[c], em, eb[r]);
+            }
+        }
+    }
+    i8_tc_fence_before();
+    i8_mbar_arrive(acc_empty);
+}
+
+// the 10 tcgen05.mma of one k-step: A digit plane p (128 x 32)  x  the first 7 - p stacked B planes  ->  accumulators p .. 6
+template <int KIND>
+__device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t a0, uint32_t b0, bool first_kstep) {
+    const uint64_t bdesc_lo = i8_smem_desc(b0, 128, 256);                     // B rows 0..   (K-major)
+    const uint64_t bdesc_hi = i8_smem_desc(b0 + 256 / 8 * 256, 128, 256);     // B rows 256..
+#pragma unroll
+    for (int p = 0; p < I8_NDIG; ++p) {
+        const uint64_t adesc = (KIND == 0) ? i8_smem_desc(a0 + p * I8_A_PLANE, 128, 256)    // K-major: LBO = k chunk, SBO = 8-row group
+                                           : i8_smem_desc(a0 + p * I8_A_PLANE, 128, 512);   // MN-major: LBO = k group of 8, SBO = 16-row block
+        const int ntot = I8_BN * (I8_NDIG - p);
+        const uint32_t acc = (!first_kstep || p > 0) ? 1u : 0u;                 // p = 0 touches every accumulator first
+        const uint32_t d = tmem + (uint32_t)(I8_BN * p);
+        if (ntot > 256) {
+            i8_mma(d, adesc, bdesc_lo, i8_idesc(256, KIND), acc);
+            i8_mma(d + 256, adesc, bdesc_hi, i8_idesc(ntot - 256, KIND), acc);
+        } else {
+            i8_mma(d, adesc, bdesc_lo, i8_idesc(ntot, KIND), acc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -373,23 +428,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                     const int sd = it % I8_DSTAGES;
                     i8_mbar_wait(full_d + 8 * sd, (uint32_t)((it / I8_DSTAGES) & 1));
                     i8_tc_fence_after();
-                    const uint32_t a0 = sA + sd * I8_A_BYTES, b0 = sB + sd * I8_B_BYTES;
-                    const uint64_t bdesc_lo = i8_smem_desc(b0, 128, 256);                     // B rows 0..   (K-major)
-                    const uint64_t bdesc_hi = i8_smem_desc(b0 + 256 / 8 * 256, 128, 256);     // B rows 256..
-#pragma unroll
-                    for (int p = 0; p < I8_NDIG; ++p) {
-                        const uint64_t adesc = (KIND == 0) ? i8_smem_desc(a0 + p * I8_A_PLANE, 128, 256)    // K-major: LBO = k chunk, SBO = 8-row group
-                                                           : i8_smem_desc(a0 + p * I8_A_PLANE, 128, 512);   // MN-major: LBO = k group of 8, SBO = 16-row block
-                        const int ntot = I8_BN * (I8_NDIG - p);                 // accumulators t = p .. 6
-                        const uint32_t acc = (kt > 0 || p > 0) ? 1u : 0u;       // p = 0 touches every accumulator first
-                        const uint32_t d = tmem + (uint32_t)(I8_BN * p);
-                        if (ntot > 256) {
-                            i8_mma(d, adesc, bdesc_lo, i8_idesc(256, KIND), acc);
-                            i8_mma(d + 256, adesc, bdesc_hi, i8_idesc(ntot - 256, KIND), acc);
-                        } else {
-                            i8_mma(d, adesc, bdesc_lo, i8_idesc(ntot, KIND), acc);
-                        }
-                    }
+                    i8_issue_kstep<KIND>(tmem, sA + sd * I8_A_BYTES, sB + sd * I8_B_BYTES, kt == 0);
                     i8_commit(empty_d + 8 * sd);                                // frees the digit slot when these MMAs are done
                 }
                 i8_commit(acc_full);                                            // accumulators of this tile are complete
@@ -413,40 +452,108 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                 i8_mbar_arrive(empty_f + 8 * sf);
             }
             if (warp < 4) {
-                // ---- epilogue: row m = 32 warp + lane of the tile ----
-                i8_mbar_wait(acc_full, (uint32_t)(w & 1));
-                i8_tc_fence_after();
-                const int64_t m = row0 + 32 * warp + lane;
-                const int em = (m < rows_out) ? ea[m] : I8_EXP_ZERO;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    double v[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = 0.0;
-#pragma unroll 1
-                    for (int t = I8_NDIG - 1; t >= 0; --t) {       // smallest weights first
-                        int a[32];
-                        i8_tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(I8_BN * t + 32 * half), a);
-                        const double wt = i8_weight(t);
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = fma((double)a[c], wt, v[c]);
-                    }
-                    if (m < rows_out) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int r = 32 * half + c;
-                            if (r < R) out[m + rows_out * (int64_t)r] = i8_finish(v[c], em, eb[r]);
-                        }
-                    }
-                }
-                i8_tc_fence_before();
-                i8_mbar_arrive(acc_empty);
+                i8_epilogue_warp(tmem, acc_full, acc_empty, w, row0, warp, lane, ea, eb, out, rows_out, R);
             }
         }
     }
     i8_tc_fence_before();
     __syncthreads();
     if (warp == 9) i8_tmem_dealloc(tmem, 512);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pre-packed variant (gemm_i8 = 2): T never changes during a decomposition, so its digit planes are computed ONCE per
+// unfolding and kept in HBM as one 28672-byte block per (row tile, k-tile), already in the canonical UMMA layout.
+// A pass then streams 7 bytes per tensor element instead of 8, needs no conversion in the loop, and the kernel is a
+// plain TMA -> tcgen05.mma -> TMEM pipeline: warp 0 producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int I8P_STAGES = 4;
+constexpr int I8P_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 43008
+constexpr int I8P_SMEM = I8P_STAGES * I8P_STAGE_BYTES + 256 + 1024;
+
+// one CTA per (row tile, k-tile): stage the 128 x 32 FP64 tile in shared memory (zero fill outside the tensor), then the
+// converter threads write the digit block.  view: element (row r, contraction index j) at T[r * sr + j * sj]
+template <int KIND>
+__global__ void __launch_bounds__(256) i8_pack_tensor_kernel(const double *__restrict__ T, int64_t nrows, int64_t nred, int64_t sr, int64_t sj,
+                                                             const int *__restrict__ ea, int64_t ktiles, uint8_t *__restrict__ Adig) {
+    __shared__ double F[I8_BM * I8_BK];
+    const int64_t blk = blockIdx.x;
+    const int64_t tile = blk / ktiles, kt = blk - tile * ktiles;
+    const int64_t row0 = tile * I8_BM, k0 = kt * I8_BK;
+    for (int e = threadIdx.x; e < I8_BM * I8_BK; e += 256) {
+        // KIND 0 staging order [k][m] (m contiguous in memory), KIND 1 [n][k] (k contiguous in memory)
+        const int rr = (KIND == 0) ? e % I8_BM : e / I8_BK, kk = (KIND == 0) ? e / I8_BM : e % I8_BK;
+        const int64_t r = row0 + rr, j = k0 + kk;
+        F[e] = (r < nrows && j < nred) ? T[r * sr + j * sj] : 0.0;
+    }
+    __syncthreads();
+    i8_convert_thread<KIND>(F, ea + row0, Adig + blk * (int64_t)I8_A_BYTES, (int)threadIdx.x);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(192, 1)
+partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea, const int *__restrict__ eb,
+                        double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count) {
+    extern __shared__ uint8_t i8_smem_raw[];
+    const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + I8P_STAGES * I8P_STAGE_BYTES;
+    const uint32_t full = bars, empty = bars + 8 * I8P_STAGES, acc_full = empty + 8 * I8P_STAGES, acc_empty = acc_full + 8, tmem_slot = acc_empty + 8;
+    uint8_t *gen_base = i8_smem_raw + (base - i8_smem_u32(i8_smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8P_STAGES; ++s) { i8_mbar_init(full + 8 * s, 1); i8_mbar_init(empty + 8 * s, 1); }
+        i8_mbar_init(acc_full, 1);
+        i8_mbar_init(acc_empty, 128);
+        i8_fence_mbar_init();
+    }
+    if (warp == 1) i8_tmem_alloc(tmem_slot, 512);
+    i8_tc_fence_before();
+    __syncthreads();
+    i8_tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int my_tiles = (num_row_tiles - cta + G - 1) / G;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int w = 0; w < my_tiles; ++w) {
+                const int64_t tile = cta + (int64_t)w * G;
+                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                    const int st = it % I8P_STAGES;
+                    if (it >= I8P_STAGES) i8_mbar_wait(empty + 8 * st, (uint32_t)((it / I8P_STAGES - 1) & 1));
+                    i8_mbar_expect_tx(full + 8 * st, I8P_STAGE_BYTES);
+                    const uint32_t dst = base + st * I8P_STAGE_BYTES;
+                    i8_bulk_1d(dst, Adig + (size_t)(tile * kt_count + kt) * I8_A_BYTES, I8_A_BYTES, full + 8 * st);
+                    i8_bulk_1d(dst + I8_A_BYTES, Bdig + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full + 8 * st);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int it = 0;
+            for (int w = 0; w < my_tiles; ++w) {
+                if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));
+                i8_tc_fence_after();
+                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                    const int st = it % I8P_STAGES;
+                    i8_mbar_wait(full + 8 * st, (uint32_t)((it / I8P_STAGES) & 1));
+                    i8_tc_fence_after();
+                    const uint32_t a0 = base + st * I8P_STAGE_BYTES;
+                    i8_issue_kstep<KIND>(tmem, a0, a0 + I8_A_BYTES, kt == 0);
+                    i8_commit(empty + 8 * st);
+                }
+                i8_commit(acc_full);
+            }
+        }
+    } else {
+        for (int w = 0; w < my_tiles; ++w)
+            i8_epilogue_warp(tmem, acc_full, acc_empty, w, (int64_t)(cta + (int64_t)w * G) * I8_BM, warp & 3, lane, ea, eb, out, rows_out, R);
+    }
+    i8_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) i8_tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -526,6 +633,30 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         attr[kind][c->device & 63] = true;
     }
 
+    // ---- pre-packed digit planes of T (gemm_i8 = 2): built once per tensor / unfolding, 7 bytes per element in HBM ----
+    const bool prepacked = c->gemm_i8 == 2;
+    I8ExpCache &pk = c->i8_apack[kind];
+    if (prepacked && (!pk.valid || pk.split != split || pk.tensor_epoch != c->i8_tensor_epoch)) {
+        TRY(pk.buf.reserve((size_t)row_tiles * ktiles * I8_A_BYTES));
+        if (kind == 0)
+            i8_pack_tensor_kernel<0><<<(unsigned)(row_tiles * ktiles), 256, 0, c->stream>>>(c->T.as<double>(), rows_out, kext, 1, Mrows, ec.buf.as<int>(), ktiles,
+                                                                                             pk.buf.as<uint8_t>());
+        else
+            i8_pack_tensor_kernel<1><<<(unsigned)(row_tiles * ktiles), 256, 0, c->stream>>>(c->T.as<double>(), rows_out, kext, Mrows, 1, ec.buf.as<int>(), ktiles,
+                                                                                             pk.buf.as<uint8_t>());
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        pk.valid = true;
+        pk.split = split;
+        pk.tensor_epoch = c->i8_tensor_epoch;
+        static bool attr_p[2][64] = {{false}};
+        if (!attr_p[kind][c->device & 63]) {
+            if (kind == 0) CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
+            else CUDA_TRY(cudaFuncSetAttribute(partial_gemm_i8p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
+            attr_p[kind][c->device & 63] = true;
+        }
+    }
+
     // ---- Khatri-Rao operand: column exponents and packed digit planes of every 64-column block ----
     I8Krp pa;
     memset(&pa, 0, sizeof(pa));
@@ -564,7 +695,11 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         const int Rb = std::min(I8_BN, R - rb * I8_BN);
         i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, eb);
         i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, eb, ktiles, bdig);
-        if (kind == 0)
+        if (prepacked && kind == 0)
+            partial_gemm_i8p_kernel<0><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+        else if (prepacked)
+            partial_gemm_i8p_kernel<1><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+        else if (kind == 0)
             partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
         else
             partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);

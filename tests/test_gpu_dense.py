@@ -446,10 +446,11 @@ def test_right_looking_cholesky_rank_deficient(engine):
 @pytest.mark.skipif(not EXPERIMENTAL, reason="gemm_i8 (INT8 tensor-core digit-split contraction) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("dims,R", [((128, 64, 32), 48), ((256, 32, 64), 64), ((128, 32, 32, 4), 20),
                                     ((100, 37, 45), 50), ((33, 17, 9), 20), ((64, 48, 40), 130)])   # ragged tiles, padded mode 0, 3 rank blocks
-def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R):
+@pytest.mark.parametrize("variant", [1, 2])   # 1: digits of T extracted on the fly, 2: pre-packed digit planes in HBM
+def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R, variant):
     """csrc/gemm_i8.cu: tcgen05.mma kind::i8 on 7 balanced base-128 digits per operand; same 1e-12 bar as the DMMA path."""
     T, cp = make_problem(dims, R, seed=91)
-    engine.set_option("gemm_i8", 1)
+    engine.set_option("gemm_i8", variant)
     try:
         engine.set_tensor(T)
         engine.set_cpd(cp.factors, cp.lam)

@@ -159,6 +159,42 @@ extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, i
     }
     return g_mma_count;
 }
+
+// the pre-packed variant: digit planes of T built once (i8_pack_tensor_kernel), then partial_gemm_i8p_kernel
+extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, double *out) {
+    const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
+    const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
+    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
+    if (kind == 0) {
+        const unsigned gx = (unsigned)((rows_out + 63) / 64);
+        for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_row_exponent_strided_kernel(T, rows_out, kext, Mrows, ea.data()); }, bx, 0, gx, 1);
+    } else {
+        const unsigned gx = (unsigned)((rows_out * 32 + 63) / 64);
+        for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_row_exponent_contig_kernel(T, rows_out, kext, Mrows, ea.data()); }, bx, 0, gx, 1);
+    }
+    I8Krp a;
+    memset(&a, 0, sizeof(a));
+    a.nf = nf; a.kext = kext; a.R = R;
+    for (int f = 0; f < nf; ++f) { a.fac[f] = fac[f]; a.ext[f] = ext[f]; a.dim[f] = ext[f]; }
+    std::vector<uint8_t> bdig(ktiles * I8_B_BYTES), adig((size_t)row_tiles * ktiles * I8_A_BYTES);
+    unsigned gx = (unsigned)((((kext + 255) / 256) * I8_BN + 63) / 64);
+    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_exponent_kernel(a, eb.data()); }, bx, 0, gx, 1);
+    gx = (unsigned)((ktiles * I8_BN * 2 + 63) / 64);
+    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_pack_kernel(a, eb.data(), ktiles, bdig.data()); }, bx, 0, gx, 1);
+    gx = (unsigned)(row_tiles * ktiles);
+    for (unsigned bx = 0; bx < gx; ++bx) {
+        if (kind == 0) emu_launch(256, 0, [&] { i8_pack_tensor_kernel<0>(T, rows_out, kext, 1, Mrows, ea.data(), ktiles, adig.data()); }, bx, 0, gx, 1);
+        else emu_launch(256, 0, [&] { i8_pack_tensor_kernel<1>(T, rows_out, kext, Mrows, 1, ea.data(), ktiles, adig.data()); }, bx, 0, gx, 1);
+    }
+    g_mma_count = 0;
+    for (int cta = 0; cta < grid; ++cta) {
+        g_bars.clear();
+        memset(TMEM, 0x5a, sizeof(TMEM));
+        if (kind == 0) emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<0>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+        else emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<1>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+    }
+    return g_mma_count;
+}
 """
 
 
@@ -177,6 +213,7 @@ def sim():
                     "-lpthread"], check=True, capture_output=True)
     lib = C.CDLL(so)
     lib.emu_gemm_i8.restype = C.c_long
+    lib.emu_gemm_i8p.restype = C.c_long
     return lib
 
 
@@ -184,8 +221,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize("kind,Mrows,Ncols,R,grid", [(0, 256, 64, 48, 2), (1, 64, 256, 64, 2), (0, 200, 40, 20, 1), (1, 40, 330, 33, 3), (0, 384, 96, 64, 2)])
-def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid):
+@pytest.mark.parametrize("variant", ["on_the_fly", "prepacked"])
+@pytest.mark.parametrize("kind,Mrows,Ncols,R,grid", [(0, 256, 64, 48, 2), (1, 64, 256, 64, 2), (0, 200, 40, 20, 1), (1, 40, 330, 33, 3), (0, 384, 160, 64, 2)])
+def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid, variant):
     rng = np.random.default_rng(100 * kind + Mrows)
     T = np.asfortranarray(rng.standard_normal((Mrows, Ncols)) * np.exp2(rng.integers(-5, 6, size=(Mrows, 1))))   # memory image T[m + Mrows n]
     kext = Ncols if kind == 0 else Mrows
@@ -197,7 +235,8 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     out = np.full((rows_out, R), np.nan, order="F")
     fac = (C.c_void_p * 2)(f1.ctypes.data, f2.ctypes.data)
     ext = np.array([e1, kext // e1], dtype=np.int64)
-    nmma = sim.emu_gemm_i8(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, grid, _p(out))
+    run = sim.emu_gemm_i8 if variant == "on_the_fly" else sim.emu_gemm_i8p
+    nmma = run(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, grid, _p(out))
     ref = (T.astype(np.longdouble) @ Kr.astype(np.longdouble)) if kind == 0 else (T.T.astype(np.longdouble) @ Kr.astype(np.longdouble))
     ref = ref.astype(np.float64)
     assert np.all(np.isfinite(out)), "some outputs were never written"

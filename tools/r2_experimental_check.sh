@@ -17,6 +17,7 @@ for chol in 1 2; do
 done
 # INT8 tensor-core contraction (draft): config B with and without it
 ITCPD_GEMM_I8=1 $B --steps 20 > gpurun_out/r2_B_gemm_i8.json 2>> gpurun_out/r2_err.log
+ITCPD_GEMM_I8=2 $B --steps 20 > gpurun_out/r2_B_gemm_i8_prepacked.json 2>> gpurun_out/r2_err.log
 $B --steps 20 > gpurun_out/r2_B_dmma.json 2>> gpurun_out/r2_err.log
 for pg in 0 1; do
   ITCPD_BENCH_PHASES=1 ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
