@@ -340,7 +340,7 @@ int itcpd_destroy(itcpd_ctx *c) {
     c->prev_lambda.release();
     c->lev_gather.release();
     c->peer_epochs.release();
-    c->i8_exp[0].buf.release(); c->i8_exp[1].buf.release(); c->i8_eb.release(); c->i8_bdig.release();
+    c->i8_exp[0].buf.release(); c->i8_exp[1].buf.release(); c->i8_eb.release(); c->i8_bdig.release(); c->i8_part.release();
     c->i8_apack[0].buf.release(); c->i8_apack[1].buf.release();
     for (auto &ev : c->gemm_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : c->phase_events) cudaEventDestroy(ev);

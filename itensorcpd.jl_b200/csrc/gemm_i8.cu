@@ -296,6 +296,26 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n, int a_mn_major) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Work unit of the persistent kernels: (row tile, k-chunk).  ksplit = 1 is the plain data-parallel schedule; a short-and-wide
+// contraction (fewer row tiles than SMs) is cut along k into ksplit chunks of kchunk k-tiles, every unit writes its scaled
+// FP64 partial tile to a slot buffer and i8_splitk_fixup_kernel adds the chunks in ascending-k order (deterministic).
+struct I8Unit { int tile, chunk, kb, ke; };
+__device__ __forceinline__ I8Unit i8_unit(int u, int ksplit, int kchunk, int kt_count) {
+    I8Unit x;
+    x.tile = u / ksplit;
+    x.chunk = u - x.tile * ksplit;
+    x.kb = x.chunk * kchunk;
+    x.ke = min(kt_count, x.kb + kchunk);
+    return x;
+}
+__global__ void i8_splitk_fixup_kernel(const double *__restrict__ part, int ksplit, int64_t chunk_stride, int64_t n, double *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = part[i];
+    for (int c = 1; c < ksplit; ++c) v += part[i + c * chunk_stride];
+    out[i] = v;
+}
+
 // Epilogue of one 128 x 64 tile by one warp: TMEM lane quarter q (= warp index mod 4, the hardware's rule for tcgen05.ld)
 // holds rows row0 + 32 q + lane.  v = sum_t acc_t 2^(-7 t) is formed smallest weights first, scaled, stored column-major.
 __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_full, uint32_t acc_empty, int tile_seq, int64_t row0, int q, int lane,
@@ -361,7 +381,8 @@ __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t a0, uint3
 template <int KIND>
 __global__ void __launch_bounds__(320, 1)
 partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea,
-                       const int *__restrict__ eb, double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count) {
+                       const int *__restrict__ eb, double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count,
+                       int ksplit, int kchunk, double *__restrict__ part) {
     extern __shared__ uint8_t i8_smem_raw[];
     const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
     const uint32_t sF = base;
@@ -389,7 +410,8 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int my_tiles = (num_row_tiles - cta + G - 1) / G;
+    const int my_tiles = (num_row_tiles * ksplit - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
+    const int64_t part_stride = rows_out * (int64_t)I8_BN;
 
     if (warp == 8) {
         // ===== TMA producers: lane 0 streams the FP64 tiles of T, lane 1 the packed digit planes of the Khatri-Rao operand
@@ -397,8 +419,9 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         if (lane == 0) {
             int itf = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                const int row0 = (cta + w * G) * I8_BM;
-                for (int kt = 0; kt < kt_count; ++kt, ++itf) {
+                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                const int row0 = u.tile * I8_BM;
+                for (int kt = u.kb; kt < u.ke; ++kt, ++itf) {
                     const int sf = itf % I8_FSTAGES;
                     if (itf >= I8_FSTAGES) i8_mbar_wait(empty_f + 8 * sf, (uint32_t)((itf / I8_FSTAGES - 1) & 1));
                     i8_mbar_expect_tx(full_f + 8 * sf, I8_F_BYTES);
@@ -409,7 +432,8 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         } else if (lane == 1) {
             int itd = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                for (int kt = 0; kt < kt_count; ++kt, ++itd) {
+                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                for (int kt = u.kb; kt < u.ke; ++kt, ++itd) {
                     const int sd = itd % I8_DSTAGES;
                     if (itd >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((itd / I8_DSTAGES - 1) & 1));
                     i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
@@ -422,13 +446,14 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
+                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
                 if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));   // the epilogue has drained the accumulators
                 i8_tc_fence_after();
-                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                     const int sd = it % I8_DSTAGES;
                     i8_mbar_wait(full_d + 8 * sd, (uint32_t)((it / I8_DSTAGES) & 1));
                     i8_tc_fence_after();
-                    i8_issue_kstep<KIND>(tmem, sA + sd * I8_A_BYTES, sB + sd * I8_B_BYTES, kt == 0);
+                    i8_issue_kstep<KIND>(tmem, sA + sd * I8_A_BYTES, sB + sd * I8_B_BYTES, kt == u.kb);
                     i8_commit(empty_d + 8 * sd);                                // frees the digit slot when these MMAs are done
                 }
                 i8_commit(acc_full);                                            // accumulators of this tile are complete
@@ -439,8 +464,9 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         const int tid = threadIdx.x;   // 0 .. 255
         int it = 0;
         for (int w = 0; w < my_tiles; ++w) {
-            const int64_t row0 = (int64_t)(cta + w * G) * I8_BM;
-            for (int kt = 0; kt < kt_count; ++kt, ++it) {
+            const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+            const int64_t row0 = (int64_t)u.tile * I8_BM;
+            for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                 const int sf = it % I8_FSTAGES, sd = it % I8_DSTAGES;
                 i8_mbar_wait(full_f + 8 * sf, (uint32_t)((it / I8_FSTAGES) & 1));
                 if (it >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((it / I8_DSTAGES - 1) & 1));
@@ -452,7 +478,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                 i8_mbar_arrive(empty_f + 8 * sf);
             }
             if (warp < 4) {
-                i8_epilogue_warp(tmem, acc_full, acc_empty, w, row0, warp, lane, ea, eb, out, rows_out, R);
+                i8_epilogue_warp(tmem, acc_full, acc_empty, w, row0, warp, lane, ea, eb, ksplit > 1 ? part + u.chunk * part_stride : out, rows_out, R);
             }
         }
     }
@@ -494,7 +520,8 @@ __global__ void __launch_bounds__(256) i8_pack_tensor_kernel(const double *__res
 template <int KIND>
 __global__ void __launch_bounds__(192, 1)
 partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea, const int *__restrict__ eb,
-                        double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count) {
+                        double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count, int ksplit, int kchunk,
+                        double *__restrict__ part) {
     extern __shared__ uint8_t i8_smem_raw[];
     const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + I8P_STAGES * I8P_STAGE_BYTES;
@@ -513,14 +540,16 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
     i8_tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int my_tiles = (num_row_tiles - cta + G - 1) / G;
+    const int my_tiles = (num_row_tiles * ksplit - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
+    const int64_t part_stride = rows_out * (int64_t)I8_BN;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                const int64_t tile = cta + (int64_t)w * G;
-                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                const int64_t tile = u.tile;
+                for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                     const int st = it % I8P_STAGES;
                     if (it >= I8P_STAGES) i8_mbar_wait(empty + 8 * st, (uint32_t)((it / I8P_STAGES - 1) & 1));
                     i8_mbar_expect_tx(full + 8 * st, I8P_STAGE_BYTES);
@@ -534,22 +563,26 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
+                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
                 if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));
                 i8_tc_fence_after();
-                for (int kt = 0; kt < kt_count; ++kt, ++it) {
+                for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                     const int st = it % I8P_STAGES;
                     i8_mbar_wait(full + 8 * st, (uint32_t)((it / I8P_STAGES) & 1));
                     i8_tc_fence_after();
                     const uint32_t a0 = base + st * I8P_STAGE_BYTES;
-                    i8_issue_kstep<KIND>(tmem, a0, a0 + I8_A_BYTES, kt == 0);
+                    i8_issue_kstep<KIND>(tmem, a0, a0 + I8_A_BYTES, kt == u.kb);
                     i8_commit(empty + 8 * st);
                 }
                 i8_commit(acc_full);
             }
         }
     } else {
-        for (int w = 0; w < my_tiles; ++w)
-            i8_epilogue_warp(tmem, acc_full, acc_empty, w, (int64_t)(cta + (int64_t)w * G) * I8_BM, warp & 3, lane, ea, eb, out, rows_out, R);
+        for (int w = 0; w < my_tiles; ++w) {
+            const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+            i8_epilogue_warp(tmem, acc_full, acc_empty, w, (int64_t)u.tile * I8_BM, warp & 3, lane, ea, eb, ksplit > 1 ? part + u.chunk * part_stride : out,
+                             rows_out, R);
+        }
     }
     i8_tc_fence_before();
     __syncthreads();
@@ -581,6 +614,25 @@ static int i8_make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint6
     return r == CUDA_SUCCESS ? ITCPD_OK : ITCPD_ERR_CUDA;
 }
 
+// picks (ksplit, kchunk): maximise the SM occupancy of the last wave, prefer the smallest split among equals
+void i8_choose_ksplit(int64_t row_tiles, int64_t ktiles, int sms, int *ksplit_out, int *kchunk_out) {
+    int best = 1;
+    double best_eff = 0.0;
+    const int64_t max_split = std::max<int64_t>(1, std::min<int64_t>(ktiles / 8, 4 * (int64_t)sms));
+    if (row_tiles < 4 * (int64_t)sms) {
+        for (int64_t ks = 1; ks <= max_split; ++ks) {
+            const int64_t chunk = ceil_div(ktiles, ks), real = ceil_div(ktiles, chunk);   // no empty chunk
+            if (real != ks) continue;
+            const int64_t units = row_tiles * ks, waves = ceil_div(units, (int64_t)sms);
+            // time ~ waves * (chunk + fill); efficiency relative to the ideal  row_tiles * ktiles / sms
+            const double eff = (double)(row_tiles * ktiles) / ((double)sms * (double)waves * (double)(chunk + 2));
+            if (eff > best_eff * 1.02) { best_eff = eff; best = (int)ks; }
+        }
+    }
+    *ksplit_out = best;
+    *kchunk_out = (int)ceil_div(ktiles, (int64_t)best);
+}
+
 __global__ void i8_fill_int_kernel(int *x, int64_t n, int v) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
@@ -598,9 +650,11 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     const int64_t rows_out = (kind == 0) ? Mrows : Ncols;
     const int64_t ktiles = ceil_div(kext, I8_BK), row_tiles = ceil_div(rows_out, I8_BM);
     if (row_tiles > INT32_MAX / I8_BM || ktiles > INT32_MAX / I8_BK || Mrows > INT32_MAX || Ncols > INT32_MAX) return ITCPD_ERR_UNSUPPORTED;
-    // no split-K yet: a short-and-wide contraction (few row tiles, long k) would leave most SMs idle -> DMMA + stream-K
-    if (row_tiles < c->sm_count && ktiles > 256) return ITCPD_ERR_UNSUPPORTED;
     const int rblocks = (int)ceil_div(R, I8_BN);
+    // split-K schedule (I8Unit): data parallel when there are enough row tiles; otherwise cut k so that the units fill the
+    // SMs in whole waves (a chunk keeps at least 8 k-tiles so the pipeline fill and the partial-tile traffic stay small)
+    int ksplit = 1, kchunk = (int)ktiles;
+    i8_choose_ksplit(row_tiles, ktiles, c->sm_count, &ksplit, &kchunk);
 
     // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
     I8ExpCache &ec = c->i8_exp[kind];
@@ -676,7 +730,10 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     TRY(c->i8_bdig.reserve((size_t)rblocks * ktiles * I8_B_BYTES));
     i8_fill_int_kernel<<<(unsigned)ceil_div(rblocks * I8_BN, 64), 64, 0, c->stream>>>(c->i8_eb.as<int>(), rblocks * I8_BN, I8_EXP_ZERO);
     c->launches++;
-    const int grid = (int)std::min<int64_t>(row_tiles, c->sm_count);
+    const int grid = (int)std::min<int64_t>(row_tiles * ksplit, c->sm_count);
+    const int64_t part_stride = rows_out * (int64_t)I8_BN;
+    if (ksplit > 1) TRY(c->i8_part.reserve((size_t)ksplit * part_stride * 8));
+    double *part = ksplit > 1 ? c->i8_part.as<double>() : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->time_gemm) {  // same bookkeeping as launch_partial_gemm: one event pair per contraction (itcpd_gemm_timing)
         if (c->gemm_events_used == c->gemm_events.size()) {
@@ -699,14 +756,19 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, eb);
         i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, eb, ktiles, bdig);
         if (prepacked && kind == 0)
-            partial_gemm_i8p_kernel<0><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+            partial_gemm_i8p_kernel<0><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
         else if (prepacked)
-            partial_gemm_i8p_kernel<1><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+            partial_gemm_i8p_kernel<1><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
         else if (kind == 0)
-            partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+            partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
         else
-            partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles);
+            partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
         c->launches += 3;
+        if (ksplit > 1) {
+            const int64_t n = rows_out * (int64_t)Rb;
+            i8_splitk_fixup_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(part, ksplit, part_stride, n, out_rb);
+            c->launches++;
+        }
         CUDA_TRY(cudaGetLastError());
     }
     if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));

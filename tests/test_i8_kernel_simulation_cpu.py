@@ -125,8 +125,16 @@ namespace itcpd_emu {
 }
 using namespace itcpd_emu;
 
+static void run_fixup(std::vector<double> &part, int ksplit, long rows_out, int R, double *out) {
+    if (ksplit <= 1) return;
+    const long n = rows_out * R;
+    const unsigned gx = (unsigned)((n + 63) / 64);
+    for (unsigned bx = 0; bx < gx; ++bx)
+        emu_launch(64, 0, [&] { i8_splitk_fixup_kernel(part.data(), ksplit, rows_out * (long)I8_BN, n, out); }, bx, 0, gx, 1);
+}
+
 // out (rows_out x R) = unfolding(T) * K  through the emulated kernel; exponents and digit planes by the emulated helpers
-extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, double *out) {
+extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, int ksplit, double *out) {
     const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
     const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
     std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
@@ -151,17 +159,21 @@ extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, i
     map.base = T; map.d0 = Mrows; map.d1 = Ncols;
     if (kind == 0) { map.box0 = I8_BM; map.box1 = I8_BK; } else { map.box0 = I8_BK; map.box1 = I8_BM; }
     g_mma_count = 0;
+    const int kchunk = (int)((ktiles + ksplit - 1) / ksplit);
+    if ((ktiles + kchunk - 1) / kchunk != ksplit) return -1;          // the host never launches an empty chunk
+    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rows_out * I8_BN : 1, NAN);
     for (int cta = 0; cta < grid; ++cta) {
         g_bars.clear();
         memset(TMEM, 0x5a, sizeof(TMEM));          // stale accumulator contents must not leak into results
-        if (kind == 0) emu_launch(320, 0, [&] { partial_gemm_i8_kernel<0>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
-        else emu_launch(320, 0, [&] { partial_gemm_i8_kernel<1>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+        if (kind == 0) emu_launch(320, 0, [&] { partial_gemm_i8_kernel<0>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
+        else emu_launch(320, 0, [&] { partial_gemm_i8_kernel<1>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
     }
+    run_fixup(part, ksplit, rows_out, R, out);
     return g_mma_count;
 }
 
 // the pre-packed variant: digit planes of T built once (i8_pack_tensor_kernel), then partial_gemm_i8p_kernel
-extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, double *out) {
+extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, int ksplit, double *out) {
     const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
     const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
     std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
@@ -187,12 +199,16 @@ extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, 
         else emu_launch(256, 0, [&] { i8_pack_tensor_kernel<1>(T, rows_out, kext, Mrows, 1, ea.data(), ktiles, adig.data()); }, bx, 0, gx, 1);
     }
     g_mma_count = 0;
+    const int kchunk = (int)((ktiles + ksplit - 1) / ksplit);
+    if ((ktiles + kchunk - 1) / kchunk != ksplit) return -1;          // the host never launches an empty chunk
+    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rows_out * I8_BN : 1, NAN);
     for (int cta = 0; cta < grid; ++cta) {
         g_bars.clear();
         memset(TMEM, 0x5a, sizeof(TMEM));
-        if (kind == 0) emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<0>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
-        else emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<1>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles); }, cta, 0, grid, 1);
+        if (kind == 0) emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<0>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
+        else emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<1>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
     }
+    run_fixup(part, ksplit, rows_out, R, out);
     return g_mma_count;
 }
 """
@@ -222,8 +238,11 @@ def _p(a):
 
 
 @pytest.mark.parametrize("variant", ["on_the_fly", "prepacked"])
-@pytest.mark.parametrize("kind,Mrows,Ncols,R,grid", [(0, 256, 64, 48, 2), (1, 64, 256, 64, 2), (0, 200, 40, 20, 1), (1, 40, 330, 33, 3), (0, 384, 160, 64, 2)])
-def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid, variant):
+@pytest.mark.parametrize("kind,Mrows,Ncols,R,grid,ksplit", [(0, 256, 64, 48, 2, 1), (1, 64, 256, 64, 2, 1), (0, 200, 40, 20, 1, 1), (1, 40, 330, 33, 3, 1),
+                                                          (0, 384, 160, 64, 2, 1),
+                                                          # split-K (short-and-wide contractions): units = row tiles x k-chunks, FP64 partial tiles + fix-up
+                                                          (0, 128, 320, 64, 3, 5), (1, 352, 100, 24, 2, 4), (0, 200, 200, 40, 5, 3)])
+def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid, ksplit, variant):
     rng = np.random.default_rng(100 * kind + Mrows)
     T = np.asfortranarray(rng.standard_normal((Mrows, Ncols)) * np.exp2(rng.integers(-5, 6, size=(Mrows, 1))))   # memory image T[m + Mrows n]
     kext = Ncols if kind == 0 else Mrows
@@ -236,7 +255,7 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     fac = (C.c_void_p * 2)(f1.ctypes.data, f2.ctypes.data)
     ext = np.array([e1, kext // e1], dtype=np.int64)
     run = sim.emu_gemm_i8 if variant == "on_the_fly" else sim.emu_gemm_i8p
-    nmma = run(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, grid, _p(out))
+    nmma = run(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, grid, ksplit, _p(out))
     ref = (T.astype(np.longdouble) @ Kr.astype(np.longdouble)) if kind == 0 else (T.T.astype(np.longdouble) @ Kr.astype(np.longdouble))
     ref = ref.astype(np.float64)
     assert np.all(np.isfinite(out)), "some outputs were never written"
@@ -244,3 +263,34 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     assert err < 1e-12, err
     ktiles, row_tiles = -(-kext // 32), -(-rows_out // 128)
     assert nmma == 10 * ktiles * row_tiles          # 28 digit products per k-step as 10 instructions
+
+
+def test_split_k_schedule_policy():
+    """i8_choose_ksplit (host, verbatim text): no empty chunk, data parallel when there are many row tiles, whole waves otherwise"""
+    text = open(SRC).read()
+    a = text.index("void i8_choose_ksplit(")
+    fn = text[a:text.index("__global__ void i8_fill_int_kernel")]
+    os.makedirs(BUILD, exist_ok=True)
+    cpp, so = os.path.join(BUILD, "i8_ksplit.cpp"), os.path.join(BUILD, "i8_ksplit.so")
+    open(cpp, "w").write("#include <algorithm>\n#include <cstdint>\nstatic inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }\n"
+                         + fn + '\nextern "C" void choose(long rt, long kt, int sms, int *ks, int *kc) { i8_choose_ksplit(rt, kt, sms, ks, kc); }\n')
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", so, cpp], check=True, capture_output=True)
+    lib = C.CDLL(so)
+
+    def choose(rt, kt, sms=148):
+        ks, kc = C.c_int(), C.c_int()
+        lib.choose(C.c_long(rt), C.c_long(kt), sms, C.byref(ks), C.byref(kc))
+        return ks.value, kc.value
+
+    for rt, kt in [(8192, 32), (8, 4096), (16, 16384), (313, 7), (1, 10), (1, 100000), (147, 64), (149, 64), (600, 9), (3, 24)]:
+        ks, kc = choose(rt, kt)
+        assert ks >= 1 and kc >= 1 and -(-kt // kc) == ks, (rt, kt, ks, kc)        # every chunk holds at least one k-tile
+        assert ks == 1 or kc >= 8, (rt, kt, ks, kc)
+        if rt >= 4 * 148:
+            assert ks == 1
+    # the per-rank slabs of configs B and D at 8 GPUs (pass A of the (1,1) tree): the units fill the SMs to >= 95 % in a few whole waves
+    for rt, kt in [(8, 4096), (16, 16384)]:
+        ks, kc = choose(rt, kt)
+        units = rt * ks
+        waves = -(-units // 148)
+        assert waves <= 4 and units / (148 * waves) >= 0.95, (rt, kt, ks, kc)
