@@ -238,6 +238,18 @@ __device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity) {
         }
     } while (!done);
 }
+// one non-blocking poll of a phase (no hardware suspend): for a thread that serves two rings at once
+__device__ __forceinline__ bool i8_mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void i8_tma_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -308,6 +320,23 @@ __device__ __forceinline__ I8Unit i8_unit(int u, int ksplit, int kchunk, int kt_
     x.ke = min(kt_count, x.kb + kchunk);
     return x;
 }
+// position of a pipeline role inside the CTA's sequence of (unit, k-tile) steps
+struct I8Cursor {
+    int w, kt;
+    I8Unit u;
+    __device__ __forceinline__ void start(int cta, int G, int my_units, int ksplit, int kchunk, int kt_count) {
+        w = 0;
+        u = i8_unit(cta, ksplit, kchunk, kt_count);
+        kt = u.kb;
+        (void)G; (void)my_units;
+    }
+    __device__ __forceinline__ void next(int cta, int G, int my_units, int ksplit, int kchunk, int kt_count) {
+        if (++kt >= u.ke) {
+            ++w;
+            if (w < my_units) { u = i8_unit(cta + w * G, ksplit, kchunk, kt_count); kt = u.kb; }
+        }
+    }
+};
 __global__ void i8_splitk_fixup_kernel(const double *__restrict__ part, int ksplit, int64_t chunk_stride, int64_t n, double *__restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -414,30 +443,42 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
     const int64_t part_stride = rows_out * (int64_t)I8_BN;
 
     if (warp == 8) {
-        // ===== TMA producers: lane 0 streams the FP64 tiles of T, lane 1 the packed digit planes of the Khatri-Rao operand
-        // (two independent rings: the 3-deep FP64 prefetch must not wait for the 2-deep digit ring) =====
-        if (lane == 0) {
-            int itf = 0;
-            for (int w = 0; w < my_tiles; ++w) {
-                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
-                const int row0 = u.tile * I8_BM;
-                for (int kt = u.kb; kt < u.ke; ++kt, ++itf) {
+        // ===== TMA producer (one thread serving two independent rings with non-blocking polls: the 3-deep FP64 prefetch of T
+        // must not wait for the 2-deep digit ring, and two spinning lanes of one warp would lean on intra-warp fairness) =====
+        if (lane == 0 && my_tiles > 0) {
+            I8Cursor cf, cd;
+            cf.start(cta, G, my_tiles, ksplit, kchunk, kt_count);
+            cd.start(cta, G, my_tiles, ksplit, kchunk, kt_count);
+            int itf = 0, itd = 0;
+            unsigned long long idle = 0;
+            while (cf.w < my_tiles || cd.w < my_tiles) {
+                bool progressed = false;
+                if (cf.w < my_tiles) {
                     const int sf = itf % I8_FSTAGES;
-                    if (itf >= I8_FSTAGES) i8_mbar_wait(empty_f + 8 * sf, (uint32_t)((itf / I8_FSTAGES - 1) & 1));
-                    i8_mbar_expect_tx(full_f + 8 * sf, I8_F_BYTES);
-                    if (KIND == 0) i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, row0, kt * I8_BK, full_f + 8 * sf);
-                    else i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, kt * I8_BK, row0, full_f + 8 * sf);
+                    if (itf < I8_FSTAGES || i8_mbar_test(empty_f + 8 * sf, (uint32_t)((itf / I8_FSTAGES - 1) & 1))) {
+                        const int row0 = cf.u.tile * I8_BM;
+                        i8_mbar_expect_tx(full_f + 8 * sf, I8_F_BYTES);
+                        if (KIND == 0) i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, row0, cf.kt * I8_BK, full_f + 8 * sf);
+                        else i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, cf.kt * I8_BK, row0, full_f + 8 * sf);
+                        ++itf;
+                        cf.next(cta, G, my_tiles, ksplit, kchunk, kt_count);
+                        progressed = true;
+                    }
                 }
-            }
-        } else if (lane == 1) {
-            int itd = 0;
-            for (int w = 0; w < my_tiles; ++w) {
-                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
-                for (int kt = u.kb; kt < u.ke; ++kt, ++itd) {
+                if (cd.w < my_tiles) {
                     const int sd = itd % I8_DSTAGES;
-                    if (itd >= I8_DSTAGES) i8_mbar_wait(empty_d + 8 * sd, (uint32_t)((itd / I8_DSTAGES - 1) & 1));
-                    i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
-                    i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
+                    if (itd < I8_DSTAGES || i8_mbar_test(empty_d + 8 * sd, (uint32_t)((itd / I8_DSTAGES - 1) & 1))) {
+                        i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
+                        i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)cd.kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
+                        ++itd;
+                        cd.next(cta, G, my_tiles, ksplit, kchunk, kt_count);
+                        progressed = true;
+                    }
+                }
+                if (progressed) idle = 0;
+                else if (++idle > (1ull << 28)) {
+                    printf("itcpd gemm_i8: producer stalled (block %d, F step %d, digit step %d)\n", (int)blockIdx.x, itf, itd);
+                    __trap();
                 }
             }
         }

@@ -69,6 +69,12 @@ inline void bar_arrive(uint32_t bar, long tx) {
 inline void bar_complete_tx(uint32_t bar, long bytes) { std::lock_guard<std::mutex> g(g_bar_mutex); auto &b = g_bars.at(bar); b.tx -= bytes; bar_flip(b); }
 inline void i8_mbar_expect_tx(uint32_t bar, uint32_t bytes) { bar_arrive(bar, (long)bytes); }
 inline void i8_mbar_arrive(uint32_t bar) { bar_arrive(bar, 0); }
+inline bool i8_mbar_test(uint32_t bar, uint32_t parity) {
+    std::lock_guard<std::mutex> g(g_bar_mutex);
+    const bool done = (g_bars.at(bar).phase & 1u) != parity;
+    if (!done) sched_yield();
+    return done;
+}
 inline void i8_mbar_wait(uint32_t bar, uint32_t parity) {
     for (long spins = 0;; ++spins) {
         { std::lock_guard<std::mutex> g(g_bar_mutex); if ((g_bars.at(bar).phase & 1u) != parity) return; }

@@ -1,5 +1,6 @@
 """Thread-level model of the mbarrier protocol of csrc/gemm_i8.cu (experimental, not yet run on hardware): the two TMA producer
-lanes, 256 converter threads (modelled as 8 warps arriving 32 times each), the single MMA thread and the 4 epilogue warps,
+rings (served in the kernel by ONE thread with non-blocking polls; modelled here as two free-running threads, a superset of
+its interleavings), 256 converter threads (modelled as 8 warps arriving 32 times each), the single MMA thread and the 4 epilogue warps,
 with the kernel's barrier counts, stage counts and wait parities transliterated.  Every stage buffer carries a
 (tile, k-tile) tag: consuming a stale or overwritten buffer, a wrong parity or a dead-lock fails the test."""
 import random
