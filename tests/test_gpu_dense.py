@@ -459,3 +459,29 @@ def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R, variant):
             assert relerr(M, cpals.mttkrp_krp_normal(T, cp.factors, n)) < 1e-12, n
     finally:
         engine.set_option("gemm_i8", 0)
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="gemm_i8 (INT8 tensor-core digit-split contraction) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dims,R", [((64, 40, 512), 64), ((100, 24, 700), 40)])   # pass A of the (1,1) tree: 1 row tile x 640 / 525 k-tiles
+@pytest.mark.parametrize("variant", [1, 2])
+def test_gemm_i8_split_k_matches_oracle(engine, dims, R, variant):
+    """short-and-wide contractions (the per-rank slab shape of the sharded runs) go through the split-K schedule of gemm_i8.cu:
+    (row tile, k-chunk) units, FP64 partial tiles, deterministic fix-up"""
+    T, cp = make_problem(dims, R, seed=92)
+    engine.set_option("split_a", 1)
+    engine.set_option("split_b", 1)
+    engine.set_option("gemm_i8", variant)
+    try:
+        engine.set_tensor(T)
+        engine.set_cpd(cp.factors, cp.lam)
+        first = None
+        for n in range(len(dims)):
+            M = engine.mttkrp(n)
+            assert relerr(M, cpals.mttkrp_krp_normal(T, cp.factors, n)) < 1e-12, n
+            first = M if n == 0 else first
+        engine.set_cpd(cp.factors, cp.lam)       # same inputs again: the fix-up order is fixed, so the result is bitwise reproducible
+        assert np.array_equal(engine.mttkrp(0), first)
+    finally:
+        engine.set_option("gemm_i8", 0)
+        engine.set_option("split_a", 0)
+        engine.set_option("split_b", 0)

@@ -7,6 +7,10 @@ mkdir -p gpurun_out
 # 0. single-instruction probe of the INT8 tensor-core building blocks (build it first: see the header of tools/i8_probe.cu)
 [ -x tools/i8_probe ] && timeout 30 ./tools/i8_probe > gpurun_out/r2_i8_probe.txt 2>&1; tail -6 gpurun_out/r2_i8_probe.txt
 export ITCPD_EXPERIMENTAL=1
+# 0b. the INT8 contraction alone first (both variants, incl. split-K shapes), so its verdict survives whatever follows
+timeout 180 python -m pytest tests/test_gpu_dense.py -m gpu -q -k gemm_i8 > gpurun_out/r2_i8_tests.log 2>&1
+echo "i8 tests rc=$?" >> gpurun_out/r2_i8_tests.log
+tail -8 gpurun_out/r2_i8_tests.log
 timeout 400 python -m pytest tests -m gpu -q > gpurun_out/r2_exp_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/r2_exp_tests.log
 tail -15 gpurun_out/r2_exp_tests.log
