@@ -64,6 +64,8 @@ struct I8ExpCache {
     bool valid = false;
     int split = 0;
     int64_t tensor_epoch = -1;
+    int64_t nofit_epoch = -1;   // i8_apack: the digit planes of this tensor did not fit in HBM (do not retry every pass)
+    int nofit_split = 0;
 };
 
 struct Comm;  // comm.cu

@@ -729,13 +729,19 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     }
 
     // ---- pre-packed digit planes of T (gemm_i8 = 2): built once per tensor / unfolding, 7 bytes per element in HBM ----
-    const bool prepacked = c->gemm_i8 == 2;
+    bool prepacked = c->gemm_i8 == 2;
     I8ExpCache &pk = c->i8_apack[kind];
+    if (prepacked && pk.nofit_epoch == c->i8_tensor_epoch && pk.nofit_split == split) prepacked = false;
     if (prepacked && (!pk.valid || pk.split != split || pk.tensor_epoch != c->i8_tensor_epoch)) {
         if (pk.buf.reserve((size_t)row_tiles * ktiles * I8_A_BYTES) != ITCPD_OK) {
-            cudaGetLastError();                 // not enough HBM for the digit planes (e.g. 2048^3): use the DMMA kernel
-            return ITCPD_ERR_UNSUPPORTED;
+            cudaGetLastError();                 // not enough HBM for the digit planes (e.g. 2048^3 on one GPU): convert on the fly instead
+            pk.valid = false;
+            pk.nofit_epoch = c->i8_tensor_epoch;
+            pk.nofit_split = split;
+            prepacked = false;
         }
+    }
+    if (prepacked && (!pk.valid || pk.split != split || pk.tensor_epoch != c->i8_tensor_epoch)) {
         if (kind == 0)
             i8_pack_tensor_kernel<0><<<(unsigned)(row_tiles * ktiles), 256, 0, c->stream>>>(c->T.as<double>(), rows_out, kext, 1, Mrows, ec.buf.as<int>(), ktiles,
                                                                                              pk.buf.as<uint8_t>());
