@@ -62,6 +62,8 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "split_a","split_b"  force the dimension-tree split points (0* = traffic cost model)
  *   "tile_warps"     4 | 8*  warps per GEMM CTA;  "swizzle" 1* | 0 (debug);  "tma3d" 1* | 0;  "stream_k" 0 | 1* | 2
  *   "overlap_factor" 1* Gram-Hadamard + Cholesky on a side stream under the GEMM;  "use_graph" 1* CUDA-graph replay of sweeps
+ *   "early_pass_b" 0* | 1: EXPERIMENTAL (not yet run on hardware): pass B of the dimension tree is launched on its own stream as soon
+ *                    as the modes it contracts are updated; the modes in [split_b, split_a) are updated underneath it (env ITCPD_EARLY_B)
  *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 64, experimental)
  *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
  *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph

@@ -236,6 +236,10 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
     c->stream = main_stream;
     TRY(st);
     if (c->overlap_factor) CUDA_TRY(cudaEventRecord(c->ev_join, c->side_stream));
+    if (c->gemm_join_pending && mode >= c->split_a) {  // early_pass_b: P_B is produced on the GEMM stream
+        CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_gemm_done, 0));
+        c->gemm_join_pending = false;
+    }
     const bool fused_peers = c->peer_on && comm_active(c) && mode != c->order - 1;
     if (fused_peers) {
         // fused all-reduce + solve over NVLink peer memory: the partial MTTKRP lands in this rank's exchange slot, is
@@ -316,6 +320,10 @@ int itcpd_create(itcpd_ctx **out, int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->gemm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gemm_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gemm_done, cudaEventDisableTiming));
+    if (const char *s = getenv("ITCPD_EARLY_B")) c->early_pass_b = atoi(s) != 0;   // experimental
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
@@ -351,6 +359,9 @@ int itcpd_destroy(itcpd_ctx *c) {
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->side_stream);
+    if (c->gemm_stream) { cudaStreamSynchronize(c->gemm_stream); cudaStreamDestroy(c->gemm_stream); }
+    if (c->ev_gemm_fork) cudaEventDestroy(c->ev_gemm_fork);
+    if (c->ev_gemm_done) cudaEventDestroy(c->ev_gemm_done);
     cudaStreamDestroy(c->stream);
     delete c;
     return ITCPD_OK;
@@ -387,6 +398,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "time_phases") { c->time_phases = value != 0; c->phase_used = 0; }
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
+    else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "use_graph") c->use_graph = value != 0;
     else if (n == "gemm_i8") { ARG_CHECK(value >= 0 && value <= 2, "gemm_i8 must be 0, 1 (convert on the fly) or 2 (pre-packed digits)"); c->gemm_i8 = (int)value; }
     else if (n == "peer_graph") {
@@ -694,7 +706,26 @@ __global__ void log_sweep_kernel(const double *__restrict__ fit2, const int *__r
 
 static int one_sweep_device(itcpd_ctx *c, double chol_tol) {
     const int N = c->order;
-    for (int mode = 0; mode < N; ++mode) TRY(mode_update_device(c, mode, chol_tol, c->status.as<int>() + 3 * mode));
+    const bool early_b = c->early_pass_b && c->mttkrp_alg != ITCPD_MTTKRP_DIRECT && c->split_b < c->split_a && !comm_active(c) && !c->time_phases;
+    for (int mode = 0; mode < N; ++mode) {
+        TRY(mode_update_device(c, mode, chol_tol, c->status.as<int>() + 3 * mode));
+        if (early_b && mode == c->split_b - 1) {
+            // every factor pass B contracts is final for this sweep: start it now on the GEMM stream; mode split_a joins
+            cudaStream_t main_stream = c->stream;
+            CUDA_TRY(cudaEventRecord(c->ev_gemm_fork, main_stream));
+            CUDA_TRY(cudaStreamWaitEvent(c->gemm_stream, c->ev_gemm_fork, 0));
+            c->stream = c->gemm_stream;
+            const int st = ensure_partial(c, 1);
+            c->stream = main_stream;
+            TRY(st);
+            CUDA_TRY(cudaEventRecord(c->ev_gemm_done, c->gemm_stream));
+            c->gemm_join_pending = true;
+        }
+    }
+    if (c->gemm_join_pending) {  // cannot happen (mode split_a always follows), but a captured fork must never be left open
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_gemm_done, 0));
+        c->gemm_join_pending = false;
+    }
     TRY(k_fit_terms(c, c->fit2.as<double>(), false));
     TRY(phase_mark(c, PH_FIT));
     log_sweep_kernel<<<1, 1, 0, c->stream>>>(c->fit2.as<double>(), c->status.as<int>(), N, c->sweep_log.as<double>() + 1,

@@ -100,6 +100,13 @@ struct itcpd_ctx {
     cudaStream_t side_stream = nullptr;   // Gram-Hadamard + factorisation run here underneath the MTTKRP
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_factor = 1;
+    // option "early_pass_b" (off by default, not yet run on hardware): pass B of the dimension tree only depends on the factors
+    // of modes < split_b, so it is launched on its own stream as soon as they are updated and the updates of the modes in
+    // [split_b, split_a) (second-level contraction from P_A, solve, normalise, Gram) run underneath it
+    int early_pass_b = 0;
+    cudaStream_t gemm_stream = nullptr;
+    cudaEvent_t ev_gemm_fork = nullptr, ev_gemm_done = nullptr;
+    bool gemm_join_pending = false;
     int chol_alg = 1;  // 0: block kernel (any n), 1: team kernel for n <= 128 (same arithmetic, bitwise), 2: + right-looking for n <= 64 (experimental)
     int64_t launches = 0;
 

@@ -485,3 +485,40 @@ def test_gemm_i8_split_k_matches_oracle(engine, dims, R, variant):
         engine.set_option("gemm_i8", 0)
         engine.set_option("split_a", 0)
         engine.set_option("split_b", 0)
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="early_pass_b (pass B on its own stream under the middle modes' updates) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dims,R,splits,graph", [((40, 36, 44), 20, (2, 1), 1), ((40, 36, 44), 20, (2, 1), 0), ((24, 20, 18, 16), 12, (3, 1), 1),
+                                                 ((64, 48, 40), 64, (2, 1), 1)])
+def test_early_pass_b_is_bitwise_the_default_sweep(engine, dims, R, splits, graph):
+    """api.cu one_sweep_device: with early_pass_b the pass-B GEMM starts right after the last mode it contracts is updated
+    and the modes in [split_b, split_a) are updated underneath it.  Same kernels, same arguments, same order per stream:
+    factors, lambda and the fit log must be bitwise those of the serial schedule (a missing dependency would show here)."""
+    T, cp = make_problem(dims, R, seed=53)
+    N = len(dims)
+    res = {}
+    engine.set_option("split_a", splits[0])
+    engine.set_option("split_b", splits[1])
+    engine.set_option("use_graph", graph)
+    try:
+        for e in (0, 1):
+            engine.set_option("early_pass_b", e)
+            engine.set_tensor(T)
+            engine.set_cpd(cp.factors, cp.lam)
+            engine.compute_grams()
+            inner, norm2 = engine.sweep(8)
+            i2, n2 = engine.sweep(4)
+            res[e] = (inner, norm2, i2, n2, [engine.get_factor(n) for n in range(N)], engine.get_lambda())
+        for a, b in zip(res[0][:4], res[1][:4]):
+            assert np.array_equal(a, b)
+        for a, b in zip(res[0][4], res[1][4]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(res[0][5], res[1][5])
+        engine.mttkrp(0)   # the per-hook API sees consistent partials afterwards
+        f = [engine.get_factor(n) for n in range(N)]
+        assert relerr(engine.mttkrp(N - 1), cpals.mttkrp_krp_normal(T, f, N - 1)) < 1e-12
+    finally:
+        engine.set_option("early_pass_b", 0)
+        engine.set_option("use_graph", 1)
+        engine.set_option("split_a", 0)
+        engine.set_option("split_b", 0)

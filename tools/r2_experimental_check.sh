@@ -23,6 +23,9 @@ done
 ITCPD_GEMM_I8=1 $B --steps 20 > gpurun_out/r2_B_gemm_i8.json 2>> gpurun_out/r2_err.log
 ITCPD_GEMM_I8=2 $B --steps 20 > gpurun_out/r2_B_gemm_i8_prepacked.json 2>> gpurun_out/r2_err.log
 $B --steps 20 > gpurun_out/r2_B_dmma.json 2>> gpurun_out/r2_err.log
+# pass B on its own stream under mode 1's update (early_pass_b), alone and on top of the pre-packed INT8 contraction
+ITCPD_EARLY_B=1 $B --steps 20 > gpurun_out/r2_B_dmma_earlyb.json 2>> gpurun_out/r2_err.log
+ITCPD_EARLY_B=1 ITCPD_GEMM_I8=2 $B --steps 20 > gpurun_out/r2_B_gemm_i8_prepacked_earlyb.json 2>> gpurun_out/r2_err.log
 for pg in 0 1; do
   ITCPD_BENCH_PHASES=1 ITCPD_PEER_GRAPH=$pg timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 \
       bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/r2_N2_peergraph$pg.json 2>> gpurun_out/r2_err.log
