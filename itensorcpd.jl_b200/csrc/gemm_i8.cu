@@ -704,7 +704,8 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         TRY(ec.buf.reserve((size_t)padded * 4));
         i8_fill_int_kernel<<<(unsigned)ceil_div(padded, 256), 256, 0, c->stream>>>(ec.buf.as<int>(), padded, I8_EXP_ZERO);
         if (kind == 0) {
-            const int ysplit = (int)std::max<int64_t>(1, std::min<int64_t>(kext, (int64_t)c->sm_count * 8 * 256 / std::max<int64_t>(rows_out, 1)));
+            const int ysplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(kext, 65535),   // gridDim.y limit
+                                                                           (int64_t)c->sm_count * 8 * 256 / std::max<int64_t>(rows_out, 1)));
             i8_row_exponent_strided_kernel<<<dim3((unsigned)ceil_div(rows_out, 256), (unsigned)ysplit), 256, 0, c->stream>>>(
                 c->T.as<double>(), rows_out, kext, Mrows, ec.buf.as<int>());
         } else {
