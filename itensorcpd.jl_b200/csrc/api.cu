@@ -24,6 +24,7 @@ int DevBuf::reserve(size_t n) {
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+        cudaGetLastError();  // the failed allocation is also the runtime's "last error": clear it, or the next launch check reports it again
         p = nullptr;
         bytes = 0;
         return ITCPD_ERR_CUDA;

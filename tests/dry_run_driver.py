@@ -1,0 +1,361 @@
+"""Driver of the CPU dry run (tests/test_dry_run_cpu.py runs it in a subprocess whose libcudart.so.12 / libnccl.so.2 are
+tests/fake_cudart.cpp).  Every scenario calls the REAL C-ABI of a `-cudart shared` link of the product objects; kernels are not
+executed, so results are meaningless -- what is checked is that every call returns ITCPD_OK and that the validating runtime saw
+no illegal launch configuration, TMA descriptor, copy range, capture topology or leak.  Prints one JSON line."""
+import ctypes as C
+import json
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import itcpd  # noqa: E402
+
+DRY = os.path.join(ROOT, "oracle", "_build", "dry")
+itcpd.package._lib.LIB_PATH = os.path.join(DRY, "libitcpd_dry.so")
+fake = C.CDLL(os.path.join(DRY, "libcudart.so.12"))
+fake.fakecuda_launches.restype = C.c_long
+fake.fakecuda_device_bytes.restype = C.c_ulonglong
+fake.fakecuda_set_device_cap.argtypes = [C.c_ulonglong]
+
+
+def violations():
+    out = []
+    for i in range(fake.fakecuda_violation_count()):
+        b = C.create_string_buffer(1024)
+        fake.fakecuda_violation(i, b, 1024)
+        out.append(b.value.decode())
+    return out
+
+
+def launches(sub=""):
+    return int(fake.fakecuda_launches(sub.encode()))
+
+
+RESULTS = {}
+
+
+def scenario(fn):
+    name = fn.__name__
+    fake.fakecuda_clear()
+    rec = {"ok": True, "error": None}
+    try:
+        info = fn()
+        if isinstance(info, dict):
+            rec.update(info)
+    except Exception:
+        rec["ok"] = False
+        rec["error"] = traceback.format_exc(limit=4)
+    rec["violations"] = violations()
+    rec["launches"] = launches()
+    rec["leaked_device_allocs"] = int(fake.fakecuda_live_device_allocs())
+    RESULTS[name] = rec
+    return fn
+
+
+def factors(dims, R, seed=1):
+    rng = np.random.default_rng(seed)
+    return [np.asfortranarray(rng.standard_normal((d, R))) for d in dims]
+
+
+def dense_roundtrip(eng, dims, R, sweeps=5):
+    """the whole dense per-hook + fused-sweep surface on whatever tensor is resident"""
+    N = len(dims)
+    eng.set_cpd(factors(dims, R), np.ones(R))
+    for n in range(N):
+        eng.mttkrp(n, fetch=False)
+    eng.compute_grams()
+    for n in range(N):
+        eng.gram_hadamard(n, fetch=False)
+        eng.mttkrp(n, fetch=False)
+        eng.solve(n, 1e-6)
+        eng.normalize(n)
+        eng.post_solve(n)
+    eng.fit_terms()
+    eng.sweep_async(sweeps)
+    eng.synchronize()
+    eng.sweep_async(3)       # re-uses the captured graph
+    eng.synchronize()
+
+
+SMALL = [((20, 30, 40), 5), ((20, 30, 40), 50), ((64, 48, 32), 64), ((13, 12, 3), 5), ((33, 17, 9), 20), ((16, 16, 16, 16), 32),
+         ((7, 6, 5, 4, 3), 9), ((40, 50), 12), ((20, 30, 40), 130), ((200, 40, 30), 24), ((2, 3, 70000), 4), ((1, 1, 1), 1), ((3, 100000), 2)]
+
+
+@scenario
+def small_shapes_default_options():
+    with itcpd.Engine(0) as eng:
+        for dims, R in SMALL:
+            eng.set_tensor(np.zeros(dims, order="F"))
+            dense_roundtrip(eng, dims, R)
+    return {"gemm_launches": launches("partial_gemm_kernel")}
+
+
+@scenario
+def small_shapes_every_option():
+    opts = [("tile_warps", 4), ("stream_k", 0), ("stream_k", 2), ("tma3d", 0), ("swizzle", 0), ("overlap_factor", 0), ("use_graph", 0), ("chol_alg", 0),
+            ("chol_alg", 2), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
+    defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 1, "mttkrp_alg": 0, "early_pass_b": 0,
+                "gemm_i8": 0, "time_gemm": 0, "time_phases": 0}
+    with itcpd.Engine(0) as eng:
+        for name, val in opts:
+            eng.set_option(name, val)
+            for dims, R in [((24, 36, 20), 40), ((33, 17, 9), 20), ((16, 12, 10, 8), 70), ((40, 50), 12)]:
+                for sa, sb in [(0, 0), (1, 1), (len(dims) - 1, 1)]:
+                    eng.set_option("split_a", sa)
+                    eng.set_option("split_b", sb)
+                    eng.set_tensor(np.zeros(dims, order="F"))
+                    dense_roundtrip(eng, dims, R)
+            if name == "time_gemm":
+                eng.gemm_timing(True)
+            if name == "time_phases":
+                eng.phase_timing(True)
+            eng.set_option(name, defaults[name])
+            eng.set_option("split_a", 0)
+            eng.set_option("split_b", 0)
+    return {"i8_launches": launches("partial_gemm_i8"), "rl_cholesky": launches("pivoted_cholesky_rl")}
+
+
+def full_size(dims, R, **options):
+    with itcpd.Engine(0) as eng:
+        for k, v in options.items():
+            eng.set_option(k, v)
+        eng.generate_tensor(dims, seed=0)
+        eng.set_cpd(factors(dims, R), np.ones(R))
+        eng.compute_grams()
+        eng.sweep_async(6)
+        eng.synchronize()
+        return {"device_gb": fake.fakecuda_device_bytes() / 1e9, "dmma": launches("partial_gemm_kernel"), "i8_on_the_fly": launches("partial_gemm_i8_kernel"),
+                "i8_prepacked": launches("partial_gemm_i8p_kernel"), "i8_fixup": launches("i8_splitk_fixup")}
+
+
+@scenario
+def config_A_200cubed_rank50():
+    return full_size((200, 200, 200), 50)
+
+
+@scenario
+def config_B_1024cubed_rank64():
+    return full_size((1024, 1024, 1024), 64)
+
+
+@scenario
+def config_B_early_pass_b():
+    return full_size((1024, 1024, 1024), 64, early_pass_b=1)
+
+
+@scenario
+def config_B_gemm_i8_on_the_fly():
+    return full_size((1024, 1024, 1024), 64, gemm_i8=1)
+
+
+@scenario
+def config_B_gemm_i8_prepacked_early_pass_b():
+    return full_size((1024, 1024, 1024), 64, gemm_i8=2, early_pass_b=1)
+
+
+@scenario
+def config_C_256pow4_rank32():
+    return full_size((256, 256, 256, 256), 32)
+
+
+@scenario
+def config_C_gemm_i8_prepacked():
+    return full_size((256, 256, 256, 256), 32, gemm_i8=2)
+
+
+@scenario
+def config_D_2048cubed_rank128():
+    return full_size((2048, 2048, 2048), 128)
+
+
+@scenario
+def config_D_gemm_i8_prepacked_planes_of_one_unfolding_fit_the_other_converts_on_the_fly():
+    r = full_size((2048, 2048, 2048), 128, gemm_i8=2)      # 68.7 GB tensor + 60 GB of digit planes per unfolding on a 180 GB device
+    assert r["i8_prepacked"] > 0 and r["i8_on_the_fly"] > 0 and r["dmma"] == 0, r
+    return r
+
+
+@scenario
+def slab_B8_gemm_i8_split_k():
+    r = full_size((1024, 1024, 128), 64, gemm_i8=2)
+    assert r["i8_fixup"] > 0 and r["dmma"] == 0, r      # pass A of the (1,1) tree is short and wide: split-K, no DMMA fallback
+    return r
+
+
+@scenario
+def slab_D8_gemm_i8_split_k():
+    r = full_size((2048, 2048, 256), 128, gemm_i8=1)
+    assert r["i8_fixup"] > 0 and r["dmma"] == 0, r
+    return r
+
+
+def sharded_pair(dims_local, R, peer, peer_graph=0, sampled=False, world=2, **options):
+    """`world` ranks in one process (the fake NCCL / IPC make that possible): slabs of the last mode"""
+    N = len(dims_local)
+    engs = [itcpd.Engine(r) for r in range(world)]
+    try:
+        uid = itcpd.Engine.comm_unique_id()
+        for r, e in enumerate(engs):
+            for k, v in options.items():
+                e.set_option(k, v)
+            e.generate_tensor(dims_local, seed=0, elem_offset=r * int(np.prod(dims_local)))
+            e.set_cpd(factors(dims_local, R, seed=1), np.ones(R))
+            e.comm_init(world, r, uid)
+        if peer:
+            for e in engs:
+                if peer_graph:
+                    e.set_option("peer_graph", 1)
+            handles = b"".join(e.peer_export() for e in engs)
+            for r, e in enumerate(engs):
+                e.peer_import(world, r, handles)
+        for e in engs:
+            e.compute_grams()
+        for _ in range(2):
+            for e in engs:
+                e.sweep_async(4)
+        for e in engs:
+            e.synchronize()
+        if sampled:
+            ns = 64
+            for e in engs:
+                for mode in range(N):
+                    piv = e.sample_factor_matrices(mode, ns, seed=5)
+                    piv = np.maximum(piv, 1)     # kernels did not run: the draw is all zeros; any in-range pivot will do
+                    for normal in (True, False):
+                        e.sampled_update(mode, piv, 1e-6, normal)
+                    e.set_projector(mode, piv)
+                    e.projected_update(mode, 1e-6, True)
+                e.cpd_snapshot()
+                e.cpd_diff_terms()
+                e.leverage_scores(N - 1)
+        for e in engs:
+            e.allgather_factor(N - 1, world * dims_local[-1])
+        return {"nccl_allreduce": launches("ncclAllReduce"), "graph_launches": launches("<graph launch>"), "peer_solve": launches("chol_solve_warp")}
+    finally:
+        for e in engs:
+            e.close()
+
+
+@scenario
+def two_ranks_nccl_only():
+    return sharded_pair((1024, 1024, 512), 64, peer=False)
+
+
+@scenario
+def two_ranks_fused_peer_solve():
+    return sharded_pair((1024, 1024, 512), 64, peer=True)
+
+
+@scenario
+def two_ranks_peer_graph_is_captured_without_nccl():
+    r = sharded_pair((1024, 1024, 512), 64, peer=True, peer_graph=1)
+    assert r["graph_launches"] > 0, r
+    return r
+
+
+@scenario
+def two_ranks_order4_small_with_sampled_path():
+    return sharded_pair((12, 10, 8, 6), 7, peer=True, sampled=True)
+
+
+@scenario
+def two_ranks_gemm_i8():
+    return sharded_pair((1024, 1024, 128), 64, peer=True, gemm_i8=2)
+
+
+@scenario
+def eight_ranks_config_B_slabs_fused_peer_solve():
+    return sharded_pair((1024, 1024, 128), 64, peer=True, world=8)
+
+
+@scenario
+def eight_ranks_config_D_slabs_peer_graph_gemm_i8():
+    r = sharded_pair((2048, 2048, 256), 128, peer=True, peer_graph=1, world=8, gemm_i8=2)
+    assert r["nccl_allreduce"] == 0 and r["graph_launches"] > 0, r
+    return r
+
+
+@scenario
+def pivot_setup_and_bench_entry_points():
+    dims, R = (24, 20, 18), 6
+    with itcpd.Engine(0) as eng:
+        eng.set_tensor(np.zeros(dims, order="F"))
+        eng.set_cpd(factors(dims, R), np.ones(R))
+        eng.compute_grams()
+        for mode in range(3):
+            eng.seqrcs(mode, 40, 3, 12, injective=False, seed=1)
+            eng.seqrcs(mode, 40, 3, 12, injective=True, seed=1)
+            eng.seqrcs_krp(mode, 40, 3, 12, injective=False, seed=1)
+            eng.qrcp_unfolding(mode)
+        eng.qrcp_matrix(np.zeros((10, 300), order="F"))
+        eng.qrcp_matrix(np.zeros((10, 300), order="F"), steps=4)
+        eng.tensor_norm()
+        eng.get_tensor()
+        eng.random_cpd(3)
+        eng.generate_lowrank_tensor(dims, 4, seed=2, noise=0.1)
+        eng.probe_dmma_peak()
+        eng.probe_dfma_peak()
+        eng.event_record(0)
+        eng.sweep_async(3)
+        eng.event_record(1)
+        eng.synchronize()
+        eng.event_elapsed_ms(0, 1)
+        eng.flush_l2()
+        eng.sweep_results(3)
+
+
+@scenario
+def sampled_path_single_rank():
+    dims, R = (40, 36, 30), 12
+    with itcpd.Engine(0) as eng:
+        eng.set_tensor(np.zeros(dims, order="F"))
+        eng.set_cpd(factors(dims, R), np.ones(R))
+        eng.compute_grams()
+        for mode in range(3):
+            eng.leverage_scores(mode)
+            piv = np.maximum(eng.sample_factor_matrices(mode, 100, seed=3), 1)
+            eng.pivot_hadamard(mode, piv)
+            eng.gather_fibers(mode, piv)
+            for normal in (True, False):
+                eng.sampled_update(mode, piv, 1e-6, normal)
+            eng.set_projector(mode, piv)
+            eng.projected_update(mode, 1e-6, True)
+        eng.qrcp_unfolding(0)
+        eng.reconstruct()
+        eng.residual_norm()
+        eng.cpd_snapshot()
+        eng.cpd_diff_terms()
+        eng.drop_tensor()
+        eng.projected_update(1, 1e-6, True)
+
+
+@scenario
+def end_to_end_call_from_host_buffers():
+    dims, R = (64, 48, 40), 16
+    with itcpd.Engine(0) as eng:
+        eng.als_from_host(np.zeros(dims, order="F"), factors(dims, R), 6)
+
+
+@scenario
+def out_of_memory_is_an_error_code_not_a_crash():
+    fake.fakecuda_set_device_cap(4 * 1000 * 1000 * 1000)
+    try:
+        with itcpd.Engine(0) as eng:
+            try:
+                eng.generate_tensor((1024, 1024, 1024), seed=0)
+                raise AssertionError("8.6 GB fit into a 4 GB device?")
+            except itcpd.package._lib.ItcpdError as e:
+                msg = str(e)
+            eng.generate_tensor((64, 64, 64), seed=0)     # the handle stays usable
+            dense_roundtrip(eng, (64, 64, 64), 16)
+        return {"message": msg[:120]}
+    finally:
+        fake.fakecuda_set_device_cap(180 * 1000 * 1000 * 1000)
+
+
+if __name__ == "__main__":
+    print("DRYRUN_JSON " + json.dumps(RESULTS))
