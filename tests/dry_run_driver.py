@@ -357,5 +357,69 @@ def out_of_memory_is_an_error_code_not_a_crash():
         fake.fakecuda_set_device_cap(180 * 1000 * 1000 * 1000)
 
 
+def _random_problem(rnd, budget):
+    N = rnd.choice([2, 3, 3, 3, 4, 4, 5, 6])
+    dims = []
+    for _ in range(N):
+        d = rnd.choice([1, 2, 3, 5, 7, 8, 16, 17, 31, 32, 33, 64, 100, 127, 128, 129, 255, 256, 257, 1000, 1024, 4096, 65537, 100000])
+        while d > 1 and np.prod(dims + [d]) > budget:
+            d = max(1, d // 4)
+        dims.append(d)
+    R = rnd.choice([1, 2, 7, 8, 9, 31, 32, 33, 63, 64, 65, 100, 128, 129, 200, 256, 300])
+    return tuple(dims), R
+
+
+@scenario
+def fuzz_dense_shapes_and_options():
+    """random orders / extents (1, odd, > 65535, padded leading mode) / ranks / forced splits / options; an out-of-memory status
+    (a forced split can ask for a partial larger than the device) is a legitimate answer, anything else is not"""
+    import random
+    rnd = random.Random(2026)
+    ran = oom = 0
+    with itcpd.Engine(0) as eng:
+        for _ in range(400):
+            dims, R = _random_problem(rnd, 2e9)
+            N = len(dims)
+            opts = {"gemm_i8": rnd.choice([0, 0, 1, 2]), "early_pass_b": rnd.choice([0, 1]), "tile_warps": rnd.choice([4, 8]), "stream_k": rnd.choice([0, 1, 2]),
+                    "chol_alg": rnd.choice([0, 1, 2]), "use_graph": rnd.choice([0, 1]), "tma3d": rnd.choice([0, 1]), "overlap_factor": rnd.choice([0, 1])}
+            sa = rnd.choice([0, 0] + list(range(1, N)))
+            sb = 0 if sa == 0 else rnd.randint(1, sa)
+            try:
+                for k, v in opts.items():
+                    eng.set_option(k, v)
+                eng.set_option("split_a", sa)
+                eng.set_option("split_b", sb)
+                eng.generate_tensor(dims, seed=0)
+                eng.set_cpd(factors(dims, R), np.ones(R))
+                for n in range(N):
+                    eng.mttkrp(n, fetch=False)
+                eng.compute_grams()
+                eng.sweep_async(4)
+                eng.synchronize()
+                ran += 1
+            except itcpd.package._lib.ItcpdError as e:
+                if "out of memory" not in str(e):
+                    raise AssertionError(f"{dims} R={R} {opts} splits=({sa},{sb}): {e}")
+                oom += 1
+    assert ran > 300, (ran, oom)
+    return {"ran": ran, "out_of_memory": oom}
+
+
+@scenario
+def fuzz_two_rank_sharded_dense_and_sampled():
+    import random
+    rnd = random.Random(7)
+    ran = 0
+    for _ in range(40):
+        dims, R = _random_problem(rnd, 3e6)
+        if len(dims) < 3:      # the fused peer path and peer_graph need order >= 3; order 2 goes through NCCL only
+            dims = dims + (5,)
+        peer = rnd.choice([0, 1])
+        sharded_pair(dims, min(R, 64), peer=bool(peer), peer_graph=peer and rnd.choice([0, 1]), sampled=rnd.choice([False, True]),
+                     gemm_i8=rnd.choice([0, 1, 2]), chol_alg=rnd.choice([1, 2]))
+        ran += 1
+    return {"ran": ran}
+
+
 if __name__ == "__main__":
     print("DRYRUN_JSON " + json.dumps(RESULTS))
