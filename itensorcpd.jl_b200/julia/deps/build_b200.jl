@@ -4,8 +4,7 @@
 csrc = joinpath(@__DIR__, "..", "..", "csrc")
 out  = joinpath(@__DIR__, "..", "..", "lib")
 mkpath(out)
-srcs = [joinpath(csrc, f) for f in ("api.cu", "gemm_dmma.cu", "kernels.cu", "solve.cu", "qrcp.cu", "qrcp_wide.cu",
-                                     "sampled.cu", "comm.cu", "sparse_sign.cu")]
+srcs = [joinpath(csrc, f) for f in sort(filter(endswith(".cu"), readdir(csrc)))]   # every translation unit (same set as csrc/build.sh)
 lib_file = joinpath(out, "libitcpd_b200.so")
 compile = `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared
            -o $lib_file $srcs -cudart static -ldl -lpthread -lrt`

@@ -20,29 +20,30 @@ using ITensorCPD: CPD, ALS, CPDOptimizer, MttkrpAlgorithm, ConvergeAlg, FitCheck
 using ITensors: ITensor, Index, inds, ind, dim, dims, array, itensor, order
 using Libdl
 
-const libitcpd = Ref{String}("")
+# same idiom as the reference's own native helper (src/ITensorCPD.jl:25-36, src/algebra/SEQRCS.jl:41-60): a module global
+# holding the library path, assigned in __init__, named directly in the (symbol, library) tuple of every ccall
+libitcpd = ""
 
 function __init__()
-    # same convention as src/ITensorCPD.jl:25-36: build on demand, remember the path in a module global
     lib = joinpath(@__DIR__, "..", "..", "lib", "libitcpd_b200.so")
     isfile(lib) || include(joinpath(@__DIR__, "..", "..", "deps", "build_b200.jl"))
-    libitcpd[] = lib
+    global libitcpd = lib
 end
 
 struct B200Error <: Exception
     code::Cint
     msg::String
 end
-lasterr() = unsafe_string(ccall((:itcpd_last_error, libitcpd[]), Cstring, ()))
+lasterr() = unsafe_string(ccall((:itcpd_last_error, libitcpd), Cstring, ()))
 chk(code) = code == 0 ? nothing : throw(B200Error(code, lasterr()))
 
 mutable struct Handle
     ptr::Ptr{Cvoid}
     function Handle(device::Integer = 0)
         p = Ref{Ptr{Cvoid}}(C_NULL)
-        chk(ccall((:itcpd_create, libitcpd[]), Cint, (Ref{Ptr{Cvoid}}, Cint), p, device))
+        chk(ccall((:itcpd_create, libitcpd), Cint, (Ref{Ptr{Cvoid}}, Cint), p, device))
         h = new(p[])
-        finalizer(x -> ccall((:itcpd_destroy, libitcpd[]), Cint, (Ptr{Cvoid},), x.ptr), h)
+        finalizer(x -> ccall((:itcpd_destroy, libitcpd), Cint, (Ptr{Cvoid},), x.ptr), h)
         return h
     end
 end
@@ -70,13 +71,13 @@ function ITensorCPD.compute_als(alg::B200Normal, target::ITensor, cp::CPD{<:ITen
     h = Handle(alg.device)
     T = array(target)                       # dense column-major Array{Float64,N}, wrapped without copy
     ds = collect(Int64, size(T))
-    chk(ccall((:itcpd_set_tensor, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}), h.ptr, length(ds), ds, T))
-    chk(ccall((:itcpd_set_rank, libitcpd[]), Cint, (Ptr{Cvoid}, Cint), h.ptr, dim(cp_rank(cp))))
+    chk(ccall((:itcpd_set_tensor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}), h.ptr, length(ds), ds, T))
+    chk(ccall((:itcpd_set_rank, libitcpd), Cint, (Ptr{Cvoid}, Cint), h.ptr, dim(cp_rank(cp))))
     for (n, f) in enumerate(cp.factors)     # ITensor (i_n, r): I_n x R column-major
-        chk(ccall((:itcpd_set_factor, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, array(f)))
+        chk(ccall((:itcpd_set_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, array(f)))
     end
-    chk(ccall((:itcpd_set_lambda, libitcpd[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, array(cp.λ)))
-    chk(ccall((:itcpd_compute_grams, libitcpd[]), Cint, (Ptr{Cvoid},), h.ptr))
+    chk(ccall((:itcpd_set_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, array(cp.λ)))
+    chk(ccall((:itcpd_compute_grams, libitcpd), Cint, (Ptr{Cvoid},), h.ptr))
     return B200ALS(target, alg, h, check)
 end
 
@@ -89,19 +90,19 @@ function ITensorCPD.optimize(cp::CPD, als::B200ALS; verbose = false)
     converge = als.check
     inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
     while iter < converge.max_counter
-        chk(ccall((:itcpd_sweep, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Float64, Ref{Float64}, Ref{Float64}),
+        chk(ccall((:itcpd_sweep, libitcpd), Cint, (Ptr{Cvoid}, Cint, Float64, Ref{Float64}, Ref{Float64}),
                   h, 1, cholesky_epsilon, inner, nrm2))
-        if b200_check_converge(converge, dim(rank), inner[], nrm2[], verbose) && break end
+        b200_check_converge(converge, dim(rank), inner[], nrm2[], verbose) && break
         iter += 1
     end
     factors = Vector{ITensor}()
     for (n, i) in enumerate(inds(cp))
         A = Matrix{Float64}(undef, dim(i), dim(rank))
-        chk(ccall((:itcpd_get_factor, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
+        chk(ccall((:itcpd_get_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
         push!(factors, itensor(A, i, rank))
     end
     lam = Vector{Float64}(undef, dim(rank))
-    chk(ccall((:itcpd_get_lambda, libitcpd[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
+    chk(ccall((:itcpd_get_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
     return CPD{typeof(als.target)}(factors, itensor(lam, rank))
 end
 
@@ -130,8 +131,16 @@ function b200_check_converge(check::FitCheck, R, inner_prod, fact_square, verbos
     end
     return false
 end
-## NoCheck never looks at the factors (no_check.jl:9-20): reuse it unchanged.
-b200_check_converge(check::NoCheck, R, _, __, verbose) = ITensorCPD.check_converge(check, nothing, itensor(zeros(R), Index(R)), nothing; verbose)
+## NoCheck never looks at the factors: no_check.jl:9-20 restated on the rank dimension alone.
+function b200_check_converge(check::NoCheck, R, _, __, verbose)
+    check.iter += 1
+    verbose && println("$(R)\t $(check.iter)")
+    if check.iter == check.max_counter
+        check.iter = 0
+        return true
+    end
+    return false
+end
 
 ## ---------------------------------------------------------------------------------------------------------------
 ## Sampled path: leverage-score sampled ALS with the whole per-mode update on the device.
@@ -161,7 +170,7 @@ function ITensorCPD.compute_als(alg::B200LevScoreSampled, target::ITensor, cp::C
     dense = ITensorCPD.compute_als(B200Normal(alg.device), target, cp; check)   # uploads T, factors, lambda
     h = dense.handle
     for n in 1:length(cp)
-        chk(ccall((:itcpd_leverage_scores, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, C_NULL))
+        chk(ccall((:itcpd_leverage_scores, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, C_NULL))
     end
     return B200SampledALS(target, alg, h, check, normal, stop_resample, UInt64(seed))
 end
@@ -179,14 +188,14 @@ function ITensorCPD.optimize(cp::CPD, als::B200SampledALS; verbose = false)
             resample = als.stop_resample < 0 || als.stop_resample > als.check.iter || !drawn[fact]   # krp_lev...:24-27
             if resample
                 seed += 1
-                chk(ccall((:itcpd_sample_factor_matrices, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Int64, UInt64, Ptr{Int64}),
+                chk(ccall((:itcpd_sample_factor_matrices, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, UInt64, Ptr{Int64}),
                           h, fact - 1, size(pivs[fact], 1), seed, pivs[fact]))
                 drawn[fact] = true
             end
-            chk(ccall((:itcpd_sampled_update, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Float64, Cint),
+            chk(ccall((:itcpd_sampled_update, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Float64, Cint),
                       h, fact - 1, size(pivs[fact], 1), pivs[fact], cholesky_epsilon, als.normal ? 1 : 0))
         end
-        if b200_sampled_converged(als.check, h, verbose) && break end
+        b200_sampled_converged(als.check, h, dim(cp_rank(cp)), verbose) && break
         iter += 1
     end
     return fetch_cpd(h, cp, als.target)
@@ -194,23 +203,23 @@ end
 
 ## CPDiffCheck from the two device scalars (cp_diff_check.jl:20-71); FitCheck is not supported for sampled solvers
 ## (ProjectionAlgorithm.jl:30-51): it only counts sweeps.
-function b200_sampled_converged(check::CPDiffCheck, h, verbose)
+function b200_sampled_converged(check::CPDiffCheck, h, R, verbose)
     check.iter += 1
     inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
     if isnothing(check.PrevCP)
-        chk(ccall((:itcpd_cpd_snapshot, libitcpd[]), Cint, (Ptr{Cvoid},), h))
-        chk(ccall((:itcpd_cpd_diff_terms, libitcpd[]), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
+        chk(ccall((:itcpd_cpd_snapshot, libitcpd), Cint, (Ptr{Cvoid},), h))
+        chk(ccall((:itcpd_cpd_diff_terms, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
         check.PrevCP = true
         check.norm_prev_iter = nrm2[]
         return false
     end
-    chk(ccall((:itcpd_cpd_diff_terms, libitcpd[]), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
+    chk(ccall((:itcpd_cpd_diff_terms, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
     normResidual = sqrt(abs(check.norm_prev_iter + nrm2[] - 2 * abs(inner[])))
     curr_fit = 1.0 - normResidual / sqrt(abs(check.norm_prev_iter))
     Δfit = abs(check.lastfit - curr_fit)
     check.lastfit = curr_fit
     check.norm_prev_iter = nrm2[]
-    chk(ccall((:itcpd_cpd_snapshot, libitcpd[]), Cint, (Ptr{Cvoid},), h))
+    chk(ccall((:itcpd_cpd_snapshot, libitcpd), Cint, (Ptr{Cvoid},), h))
     verbose && println("$(check.iter) \t $(curr_fit) \t $(Δfit)")
     done = false
     if Δfit < check.tolerance
@@ -225,24 +234,24 @@ function b200_sampled_converged(check::CPDiffCheck, h, verbose)
     end
     return done
 end
-function b200_sampled_converged(check::FitCheck, h, verbose)
+function b200_sampled_converged(check::FitCheck, h, R, verbose)
     check.iter == 0 && println("Warning: FitCheck is not enabled for B200LevScoreSampled will run $(check.max_counter) iterations.")
     check.iter += 1
     check.iter >= check.max_counter && (check.iter = 0)
     return false
 end
-b200_sampled_converged(check::NoCheck, h, verbose) = b200_check_converge(check, 0, 0.0, 0.0, verbose)
+b200_sampled_converged(check::NoCheck, h, R, verbose) = b200_check_converge(check, R, 0.0, 0.0, verbose)
 
 function fetch_cpd(h, cp::CPD, target)
     rank = cp_rank(cp)
     factors = Vector{ITensor}()
     for (n, i) in enumerate(inds(cp))
         A = Matrix{Float64}(undef, dim(i), dim(rank))
-        chk(ccall((:itcpd_get_factor, libitcpd[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
+        chk(ccall((:itcpd_get_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
         push!(factors, itensor(A, i, rank))
     end
     lam = Vector{Float64}(undef, dim(rank))
-    chk(ccall((:itcpd_get_lambda, libitcpd[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
+    chk(ccall((:itcpd_get_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
     return CPD{typeof(target)}(factors, itensor(lam, rank))
 end
 
@@ -250,8 +259,8 @@ end
 ## global `ITensorCPD.libsparse` at libitcpd_b200 and the symbols at itcpd_sparse_sign / itcpd_sparsestack
 ## yields bit-identical (vals, rows, colstarts).
 b200_sparse_sign_call(::Val{false}, l, n, s, vals, rows, colstarts) =
-    ccall((:itcpd_sparse_sign, libitcpd[]), Cvoid, (Cint, Cint, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), l, n, s, vals, rows, colstarts)
+    ccall((:itcpd_sparse_sign, libitcpd), Cvoid, (Cint, Cint, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), l, n, s, vals, rows, colstarts)
 b200_sparse_sign_call(::Val{true}, l, n, s, vals, rows, colstarts) =
-    ccall((:itcpd_sparsestack, libitcpd[]), Cvoid, (Cint, Cint, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), l, n, s, vals, rows, colstarts)
+    ccall((:itcpd_sparsestack, libitcpd), Cvoid, (Cint, Cint, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), l, n, s, vals, rows, colstarts)
 
 end

@@ -137,3 +137,19 @@ def test_bench_reference_arm_runs_on_cpu():
 
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_build_recipes_cover_every_translation_unit():
+    """csrc/build.sh and the Julia deps/build_b200.jl must compile the same, complete set of .cu files (a stale list links with
+    undefined symbols only on the maintainer's machine)."""
+    csrc = os.path.join(ROOT, "itensorcpd.jl_b200", "csrc")
+    units = sorted(f[:-3] for f in os.listdir(csrc) if f.endswith(".cu"))
+    sh = open(os.path.join(csrc, "build.sh")).read()
+    listed = re.search(r"for f in ([a-z0-9_ ]+); do", sh).group(1).split()
+    assert sorted(listed) == units
+    jl = open(os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "deps", "build_b200.jl")).read()
+    assert 'readdir(csrc)' in jl and 'endswith(".cu")' in jl
+    ext = open(os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "ext", "ITCPDB200Ext", "ITCPDB200Ext.jl")).read()
+    # every entry point the extension ccalls is declared in the header
+    called = set(re.findall(r"ccall\(\(:(itcpd_[a-z0-9_]+), libitcpd\)", ext))
+    assert len(called) >= 12 and called <= set(header_symbols()), called - set(header_symbols())
