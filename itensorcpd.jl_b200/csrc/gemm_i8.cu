@@ -19,6 +19,7 @@
 //   warp 8     TMA producer (FP64 tiles of T, packed digit planes of the Khatri-Rao operand)
 //   warp 9     TMEM allocation + the single-thread MMA issuer
 #include "common.cuh"
+#include <cfloat>
 
 namespace itcpd {
 
@@ -32,20 +33,27 @@ constexpr int I8_A_BYTES = I8_NDIG * I8_A_PLANE;               // 28672
 constexpr int I8_B_BYTES = I8_NDIG * I8_BN * I8_BK;            // 14336
 constexpr int I8_SMEM = I8_FSTAGES * I8_F_BYTES + I8_DSTAGES * (I8_A_BYTES + I8_B_BYTES) + 256 + 1024;
 constexpr int I8_EXP_ZERO = -100000;                           // exponent of an all-zero row / column
+constexpr int I8_EXP_NONFINITE = 100000;                       // a NaN / Inf was seen: the whole output row / column becomes NaN (as in FP64)
 
 // ------------------------------------------------------------------------------------------------------------------
 // digit arithmetic (barrier-free device code: exercised on the CPU by tests/test_i8_digits_emulation_cpu.py)
 // ------------------------------------------------------------------------------------------------------------------
 // smallest E with |x| 2^-E < 1/2
+// running maximum of |x| that a NaN or an infinity turns into +inf for good (fmax alone would drop a NaN)
+__device__ __forceinline__ double i8_amax(double amax, double x) {
+    const double a = fabs(x);
+    return (a <= DBL_MAX) ? fmax(amax, a) : __longlong_as_double(0x7ff0000000000000ll);
+}
 __device__ __forceinline__ int i8_exponent(double amax) {
     if (!(amax > 0.0)) return I8_EXP_ZERO;
     const int biased = (int)((unsigned long long)__double_as_longlong(amax) >> 52) & 0x7ff;
+    if (biased == 0x7ff) return I8_EXP_NONFINITE;
     if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(49-E) representable)
     return biased - 1022 + 1;          // amax in [2^(b-1023), 2^(b-1022))  ->  amax 2^-(b-1021) < 1/2
 }
 // 2^(49 - E) as a double (0 for an all-zero row: every digit is then 0)
 __device__ __forceinline__ double i8_scale(int E) {
-    if (E == I8_EXP_ZERO) return 0.0;
+    if (E == I8_EXP_ZERO || E == I8_EXP_NONFINITE) return 0.0;
     return __longlong_as_double((long long)(1023 + I8_FRAC - E) << 52);
 }
 // X = rint(x scale), |X| <= 2^48.  Returns the seven 7-bit fields of Y = X + C (C = 0x40 in every field) as bytes:
@@ -91,7 +99,7 @@ __global__ void i8_row_exponent_strided_kernel(const double *__restrict__ base, 
     const int64_t chunk = (nred + gridDim.y - 1) / gridDim.y;
     const int64_t j0 = blockIdx.y * chunk, j1 = min(nred, j0 + chunk);
     double amax = 0.0;
-    for (int64_t j = j0; j < j1; ++j) amax = fmax(amax, fabs(base[r + j * sj]));
+    for (int64_t j = j0; j < j1; ++j) amax = i8_amax(amax, base[r + j * sj]);
     atomicMax(&E[r], i8_exponent(amax));
 }
 // (b) sj == 1 (reduction index contiguous): one warp per row
@@ -100,7 +108,7 @@ __global__ void i8_row_exponent_contig_kernel(const double *__restrict__ base, i
     const int lane = threadIdx.x & 31;
     if (r >= nrows) return;
     double amax = 0.0;
-    for (int64_t j = lane; j < nred; j += 32) amax = fmax(amax, fabs(base[r * sr + j]));
+    for (int64_t j = lane; j < nred; j += 32) amax = i8_amax(amax, base[r * sr + j]);
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if (lane == 0) E[r] = i8_exponent(amax);
 }
@@ -134,7 +142,7 @@ __global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
     const int64_t k0 = (idx / I8_BN) * 256;
     if (k0 >= a.kext) return;
     double amax = 0.0;
-    for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k) amax = fmax(amax, fabs(i8_krp_value(a, k, r)));
+    for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k) amax = i8_amax(amax, i8_krp_value(a, k, r));
     atomicMax(&E[r], i8_exponent(amax));
 }
 // digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 14336-byte block per k-tile of 32:
@@ -203,6 +211,7 @@ __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, 
 // C = 2^(ea + eb - 98 + 84) sum_t acc_t 2^(-7 t):  v = sum_t acc_t 2^(-7 t) is formed by the caller, smallest weights first
 __device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 7 * t) << 52); }
 __device__ __forceinline__ double i8_finish(double v, int em, int er) {
+    if (em == I8_EXP_NONFINITE || er == I8_EXP_NONFINITE) return __longlong_as_double(0x7ff8000000000000ll);   // NaN, like the FP64 contraction
     return (em == I8_EXP_ZERO || er == I8_EXP_ZERO) ? 0.0 : ldexp(v, em + er - 14);
 }
 

@@ -300,3 +300,37 @@ def test_split_k_schedule_policy():
         units = rt * ks
         waves = -(-units // 148)
         assert waves <= 4 and units / (148 * waves) >= 0.95, (rt, kt, ks, kc)
+
+
+@pytest.mark.parametrize("variant", ["on_the_fly", "prepacked"])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_non_finite_inputs_become_nan_rows_and_columns(sim, kind, variant):
+    """A NaN / Inf in T poisons its output row, one in a factor its rank column -- what the FP64 contraction does, so that the
+    host still raises the reference's "Error NAN" (fit_check.jl:40-42); every other entry keeps the 1e-12 bar."""
+    rng = np.random.default_rng(5)
+    Mrows, Ncols, R = (256, 96, 40) if kind == 0 else (96, 256, 40)
+    T = np.asfortranarray(rng.standard_normal((Mrows, Ncols)))
+    kext = Ncols if kind == 0 else Mrows
+    rows_out = Mrows if kind == 0 else Ncols
+    bad_rows = [3, 130]
+    if kind == 0:
+        T[3, 7], T[130, 50] = np.nan, -np.inf
+    else:
+        T[7, 3], T[50, 130] = np.inf, np.nan
+    f1 = np.asfortranarray(rng.standard_normal((8, R)))
+    f2 = np.asfortranarray(rng.standard_normal((kext // 8, R)))
+    f2[5, 11] = np.nan
+    Kr = (f2[:, None, :] * f1[None, :, :]).reshape(kext, R)
+    out = np.full((rows_out, R), 777.0, order="F")
+    fac = (C.c_void_p * 2)(f1.ctypes.data, f2.ctypes.data)
+    ext = np.array([8, kext // 8], dtype=np.int64)
+    run = sim.emu_gemm_i8 if variant == "on_the_fly" else sim.emu_gemm_i8p
+    run(kind, _p(T), Mrows, Ncols, 2, fac, _p(ext), R, 2, 1, _p(out))
+    assert np.all(np.isnan(out[bad_rows, :])) and np.all(np.isnan(out[:, 11]))
+    good_r = [r for r in range(R) if r != 11]
+    good_m = [m for m in range(rows_out) if m not in bad_rows]
+    Tc = np.where(np.isfinite(T), T, 0.0)
+    ref = (Tc @ Kr[:, good_r]) if kind == 0 else (Tc.T @ Kr[:, good_r])
+    got = out[np.ix_(good_m, good_r)]
+    assert np.all(np.isfinite(got))
+    assert np.linalg.norm(got - ref[good_m]) / np.linalg.norm(ref[good_m]) < 1e-12
