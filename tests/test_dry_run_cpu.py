@@ -123,3 +123,28 @@ int main() {
     subprocess.run(["g++", "-std=c++17", cpp, "-I", CUDA_INC, "-L", DRY, "-l:libcudart.so.12", f"-Wl,-rpath,{DRY}", "-o", exe], check=True, capture_output=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=DRY)).stdout.split()
     assert out == ["4", "1"], out
+
+
+@pytest.mark.parametrize("env_extra,args", [({}, []), ({"ITCPD_GEMM_I8": "2", "ITCPD_EARLY_B": "1"}, []), ({}, ["--config", "B8"]), ({}, ["--config", "A"])])
+def test_bench_line_contract_in_the_dry_run(dry_results, env_extra, args):
+    """bench.py's own arm at N = 1, start to finish, behind the fake runtime (numbers are meaningless, the JSON contract is not)"""
+    wrapper = (f"import sys, runpy; sys.path.insert(0, {ROOT!r}); import itcpd; "
+               f"itcpd.package._lib.LIB_PATH = {os.path.join(DRY, 'libitcpd_dry.so')!r}; "
+               f"sys.argv = ['bench.py', '--steps', '4', '--warmup', '3', '--no-cpu'] + {args!r}; "
+               f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')")
+    env = dict(os.environ, LD_LIBRARY_PATH=DRY, FAKECUDA_KERNEL_TABLE=os.path.join(DRY, "kernels.tbl"), **env_extra)
+    p = subprocess.run([sys.executable, "-W", "ignore", "-c", wrapper], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-1500:]
+    line = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "clocks", "gpu_launches", "roofline", "e2e"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] >= 3 and line["dtype"] == "f64" and line["unit"] == "sweeps/s"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["gpu_launches"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in line["roofline"], k
+    assert line["roofline"]["bound"] == ("hbm" if env_extra.get("ITCPD_GEMM_I8") else "tensor")
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in line["e2e"], k
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
