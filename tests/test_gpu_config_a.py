@@ -30,3 +30,31 @@ def test_config_a_fit_trajectory_100_sweeps_and_readme_rule(engine):
     c2 = itcpd.FitCheck(1e-3, 100, nT)
     itcpd.als_optimize(T, itcpd.CPD(cp.factors, cp.lam), check=c2)
     assert c2.total_iter == r2.total_iter and abs(c2.final_fit - r2.final_fit) <= 1e-9
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ITCPD_EXPERIMENTAL", "0") == "0",
+                    reason="gemm_i8 / early_pass_b have not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("gemm_i8,early_b", [(1, 0), (2, 0), (0, 1), (2, 1)])
+def test_config_a_trajectory_with_the_experimental_contraction_paths(engine, gemm_i8, early_b):
+    """the same north-star criterion (per-sweep fit within 1e-9 of the oracle over 100 sweeps) with the MTTKRP on the INT8
+    tensor cores (7-digit split: 1e-13-level MTTKRP error) and / or pass B overlapped with mode 1's update"""
+    import itcpd
+
+    dims, R, nsweeps = (200, 200, 200), 50, 100
+    rng = np.random.default_rng(0)
+    T = np.asfortranarray(rng.standard_normal(dims))
+    cp = cpals.random_CPD(T, R, np.random.default_rng(1))
+    nT = float(np.linalg.norm(T))
+    ref = cpals.FitCheck(0.0, nsweeps, nT)
+    cpals.als_optimize(T, cp, alg=cpals.KRPNormal(), check=ref)
+    engine.set_option("gemm_i8", gemm_i8)
+    engine.set_option("early_pass_b", early_b)
+    try:
+        engine.set_tensor(T)
+        chk = itcpd.FitCheck(0.0, nsweeps, nT)
+        itcpd.als_optimize(engine, itcpd.CPD(cp.factors, cp.lam), check=chk)
+        d = np.abs(np.array(chk.history) - np.array(ref.history))
+        assert d.shape == (nsweeps,) and d.max() <= 1e-9, (d.max(), int(d.argmax()))
+    finally:
+        engine.set_option("gemm_i8", 0)
+        engine.set_option("early_pass_b", 0)
