@@ -1,0 +1,29 @@
+#!/bin/bash
+# Round-2 opener, part 1 (ONE GPU, ~8 min):  gpurun --timeout 900 -- 'bash tools/r2_single_gpu.sh'
+# First hardware run of what was written after round 1's GPU budget was spent.  Ordered so that the most valuable verdicts
+# survive a time-out; everything lands in gpurun_out/r2_*.
+mkdir -p gpurun_out
+# 0. single-instruction probe of the INT8 tensor-core building blocks; diagnoses itself on a mismatch (tools/i8_probe.cu)
+if [ ! -x tools/i8_probe ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -DITCPD_I8_PROBE -o tools/i8_probe tools/i8_probe.cu > gpurun_out/r2_i8_probe_build.log 2>&1
+fi
+timeout 60 ./tools/i8_probe > gpurun_out/r2_i8_probe.txt 2>&1; tail -25 gpurun_out/r2_i8_probe.txt
+export ITCPD_EXPERIMENTAL=1
+# 1. the INT8 contraction alone (both variants, ragged, 3 rank blocks, split-K), then the other single-GPU opt-in tests
+timeout 200 python -m pytest tests/test_gpu_dense.py -m gpu -q -x -k "gemm_i8" > gpurun_out/r2_i8_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2_i8_tests.log; tail -6 gpurun_out/r2_i8_tests.log
+timeout 200 python -m pytest tests/test_gpu_dense.py tests/test_gpu_config_a.py -m gpu -q -k "early_pass_b or right_looking or experimental_contraction" > gpurun_out/r2_exp_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2_exp_tests.log; tail -8 gpurun_out/r2_exp_tests.log
+# 2. A/B bench lines (config B unless stated), 20 timed sweeps each
+B="timeout 90 python bench.py --no-cpu --no-e2e --steps 20"
+$B > gpurun_out/r2_B_dmma.json 2>> gpurun_out/r2_err.log
+ITCPD_EARLY_B=1 $B > gpurun_out/r2_B_dmma_earlyb.json 2>> gpurun_out/r2_err.log
+ITCPD_GEMM_I8=2 $B > gpurun_out/r2_B_i8_prepacked.json 2>> gpurun_out/r2_err.log
+ITCPD_GEMM_I8=2 ITCPD_EARLY_B=1 $B > gpurun_out/r2_B_i8_prepacked_earlyb.json 2>> gpurun_out/r2_err.log
+ITCPD_GEMM_I8=1 $B > gpurun_out/r2_B_i8_on_the_fly.json 2>> gpurun_out/r2_err.log
+for chol in 1 2; do
+  ITCPD_CHOL=$chol $B --config B8 --steps 50 > gpurun_out/r2_B8_chol$chol.json 2>> gpurun_out/r2_err.log
+  ITCPD_CHOL=$chol $B --config A --steps 50 > gpurun_out/r2_A_chol$chol.json 2>> gpurun_out/r2_err.log
+done
+ITCPD_GEMM_I8=2 $B --config B8 --steps 50 > gpurun_out/r2_B8_i8_prepacked.json 2>> gpurun_out/r2_err.log
+python tools/r2_summary.py gpurun_out/r2_*.json | tee gpurun_out/r2_summary.txt
+# 3. the rest of the single-GPU suite with the opt-in tests on (regression of the default path included)
+timeout 400 python -m pytest tests -m gpu -q --deselect tests/test_gpu_multi.py > gpurun_out/r2_all_tests.log 2>&1; echo "rc=$?" >> gpurun_out/r2_all_tests.log; tail -5 gpurun_out/r2_all_tests.log
