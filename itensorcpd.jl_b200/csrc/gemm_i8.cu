@@ -320,37 +320,50 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n, int a_mn_major) {
 // Work unit of the persistent kernels: (row tile, k-chunk).  ksplit = 1 is the plain data-parallel schedule; a short-and-wide
 // contraction (fewer row tiles than SMs) is cut along k into ksplit chunks of kchunk k-tiles, every unit writes its scaled
 // FP64 partial tile to a slot buffer and i8_splitk_fixup_kernel adds the chunks in ascending-k order (deterministic).
-struct I8Unit { int tile, chunk, kb, ke; };
-__device__ __forceinline__ I8Unit i8_unit(int u, int ksplit, int kchunk, int kt_count) {
+// All rank blocks of 64 columns ride in ONE launch, the rank block fastest in the unit index: neighbouring CTAs then stream the
+// same digit planes of T for different rank blocks at the same time, so the second reader is served by the L2 and a rank above
+// 64 does not multiply the HBM traffic of the pass.
+struct I8Sched {
+    int num_row_tiles, kt_count, ksplit, kchunk, rblocks;
+    long long bdig_rb_stride;     // bytes between the packed Khatri-Rao digit planes of consecutive rank blocks
+};
+struct I8Unit { int tile, chunk, rb, kb, ke; };
+__device__ __forceinline__ I8Unit i8_unit(int u, const I8Sched &sc) {
     I8Unit x;
-    x.tile = u / ksplit;
-    x.chunk = u - x.tile * ksplit;
-    x.kb = x.chunk * kchunk;
-    x.ke = min(kt_count, x.kb + kchunk);
+    const int v = u / sc.rblocks;
+    x.rb = u - v * sc.rblocks;
+    x.tile = v / sc.ksplit;
+    x.chunk = v - x.tile * sc.ksplit;
+    x.kb = x.chunk * sc.kchunk;
+    x.ke = min(sc.kt_count, x.kb + sc.kchunk);
     return x;
 }
+__device__ __forceinline__ int i8_units(const I8Sched &sc) { return sc.num_row_tiles * sc.ksplit * sc.rblocks; }
 // position of a pipeline role inside the CTA's sequence of (unit, k-tile) steps
 struct I8Cursor {
     int w, kt;
     I8Unit u;
-    __device__ __forceinline__ void start(int cta, int G, int my_units, int ksplit, int kchunk, int kt_count) {
+    __device__ __forceinline__ void start(int cta, const I8Sched &sc) {
         w = 0;
-        u = i8_unit(cta, ksplit, kchunk, kt_count);
+        u = i8_unit(cta, sc);
         kt = u.kb;
-        (void)G; (void)my_units;
     }
-    __device__ __forceinline__ void next(int cta, int G, int my_units, int ksplit, int kchunk, int kt_count) {
+    __device__ __forceinline__ void next(int cta, int G, int my_units, const I8Sched &sc) {
         if (++kt >= u.ke) {
             ++w;
-            if (w < my_units) { u = i8_unit(cta + w * G, ksplit, kchunk, kt_count); kt = u.kb; }
+            if (w < my_units) { u = i8_unit(cta + w * G, sc); kt = u.kb; }
         }
     }
 };
-__global__ void i8_splitk_fixup_kernel(const double *__restrict__ part, int ksplit, int64_t chunk_stride, int64_t n, double *__restrict__ out) {
+// part = [chunk][rank block][rows_out x 64]; out = rows_out x R (column-major)
+__global__ void i8_splitk_fixup_kernel(const double *__restrict__ part, int ksplit, int rblocks, int64_t rows_out, int64_t n, double *__restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double v = part[i];
-    for (int c = 1; c < ksplit; ++c) v += part[i + c * chunk_stride];
+    const int64_t r = i / rows_out, m = i - r * rows_out;
+    const int64_t blk = rows_out * (int64_t)I8_BN;
+    const double *p = part + (r / I8_BN) * blk + m + rows_out * (r % I8_BN);
+    double v = p[0];
+    for (int c = 1; c < ksplit; ++c) v += p[(int64_t)c * rblocks * blk];
     out[i] = v;
 }
 
@@ -419,8 +432,7 @@ __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t a0, uint3
 template <int KIND>
 __global__ void __launch_bounds__(320, 1)
 partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea,
-                       const int *__restrict__ eb, double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count,
-                       int ksplit, int kchunk, double *__restrict__ part) {
+                       const int *__restrict__ eb, double *__restrict__ out, int64_t rows_out, int R, const I8Sched sc, double *__restrict__ part) {
     extern __shared__ uint8_t i8_smem_raw[];
     const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
     const uint32_t sF = base;
@@ -448,7 +460,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
 
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int my_tiles = (num_row_tiles * ksplit - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
+    const int my_tiles = (i8_units(sc) - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
     const int64_t part_stride = rows_out * (int64_t)I8_BN;
 
     if (warp == 8) {
@@ -456,8 +468,8 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         // must not wait for the 2-deep digit ring, and two spinning lanes of one warp would lean on intra-warp fairness) =====
         if (lane == 0 && my_tiles > 0) {
             I8Cursor cf, cd;
-            cf.start(cta, G, my_tiles, ksplit, kchunk, kt_count);
-            cd.start(cta, G, my_tiles, ksplit, kchunk, kt_count);
+            cf.start(cta, sc);
+            cd.start(cta, sc);
             int itf = 0, itd = 0;
             unsigned long long idle = 0;
             while (cf.w < my_tiles || cd.w < my_tiles) {
@@ -470,7 +482,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                         if (KIND == 0) i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, row0, cf.kt * I8_BK, full_f + 8 * sf);
                         else i8_tma_2d(sF + sf * I8_F_BYTES, &tmap, cf.kt * I8_BK, row0, full_f + 8 * sf);
                         ++itf;
-                        cf.next(cta, G, my_tiles, ksplit, kchunk, kt_count);
+                        cf.next(cta, G, my_tiles, sc);
                         progressed = true;
                     }
                 }
@@ -478,9 +490,9 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                     const int sd = itd % I8_DSTAGES;
                     if (itd < I8_DSTAGES || i8_mbar_test(empty_d + 8 * sd, (uint32_t)((itd / I8_DSTAGES - 1) & 1))) {
                         i8_mbar_expect_tx(full_d + 8 * sd, I8_B_BYTES);
-                        i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)cd.kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
+                        i8_bulk_1d(sB + sd * I8_B_BYTES, Bdig + (size_t)cd.u.rb * sc.bdig_rb_stride + (size_t)cd.kt * I8_B_BYTES, I8_B_BYTES, full_d + 8 * sd);
                         ++itd;
-                        cd.next(cta, G, my_tiles, ksplit, kchunk, kt_count);
+                        cd.next(cta, G, my_tiles, sc);
                         progressed = true;
                     }
                 }
@@ -496,7 +508,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                const I8Unit u = i8_unit(cta + w * G, sc);
                 if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));   // the epilogue has drained the accumulators
                 i8_tc_fence_after();
                 for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
@@ -514,7 +526,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
         const int tid = threadIdx.x;   // 0 .. 255
         int it = 0;
         for (int w = 0; w < my_tiles; ++w) {
-            const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+            const I8Unit u = i8_unit(cta + w * G, sc);
             const int64_t row0 = (int64_t)u.tile * I8_BM;
             for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                 const int sf = it % I8_FSTAGES, sd = it % I8_DSTAGES;
@@ -528,7 +540,9 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                 i8_mbar_arrive(empty_f + 8 * sf);
             }
             if (warp < 4) {
-                i8_epilogue_warp(tmem, acc_full, acc_empty, w, row0, warp, lane, ea, eb, ksplit > 1 ? part + u.chunk * part_stride : out, rows_out, R);
+                i8_epilogue_warp(tmem, acc_full, acc_empty, w, row0, warp, lane, ea, eb + u.rb * I8_BN,
+                                 sc.ksplit > 1 ? part + (int64_t)(u.chunk * sc.rblocks + u.rb) * part_stride : out + (int64_t)u.rb * part_stride, rows_out,
+                                 min(I8_BN, R - u.rb * I8_BN));
             }
         }
     }
@@ -570,8 +584,7 @@ __global__ void __launch_bounds__(256) i8_pack_tensor_kernel(const double *__res
 template <int KIND>
 __global__ void __launch_bounds__(192, 1)
 partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restrict__ Bdig, const int *__restrict__ ea, const int *__restrict__ eb,
-                        double *__restrict__ out, int64_t rows_out, int R, int num_row_tiles, int kt_count, int ksplit, int kchunk,
-                        double *__restrict__ part) {
+                        double *__restrict__ out, int64_t rows_out, int R, const I8Sched sc, double *__restrict__ part) {
     extern __shared__ uint8_t i8_smem_raw[];
     const uint32_t base = (i8_smem_u32(i8_smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + I8P_STAGES * I8P_STAGE_BYTES;
@@ -590,14 +603,15 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
     i8_tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen_base + (tmem_slot - base));
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int my_tiles = (num_row_tiles * ksplit - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
+    const int my_tiles = (i8_units(sc) - cta + G - 1) / G;   // work units of this CTA (see I8Unit)
     const int64_t part_stride = rows_out * (int64_t)I8_BN;
+    const int kt_count = sc.kt_count;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                const I8Unit u = i8_unit(cta + w * G, sc);
                 const int64_t tile = u.tile;
                 for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
                     const int st = it % I8P_STAGES;
@@ -605,7 +619,7 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
                     i8_mbar_expect_tx(full + 8 * st, I8P_STAGE_BYTES);
                     const uint32_t dst = base + st * I8P_STAGE_BYTES;
                     i8_bulk_1d(dst, Adig + (size_t)(tile * kt_count + kt) * I8_A_BYTES, I8_A_BYTES, full + 8 * st);
-                    i8_bulk_1d(dst + I8_A_BYTES, Bdig + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full + 8 * st);
+                    i8_bulk_1d(dst + I8_A_BYTES, Bdig + (size_t)u.rb * sc.bdig_rb_stride + (size_t)kt * I8_B_BYTES, I8_B_BYTES, full + 8 * st);
                 }
             }
         }
@@ -613,7 +627,7 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
         if (lane == 0) {
             int it = 0;
             for (int w = 0; w < my_tiles; ++w) {
-                const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
+                const I8Unit u = i8_unit(cta + w * G, sc);
                 if (w > 0) i8_mbar_wait(acc_empty, (uint32_t)((w - 1) & 1));
                 i8_tc_fence_after();
                 for (int kt = u.kb; kt < u.ke; ++kt, ++it) {
@@ -629,9 +643,10 @@ partial_gemm_i8p_kernel(const uint8_t *__restrict__ Adig, const uint8_t *__restr
         }
     } else {
         for (int w = 0; w < my_tiles; ++w) {
-            const I8Unit u = i8_unit(cta + w * G, ksplit, kchunk, kt_count);
-            i8_epilogue_warp(tmem, acc_full, acc_empty, w, (int64_t)u.tile * I8_BM, warp & 3, lane, ea, eb, ksplit > 1 ? part + u.chunk * part_stride : out,
-                             rows_out, R);
+            const I8Unit u = i8_unit(cta + w * G, sc);
+            i8_epilogue_warp(tmem, acc_full, acc_empty, w, (int64_t)u.tile * I8_BM, warp & 3, lane, ea, eb + u.rb * I8_BN,
+                             sc.ksplit > 1 ? part + (int64_t)(u.chunk * sc.rblocks + u.rb) * part_stride : out + (int64_t)u.rb * part_stride, rows_out,
+                             min(I8_BN, R - u.rb * I8_BN));
         }
     }
     i8_tc_fence_before();
@@ -704,7 +719,7 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     // split-K schedule (I8Unit): data parallel when there are enough row tiles; otherwise cut k so that the units fill the
     // SMs in whole waves (a chunk keeps at least 8 k-tiles so the pipeline fill and the partial-tile traffic stay small)
     int ksplit = 1, kchunk = (int)ktiles;
-    i8_choose_ksplit(row_tiles, ktiles, c->sm_count, &ksplit, &kchunk);
+    i8_choose_ksplit(row_tiles * rblocks, ktiles, c->sm_count, &ksplit, &kchunk);   // rank blocks are independent units too
 
     // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
     I8ExpCache &ec = c->i8_exp[kind];
@@ -787,9 +802,11 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     TRY(c->i8_bdig.reserve((size_t)rblocks * ktiles * I8_B_BYTES));
     i8_fill_int_kernel<<<(unsigned)ceil_div(rblocks * I8_BN, 64), 64, 0, c->stream>>>(c->i8_eb.as<int>(), rblocks * I8_BN, I8_EXP_ZERO);
     c->launches++;
-    const int grid = (int)std::min<int64_t>(row_tiles * ksplit, c->sm_count);
+    // one launch covers every rank block (I8Sched): the grid is a multiple of rblocks so that CTA c always serves rank block c % rblocks
+    const int64_t units = row_tiles * ksplit * rblocks;
+    const int grid = (int)std::min<int64_t>(units, std::max(rblocks, c->sm_count / rblocks * rblocks));
     const int64_t part_stride = rows_out * (int64_t)I8_BN;
-    if (ksplit > 1) TRY(c->i8_part.reserve((size_t)ksplit * part_stride * 8));
+    if (ksplit > 1) TRY(c->i8_part.reserve((size_t)ksplit * rblocks * part_stride * 8));
     double *part = ksplit > 1 ? c->i8_part.as<double>() : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->time_gemm) {  // same bookkeeping as launch_partial_gemm: one event pair per contraction (itcpd_gemm_timing)
@@ -808,26 +825,30 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         pa.r0 = rb * I8_BN;
         int *eb = c->i8_eb.as<int>() + rb * I8_BN;
         uint8_t *bdig = c->i8_bdig.as<uint8_t>() + (size_t)rb * ktiles * I8_B_BYTES;
-        double *out_rb = out + (size_t)rb * I8_BN * rows_out;
-        const int Rb = std::min(I8_BN, R - rb * I8_BN);
         i8_krp_exponent_kernel<<<(unsigned)ceil_div(ceil_div(kext, 256) * I8_BN, 256), 256, 0, c->stream>>>(pa, eb);
         i8_krp_pack_kernel<<<(unsigned)ceil_div(ktiles * I8_BN * 2, 256), 256, 0, c->stream>>>(pa, eb, ktiles, bdig);
-        if (prepacked && kind == 0)
-            partial_gemm_i8p_kernel<0><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
-        else if (prepacked)
-            partial_gemm_i8p_kernel<1><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
-        else if (kind == 0)
-            partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
-        else
-            partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out_rb, rows_out, Rb, (int)row_tiles, (int)ktiles, ksplit, kchunk, part);
-        c->launches += 3;
-        if (ksplit > 1) {
-            const int64_t n = rows_out * (int64_t)Rb;
-            i8_splitk_fixup_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(part, ksplit, part_stride, n, out_rb);
-            c->launches++;
-        }
-        CUDA_TRY(cudaGetLastError());
+        c->launches += 2;
     }
+    I8Sched sc;
+    sc.num_row_tiles = (int)row_tiles;
+    sc.kt_count = (int)ktiles;
+    sc.ksplit = ksplit;
+    sc.kchunk = kchunk;
+    sc.rblocks = rblocks;
+    sc.bdig_rb_stride = (long long)ktiles * I8_B_BYTES;
+    const uint8_t *bdig = c->i8_bdig.as<uint8_t>();
+    const int *eb = c->i8_eb.as<int>();
+    if (prepacked && kind == 0) partial_gemm_i8p_kernel<0><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out, rows_out, R, sc, part);
+    else if (prepacked) partial_gemm_i8p_kernel<1><<<grid, 192, I8P_SMEM, c->stream>>>(pk.buf.as<uint8_t>(), bdig, ec.buf.as<int>(), eb, out, rows_out, R, sc, part);
+    else if (kind == 0) partial_gemm_i8_kernel<0><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out, rows_out, R, sc, part);
+    else partial_gemm_i8_kernel<1><<<grid, 320, I8_SMEM, c->stream>>>(map, bdig, ec.buf.as<int>(), eb, out, rows_out, R, sc, part);
+    c->launches++;
+    if (ksplit > 1) {
+        const int64_t n = rows_out * (int64_t)R;
+        i8_splitk_fixup_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(part, ksplit, rblocks, rows_out, n, out);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
     if (e1) CUDA_TRY(cudaEventRecord(e1, c->stream));
     return ITCPD_OK;
 }

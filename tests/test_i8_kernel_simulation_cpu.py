@@ -131,19 +131,32 @@ namespace itcpd_emu {
 }
 using namespace itcpd_emu;
 
-static void run_fixup(std::vector<double> &part, int ksplit, long rows_out, int R, double *out) {
+static void run_fixup(std::vector<double> &part, int ksplit, int rblocks, long rows_out, int R, double *out) {
     if (ksplit <= 1) return;
     const long n = rows_out * R;
     const unsigned gx = (unsigned)((n + 63) / 64);
     for (unsigned bx = 0; bx < gx; ++bx)
-        emu_launch(64, 0, [&] { i8_splitk_fixup_kernel(part.data(), ksplit, rows_out * (long)I8_BN, n, out); }, bx, 0, gx, 1);
+        emu_launch(64, 0, [&] { i8_splitk_fixup_kernel(part.data(), ksplit, rblocks, rows_out, n, out); }, bx, 0, gx, 1);
+}
+// column exponents and packed digit planes of every 64-column rank block (what launch_partial_gemm_i8 does per block)
+static void pack_krp_blocks(I8Krp a, int rblocks, long kext, long ktiles, std::vector<int> &eb, std::vector<uint8_t> &bdig) {
+    for (int rb = 0; rb < rblocks; ++rb) {
+        a.r0 = rb * I8_BN;
+        int *e = eb.data() + rb * I8_BN;
+        uint8_t *b = bdig.data() + (size_t)rb * ktiles * I8_B_BYTES;
+        unsigned gx = (unsigned)((((kext + 255) / 256) * I8_BN + 63) / 64);
+        for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_exponent_kernel(a, e); }, bx, 0, gx, 1);
+        gx = (unsigned)((ktiles * I8_BN * 2 + 63) / 64);
+        for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_pack_kernel(a, e, ktiles, b); }, bx, 0, gx, 1);
+    }
 }
 
 // out (rows_out x R) = unfolding(T) * K  through the emulated kernel; exponents and digit planes by the emulated helpers
 extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, int ksplit, double *out) {
     const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
     const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
-    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
+    const int rblocks = (R + I8_BN - 1) / I8_BN;
+    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(rblocks * I8_BN, I8_EXP_ZERO);
     if (kind == 0) {
         const unsigned gx = (unsigned)((rows_out + 63) / 64), gy = 2;
         for (unsigned bx = 0; bx < gx; ++bx) for (unsigned by = 0; by < gy; ++by)
@@ -156,25 +169,26 @@ extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, i
     memset(&a, 0, sizeof(a));
     a.nf = nf; a.kext = kext; a.R = R;
     for (int f = 0; f < nf; ++f) { a.fac[f] = fac[f]; a.ext[f] = ext[f]; a.dim[f] = ext[f]; }
-    std::vector<uint8_t> bdig(ktiles * I8_B_BYTES);
-    unsigned gx = (unsigned)((((kext + 255) / 256) * I8_BN + 63) / 64);
-    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_exponent_kernel(a, eb.data()); }, bx, 0, gx, 1);
-    gx = (unsigned)((ktiles * I8_BN * 2 + 63) / 64);
-    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_pack_kernel(a, eb.data(), ktiles, bdig.data()); }, bx, 0, gx, 1);
+    std::vector<uint8_t> bdig((size_t)rblocks * ktiles * I8_B_BYTES);
+    unsigned gx = 0;
+    pack_krp_blocks(a, rblocks, kext, ktiles, eb, bdig);
     CUtensorMap map;
     map.base = T; map.d0 = Mrows; map.d1 = Ncols;
     if (kind == 0) { map.box0 = I8_BM; map.box1 = I8_BK; } else { map.box0 = I8_BK; map.box1 = I8_BM; }
     g_mma_count = 0;
     const int kchunk = (int)((ktiles + ksplit - 1) / ksplit);
     if ((ktiles + kchunk - 1) / kchunk != ksplit) return -1;          // the host never launches an empty chunk
-    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rows_out * I8_BN : 1, NAN);
+    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rblocks * rows_out * I8_BN : 1, NAN);
+    I8Sched sc;
+    sc.num_row_tiles = (int)row_tiles; sc.kt_count = (int)ktiles; sc.ksplit = ksplit; sc.kchunk = kchunk; sc.rblocks = rblocks;
+    sc.bdig_rb_stride = (long long)ktiles * I8_B_BYTES;
     for (int cta = 0; cta < grid; ++cta) {
         g_bars.clear();
         memset(TMEM, 0x5a, sizeof(TMEM));          // stale accumulator contents must not leak into results
-        if (kind == 0) emu_launch(320, 0, [&] { partial_gemm_i8_kernel<0>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
-        else emu_launch(320, 0, [&] { partial_gemm_i8_kernel<1>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
+        if (kind == 0) emu_launch(320, 0, [&] { partial_gemm_i8_kernel<0>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, sc, part.data()); }, cta, 0, grid, 1);
+        else emu_launch(320, 0, [&] { partial_gemm_i8_kernel<1>(map, bdig.data(), ea.data(), eb.data(), out, rows_out, R, sc, part.data()); }, cta, 0, grid, 1);
     }
-    run_fixup(part, ksplit, rows_out, R, out);
+    run_fixup(part, ksplit, rblocks, rows_out, R, out);
     return g_mma_count;
 }
 
@@ -182,7 +196,8 @@ extern "C" long emu_gemm_i8(int kind, const double *T, long Mrows, long Ncols, i
 extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, int nf, const double *const *fac, const long *ext, int R, int grid, int ksplit, double *out) {
     const long kext = kind == 0 ? Ncols : Mrows, rows_out = kind == 0 ? Mrows : Ncols;
     const long ktiles = (kext + I8_BK - 1) / I8_BK, row_tiles = (rows_out + I8_BM - 1) / I8_BM;
-    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(I8_BN, I8_EXP_ZERO);
+    const int rblocks = (R + I8_BN - 1) / I8_BN;
+    std::vector<int> ea(row_tiles * I8_BM, I8_EXP_ZERO), eb(rblocks * I8_BN, I8_EXP_ZERO);
     if (kind == 0) {
         const unsigned gx = (unsigned)((rows_out + 63) / 64);
         for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_row_exponent_strided_kernel(T, rows_out, kext, Mrows, ea.data()); }, bx, 0, gx, 1);
@@ -194,11 +209,9 @@ extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, 
     memset(&a, 0, sizeof(a));
     a.nf = nf; a.kext = kext; a.R = R;
     for (int f = 0; f < nf; ++f) { a.fac[f] = fac[f]; a.ext[f] = ext[f]; a.dim[f] = ext[f]; }
-    std::vector<uint8_t> bdig(ktiles * I8_B_BYTES), adig((size_t)row_tiles * ktiles * I8_A_BYTES);
-    unsigned gx = (unsigned)((((kext + 255) / 256) * I8_BN + 63) / 64);
-    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_exponent_kernel(a, eb.data()); }, bx, 0, gx, 1);
-    gx = (unsigned)((ktiles * I8_BN * 2 + 63) / 64);
-    for (unsigned bx = 0; bx < gx; ++bx) emu_launch(64, 0, [&] { i8_krp_pack_kernel(a, eb.data(), ktiles, bdig.data()); }, bx, 0, gx, 1);
+    std::vector<uint8_t> bdig((size_t)rblocks * ktiles * I8_B_BYTES), adig((size_t)row_tiles * ktiles * I8_A_BYTES);
+    unsigned gx = 0;
+    pack_krp_blocks(a, rblocks, kext, ktiles, eb, bdig);
     gx = (unsigned)(row_tiles * ktiles);
     for (unsigned bx = 0; bx < gx; ++bx) {
         if (kind == 0) emu_launch(256, 0, [&] { i8_pack_tensor_kernel<0>(T, rows_out, kext, 1, Mrows, ea.data(), ktiles, adig.data()); }, bx, 0, gx, 1);
@@ -207,14 +220,17 @@ extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, 
     g_mma_count = 0;
     const int kchunk = (int)((ktiles + ksplit - 1) / ksplit);
     if ((ktiles + kchunk - 1) / kchunk != ksplit) return -1;          // the host never launches an empty chunk
-    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rows_out * I8_BN : 1, NAN);
+    std::vector<double> part(ksplit > 1 ? (size_t)ksplit * rblocks * rows_out * I8_BN : 1, NAN);
+    I8Sched sc;
+    sc.num_row_tiles = (int)row_tiles; sc.kt_count = (int)ktiles; sc.ksplit = ksplit; sc.kchunk = kchunk; sc.rblocks = rblocks;
+    sc.bdig_rb_stride = (long long)ktiles * I8_B_BYTES;
     for (int cta = 0; cta < grid; ++cta) {
         g_bars.clear();
         memset(TMEM, 0x5a, sizeof(TMEM));
-        if (kind == 0) emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<0>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
-        else emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<1>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, (int)row_tiles, (int)ktiles, ksplit, kchunk, part.data()); }, cta, 0, grid, 1);
+        if (kind == 0) emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<0>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, sc, part.data()); }, cta, 0, grid, 1);
+        else emu_launch(192, 0, [&] { partial_gemm_i8p_kernel<1>(adig.data(), bdig.data(), ea.data(), eb.data(), out, rows_out, R, sc, part.data()); }, cta, 0, grid, 1);
     }
-    run_fixup(part, ksplit, rows_out, R, out);
+    run_fixup(part, ksplit, rblocks, rows_out, R, out);
     return g_mma_count;
 }
 """
@@ -247,7 +263,9 @@ def _p(a):
 @pytest.mark.parametrize("kind,Mrows,Ncols,R,grid,ksplit", [(0, 256, 64, 48, 2, 1), (1, 64, 256, 64, 2, 1), (0, 200, 40, 20, 1, 1), (1, 40, 330, 33, 3, 1),
                                                           (0, 384, 160, 64, 2, 1),
                                                           # split-K (short-and-wide contractions): units = row tiles x k-chunks, FP64 partial tiles + fix-up
-                                                          (0, 128, 320, 64, 3, 5), (1, 352, 100, 24, 2, 4), (0, 200, 200, 40, 5, 3)])
+                                                          (0, 128, 320, 64, 3, 5), (1, 352, 100, 24, 2, 4), (0, 200, 200, 40, 5, 3),
+                                                          # several rank blocks of 64 columns in ONE launch (rank block fastest in the unit index)
+                                                          (0, 256, 64, 100, 2, 1), (1, 96, 200, 130, 3, 1), (0, 128, 320, 70, 4, 2)])
 def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, grid, ksplit, variant):
     rng = np.random.default_rng(100 * kind + Mrows)
     T = np.asfortranarray(rng.standard_normal((Mrows, Ncols)) * np.exp2(rng.integers(-5, 6, size=(Mrows, 1))))   # memory image T[m + Mrows n]
@@ -268,7 +286,7 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     assert err < 1e-12, err
     ktiles, row_tiles = -(-kext // 32), -(-rows_out // 128)
-    assert nmma == 10 * ktiles * row_tiles          # 28 digit products per k-step as 10 instructions
+    assert nmma == 10 * ktiles * row_tiles * -(-R // 64)          # 28 digit products per k-step and rank block as 10 instructions
 
 
 def test_split_k_schedule_policy():
