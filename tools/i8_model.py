@@ -27,8 +27,10 @@ def one_pass(rows, kext, R):
     a_bytes, b_reads = NDIG * BM * BK, sum(NDIG - p for p in range(NDIG)) * BN * BK
     t = {
         "dmma": 2.0 * R * P / DMMA,
-        "hbm8": rb * 8.0 * P / HBM,                   # variant 1 streams the FP64 tensor once per rank block
-        "hbm7": rb * 7.0 * P / HBM,                   # variant 2 streams the 7 digit planes
+        # all rank blocks ride in one launch, neighbouring CTAs stream the same rows of T for different rank blocks: if the L2
+        # catches the second reader a pass costs ONE stream of T (shown); if it does not, multiply by the number of rank blocks
+        "hbm8": 8.0 * P / HBM,                        # variant 1 streams the FP64 tensor
+        "hbm7": 7.0 * P / HBM,                        # variant 2 streams the 7 digit planes
         "mma": mma_ops / I8,
         # shared-memory traffic per k-step: operand reads of the 10 instructions (A planes once, stacked B planes re-read)
         "smem1": ksteps * (a_bytes + b_reads + BM * BK * 8 * 2 + a_bytes + NDIG * BN * BK) / SMEM,   # + TMA FP64 in, converter read, planes written, B in
@@ -63,6 +65,6 @@ if __name__ == "__main__":
               f"{ms['i8_v1']:8.3f} {ms['i8_v2']:8.3f} {t['dmma'] / t['i8_v2']:8.2f}x")
     print("\nReading: 'i8 v1' / 'i8 v2' are the largest of their bounds (perfect overlap). Variant 1 is bound by the converters' integer")
     print("work and shared-memory traffic, variant 2 by the HBM stream of the digit planes (R <= 64) or by the INT8 pipe (R = 128: two")
-    print("rank blocks = two passes over T).  Config B sweep estimate with variant 2: 2 passes + 0.55 ms of other kernels.")
+    print("rank blocks share one stream of T through the L2, the MMA work doubles).  Config B sweep estimate with variant 2: 2 passes + 0.55 ms of other kernels.")
     t = one_pass(1024 * 1024, 1024, 64)
     print(f"  DMMA today: {1e3 * (2 * 3.92e-3 + 0.55e-3):.2f} ms measured;  variant 2 bound: {1e3 * (2 * t['i8_v2'] + 0.55e-3):.2f} ms -> {1 / (2 * t['i8_v2'] + 0.55e-3):.0f} sweeps/s")
