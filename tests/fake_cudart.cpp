@@ -40,7 +40,11 @@ struct Alloc { size_t size; bool host; };
 std::map<uintptr_t, Alloc> g_allocs;
 size_t g_device_bytes = 0;
 size_t g_device_cap = (size_t)180 * 1000 * 1000 * 1000;
-const size_t REAL_COPY_LIMIT = (size_t)1 << 20;   // larger copies / memsets are only range-checked
+size_t REAL_COPY_LIMIT = (size_t)1 << 20;   // larger copies / memsets are only range-checked (fakecuda_set_real_copy_limit)
+// Optional launch hook (tests/test_i8_host_device_cpu.py): a plug-in that EXECUTES selected kernels on the host -- the verbatim
+// gemm_i8.cu kernels on the functional tcgen05 / TMEM / TMA model -- so that the real host code drives real (emulated) device code.
+typedef int (*launch_hook_t)(const char *name, void **args, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, size_t smem);
+launch_hook_t g_launch_hook = nullptr;
 
 const std::pair<const uintptr_t, Alloc> *find_alloc(const void *p) {
     const uintptr_t a = (uintptr_t)p;
@@ -144,6 +148,8 @@ long fakecuda_launches(const char *substr) {
         if (!substr || !*substr || kv.first.find(substr) != std::string::npos) n += kv.second;
     return n;
 }
+void fakecuda_set_real_copy_limit(unsigned long long bytes) { std::lock_guard<std::mutex> g(g_mu); REAL_COPY_LIMIT = bytes; }
+void fakecuda_set_launch_hook(void *fn) { std::lock_guard<std::mutex> g(g_mu); g_launch_hook = (launch_hook_t)fn; }
 void fakecuda_set_device_cap(unsigned long long bytes) { std::lock_guard<std::mutex> g(g_mu); g_device_cap = bytes; }
 unsigned long long fakecuda_device_bytes() { std::lock_guard<std::mutex> g(g_mu); return g_device_bytes; }
 int fakecuda_live_device_allocs() {
@@ -180,8 +186,8 @@ cudaError_t __cudaPopCallConfiguration(dim3 *grid, dim3 *block, size_t *smem, vo
     return cudaSuccess;
 }
 
-cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **, size_t smem, cudaStream_t stream) {
-    std::lock_guard<std::mutex> g(g_mu);
+cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t stream) {
+    std::unique_lock<std::mutex> g(g_mu);
     auto it = g_kernels.find(func);
     const KernelInfo unknown{"<unregistered kernel>"};
     const KernelInfo &k = it == g_kernels.end() ? unknown : it->second;
@@ -205,6 +211,15 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **, s
     if (!st) bad = true;
     if (bad) { g_last_error = cudaErrorInvalidConfiguration; return g_last_error; }
     stream_work(st);
+    if (g_launch_hook && !st->cap) {
+        launch_hook_t hook = g_launch_hook;
+        const std::string name = k.name;
+        g.unlock();   // the emulated kernel runs thousands of host threads; it never calls back into the runtime
+        if (hook(name.c_str(), args, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem)) {
+            g.lock();
+            g_launch_count["<executed> " + name]++;
+        }
+    }
     return cudaSuccess;
 }
 
@@ -514,6 +529,12 @@ static CUresult fake_encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuui
     }
     if (!ok) return CUDA_ERROR_INVALID_VALUE;
     memset(map, 0xab, sizeof(*map));
+    if (rank == 2 && dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT64 && sw == CU_TENSOR_MAP_SWIZZLE_NONE) {
+        // layout read by the functional model of the launch hook: { const double *base; long d0, d1; int box0, box1; }
+        struct { const double *base; long d0, d1; int box0, box1; } m = {(const double *)addr, (long)gdim[0], (long)gdim[1], (int)box[0], (int)box[1]};
+        if (gstr[0] != gdim[0] * 8) { violation("cuTensorMapEncodeTiled: the functional model needs a dense 2-D view (stride %llu)", (unsigned long long)gstr[0]); return CUDA_ERROR_INVALID_VALUE; }
+        memcpy(map, &m, sizeof(m));
+    }
     return CUDA_SUCCESS;
 }
 cudaError_t cudaGetDriverEntryPoint(const char *sym, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {

@@ -236,17 +236,23 @@ extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, 
 """
 
 
-@pytest.fixture(scope="module")
-def sim():
+def model_source():
+    """the functional model with the VERBATIM device text of csrc/gemm_i8.cu spliced in (also used by test_i8_host_device_cpu.py)"""
     text = open(SRC).read()
     numerics = text[text.index("constexpr int I8_NDIG = 7;"):text.index("#ifndef ITCPD_I8_HOST_EMULATION")]
     descs = text[text.index("// shared-memory matrix descriptor, SWIZZLE_NONE"):text.index("// ------------------------------------------------------------------------------------------------------------------\n// the kernel")]
     k0 = text.index("template <int KIND>\n__global__ void __launch_bounds__(320, 1)")
     k1 = text.index("// ------------------------------------------------------------------------------------------------------------------\n// host side")
     kernel = text[k0:k1].replace("extern __shared__ uint8_t i8_smem_raw[];", "")
+    fill = text[text.index("__global__ void i8_fill_int_kernel"):text.index("// Same contract as launch_partial_gemm")]
+    return MODEL.replace("@@NUMERICS@@", numerics).replace("@@DESCS@@", descs).replace("@@KERNEL@@", kernel + "\n" + fill)
+
+
+@pytest.fixture(scope="module")
+def sim():
     os.makedirs(BUILD, exist_ok=True)
     cpp, so = os.path.join(BUILD, "i8_sim.cpp"), os.path.join(BUILD, "i8_sim.so")
-    open(cpp, "w").write(MODEL.replace("@@NUMERICS@@", numerics).replace("@@DESCS@@", descs).replace("@@KERNEL@@", kernel))
+    open(cpp, "w").write(model_source())
     subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-Wl,-Bsymbolic", "-I", os.path.join(ROOT, "tests"), "-o", so, cpp,
                     "-lpthread"], check=True, capture_output=True)
     lib = C.CDLL(so)
