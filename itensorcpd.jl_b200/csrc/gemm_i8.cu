@@ -209,6 +209,11 @@ __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, 
 }
 
 // C = 2^(ea + eb - 98 + 84) sum_t acc_t 2^(-7 t):  v = sum_t acc_t 2^(-7 t) is formed by the caller, smallest weights first
+// exact int32 -> double without the (quarter-rate) I2F.F64 conversion: the double whose high word is 0x43300000 and whose low
+// word is a + 2^31 equals 2^52 + 2^31 + a; one DADD removes the offset exactly
+__device__ __forceinline__ double i8_i2d(int a) {
+    return __hiloint2double(0x43300000, (int)((unsigned)a ^ 0x80000000u)) - 4503601774854144.0;
+}
 __device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 7 * t) << 52); }
 __device__ __forceinline__ double i8_finish(double v, int em, int er) {
     if (em == I8_EXP_NONFINITE || er == I8_EXP_NONFINITE) return __longlong_as_double(0x7ff8000000000000ll);   // NaN, like the FP64 contraction
@@ -387,7 +392,7 @@ __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_ful
             i8_tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(I8_BN * t + 32 * half), a);
             const double wt = i8_weight(t);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = fma((double)a[c], wt, v[c]);
+            for (int c = 0; c < 32; ++c) v[c] = fma(i8_i2d(a[c]), wt, v[c]);
         }
         if (m < rows_out) {
 #pragma unroll

@@ -35,6 +35,7 @@ using std::min;
 struct uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 inline long long __double2ll_rn(double x) { return llrint(x); }
+inline double __hiloint2double(int hi, int lo) { unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; memcpy(&d, &b, 8); return d; }
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     const unsigned long long xy = ((unsigned long long)y << 32) | x;
     unsigned r = 0;
