@@ -217,7 +217,11 @@ __device__ __forceinline__ double i8_i2d(int a) {
 __device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 7 * t) << 52); }
 __device__ __forceinline__ double i8_finish(double v, int em, int er) {
     if (em == I8_EXP_NONFINITE || er == I8_EXP_NONFINITE) return __longlong_as_double(0x7ff8000000000000ll);   // NaN, like the FP64 contraction
-    return (em == I8_EXP_ZERO || er == I8_EXP_ZERO) ? 0.0 : ldexp(v, em + er - 14);
+    if (em == I8_EXP_ZERO || er == I8_EXP_ZERO) return 0.0;
+    // v 2^e as two exact power-of-two multiplications (e = em + er - 14 lies in [-1800, 2036]: each half is a normal double);
+    // ldexp() is a ~20-instruction library routine, and this runs once per output element
+    const int e = em + er - 14, h = e >> 1;
+    return v * __longlong_as_double((long long)(1023 + h) << 52) * __longlong_as_double((long long)(1023 + e - h) << 52);
 }
 
 #ifndef ITCPD_I8_HOST_EMULATION
@@ -297,8 +301,13 @@ __device__ __forceinline__ void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ void i8_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 consecutive int32 columns of this thread's TMEM lane
-__device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
+// 32 consecutive int32 columns of this thread's TMEM lane.  The load is asynchronous: the registers are defined only after
+// tcgen05.wait::ld, so the wait takes them as in/out operands -- the compiler then cannot schedule a consumer above it -- and
+// issue / wait are separate calls so that the next load can be in flight while the previous buffer is being consumed.
+#define I8_R32(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),      \
+                  "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]),      \
+                  "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+__device__ __forceinline__ void i8_tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
         "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -308,7 +317,11 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void i8_tmem_ld_wait(int (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : I8_R32(v)::"memory"); }
+__device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    i8_tmem_ld32_issue(taddr, v);
+    i8_tmem_ld_wait(v);
 }
 
 // shared-memory matrix descriptor, SWIZZLE_NONE ("interleave"): start address, leading / stride byte offsets in 16-byte
@@ -386,13 +399,19 @@ __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_ful
         double v[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = 0.0;
-#pragma unroll 1
-        for (int t = I8_NDIG - 1; t >= 0; --t) {
-            int a[32];
-            i8_tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(I8_BN * t + 32 * half), a);
+        // software pipeline over the 7 accumulators (smallest weight first): the load of accumulator t - 1 is in flight while
+        // accumulator t is folded in; fully unrolled so that both buffers stay in registers
+        const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * half);
+        int a[2][32];
+        i8_tmem_ld32(tbase + (uint32_t)(I8_BN * (I8_NDIG - 1)), a[0]);
+#pragma unroll
+        for (int i = 0; i < I8_NDIG; ++i) {
+            const int t = I8_NDIG - 1 - i;
+            if (t > 0) i8_tmem_ld32_issue(tbase + (uint32_t)(I8_BN * (t - 1)), a[(i + 1) & 1]);
             const double wt = i8_weight(t);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = fma(i8_i2d(a[c]), wt, v[c]);
+            for (int c = 0; c < 32; ++c) v[c] = fma(i8_i2d(a[i & 1][c]), wt, v[c]);
+            if (t > 0) i8_tmem_ld_wait(a[(i + 1) & 1]);
         }
         if (m < rows_out) {
 #pragma unroll

@@ -119,7 +119,10 @@ inline void i8_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t ide
     ++g_mma_count;
 }
 inline void i8_commit(uint32_t bar) { bar_arrive(bar, 0); }
-inline void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) {
+inline void i8_tmem_ld32_issue(uint32_t taddr, int (&v)[32]);
+inline void i8_tmem_ld_wait(int (&)[32]) {}
+inline void i8_tmem_ld32(uint32_t taddr, int (&v)[32]) { i8_tmem_ld32_issue(taddr, v); }
+inline void i8_tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
     const int lane0 = (int)(taddr >> 16), col = (int)(taddr & 0xffff), warp = (int)(threadIdx.x >> 5);
     if (lane0 != 32 * (warp % 4) || col + 32 > 512) { fprintf(stderr, "tcgen05.ld outside the warp's lane quarter / allocation\n"); abort(); }
     for (int c = 0; c < 32; ++c) v[c] = TMEM[lane0 + (threadIdx.x & 31)][col + c];
