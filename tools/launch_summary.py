@@ -5,7 +5,7 @@ lines = [l for l in open(path) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
 names = [re.sub(r'\(.*', '', x['Kernel Name'])[:60] for x in rows]
 vals = [float(x['Metric Value'].replace(',', '')) for x in rows]
-idx = [i for i, n in enumerate(names) if 'partial_gemm_kernel' in n and ', 0>' in n]
+idx = [i for i, n in enumerate(names) if 'partial_gemm' in n and (', 0>' in n or '<0>' in n)]   # pass A of each sweep (DMMA or INT8 kernel)
 start = idx[-2] - 2 if len(idx) >= 2 else 0
 tail = list(zip(names, vals))[start:]
 tot = collections.Counter(); cnt = collections.Counter()
