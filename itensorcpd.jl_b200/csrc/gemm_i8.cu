@@ -521,9 +521,11 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
                     }
                 }
                 if (progressed) idle = 0;
-                else if (++idle > (1ull << 28)) {
+                else if (++idle > (1ull << 24)) {
                     printf("itcpd gemm_i8: producer stalled (block %d, F step %d, digit step %d)\n", (int)blockIdx.x, itf, itd);
                     __trap();
+                } else {
+                    __nanosleep(64);   // both rings are full: do not spin hot on the scheduler this warp shares with two converter warps
                 }
             }
         }

@@ -44,6 +44,7 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 }
 inline int atomicMax(int *p, int v) { static std::mutex m; std::lock_guard<std::mutex> g(m); int o = *p; if (v > o) *p = v; return o; }
 inline void __trap() { abort(); }
+inline void __nanosleep(unsigned) { sched_yield(); }
 
 // ---------------- the modelled machine ----------------
 alignas(1024) static uint8_t i8_smem_raw[232448 + 2048];
