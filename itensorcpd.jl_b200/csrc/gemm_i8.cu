@@ -135,6 +135,44 @@ __device__ __forceinline__ double i8_krp_value(const I8Krp &a, int64_t k, int r)
     }
     return v;
 }
+// The same values for CONSECUTIVE k without a 64-bit division per element: the multi-index is decomposed once and then
+// incremented with carries (same factors multiplied in the same order: bitwise the values of i8_krp_value).
+struct I8KrpIter {
+    int64_t i[ITCPD_MAX_ORDER];
+    int64_t k;
+    __device__ __forceinline__ void init(const I8Krp &a, int64_t k0) {
+        k = k0;
+        int64_t rem = k0;
+#pragma unroll
+        for (int f = 0; f < ITCPD_MAX_ORDER; ++f) {
+            i[f] = 0;
+            if (f < a.nf) { i[f] = rem % a.ext[f]; rem /= a.ext[f]; }
+        }
+    }
+    __device__ __forceinline__ double value(const I8Krp &a, int r) const {
+        r += a.r0;
+        if (k >= a.kext || r >= a.R) return 0.0;
+        double v = 1.0;
+        bool pad = false;
+#pragma unroll
+        for (int f = 0; f < ITCPD_MAX_ORDER; ++f)
+            if (f < a.nf) {
+                if (i[f] >= a.dim[f]) pad = true;                           // padded row of a leading mode
+                else v *= a.fac[f][i[f] + a.dim[f] * (int64_t)r];
+            }
+        return pad ? 0.0 : v;
+    }
+    __device__ __forceinline__ void next(const I8Krp &a) {
+        ++k;
+        bool carry = true;
+#pragma unroll
+        for (int f = 0; f < ITCPD_MAX_ORDER; ++f)
+            if (f < a.nf && carry) {
+                if (++i[f] < a.ext[f]) carry = false;
+                else i[f] = 0;
+            }
+    }
+};
 // column exponents eb[r] (E must be pre-set to I8_EXP_ZERO); one thread per (chunk of 256 k, r), r fastest
 __global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -142,7 +180,9 @@ __global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
     const int64_t k0 = (idx / I8_BN) * 256;
     if (k0 >= a.kext) return;
     double amax = 0.0;
-    for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k) amax = i8_amax(amax, i8_krp_value(a, k, r));
+    I8KrpIter it;
+    it.init(a, k0);
+    for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k, it.next(a)) amax = i8_amax(amax, it.value(a, r));
     atomicMax(&E[r], i8_exponent(amax));
 }
 // digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 14336-byte block per k-tile of 32:
@@ -156,11 +196,13 @@ __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t k
     const int64_t kt = (idx >> 1) / I8_BN;
     const double scale = i8_scale(E[n]);
     unsigned plane[I8_NDIG][4];
+    I8KrpIter it;
+    it.init(a, kt * I8_BK + 16 * half);
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         unsigned lo[4], hi[4], o[I8_NDIG];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) i8_fields(i8_krp_value(a, kt * I8_BK + 16 * half + 4 * w + j, n), scale, lo[j], hi[j]);
+        for (int j = 0; j < 4; ++j, it.next(a)) i8_fields(it.value(a, n), scale, lo[j], hi[j]);
         i8_pack4(lo, hi, o);
 #pragma unroll
         for (int p = 0; p < I8_NDIG; ++p) plane[p][w] = o[p];
