@@ -64,6 +64,8 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "overlap_factor" 1* Gram-Hadamard + Cholesky on a side stream under the GEMM;  "use_graph" 1* CUDA-graph replay of sweeps
  *   "early_pass_b" 0* | 1: EXPERIMENTAL (not yet run on hardware): pass B of the dimension tree is launched on its own stream as soon
  *                    as the modes it contracts are updated; the modes in [split_b, split_a) are updated underneath it (env ITCPD_EARLY_B)
+ *   "graph_single"  0* | 1: EXPERIMENTAL (not yet run on hardware): repeated itcpd_sweep(1) calls -- the per-iteration loop of the
+ *                    reference API -- capture the sweep graph on the second call and replay it afterwards (env ITCPD_GRAPH_SINGLE)
  *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 64, experimental)
  *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
  *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph

@@ -173,6 +173,12 @@ struct itcpd_ctx {
     int64_t graph_epoch = 0;
     cudaGraphExec_t sweep_graph_exec = nullptr;
     int64_t sweep_graph_key[24] = {0};
+    // option "graph_single" (off by default, not yet run on hardware): the reference-facing loop calls itcpd_sweep(1) once per
+    // iteration (optimize.jl:15-31), which never reaches the nsweeps >= 3 rule; with the option on, the second single-sweep call
+    // with an unchanged configuration captures the graph and later calls replay it
+    int graph_single = 0;
+    int64_t plain_sweep_key[24] = {0};
+    bool plain_sweep_key_valid = false;
     int64_t sweep_graph_launches = 0;
     itcpd::DevBuf sweep_log;      // [0] = counter (u64), then inner[cap] | norm2[cap] | fallbacks[cap]
     int64_t sweep_log_cap = 0;

@@ -334,6 +334,32 @@ def sampled_path_single_rank():
 
 
 @scenario
+def single_sweep_calls_replay_a_graph_only_with_the_option():
+    dims, R = (64, 48, 40), 16
+    counts = {}
+    for opt in (0, 1):
+        fake.fakecuda_clear()
+        with itcpd.Engine(0) as eng:
+            eng.set_option("graph_single", opt)
+            eng.set_tensor(np.zeros(dims, order="F"))
+            eng.set_cpd(factors(dims, R), np.ones(R))
+            eng.compute_grams()
+            for _ in range(6):          # the per-iteration loop of the reference API (optimize.jl:15-31)
+                eng.sweep_async(1)
+                eng.synchronize()
+            eng.set_factor(1, factors(dims, R, seed=9)[1])    # new factor VALUES do not invalidate the graph
+            eng.sweep_async(1)
+            eng.synchronize()
+            eng.set_option("tile_warps", 4)                   # a changed option does: plain sweep again, then a new capture
+            for _ in range(3):
+                eng.sweep_async(1)
+                eng.synchronize()
+        counts[opt] = launches("<graph launch>")
+    assert counts[0] == 0 and counts[1] == 5 + 1 + 2, counts
+    return {"graph_launches": counts}
+
+
+@scenario
 def end_to_end_call_from_host_buffers():
     dims, R = (64, 48, 40), 16
     with itcpd.Engine(0) as eng:

@@ -522,3 +522,26 @@ def test_early_pass_b_is_bitwise_the_default_sweep(engine, dims, R, splits, grap
         engine.set_option("use_graph", 1)
         engine.set_option("split_a", 0)
         engine.set_option("split_b", 0)
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="graph_single has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
+def test_single_sweep_calls_through_the_graph_are_bitwise_the_plain_calls(engine):
+    """option graph_single: the per-iteration loop of the reference API (itcpd_sweep(1) per iteration) replays the captured
+    sweep from its third call on; trajectory, factors and lambda must be bitwise those of kernel-by-kernel launches."""
+    dims, R = (40, 36, 44), 20
+    T, cp = make_problem(dims, R, seed=59)
+    res = {}
+    try:
+        for g in (0, 1):
+            engine.set_option("graph_single", g)
+            engine.set_tensor(T)
+            engine.set_cpd(cp.factors, cp.lam)
+            engine.compute_grams()
+            traj = [engine.sweep(1) for _ in range(15)]
+            res[g] = (np.array([t[0][0] for t in traj]), np.array([t[1][0] for t in traj]), [engine.get_factor(n) for n in range(3)], engine.get_lambda())
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        for a, b in zip(res[0][2], res[1][2]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(res[0][3], res[1][3])
+    finally:
+        engine.set_option("graph_single", 0)
