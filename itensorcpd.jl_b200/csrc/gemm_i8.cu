@@ -293,7 +293,10 @@ __device__ __forceinline__ void i8_mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (!done && ++spins > (1ull << 26)) {
-            printf("itcpd gemm_i8: mbarrier 0x%x parity %u never completed (block %d thread %d)\n", bar, parity, (int)blockIdx.x, (int)threadIdx.x);
+            // bar & 1023 names the barrier (both kernels put the barrier block at a multiple of 1024 bytes):
+            //   partial_gemm_i8_kernel : full_f 0/8/16, empty_f 24/32/40, full_d 48/56, empty_d 64/72, acc_full 80, acc_empty 88
+            //   partial_gemm_i8p_kernel: full 0/8/16/24, empty 32/40/48/56, acc_full 64, acc_empty 72
+            printf("itcpd gemm_i8: mbarrier +%u parity %u never completed (block %d thread %d)\n", bar & 1023u, parity, (int)blockIdx.x, (int)threadIdx.x);
             __trap();
         }
     } while (!done);
