@@ -335,9 +335,9 @@ def run_ours(args, cfg):
                 "hbm_achieved_GBs": 8.0 * P / world / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0, "hbm_peak_GBs": mp.get("hbm_gbs"),
                 "sweep_roofline_frac": (2 * flops_per_launch / (peaks["dmma_tflops"] * 1e12)) / (ms * 1e-3 / K)}
         if i8 and gemm_ms > 0 and mp.get("hbm_gbs"):
-            bytes_per_elem = 7.0 if os.environ.get("ITCPD_GEMM_I8") == "2" else 8.0   # pre-packed digit planes stream 7 B per element
+            bytes_per_elem = 6.0 if os.environ.get("ITCPD_GEMM_I8") == "2" else 8.0   # pre-packed digit planes stream 6 B per element
             gbs = bytes_per_elem * P / world / (gemm_ms * 1e-3) / 1e9
-            roof.update({"bound": "hbm", "kernel": "partial_gemm_i8_kernel (TMA + tcgen05.mma kind::i8 on 7 base-128 digits, TMEM accumulators)",
+            roof.update({"bound": "hbm", "kernel": "partial_gemm_i8(p)_kernel (TMA + tcgen05.mma kind::i8 on 6 base-256 digits, TMEM accumulators)",
                          "achieved": gbs, "peak": mp["hbm_gbs"], "unit": "GB/s", "frac": gbs / mp["hbm_gbs"],
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs", "fp64_equivalent_tflops": ach,
                          "algorithmic_bytes_per_launch": bytes_per_elem * P / world,

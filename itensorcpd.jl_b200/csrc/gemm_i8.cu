@@ -1,21 +1,24 @@
 // EXPERIMENTAL (option "gemm_i8", off by default; written without GPU access, not yet run on hardware):
 // the partial contraction of the dimension tree on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators)
-// with FP64-equivalent accuracy, by splitting both operands into 7 balanced base-128 digits (an Ozaki-style scheme).
+// with FP64-equivalent accuracy, by splitting both operands into 6 balanced base-256 digits (an Ozaki-style scheme).
 //
 //   out[m, r] = sum_k T[m, k] K[k, r]                                  (kind 0; kind 1 is the transposed view of T)
-//   T[m, k] ~= XA[m, k] 2^(ea[m] - 49),  K[k, r] ~= XB[k, r] 2^(eb[r] - 49),   X* = 49-bit signed fixed point
-//   X = sum_{p=0..6} d_p 128^(6-p),  d_p in [-64, 64]  (balanced digits: add 0x40 to every 7-bit field, extract, subtract)
-//   sum_k XA XB = sum_{p,q} 128^(12-p-q) S_pq,   S_pq = sum_k dA_p dB_q   exact in int32 (|S| <= K * 4096)
-// Only the 28 digit pairs with p + q <= 6 are formed (relative Frobenius error 5e-14 .. 1e-13 for the operands of this
-// path, tools/ozaki_numerics.py); all pairs of equal weight p + q = t share ONE int32 accumulator in TMEM, so a 128 x 64
-// tile needs 7 x 64 = 448 of the 512 TMEM columns.  Stacking the B digit planes along N turns the 28 products of a
-// k-step into 10 instructions:  A_p (128 x 32)  x  [B_0; B_1; ..; B_{6-p}] (64 (7-p) x 32)  ->  accumulators t = p .. 6.
-// At 4.5 POPS the 28 products cost what 0.3 of the FP64 DMMA pass costs; digit extraction (~30 integer ops per element)
-// and the HBM stream of T (1.33 ms at 1024^3) then bound the pass instead of the FP64 pipe (3.9 ms).
+//   T[m, k] ~= XA[m, k] 2^(ea[m] - 47),  K[k, r] ~= XB[k, r] 2^(eb[r] - 47),   X* = 47-bit signed fixed point, |X| <= 2^46
+//   X = sum_{p=0..5} d_p 256^(5-p),  d_p in [-128, 127] (d_0 in [-65, 65]): the bytes of X + 0x8080808080 with bit 7 of the five
+//   low bytes flipped ARE the digits as int8 -- one 64-bit add and one xor per element
+//   sum_k XA XB = sum_{p,q} 256^(10-p-q) S_pq,   S_pq = sum_k dA_p dB_q   exact in int32 while 6 K 2^14 < 2^31 (K <= 21845: the
+//   split-K schedule keeps a chunk below that)
+// The 26 digit pairs with p + q <= 6 are formed (relative Frobenius error 4e-14 .. 6e-14 for the operands of this path, against
+// 5e-14 .. 1e-13 for the 7-digit base-128 split with 28 products this replaced: profiles/r1_ozaki_int8_numerics.txt); all pairs of
+// equal weight p + q = t share ONE int32 accumulator in TMEM, so a 128 x 64 tile needs 7 x 64 = 448 of the 512 TMEM columns.
+// Stacking the B digit planes along N turns the 26 products of a k-step into 9 instructions:
+//   A_p (128 x 32)  x  [B_0; ..; B_{min(5, 6-p)}]  ->  accumulators t = p .. min(p + 5, 6).
+// T costs 6 bytes per element as pre-packed digit planes (variant 2), so the pass is bound by that HBM stream (0.98 ms at 1024^3)
+// instead of the FP64 pipe (3.9 ms); at 4.5 POPS the 26 products take 0.80 ms.
 //
 // Warp roles (10 warps, 1 CTA per SM, persistent over 128-row tiles):
-//   warps 0-7  converters: FP64 tile (TMA) -> 7 int8 digit planes in the canonical UMMA shared-memory layout
-//   warps 0-3  also the epilogue: TMEM -> registers -> sum_t acc_t 2^(-7t) in FP64 -> scale -> global
+//   warps 0-7  converters: FP64 tile (TMA) -> 6 int8 digit planes in the canonical UMMA shared-memory layout
+//   warps 0-3  also the epilogue: TMEM -> registers -> sum_t acc_t 2^(-8t) in FP64 -> scale -> global
 //   warp 8     TMA producer (FP64 tiles of T, packed digit planes of the Khatri-Rao operand)
 //   warp 9     TMEM allocation + the single-thread MMA issuer
 #include "common.cuh"
@@ -23,14 +26,16 @@
 
 namespace itcpd {
 
-constexpr int I8_NDIG = 7;
-constexpr int I8_FRAC = 49;             // fixed-point bits = 7 * I8_NDIG
+constexpr int I8_NDIG = 6;              // base-256 digits per operand
+constexpr int I8_NACC = 7;              // int32 accumulators per output element: digit pairs with p + q = t, t = 0 .. 6
+constexpr int I8_FRAC = 47;             // fixed-point bits (one below 8 * I8_NDIG: the signed top digit keeps headroom)
+constexpr int I8_MAX_KCHUNK = 680;      // k-tiles one accumulator may sum: 6 pairs x 680 x 32 x 2^14 < 2^31
 constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 32;
 constexpr int I8_FSTAGES = 3, I8_DSTAGES = 2;
 constexpr int I8_F_BYTES = I8_BM * I8_BK * 8;                  // 32768: one FP64 tile
 constexpr int I8_A_PLANE = I8_BM * I8_BK;                      // 4096
-constexpr int I8_A_BYTES = I8_NDIG * I8_A_PLANE;               // 28672
-constexpr int I8_B_BYTES = I8_NDIG * I8_BN * I8_BK;            // 14336
+constexpr int I8_A_BYTES = I8_NDIG * I8_A_PLANE;               // 24576
+constexpr int I8_B_BYTES = I8_NDIG * I8_BN * I8_BK;            // 12288
 constexpr int I8_SMEM = I8_FSTAGES * I8_F_BYTES + I8_DSTAGES * (I8_A_BYTES + I8_B_BYTES) + 256 + 1024;
 constexpr int I8_EXP_ZERO = -100000;                           // exponent of an all-zero row / column
 constexpr int I8_EXP_NONFINITE = 100000;                       // a NaN / Inf was seen: the whole output row / column becomes NaN (as in FP64)
@@ -48,47 +53,34 @@ __device__ __forceinline__ int i8_exponent(double amax) {
     if (!(amax > 0.0)) return I8_EXP_ZERO;
     const int biased = (int)((unsigned long long)__double_as_longlong(amax) >> 52) & 0x7ff;
     if (biased == 0x7ff) return I8_EXP_NONFINITE;
-    if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(49-E) representable)
+    if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(47-E) representable)
     return biased - 1022 + 1;          // amax in [2^(b-1023), 2^(b-1022))  ->  amax 2^-(b-1021) < 1/2
 }
-// 2^(49 - E) as a double (0 for an all-zero row: every digit is then 0)
+// 2^(47 - E) as a double (0 for an all-zero row: every digit is then 0)
 __device__ __forceinline__ double i8_scale(int E) {
     if (E == I8_EXP_ZERO || E == I8_EXP_NONFINITE) return 0.0;
     return __longlong_as_double((long long)(1023 + I8_FRAC - E) << 52);
 }
-// X = rint(x scale), |X| <= 2^48.  Returns the seven 7-bit fields of Y = X + C (C = 0x40 in every field) as bytes:
-// `lo` = planes 0..3, `hi` = planes 4..6; plane 0 (the signed top digit, -64 .. 64) is already final, planes 1..6 still
-// carry the +64 offset, which i8_pack4 removes on whole words after the transposition.
+// X = rint(x scale), |X| <= 2^46.  The bytes of Z = (X + 0x8080808080) ^ 0x8080808080 are the balanced base-256 digits as
+// int8: byte j (j = 0 .. 4) of the sum is d + 128 for digit plane 5 - j, flipping its bit 7 gives d; byte 5 is the signed
+// top digit (plane 0).  `lo` = planes 5, 4, 3, 2 (bytes 0..3), `hi` = planes 1, 0 (bytes 0, 1).
 __device__ __forceinline__ void i8_fields(double x, double scale, unsigned &lo, unsigned &hi) {
     const long long X = __double2ll_rn(x * scale);
-    const unsigned long long C = 0x0001020408102040ull;                  // bits 6, 13, .., 48
-    const unsigned long long Y = (unsigned long long)(X + (long long)C);   // in [0, 2^49 + C]
-    const unsigned yl = (unsigned)Y, yh = (unsigned)(Y >> 32);
-    const unsigned f6 = yl & 127u, f5 = (yl >> 7) & 127u, f4 = (yl >> 14) & 127u, f3 = (yl >> 21) & 127u;
-    const unsigned f2 = ((yl >> 28) | (yh << 4)) & 127u, f1 = (yh >> 3) & 127u;
-    const unsigned f0 = ((yh >> 10) - 64u) & 255u;                         // top digit: -64 .. 64 as int8
-    lo = f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
-    hi = f4 | (f5 << 8) | (f6 << 16);
+    const unsigned long long Z = (unsigned long long)(X + 0x8080808080ll) ^ 0x8080808080ull;
+    lo = (unsigned)Z;
+    hi = (unsigned)(Z >> 32) & 0xffffu;
 }
-// bytes of four consecutive elements -> one word per plane (byte i = element i): a 4 x 4 byte transpose with PRMT,
-// then  f - 64  on planes 1..6 without borrows:  t = f ^ 0x40;  d = t | ((t & 0x40) << 1)   (f in [0, 127])
+// bytes of four consecutive elements -> one word per plane (byte i = element i): a 4 x 4 byte transpose with PRMT
 __device__ __forceinline__ void i8_pack4(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned (&out)[I8_NDIG]) {
-    const unsigned a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[2], lo[3], 0x5140);
-    const unsigned c = __byte_perm(lo[0], lo[1], 0x7362), d = __byte_perm(lo[2], lo[3], 0x7362);
-    const unsigned e = __byte_perm(hi[0], hi[1], 0x5140), f = __byte_perm(hi[2], hi[3], 0x5140);
-    const unsigned g = __byte_perm(hi[0], hi[1], 0x7362), h = __byte_perm(hi[2], hi[3], 0x7362);
-    out[0] = __byte_perm(a, b, 0x5410);
-    out[1] = __byte_perm(a, b, 0x7632);
-    out[2] = __byte_perm(c, d, 0x5410);
-    out[3] = __byte_perm(c, d, 0x7632);
-    out[4] = __byte_perm(e, f, 0x5410);
-    out[5] = __byte_perm(e, f, 0x7632);
-    out[6] = __byte_perm(g, h, 0x5410);
-#pragma unroll
-    for (int p = 1; p < I8_NDIG; ++p) {
-        const unsigned t = out[p] ^ 0x40404040u;
-        out[p] = t | ((t & 0x40404040u) << 1);
-    }
+    const unsigned a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[2], lo[3], 0x5140);   // bytes 0 and 1 of the four lo words
+    const unsigned c = __byte_perm(lo[0], lo[1], 0x7362), d = __byte_perm(lo[2], lo[3], 0x7362);   // bytes 2 and 3
+    const unsigned e = __byte_perm(hi[0], hi[1], 0x5140), f = __byte_perm(hi[2], hi[3], 0x5140);   // bytes 0 and 1 of the four hi words
+    out[5] = __byte_perm(a, b, 0x5410);
+    out[4] = __byte_perm(a, b, 0x7632);
+    out[3] = __byte_perm(c, d, 0x5410);
+    out[2] = __byte_perm(c, d, 0x7632);
+    out[1] = __byte_perm(e, f, 0x5410);
+    out[0] = __byte_perm(e, f, 0x7632);
 }
 
 // exponents of the rows of a strided matrix view: row r, reduction index j at  base[r * sr + j * sj]
@@ -185,7 +177,7 @@ __global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
     for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k, it.next(a)) amax = i8_amax(amax, it.value(a, r));
     atomicMax(&E[r], i8_exponent(amax));
 }
-// digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 14336-byte block per k-tile of 32:
+// digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 12288-byte block per k-tile of 32:
 //   byte(q, n, kk) = ((q*64 + n) % 8) * 16 + ((q*64 + n) / 8) * 256 + (kk / 16) * 128 + (kk % 16)
 // one thread per (k-tile, n, half): 16 consecutive k of one column -> one 16-byte store per plane
 __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t ktiles, uint8_t *__restrict__ out) {
@@ -216,7 +208,7 @@ __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t k
     }
 }
 
-// One converter thread's share of a 128 x 32 FP64 tile -> 7 digit planes (16 elements, one 16-byte store per plane).
+// One converter thread's share of a 128 x 32 FP64 tile -> 6 digit planes (16 elements, one 16-byte store per plane).
 //   KIND 0: F = [k (32)][m (128)] doubles; thread tid (0..255) owns row m = tid % 128 and k = 16 (tid / 128) .. +15;
 //           K-major planes   byte(m, kk) = (m % 8) * 16 + (m / 8) * 256 + (kk / 16) * 128 + (kk % 16)
 //   KIND 1: F = [n (128)][k (32)] doubles; thread (warp = tid / 32, lane) owns k = lane and rows n = 16 warp .. +15;
@@ -250,13 +242,13 @@ __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, 
         *reinterpret_cast<uint4 *>(A + p * I8_A_PLANE + off) = make_uint4(plane[p][0], plane[p][1], plane[p][2], plane[p][3]);
 }
 
-// C = 2^(ea + eb - 98 + 84) sum_t acc_t 2^(-7 t):  v = sum_t acc_t 2^(-7 t) is formed by the caller, smallest weights first
+// C = 2^(ea + eb - 94 + 80) sum_t acc_t 2^(-8 t):  v = sum_t acc_t 2^(-8 t) is formed by the caller, smallest weights first
 // exact int32 -> double without the (quarter-rate) I2F.F64 conversion: the double whose high word is 0x43300000 and whose low
 // word is a + 2^31 equals 2^52 + 2^31 + a; one DADD removes the offset exactly
 __device__ __forceinline__ double i8_i2d(int a) {
     return __hiloint2double(0x43300000, (int)((unsigned)a ^ 0x80000000u)) - 4503601774854144.0;
 }
-__device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 7 * t) << 52); }
+__device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double((long long)(1023 - 8 * t) << 52); }
 __device__ __forceinline__ double i8_finish(double v, int em, int er) {
     if (em == I8_EXP_NONFINITE || er == I8_EXP_NONFINITE) return __longlong_as_double(0x7ff8000000000000ll);   // NaN, like the FP64 contraction
     if (em == I8_EXP_ZERO || er == I8_EXP_ZERO) return 0.0;
@@ -431,7 +423,7 @@ __global__ void i8_splitk_fixup_kernel(const double *__restrict__ part, int kspl
 }
 
 // Epilogue of one 128 x 64 tile by one warp: TMEM lane quarter q (= warp index mod 4, the hardware's rule for tcgen05.ld)
-// holds rows row0 + 32 q + lane.  v = sum_t acc_t 2^(-7 t) is formed smallest weights first, scaled, stored column-major.
+// holds rows row0 + 32 q + lane.  v = sum_t acc_t 2^(-8 t) is formed smallest weights first, scaled, stored column-major.
 __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_full, uint32_t acc_empty, int tile_seq, int64_t row0, int q, int lane,
                                                  const int *__restrict__ ea, const int *__restrict__ eb, double *__restrict__ out,
                                                  int64_t rows_out, int R) {
@@ -448,10 +440,10 @@ __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_ful
         // accumulator t is folded in; fully unrolled so that both buffers stay in registers
         const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * half);
         int a[2][32];
-        i8_tmem_ld32(tbase + (uint32_t)(I8_BN * (I8_NDIG - 1)), a[0]);
+        i8_tmem_ld32(tbase + (uint32_t)(I8_BN * (I8_NACC - 1)), a[0]);
 #pragma unroll
-        for (int i = 0; i < I8_NDIG; ++i) {
-            const int t = I8_NDIG - 1 - i;
+        for (int i = 0; i < I8_NACC; ++i) {
+            const int t = I8_NACC - 1 - i;
             if (t > 0) i8_tmem_ld32_issue(tbase + (uint32_t)(I8_BN * (t - 1)), a[(i + 1) & 1]);
             const double wt = i8_weight(t);
 #pragma unroll
@@ -470,23 +462,34 @@ __device__ __forceinline__ void i8_epilogue_warp(uint32_t tmem, uint32_t acc_ful
     i8_mbar_arrive(acc_empty);
 }
 
-// the 10 tcgen05.mma of one k-step: A digit plane p (128 x 32)  x  the first 7 - p stacked B planes  ->  accumulators p .. 6
+// one A digit plane  x  the stacked B planes q0 .. q0 + nq - 1  ->  accumulators t0 .. t0 + nq - 1 (split at 256 columns)
+__device__ __forceinline__ void i8_mma_cols(uint32_t tmem, uint64_t adesc, uint32_t b0, int a_mn_major, int t0, int q0, int nq, uint32_t acc) {
+    const int ncols = I8_BN * nq;
+    const uint32_t d = tmem + (uint32_t)(I8_BN * t0);
+    const uint32_t brow = (uint32_t)(I8_BN * q0);                                    // first B row: 8-row groups are 256 bytes apart
+    const uint64_t bdesc = i8_smem_desc(b0 + brow / 8 * 256, 128, 256);
+    if (ncols > 256) {
+        i8_mma(d, adesc, bdesc, i8_idesc(256, a_mn_major), acc);
+        i8_mma(d + 256, adesc, i8_smem_desc(b0 + (brow + 256) / 8 * 256, 128, 256), i8_idesc(ncols - 256, a_mn_major), acc);
+    } else {
+        i8_mma(d, adesc, bdesc, i8_idesc(ncols, a_mn_major), acc);
+    }
+}
+// the 9 tcgen05.mma of one k-step: A digit plane p (128 x 32)  x  B planes 0 .. min(5, 6 - p)  ->  accumulators p .. min(p + 5, 6).
+// On the first k-step of a unit an accumulator's FIRST product overwrites: plane 0 initialises t = 0 .. 5, and t = 6 is first
+// touched by (p = 1, q = 5), which therefore gets its own overwriting instruction there (10 instructions on that k-step).
 template <int KIND>
 __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t a0, uint32_t b0, bool first_kstep) {
-    const uint64_t bdesc_lo = i8_smem_desc(b0, 128, 256);                     // B rows 0..   (K-major)
-    const uint64_t bdesc_hi = i8_smem_desc(b0 + 256 / 8 * 256, 128, 256);     // B rows 256..
 #pragma unroll
     for (int p = 0; p < I8_NDIG; ++p) {
         const uint64_t adesc = (KIND == 0) ? i8_smem_desc(a0 + p * I8_A_PLANE, 128, 256)    // K-major: LBO = k chunk, SBO = 8-row group
                                            : i8_smem_desc(a0 + p * I8_A_PLANE, 128, 512);   // MN-major: LBO = k group of 8, SBO = 16-row block
-        const int ntot = I8_BN * (I8_NDIG - p);
-        const uint32_t acc = (!first_kstep || p > 0) ? 1u : 0u;                 // p = 0 touches every accumulator first
-        const uint32_t d = tmem + (uint32_t)(I8_BN * p);
-        if (ntot > 256) {
-            i8_mma(d, adesc, bdesc_lo, i8_idesc(256, KIND), acc);
-            i8_mma(d + 256, adesc, bdesc_hi, i8_idesc(ntot - 256, KIND), acc);
+        const int nq = (I8_NACC - p < I8_NDIG) ? I8_NACC - p : I8_NDIG;
+        if (first_kstep && p == 1) {
+            i8_mma_cols(tmem, adesc, b0, KIND, 1, 0, nq - 1, 1u);
+            i8_mma_cols(tmem, adesc, b0, KIND, I8_NACC - 1, nq - 1, 1, 0u);
         } else {
-            i8_mma(d, adesc, bdesc_lo, i8_idesc(ntot, KIND), acc);
+            i8_mma_cols(tmem, adesc, b0, KIND, p, 0, nq, (first_kstep && p == 0) ? 0u : 1u);
         }
     }
 }
@@ -625,12 +628,12 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
 
 // ------------------------------------------------------------------------------------------------------------------
 // Pre-packed variant (gemm_i8 = 2): T never changes during a decomposition, so its digit planes are computed ONCE per
-// unfolding and kept in HBM as one 28672-byte block per (row tile, k-tile), already in the canonical UMMA layout.
-// A pass then streams 7 bytes per tensor element instead of 8, needs no conversion in the loop, and the kernel is a
+// unfolding and kept in HBM as one 24576-byte block per (row tile, k-tile), already in the canonical UMMA layout.
+// A pass then streams 6 bytes per tensor element instead of 8, needs no conversion in the loop, and the kernel is a
 // plain TMA -> tcgen05.mma -> TMEM pipeline: warp 0 producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int I8P_STAGES = 4;
-constexpr int I8P_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 43008
+constexpr int I8P_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 36864
 constexpr int I8P_SMEM = I8P_STAGES * I8P_STAGE_BYTES + 256 + 1024;
 
 // one CTA per (row tile, k-tile): stage the 128 x 32 FP64 tile in shared memory (zero fill outside the tensor), then the
@@ -750,23 +753,26 @@ static int i8_make_tmap(CUtensorMap *map, const double *base, uint64_t d0, uint6
     return r == CUDA_SUCCESS ? ITCPD_OK : ITCPD_ERR_CUDA;
 }
 
-// picks (ksplit, kchunk): maximise the SM occupancy of the last wave, prefer the smallest split among equals
+// picks (ksplit, kchunk): a chunk never exceeds I8_MAX_KCHUNK k-tiles (the int32 accumulators stay exact); beyond that,
+// maximise the SM occupancy of the last wave and prefer the smallest split among equals
 void i8_choose_ksplit(int64_t row_tiles, int64_t ktiles, int sms, int *ksplit_out, int *kchunk_out) {
-    int best = 1;
+    const int64_t min_split = ceil_div(ktiles, (int64_t)I8_MAX_KCHUNK);
+    int64_t best = min_split;
     double best_eff = 0.0;
-    const int64_t max_split = std::max<int64_t>(1, std::min<int64_t>(ktiles / 8, 4 * (int64_t)sms));
+    const int64_t max_split = std::max<int64_t>(min_split, std::min<int64_t>(ktiles / 8, 4 * (int64_t)sms));
     if (row_tiles < 4 * (int64_t)sms) {
-        for (int64_t ks = 1; ks <= max_split; ++ks) {
+        for (int64_t ks = min_split; ks <= max_split; ++ks) {
             const int64_t chunk = ceil_div(ktiles, ks), real = ceil_div(ktiles, chunk);   // no empty chunk
             if (real != ks) continue;
             const int64_t units = row_tiles * ks, waves = ceil_div(units, (int64_t)sms);
             // time ~ waves * (chunk + fill); efficiency relative to the ideal  row_tiles * ktiles / sms
             const double eff = (double)(row_tiles * ktiles) / ((double)sms * (double)waves * (double)(chunk + 2));
-            if (eff > best_eff * 1.02) { best_eff = eff; best = (int)ks; }
+            if (eff > best_eff * 1.02) { best_eff = eff; best = ks; }
         }
     }
-    *ksplit_out = best;
-    *kchunk_out = (int)ceil_div(ktiles, (int64_t)best);
+    const int64_t chunk = ceil_div(ktiles, best);
+    *kchunk_out = (int)chunk;
+    *ksplit_out = (int)ceil_div(ktiles, chunk);     // == best unless min_split itself left an empty chunk
 }
 
 __global__ void i8_fill_int_kernel(int *x, int64_t n, int v) {
@@ -824,7 +830,7 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
         attr[kind][c->device & 63] = true;
     }
 
-    // ---- pre-packed digit planes of T (gemm_i8 = 2): built once per tensor / unfolding, 7 bytes per element in HBM ----
+    // ---- pre-packed digit planes of T (gemm_i8 = 2): built once per tensor / unfolding, 6 bytes per element in HBM ----
     bool prepacked = c->gemm_i8 == 2;
     I8ExpCache &pk = c->i8_apack[kind];
     if (prepacked && pk.nofit_epoch == c->i8_tensor_epoch && pk.nofit_split == split) prepacked = false;

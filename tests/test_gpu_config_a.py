@@ -37,7 +37,7 @@ def test_config_a_fit_trajectory_100_sweeps_and_readme_rule(engine):
 @pytest.mark.parametrize("gemm_i8,early_b", [(1, 0), (2, 0), (0, 1), (2, 1)])
 def test_config_a_trajectory_with_the_experimental_contraction_paths(engine, gemm_i8, early_b):
     """the same north-star criterion (per-sweep fit within 1e-9 of the oracle over 100 sweeps) with the MTTKRP on the INT8
-    tensor cores (7-digit split: 1e-13-level MTTKRP error) and / or pass B overlapped with mode 1's update"""
+    tensor cores (6-digit base-256 split: 5e-14-level MTTKRP error) and / or pass B overlapped with mode 1's update"""
     import itcpd
 
     dims, R, nsweeps = (200, 200, 200), 50, 100

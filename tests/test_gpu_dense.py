@@ -448,7 +448,7 @@ def test_right_looking_cholesky_rank_deficient(engine):
                                     ((100, 37, 45), 50), ((33, 17, 9), 20), ((64, 48, 40), 130)])   # ragged tiles, padded mode 0, 3 rank blocks
 @pytest.mark.parametrize("variant", [1, 2])   # 1: digits of T extracted on the fly, 2: pre-packed digit planes in HBM
 def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R, variant):
-    """csrc/gemm_i8.cu: tcgen05.mma kind::i8 on 7 balanced base-128 digits per operand; same 1e-12 bar as the DMMA path."""
+    """csrc/gemm_i8.cu: tcgen05.mma kind::i8 on 6 balanced base-256 digits per operand; same 1e-12 bar as the DMMA path."""
     T, cp = make_problem(dims, R, seed=91)
     engine.set_option("gemm_i8", variant)
     try:

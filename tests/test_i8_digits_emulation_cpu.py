@@ -66,17 +66,19 @@ extern "C" void emu_convert_tile(int kind, const double *F, const int *ea_tile, 
 }
 extern "C" double emu_combine(const long long *acc7, int em, int er) {
     double v = 0.0;
-    for (int t = I8_NDIG - 1; t >= 0; --t) v = fma((double)acc7[t], i8_weight(t), v);
+    for (int t = I8_NACC - 1; t >= 0; --t) v = fma(i8_i2d((int)acc7[t]), i8_weight(t), v);
     return i8_finish(v, em, er);
 }
-extern "C" int emu_consts(int which) { return which == 0 ? I8_B_BYTES : which == 1 ? I8_A_BYTES : which == 2 ? I8_EXP_ZERO : I8_A_PLANE; }
+extern "C" int emu_consts(int which) {
+    return which == 0 ? I8_B_BYTES : which == 1 ? I8_A_BYTES : which == 2 ? I8_EXP_ZERO : which == 3 ? I8_A_PLANE : which == 4 ? I8_NDIG : which == 5 ? I8_NACC : I8_FRAC;
+}
 """
 
 
 @pytest.fixture(scope="module")
 def emu():
     text = open(SRC).read()
-    start = text.index("constexpr int I8_NDIG = 7;")
+    start = text.index("constexpr int I8_NDIG = 6;")
     end = text.index("#ifndef ITCPD_I8_HOST_EMULATION")
     os.makedirs(BUILD, exist_ok=True)
     cpp, so = os.path.join(BUILD, "i8_emu.cpp"), os.path.join(BUILD, "i8_emu.so")
@@ -116,14 +118,15 @@ def decode_mnmajor(plane_bytes, rows):
 def test_i8_digit_pipeline_reproduces_the_fp64_contraction(emu, kind):
     rng = np.random.default_rng(3 + kind)
     M, K, R = 256, 64, 48                       # two 128-row tiles, two k-tiles, 48 of the 64 columns used
-    B_BYTES, A_BYTES, EXP_ZERO, A_PLANE = (emu.emu_consts(i) for i in range(4))
+    B_BYTES, A_BYTES, EXP_ZERO, A_PLANE, NDIG, NACC, FRAC = (emu.emu_consts(i) for i in range(7))
+    assert (NDIG, NACC, FRAC) == (6, 7, 47)          # 6 balanced base-256 digits, accumulators t = p + q = 0 .. 6, 47-bit fixed point
     f1 = rng.standard_normal((8, R)); f1 /= np.linalg.norm(f1, axis=0)
     f2 = rng.standard_normal((K // 8, R)); f2 /= np.linalg.norm(f2, axis=0)
     f1, f2 = np.asfortranarray(f1), np.asfortranarray(f2)
     Kr = (f2[:, None, :] * f1[None, :, :]).reshape(K, R)              # k = i1 + 8 i2  (first factor fastest)
     A = rng.standard_normal((M, K)) * np.exp2(rng.integers(-6, 7, size=(M, 1)))   # rows of very different scale
     A[5, :] = 0.0                                                        # an all-zero row
-    A[9, 3] = np.nextafter(4.0, 0.0)                                     # rounds up to 2^48 in 49-bit fixed point: top digit +64
+    A[9, 3] = np.nextafter(4.0, 0.0)                                     # rounds up to 2^46 in 47-bit fixed point: top digit +64
     A[9, 4] = -np.nextafter(4.0, 0.0)
     # memory image of the tensor view: kind 0 has the output rows contiguous (T[m + M k]), kind 1 the contraction index
     if kind == 0:
@@ -147,7 +150,7 @@ def test_i8_digit_pipeline_reproduces_the_fp64_contraction(emu, kind):
     ext = np.array([8, K // 8], dtype=np.int64)
     emu.emu_krp_pack(2, fac, _p(ext), K, R, _p(eb), _p(Bdig))
     assert np.all(eb[R:] == EXP_ZERO)
-    acc = np.zeros((M, 64, 7), dtype=np.int64)
+    acc = np.zeros((M, 64, NACC), dtype=np.int64)
     XA = np.zeros((M, K), dtype=object)
     for tile in range(M // 128):
         rows = slice(128 * tile, 128 * tile + 128)
@@ -156,22 +159,23 @@ def test_i8_digit_pipeline_reproduces_the_fp64_contraction(emu, kind):
             F = np.ascontiguousarray(A[rows, ks].T if kind == 0 else A[rows, ks])      # [k][m] or [n][k] as TMA would land it
             Adig = np.zeros(A_BYTES, dtype=np.uint8)
             emu.emu_convert_tile(kind, _p(F), _p(ea[rows]), _p(Adig))
-            dA = [(decode_kmajor if kind == 0 else decode_mnmajor)(Adig[p * A_PLANE:(p + 1) * A_PLANE], 128) for p in range(7)]
+            dA = [(decode_kmajor if kind == 0 else decode_mnmajor)(Adig[p * A_PLANE:(p + 1) * A_PLANE], 128) for p in range(NDIG)]
             blk = Bdig[kt * B_BYTES:(kt + 1) * B_BYTES]
-            dBall = decode_kmajor(blk, 7 * 64)                                          # planes stacked along N: row = q*64 + n
-            for p in range(7):
-                XA[rows, ks] += dA[p].astype(object) * (128 ** (6 - p))
-                for q in range(7 - p):
+            dBall = decode_kmajor(blk, NDIG * 64)                                       # planes stacked along N: row = q*64 + n
+            for p in range(NDIG):
+                XA[rows, ks] += dA[p].astype(object) * (256 ** (NDIG - 1 - p))
+                for q in range(min(NDIG, NACC - p)):                                     # the 26 pairs with p + q <= 6
                     acc[rows, :, p + q] += dA[p] @ dBall[q * 64:(q + 1) * 64].T
-                assert np.max(np.abs(dA[p])) <= 64
+                assert -128 <= np.min(dA[p]) and np.max(dA[p]) <= 127 and (p > 0 or np.max(np.abs(dA[p])) <= 65)
     # digits reconstruct the rounded fixed-point value exactly
     for m in (0, 5, 17, 200):
-        sc = 0.0 if ea[m] == EXP_ZERO else 2.0 ** (49 - float(ea[m]))
+        sc = 0.0 if ea[m] == EXP_ZERO else 2.0 ** (FRAC - float(ea[m]))
         assert all(int(XA[m, k]) == int(np.rint(A[m, k] * sc)) for k in range(K))
     out = np.zeros((M, R))
     for m in range(M):
         for r in range(R):
             a7 = np.ascontiguousarray(acc[m, r, :])
+            assert np.max(np.abs(a7)) < 2 ** 31
             out[m, r] = emu.emu_combine(_p(a7), int(ea[m]), int(eb[r]))
     ref = (A.astype(np.longdouble) @ Kr.astype(np.longdouble)).astype(np.float64)
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)

@@ -244,7 +244,7 @@ extern "C" long emu_gemm_i8p(int kind, const double *T, long Mrows, long Ncols, 
 def model_source():
     """the functional model with the VERBATIM device text of csrc/gemm_i8.cu spliced in (also used by test_i8_host_device_cpu.py)"""
     text = open(SRC).read()
-    numerics = text[text.index("constexpr int I8_NDIG = 7;"):text.index("#ifndef ITCPD_I8_HOST_EMULATION")]
+    numerics = text[text.index("constexpr int I8_NDIG = 6;"):text.index("#ifndef ITCPD_I8_HOST_EMULATION")]
     descs = text[text.index("// shared-memory matrix descriptor, SWIZZLE_NONE"):text.index("// ------------------------------------------------------------------------------------------------------------------\n// the kernel")]
     k0 = text.index("template <int KIND>\n__global__ void __launch_bounds__(320, 1)")
     k1 = text.index("// ------------------------------------------------------------------------------------------------------------------\n// host side")
@@ -297,7 +297,8 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     assert err < 1e-12, err
     ktiles, row_tiles = -(-kext // 32), -(-rows_out // 128)
-    assert nmma == 10 * ktiles * row_tiles * -(-R // 64)          # 28 digit products per k-step and rank block as 10 instructions
+    units = row_tiles * ksplit * -(-R // 64)
+    assert nmma == 9 * ktiles * row_tiles * -(-R // 64) + units       # 26 digit products per k-step as 9 instructions, one more on a unit's first k-step
 
 
 def test_split_k_schedule_policy():
@@ -307,7 +308,9 @@ def test_split_k_schedule_policy():
     fn = text[a:text.index("__global__ void i8_fill_int_kernel")]
     os.makedirs(BUILD, exist_ok=True)
     cpp, so = os.path.join(BUILD, "i8_ksplit.cpp"), os.path.join(BUILD, "i8_ksplit.so")
+    maxk = re.search(r"constexpr int I8_MAX_KCHUNK = (\d+);", text).group(1)
     open(cpp, "w").write("#include <algorithm>\n#include <cstdint>\nstatic inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }\n"
+                         f"constexpr int I8_MAX_KCHUNK = {maxk};\n"
                          + fn + '\nextern "C" void choose(long rt, long kt, int sms, int *ks, int *kc) { i8_choose_ksplit(rt, kt, sms, ks, kc); }\n')
     subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-o", so, cpp], check=True, capture_output=True)
     lib = C.CDLL(so)
@@ -317,12 +320,14 @@ def test_split_k_schedule_policy():
         lib.choose(C.c_long(rt), C.c_long(kt), sms, C.byref(ks), C.byref(kc))
         return ks.value, kc.value
 
-    for rt, kt in [(8192, 32), (8, 4096), (16, 16384), (313, 7), (1, 10), (1, 100000), (147, 64), (149, 64), (600, 9), (3, 24)]:
+    for rt, kt in [(8192, 32), (8, 4096), (16, 16384), (313, 7), (1, 10), (1, 100000), (147, 64), (149, 64), (600, 9), (3, 24), (512, 2048), (4096, 3000)]:
         ks, kc = choose(rt, kt)
         assert ks >= 1 and kc >= 1 and -(-kt // kc) == ks, (rt, kt, ks, kc)        # every chunk holds at least one k-tile
-        assert ks == 1 or kc >= 8, (rt, kt, ks, kc)
+        assert kc <= int(maxk), (rt, kt, ks, kc)        # 6 pairs x kc x 32 x 2^14 < 2^31: the int32 accumulators stay exact
+        assert 6 * int(maxk) * 32 * 2 ** 14 < 2 ** 31
+        assert ks == -(-kt // int(maxk)) or kc >= 8, (rt, kt, ks, kc)
         if rt >= 4 * 148:
-            assert ks == 1
+            assert ks == -(-kt // int(maxk))
     # the per-rank slabs of configs B and D at 8 GPUs (pass A of the (1,1) tree): the units fill the SMs to >= 95 % in a few whole waves
     for rt, kt in [(8, 4096), (16, 16384)]:
         ks, kc = choose(rt, kt)

@@ -1,20 +1,22 @@
-"""Is the accuracy of the 7-digit INT8 contraction (csrc/gemm_i8.cu, experimental) enough for the north-star trajectory bar?
-A vectorised numpy statement of the same arithmetic (49-bit fixed point per row / column, balanced base-128 digits by the
-add-0x40-per-field trick, the 28 digit-plane products with p + q <= 6, combination smallest weights first) replaces the
-oracle's MTTKRP inside its ALS loop; the fit trajectory over 100 sweeps must stay within 1e-9 of the plain oracle's."""
+"""Is the accuracy of the 6-digit INT8 contraction (csrc/gemm_i8.cu, experimental) enough for the north-star trajectory bar?
+A vectorised numpy statement of the same arithmetic (47-bit fixed point per row / column, balanced base-256 digits as the
+bytes of (X + 0x8080808080) ^ 0x8080808080, the 26 digit-plane products with p + q <= 6, combination smallest weights first)
+replaces the oracle's MTTKRP inside its ALS loop; the fit trajectory over 100 sweeps must stay within 1e-9 of the plain oracle's."""
 import numpy as np
 
 from oracle import cpals
 
-C49 = sum(1 << (7 * k + 6) for k in range(7))
+NDIG, NACC, FRAC = 6, 7, 47
 
 
 def digits(X):
-    """X: int64 array, |X| <= 2^48 -> list of 7 float64 digit planes, most significant first (i8_digits in gemm_i8.cu)"""
-    Y = X + C49
-    planes = [((Y >> (7 * k)) & 127) - 64 for k in range(6)]
-    planes.append((Y >> 42) - 64)
-    return [p.astype(np.float64) for p in planes[::-1]]
+    """X: int64 array, |X| <= 2^46 -> list of 6 float64 digit planes, most significant first (i8_fields in gemm_i8.cu)"""
+    Z = (X + 0x8080808080) ^ 0x8080808080
+    planes = [((Z >> (8 * j)) & 0xff).astype(np.uint8).view(np.int8).reshape(X.shape) for j in range(5)]   # planes 5 .. 1 as int8
+    planes.append(((Z >> 40) & 0xff).astype(np.uint8).view(np.int8).reshape(X.shape))                        # signed top digit
+    out = [p.astype(np.float64) for p in planes[::-1]]
+    assert np.array_equal(sum(out[p].astype(np.int64) << (8 * (NDIG - 1 - p)) for p in range(NDIG)), X)    # the digits ARE X
+    return out
 
 
 def exponents(A, axis):
@@ -26,16 +28,18 @@ def exponents(A, axis):
 def gemm_i8(A, B):
     """A (M x K) @ B (K x N) through the digit-split scheme"""
     ea, eb = exponents(A, 1), exponents(B, 0)
-    XA = np.rint(np.ldexp(A, 49 - ea)).astype(np.int64)
-    XB = np.rint(np.ldexp(B, 49 - eb)).astype(np.int64)
+    XA = np.rint(np.ldexp(A, FRAC - ea)).astype(np.int64)
+    XB = np.rint(np.ldexp(B, FRAC - eb)).astype(np.int64)
     dA, dB = digits(XA), digits(XB)
     v = np.zeros((A.shape[0], B.shape[1]))
-    for t in range(6, -1, -1):
+    for t in range(NACC - 1, -1, -1):
         acc = np.zeros_like(v)
-        for p in range(t + 1):
-            acc += dA[p] @ dB[t - p]                      # exact: |entries| < 2^53
-        v = acc * 2.0 ** (-7 * t) + v
-    return np.ldexp(v, ea + eb - 14)
+        for p in range(NDIG):
+            if 0 <= t - p < NDIG:
+                acc += dA[p] @ dB[t - p]                  # exact: |entries| < 2^53
+        assert np.max(np.abs(acc)) < 2 ** 31              # what the int32 TMEM accumulators must hold
+        v = acc * 2.0 ** (-8 * t) + v
+    return np.ldexp(v, ea + eb - 2 * FRAC + 8 * 2 * (NDIG - 1))
 
 
 def mttkrp_i8(T, factors, n):

@@ -3,8 +3,8 @@
 #   gpurun --timeout 900 -- 'bash tools/r2_ncu.sh'
 # 1. launch list of a short config-B run with the pre-packed INT8 contraction (shares per kernel; cold-cache, serialised)
 # 2. one `--set full` capture of the dominant kernel (partial_gemm_i8p_kernel) with source correlation (-lineinfo is on)
-# Expectations to hold the capture against (profiles/r1_i8_model.txt): 7.5 GB read + 0.54 GB written per launch = the
-# algorithmic bytes; DRAM throughput > 80 % of peak; tensor pipe ~ 75 %; duration 1.15 - 1.4 ms.
+# Expectations to hold the capture against (profiles/r1_i8_model.txt): 6.4 GB read + 0.54 GB written per launch = the
+# algorithmic bytes; DRAM throughput > 80 % of peak; tensor pipe ~ 75 %; duration 1.0 - 1.3 ms.
 mkdir -p gpurun_out
 export ITCPD_GEMM_I8=${ITCPD_GEMM_I8:-2}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
