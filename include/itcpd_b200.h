@@ -71,6 +71,7 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph
  *   "gemm_i8"        0* | 1 | 2 (experimental, not yet run on hardware) INT8 tensor-core digit-split contraction
  *                    (csrc/gemm_i8.cu): 1 converts T on the fly, 2 keeps T's digit planes pre-packed in HBM (6 B / element / unfolding)
+ *   "i8_spare_sms"   0* .. 63: SMs the persistent INT8 GEMM leaves to the side-stream factorisation (R = 128: its 132 KB Cholesky cannot co-reside)
  *   "peer_graph"     0* | 1 (experimental) NCCL-free sharded sweeps with device-side exchange epochs; set before itcpd_peer_export
  * environment at itcpd_create: ITCPD_CHOL=0|1|2, ITCPD_NO_GRAPH=1, ITCPD_NO_SWIZZLE=1, ITCPD_GEMM_I8=1 */
 int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);

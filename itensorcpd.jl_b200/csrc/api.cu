@@ -402,6 +402,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "graph_single") c->graph_single = value != 0;
+    else if (n == "i8_spare_sms") { ARG_CHECK(value >= 0 && value < 64, "i8_spare_sms must be in [0, 64)"); c->i8_spare_sms = (int)value; }
     else if (n == "use_graph") c->use_graph = value != 0;
     else if (n == "gemm_i8") { ARG_CHECK(value >= 0 && value <= 2, "gemm_i8 must be 0, 1 (convert on the fly) or 2 (pre-packed digits)"); c->gemm_i8 = (int)value; }
     else if (n == "peer_graph") {

@@ -206,6 +206,7 @@ struct itcpd_ctx {
     int64_t i8_tensor_epoch = 0;      // bumped whenever the tensor contents change
     itcpd::I8ExpCache i8_exp[2];
     itcpd::I8ExpCache i8_apack[2];    // gemm_i8 = 2: pre-packed digit planes of T per unfolding kind
+    int i8_spare_sms = 0;   // option "i8_spare_sms": SMs the persistent INT8 GEMM leaves free for the side-stream factorisation (a 132 KB Cholesky at R = 128 cannot share an SM with it)
     itcpd::DevBuf i8_eb, i8_bdig, i8_part;   // i8_part: split-K partial tiles (short-and-wide contractions)
 };
 

@@ -796,7 +796,8 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     // split-K schedule (I8Unit): data parallel when there are enough row tiles; otherwise cut k so that the units fill the
     // SMs in whole waves (a chunk keeps at least 8 k-tiles so the pipeline fill and the partial-tile traffic stay small)
     int ksplit = 1, kchunk = (int)ktiles;
-    i8_choose_ksplit(row_tiles * rblocks, ktiles, c->sm_count, &ksplit, &kchunk);   // rank blocks are independent units too
+    const int sms = std::max(1, c->sm_count - c->i8_spare_sms);   // SMs this persistent kernel may occupy
+    i8_choose_ksplit(row_tiles * rblocks, ktiles, sms, &ksplit, &kchunk);   // rank blocks are independent units too
 
     // ---- row exponents of this unfolding of T: computed once per tensor and split, cached in the handle ----
     I8ExpCache &ec = c->i8_exp[kind];
@@ -881,7 +882,7 @@ int launch_partial_gemm_i8(itcpd_ctx *c, int kind, int split, double *out) {
     c->launches++;
     // one launch covers every rank block (I8Sched): the grid is a multiple of rblocks so that CTA c always serves rank block c % rblocks
     const int64_t units = row_tiles * ksplit * rblocks;
-    const int grid = (int)std::min<int64_t>(units, std::max(rblocks, c->sm_count / rblocks * rblocks));
+    const int grid = (int)std::min<int64_t>(units, std::max(rblocks, sms / rblocks * rblocks));
     const int64_t part_stride = rows_out * (int64_t)I8_BN;
     if (ksplit > 1) TRY(c->i8_part.reserve((size_t)ksplit * rblocks * part_stride * 8));
     double *part = ksplit > 1 ? c->i8_part.as<double>() : nullptr;

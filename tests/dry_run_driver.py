@@ -407,7 +407,8 @@ def fuzz_dense_shapes_and_options():
             dims, R = _random_problem(rnd, 2e9)
             N = len(dims)
             opts = {"gemm_i8": rnd.choice([0, 0, 1, 2]), "early_pass_b": rnd.choice([0, 1]), "tile_warps": rnd.choice([4, 8]), "stream_k": rnd.choice([0, 1, 2]),
-                    "chol_alg": rnd.choice([0, 1, 2]), "use_graph": rnd.choice([0, 1]), "tma3d": rnd.choice([0, 1]), "overlap_factor": rnd.choice([0, 1])}
+                    "chol_alg": rnd.choice([0, 1, 2]), "use_graph": rnd.choice([0, 1]), "tma3d": rnd.choice([0, 1]), "overlap_factor": rnd.choice([0, 1]), "i8_spare_sms": rnd.choice([0, 0, 1, 5]),
+                    "graph_single": rnd.choice([0, 1])}
             sa = rnd.choice([0, 0] + list(range(1, N)))
             sb = 0 if sa == 0 else rnd.randint(1, sa)
             try:
