@@ -40,6 +40,7 @@ CONFIGS = {
     "D": {"dims": (2048, 2048, 2048), "rank": 128},
     "S": {"dims": (256, 256, 256), "rank": 32},  # small smoke configuration
     "B8": {"dims": (1024, 1024, 128), "rank": 64},  # one rank's slab of config B at 8 GPUs (per-rank chain without collectives)
+    "D8": {"dims": (2048, 2048, 256), "rank": 128},  # one rank's slab of config D at 8 GPUs
 }
 
 

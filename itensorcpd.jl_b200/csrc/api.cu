@@ -326,6 +326,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gemm_done, cudaEventDisableTiming));
     if (const char *s = getenv("ITCPD_EARLY_B")) c->early_pass_b = atoi(s) != 0;   // experimental
     if (const char *s = getenv("ITCPD_GRAPH_SINGLE")) c->graph_single = atoi(s) != 0;   // experimental
+    if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;

@@ -368,6 +368,117 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
+// ---- right-looking variant for 64 < n <= 128 (chol_alg = 2, EXPERIMENTAL like the kernel above) --------------------------
+// A 128-entry column does not fit one thread's registers, so every column is owned by TWO threads: thread (k, h) keeps rows
+// 64 h .. 64 h + 63 of original column k (k = tid & 127, h = tid >> 7: 256 threads).  The pivot search runs on the h = 0 threads
+// (they carry the running diagonals; both halves update theirs identically from the published u), the thread whose half holds
+// the pivot row fetches u_k = A[q, k] / d and publishes it, and after one block barrier both halves apply the rank-1 update to
+// their 64 rows.  Two block barriers per step; every element sees exactly the operations of pivoted_cholesky_rl_kernel, so for
+// n <= 64 the two kernels are bitwise identical (tests/test_cholesky_emulation_cpu.py) and pivots / tie-breaking are LAPACK's.
+// The team kernel needs 268 us at n = 128 (profiles/r1_cholesky_probe.txt) and, at 132 KB of shared memory, cannot share an SM
+// with a GEMM CTA: this is the factorisation the rank-128 sweeps wait for.
+__global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl2_kernel(const double *__restrict__ Gin, int n, double tol,
+                                                                           double *__restrict__ Wg, int *__restrict__ piv,
+                                                                           int *__restrict__ status) {
+    extern __shared__ double sm_dyn[];            // Gamma staging, then Uo[l + ldw * original column] = row l of the factor
+    __shared__ __align__(16) double s_u[128];     // u of the current step by original column; 0 once a column is eliminated
+    __shared__ unsigned long long s_key[4];
+    __shared__ int s_idx[4], s_bad[4];
+    __shared__ int s_orig[128];                   // position -> original column
+    __shared__ int s_rank;
+    const int ldw = n | 1;
+    const int tid = threadIdx.x;
+    const int k = tid & 127, h = tid >> 7, lane = tid & 31, w = (tid >> 5) & 3;
+    double *W = sm_dyn;
+    for (int e = tid; e < n * n; e += CHT_THREADS) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
+    if (tid < 128) { s_orig[tid] = tid; s_u[tid] = 0.0; }
+    if (tid == 0) s_rank = n;
+    __syncthreads();
+    const bool mine = k < n;
+    double col[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) col[i] = (mine && 64 * h + i < n) ? W[(64 * h + i) + (size_t)ldw * k] : 0.0;
+    double ddk = mine ? W[k + (size_t)ldw * k] : 0.0;
+    bool alive = mine;
+    int posk = k;
+    double stop = 0.0;
+    int rank = n;
+    __syncthreads();  // every column is in registers: the staging area becomes Uo
+    for (int j = 0; j < n; ++j) {
+        // ---- pivot: first maximum of the running diagonal in position order (h = 0 threads: warps 0 .. 3) ----
+        if (h == 0) {
+            const unsigned long long key = alive ? ordered_key(ddk) : 0ull;
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mh) ? (unsigned)key : 0u;
+            const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+            const bool win = alive && hi == mh && (unsigned)key == ml;
+            const unsigned mi = __reduce_min_sync(0xffffffffu, win ? (((unsigned)posk << 8) | (unsigned)k) : 0x7fffffffu);
+            const int bad = __any_sync(0xffffffffu, alive && ddk != ddk);
+            if (lane == 0) { s_key[w] = ((unsigned long long)mh << 32) | ml; s_idx[w] = (int)mi; s_bad[w] = bad; }
+        }
+        __syncthreads();
+        unsigned long long bk = s_key[0];
+        int bi = s_idx[0], bb = s_bad[0];
+#pragma unroll
+        for (int q4 = 1; q4 < 4; ++q4) {
+            const unsigned long long kq = s_key[q4];
+            const int iq = s_idx[q4];
+            if (kq > bk || (kq == bk && iq < bi)) { bk = kq; bi = iq; }
+            bb |= s_bad[q4];
+        }
+        const double bv = key_value(bk);
+        bool fail;
+        if (j == 0) {
+            stop = (tol < 0.0) ? n * DBL_EPSILON * bv : tol;
+            fail = bb || !(bv > 0.0);
+        } else {
+            fail = bb || !(bv > stop);
+        }
+        if (fail) { rank = j; break; }  // uniform over the block
+        const int q = bi & 0xff, p = bi >> 8;
+        const double d = sqrt(bv);
+        // ---- interchange bookkeeping only: the pivot goes to position j, the column that sat there to position p ----
+        if (h == 0 && mine) {
+            if (k == q) { posk = j; s_orig[j] = k; }
+            else if (posk == j) { posk = p; s_orig[p] = k; }
+        }
+        // ---- row j of the factor: the half that holds row q of my column fetches it ----
+        if (alive) {
+            if (k == q) {
+                if (h == 0) { W[j + (size_t)ldw * k] = d; s_u[k] = 0.0; }
+                alive = false;
+            } else if (h == (q >> 6)) {
+                const double u = rl_fetch<64>(col, q & 63) / d;
+                W[j + (size_t)ldw * k] = u;
+                s_u[k] = u;
+            }
+        }
+        __syncthreads();
+        // ---- rank-1 update of my 64 rows (rows of eliminated columns see u = 0); the next step's first barrier orders these
+        // reads of s_u before its next writes ----
+        if (alive) {
+            const double u = s_u[k];
+            ddk = fma(-u, u, ddk);
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+                const double2 uu = *reinterpret_cast<const double2 *>(&s_u[64 * h + i]);
+                col[i] = fma(-uu.x, u, col[i]);
+                col[i + 1] = fma(-uu.y, u, col[i + 1]);
+            }
+        }
+    }
+    if (tid == 0) s_rank = rank;
+    __syncthreads();
+    rank = s_rank;
+    for (int e = tid; e < ldw * n; e += CHT_THREADS) {
+        const int c = e / ldw, l = e - c * ldw;
+        Wg[e] = (l <= c && l < rank) ? W[l + (size_t)ldw * s_orig[c]] : 0.0;
+    }
+    for (int e = tid; e < n; e += CHT_THREADS) piv[e] = s_orig[e];
+    if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
+}
+
 // One warp per right-hand side: x = P (U^T U)^{-1} P^T b with b = row i of M, result to row i of X.
 // Lane l keeps entries k = l + 32 e (e < E) in registers.  mode: 0 full solve, 1 forward only and
 // return ||y[0:nn]||^2 (leverage scores).
@@ -506,6 +617,17 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
     if (!attr[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr[c->device & 63] = true;
+    }
+    if (c->chol_alg == 2 && R > 64 && R <= 128) {  // two threads per column (experimental)
+        static bool attr_r[64] = {false};
+        if (!attr_r[c->device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_rl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
+            attr_r[c->device & 63] = true;
+        }
+        pivoted_cholesky_rl2_kernel<<<1, CHT_THREADS, (size_t)ldw * R * 8, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ITCPD_OK;
     }
     if (c->chol_alg == 2 && R <= 64) {
         const size_t smem = (size_t)ldw * R * 8;

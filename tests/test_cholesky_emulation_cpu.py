@@ -33,6 +33,8 @@ extern "C" int run_cholesky(int which, int n, double tol, const double *G, doubl
         emu_launch(threads, 0, [&] { pivoted_cholesky_kernel(G, n, tol, W, piv, status, 1); });
     } else if (which == 1) {
         emu_launch(256, team, [&] { pivoted_cholesky_team_kernel(G, n, tol, W, piv, status); });
+    } else if (which == 3) {
+        emu_launch(256, 0, [&] { pivoted_cholesky_rl2_kernel(G, n, tol, W, piv, status); });     // two threads per column, n <= 128
     } else if (n <= 32) {
         emu_launch(256, 32, [&] { pivoted_cholesky_rl_kernel<32>(G, n, tol, W, piv, status); });
     } else {
@@ -125,10 +127,35 @@ def test_emulated_team_kernel_up_to_128(emu):
         assert np.array_equal(np.triu(W0), np.triu(W1)) and np.array_equal(p0, p1)
 
 
+@pytest.mark.parametrize("n,deficient,ties", CASES)
+def test_two_thread_right_looking_kernel_is_bitwise_the_one_thread_kernel_up_to_64(emu, n, deficient, ties):
+    """pivoted_cholesky_rl2_kernel splits every column over two threads but applies the same operations to every element"""
+    G = gamma(n, 300 + n, deficient, ties)
+    W2, p2, s2 = run(emu, 2, G)
+    W3, p3, s3 = run(emu, 3, G)
+    assert np.array_equal(s2, s3) and np.array_equal(p2, p3) and np.array_equal(W2, W3)
+
+
+@pytest.mark.parametrize("n,deficient,ties", [(65, False, False), (66, True, False), (100, False, True), (127, False, False), (128, False, False), (128, True, True)])
+def test_two_thread_right_looking_kernel_matches_lapack_up_to_128(emu, n, deficient, ties):
+    G = gamma(n, 400 + n, deficient, ties)
+    c, pl, rl, info = lapack.dpstrf(G, tol=1e-6, lower=0)
+    W, piv, st = run(emu, 3, G)
+    assert st[1] == rl and st[0] == (0 if rl == n else 1), (st, rl)
+    assert np.array_equal(piv[:rl], pl[:rl] - 1)
+    assert np.allclose(np.triu(W)[:rl, :], np.triu(c)[:rl, :], rtol=0, atol=1e-10)
+    W1, p1, s1 = run(emu, 1, G)                                  # the shipped team kernel: same pivots, same status
+    assert np.array_equal(p1, piv) and np.array_equal(s1, st)
+    U = np.triu(W)[:rl, :]
+    Gp = G[np.ix_(piv, piv)]
+    if rl == n:
+        assert np.linalg.norm(U.T @ U - Gp) / np.linalg.norm(Gp) < 1e-14
+
+
 def test_emulated_nan_and_negative_tolerance(emu):
     G = gamma(12, 5)
     Gn = G.copy(); Gn[3, 3] = np.nan
-    for which in (0, 1, 2):
+    for which in (0, 1, 2, 3):
         assert run(emu, which, Gn)[2][1] == 0            # NaN on the diagonal: fail at column 0
         W, piv, st = run(emu, which, G, tol=-1.0)          # LAPACK default tolerance n * eps * max diag (leverage-score path)
         assert st[1] == 12
@@ -150,14 +177,17 @@ print("TSAN_RUN_DONE")
     rt = sorted(glob.glob("/usr/lib/gcc/x86_64-linux-gnu/*/libtsan.so")) + sorted(glob.glob("/usr/lib/x86_64-linux-gnu/libtsan.so*"))
     if not rt:
         pytest.skip("libtsan not found")
-    env = dict(os.environ, LD_PRELOAD=rt[0], TSAN_OPTIONS="report_bugs=1 exitcode=0 halt_on_error=0", PYTHONPATH=ROOT)
+    env = dict(os.environ, LD_PRELOAD=rt[0], TSAN_OPTIONS="report_bugs=1 exitcode=0 halt_on_error=0", PYTHONPATH=ROOT,
+               OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")   # numpy's BLAS threads are not instrumented: keep them out of the picture
     out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert "TSAN_RUN_DONE" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
     return out.stderr
 
 
 def test_kernels_are_race_free_under_thread_sanitizer():
-    err = _tsan_run(_build(True), [(5, False, False), (33, True, True), (64, False, False)], (0, 1, 2))
+    err = _tsan_run(_build(True), [(5, False, False), (33, True, True), (64, False, False)], (0, 1, 2, 3))
+    assert "WARNING: ThreadSanitizer" not in err, err[-6000:]
+    err = _tsan_run(_build(True), [(70, False, True), (128, True, False)], (3,))
     assert "WARNING: ThreadSanitizer" not in err, err[-6000:]
 
 

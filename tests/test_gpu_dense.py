@@ -390,9 +390,10 @@ EXPERIMENTAL = os.environ.get("ITCPD_EXPERIMENTAL", "0") != "0"
 
 
 @pytest.mark.skipif(not EXPERIMENTAL, reason="chol_alg=2 (right-looking Cholesky) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
-@pytest.mark.parametrize("R", [1, 5, 31, 32, 33, 50, 64])
+@pytest.mark.parametrize("R", [1, 5, 31, 32, 33, 50, 64, 65, 100, 128])
 def test_right_looking_cholesky_matches_team_kernel(engine, R):
-    """solve.cu: pivoted_cholesky_rl_kernel -- same pivots/rank/status as the team kernel, values within rounding."""
+    """solve.cu: pivoted_cholesky_rl_kernel (R <= 64) / pivoted_cholesky_rl2_kernel (two threads per column, R <= 128) -- same
+    pivots/rank/status as the team kernel, values within rounding."""
     dims = (36, 40, 28)
     T, cp = make_problem(dims, R, seed=171 + R)
     res = {}
