@@ -66,7 +66,7 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *                    as the modes it contracts are updated; the modes in [split_b, split_a) are updated underneath it (env ITCPD_EARLY_B)
  *   "graph_single"  0* | 1: EXPERIMENTAL (not yet run on hardware): repeated itcpd_sweep(1) calls -- the per-iteration loop of the
  *                    reference API -- capture the sweep graph on the second call and replay it afterwards (env ITCPD_GRAPH_SINGLE)
- *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 128, experimental)
+ *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 128, experimental), 3 right-looking only where the factorisation is exposed (experimental)
  *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
  *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph
  *   "gemm_i8"        0* | 1 | 2 (experimental, not yet run on hardware) INT8 tensor-core digit-split contraction

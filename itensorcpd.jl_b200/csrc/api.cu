@@ -136,14 +136,22 @@ static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
     return ITCPD_OK;
 }
 
+// is the cached partial of this kind still the contraction of the CURRENT factors?
+static bool partial_is_current(const itcpd_ctx *c, int kind) {
+    const Partial &P = (kind == 0) ? c->PA : c->PB;
+    const int split = (kind == 0) ? c->split_a : c->split_b;
+    const int d0 = (kind == 0) ? split : 0, d1 = (kind == 0) ? c->order : split;
+    bool ok = P.valid && P.split == split;
+    for (int n = d0; ok && n < d1; ++n) ok = (P.dep_version[n] == c->fver[n]);
+    return ok;
+}
+
 // the partial contraction feeding `mode`, recomputed only when a contracted factor changed
 static int ensure_partial(itcpd_ctx *c, int kind) {
     Partial &P = (kind == 0) ? c->PA : c->PB;
     const int split = (kind == 0) ? c->split_a : c->split_b;
     const int d0 = (kind == 0) ? split : 0, d1 = (kind == 0) ? c->order : split;
-    bool ok = P.valid && P.split == split;
-    for (int n = d0; ok && n < d1; ++n) ok = (P.dep_version[n] == c->fver[n]);
-    if (ok) return ITCPD_OK;
+    if (partial_is_current(c, kind)) return ITCPD_OK;
     int64_t rows = 1;
     if (kind == 0) { rows = c->ld0; for (int n = 1; n < split; ++n) rows *= c->dims[n]; }
     else { for (int n = split; n < c->order; ++n) rows *= c->dims[n]; }
@@ -232,6 +240,9 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
         c->stream = c->side_stream;
     }
+    // chol_alg = 3: the factorisation hides under a GEMM if one runs in this mode's update (or pass B is in flight: early_pass_b)
+    c->chol_exposed = !(c->overlap_factor && (c->gemm_join_pending ||
+                                              (c->mttkrp_alg != ITCPD_MTTKRP_DIRECT && !partial_is_current(c, mode < c->split_a ? 0 : 1))));
     int st = k_gram_hadamard(c, mode, c->Gamma.as<double>());
     if (st == ITCPD_OK) st = k_solve_factor(c, c->Gamma.as<double>(), c->rank, tol, status_dev);
     c->stream = main_stream;
@@ -328,7 +339,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_GRAPH_SINGLE")) c->graph_single = atoi(s) != 0;   // experimental
     if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
-    if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(2, std::max(0, atoi(s)));
+    if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(3, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
@@ -410,7 +421,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
         ARG_CHECK(!c->peer_on, "set peer_graph before itcpd_peer_export / itcpd_peer_import");
         c->peer_graph = value != 0;
     }
-    else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 2, "chol_alg must be 0, 1 or 2"); c->chol_alg = (int)value; }
+    else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 3, "chol_alg must be 0, 1, 2 or 3"); c->chol_alg = (int)value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     c->graph_epoch++;

@@ -108,6 +108,9 @@ struct itcpd_ctx {
     cudaEvent_t ev_gemm_fork = nullptr, ev_gemm_done = nullptr;
     bool gemm_join_pending = false;
     int chol_alg = 1;  // 0: block kernel (any n), 1: team kernel for n <= 128 (same arithmetic, bitwise), 2: + right-looking for n <= 64 (experimental)
+    // chol_alg = 3 (experimental): right-looking kernels only where the factorisation is EXPOSED (no GEMM runs in that mode's update, or
+    // R > 64 where no factorisation kernel can share an SM with a GEMM CTA); the team kernel (40 registers: co-resident) where it hides
+    bool chol_exposed = true;   // set by the sweep driver before every factorisation
     int64_t launches = 0;
 
     // options

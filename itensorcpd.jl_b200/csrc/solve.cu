@@ -618,7 +618,8 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
         CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
         attr[c->device & 63] = true;
     }
-    if (c->chol_alg == 2 && R > 64 && R <= 128) {  // two threads per column (experimental)
+    const bool right_looking = c->chol_alg == 2 || (c->chol_alg == 3 && (c->chol_exposed || R > 64));
+    if (right_looking && R > 64 && R <= 128) {  // two threads per column (experimental)
         static bool attr_r[64] = {false};
         if (!attr_r[c->device & 63]) {
             CUDA_TRY(cudaFuncSetAttribute(pivoted_cholesky_rl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
@@ -629,7 +630,7 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
         CUDA_TRY(cudaGetLastError());
         return ITCPD_OK;
     }
-    if (c->chol_alg == 2 && R <= 64) {
+    if (right_looking && R <= 64) {
         const size_t smem = (size_t)ldw * R * 8;
         if (R <= 32) pivoted_cholesky_rl_kernel<32><<<1, CHT_THREADS, smem, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev);
         else pivoted_cholesky_rl_kernel<64><<<1, CHT_THREADS, smem, c->stream>>>(Gamma, R, tol, c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev);

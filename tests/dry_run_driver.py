@@ -97,7 +97,7 @@ def small_shapes_default_options():
 @scenario
 def small_shapes_every_option():
     opts = [("tile_warps", 4), ("stream_k", 0), ("stream_k", 2), ("tma3d", 0), ("swizzle", 0), ("overlap_factor", 0), ("use_graph", 0), ("chol_alg", 0),
-            ("chol_alg", 2), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
+            ("chol_alg", 2), ("chol_alg", 3), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
     defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 1, "mttkrp_alg": 0, "early_pass_b": 0,
                 "gemm_i8": 0, "time_gemm": 0, "time_phases": 0}
     with itcpd.Engine(0) as eng:
@@ -360,6 +360,40 @@ def single_sweep_calls_replay_a_graph_only_with_the_option():
 
 
 @scenario
+def chol_alg_3_uses_the_right_looking_kernel_only_where_the_factorisation_is_exposed():
+    dims, R = (64, 48, 40), 16
+    out = {}
+    for early in (0, 1):
+        fake.fakecuda_clear()
+        with itcpd.Engine(0) as eng:
+            eng.set_option("chol_alg", 3)
+            eng.set_option("split_a", 2)
+            eng.set_option("split_b", 1)
+            eng.set_option("use_graph", 0)
+            eng.set_option("early_pass_b", early)
+            eng.set_tensor(np.zeros(dims, order="F"))
+            eng.set_cpd(factors(dims, R), np.ones(R))
+            eng.compute_grams()
+            eng.sweep_async(4)
+            eng.synchronize()
+        out[early] = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl"))
+    # (2,1) tree: GEMMs run in the updates of modes 0 and 2 -> team kernel there; mode 1 is exposed -> right-looking, unless pass B
+    # is already in flight underneath it (early_pass_b)
+    assert out[0] == (8, 4) and out[1] == (12, 0), out
+    with itcpd.Engine(0) as eng:          # R > 64: no factorisation kernel shares an SM with a GEMM CTA -> always right-looking
+        fake.fakecuda_clear()
+        eng.set_option("chol_alg", 3)
+        eng.set_tensor(np.zeros(dims, order="F"))
+        eng.set_cpd(factors(dims, 100), np.ones(100))
+        eng.compute_grams()
+        eng.sweep_async(2)
+        eng.synchronize()
+        big = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl2"))
+    assert big == (0, 6), big
+    return {"team_rl_counts": out, "rank_100": big}
+
+
+@scenario
 def end_to_end_call_from_host_buffers():
     dims, R = (64, 48, 40), 16
     with itcpd.Engine(0) as eng:
@@ -407,7 +441,7 @@ def fuzz_dense_shapes_and_options():
             dims, R = _random_problem(rnd, 2e9)
             N = len(dims)
             opts = {"gemm_i8": rnd.choice([0, 0, 1, 2]), "early_pass_b": rnd.choice([0, 1]), "tile_warps": rnd.choice([4, 8]), "stream_k": rnd.choice([0, 1, 2]),
-                    "chol_alg": rnd.choice([0, 1, 2]), "use_graph": rnd.choice([0, 1]), "tma3d": rnd.choice([0, 1]), "overlap_factor": rnd.choice([0, 1]), "i8_spare_sms": rnd.choice([0, 0, 1, 5]),
+                    "chol_alg": rnd.choice([0, 1, 2, 3]), "use_graph": rnd.choice([0, 1]), "tma3d": rnd.choice([0, 1]), "overlap_factor": rnd.choice([0, 1]), "i8_spare_sms": rnd.choice([0, 0, 1, 5]),
                     "graph_single": rnd.choice([0, 1])}
             sa = rnd.choice([0, 0] + list(range(1, N)))
             sb = 0 if sa == 0 else rnd.randint(1, sa)

@@ -75,6 +75,7 @@ SCENARIOS = [
     "eight_ranks_config_D_slabs_peer_graph_gemm_i8", "pivot_setup_and_bench_entry_points", "sampled_path_single_rank", "end_to_end_call_from_host_buffers",
     "out_of_memory_is_an_error_code_not_a_crash", "fuzz_dense_shapes_and_options", "fuzz_two_rank_sharded_dense_and_sampled",
     "single_sweep_calls_replay_a_graph_only_with_the_option",
+    "chol_alg_3_uses_the_right_looking_kernel_only_where_the_factorisation_is_exposed",
 ]
 
 

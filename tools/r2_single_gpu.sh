@@ -19,13 +19,13 @@ ITCPD_EARLY_B=1 $B > gpurun_out/r2_B_dmma_earlyb.json 2>> gpurun_out/r2_err.log
 ITCPD_GEMM_I8=2 $B > gpurun_out/r2_B_i8_prepacked.json 2>> gpurun_out/r2_err.log
 ITCPD_GEMM_I8=2 ITCPD_EARLY_B=1 $B > gpurun_out/r2_B_i8_prepacked_earlyb.json 2>> gpurun_out/r2_err.log
 ITCPD_GEMM_I8=1 $B > gpurun_out/r2_B_i8_on_the_fly.json 2>> gpurun_out/r2_err.log
-for chol in 1 2; do   # B8 / A at R = 64 and 50; the rank-128 kernel shows in config D slabs (bench --config D8 if present)
+for chol in 1 2 3; do   # B8 / A at R = 64 and 50; the rank-128 kernel shows in config D slabs (bench --config D8 if present)
   ITCPD_CHOL=$chol $B --config B8 --steps 50 > gpurun_out/r2_B8_chol$chol.json 2>> gpurun_out/r2_err.log
   ITCPD_CHOL=$chol $B --config A --steps 50 > gpurun_out/r2_A_chol$chol.json 2>> gpurun_out/r2_err.log
 done
 ITCPD_GEMM_I8=2 $B --config B8 --steps 50 > gpurun_out/r2_B8_i8_prepacked.json 2>> gpurun_out/r2_err.log
 # config D's per-rank slab (R = 128: the two-thread right-looking Cholesky, two rank blocks in one INT8 launch, one SM left to the factorisation)
-for chol in 1 2; do ITCPD_CHOL=$chol $B --config D8 --steps 20 > gpurun_out/r2_D8_chol$chol.json 2>> gpurun_out/r2_err.log; done
+for chol in 1 2 3; do ITCPD_CHOL=$chol $B --config D8 --steps 20 > gpurun_out/r2_D8_chol$chol.json 2>> gpurun_out/r2_err.log; done
 ITCPD_CHOL=2 ITCPD_GEMM_I8=2 $B --config D8 --steps 20 > gpurun_out/r2_D8_i8_chol2.json 2>> gpurun_out/r2_err.log
 ITCPD_CHOL=2 ITCPD_GEMM_I8=2 ITCPD_I8_SPARE_SMS=1 $B --config D8 --steps 20 > gpurun_out/r2_D8_i8_chol2_spare1.json 2>> gpurun_out/r2_err.log
 python tools/r2_summary.py gpurun_out/r2_*.json | tee gpurun_out/r2_summary.txt
