@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 opener, part 1 (ONE GPU, ~8 min):  gpurun --timeout 900 -- 'bash tools/r2_single_gpu.sh'
+# Round-2 opener, part 1 (ONE GPU, ~12 min):  gpurun --timeout 1200 -- 'bash tools/r2_single_gpu.sh'
 # First hardware run of what was written after round 1's GPU budget was spent.  Ordered so that the most valuable verdicts
 # survive a time-out; everything lands in gpurun_out/r2_*.
 mkdir -p gpurun_out
