@@ -338,7 +338,7 @@ def run_ours(args, cfg):
         if i8 and gemm_ms > 0 and mp.get("hbm_gbs"):
             bytes_per_elem = 6.0 if os.environ.get("ITCPD_GEMM_I8") == "2" else 8.0   # pre-packed digit planes stream 6 B per element
             gbs = bytes_per_elem * P / world / (gemm_ms * 1e-3) / 1e9
-            roof.update({"bound": "hbm", "kernel": "partial_gemm_i8(p)_kernel (TMA + tcgen05.mma kind::i8 on 6 base-256 digits, TMEM accumulators)",
+            roof.update({"bound": "hbm", "kernel": "partial_gemm_i8(p)_kernel (TMA + tcgen05.mma kind::i8 on 6 / 7 base-256 digits, TMEM accumulators)",
                          "achieved": gbs, "peak": mp["hbm_gbs"], "unit": "GB/s", "frac": gbs / mp["hbm_gbs"],
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs", "fp64_equivalent_tflops": ach,
                          "algorithmic_bytes_per_launch": bytes_per_elem * P / world,

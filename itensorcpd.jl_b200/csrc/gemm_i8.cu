@@ -1,20 +1,23 @@
 // EXPERIMENTAL (option "gemm_i8", off by default; written without GPU access, not yet run on hardware):
 // the partial contraction of the dimension tree on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators)
-// with FP64-equivalent accuracy, by splitting both operands into 6 balanced base-256 digits (an Ozaki-style scheme).
+// with FP64-equivalent accuracy, by splitting the operands into balanced base-256 digits (an Ozaki-style scheme): 6 digits for
+// the tensor, 7 for the Khatri-Rao operand.
 //
 //   out[m, r] = sum_k T[m, k] K[k, r]                                  (kind 0; kind 1 is the transposed view of T)
-//   T[m, k] ~= XA[m, k] 2^(ea[m] - 47),  K[k, r] ~= XB[k, r] 2^(eb[r] - 47),   X* = 47-bit signed fixed point, |X| <= 2^46
-//   X = sum_{p=0..5} d_p 256^(5-p),  d_p in [-128, 127] (d_0 in [-65, 65]): the bytes of X + 0x8080808080 with bit 7 of the five
-//   low bytes flipped ARE the digits as int8 -- one 64-bit add and one xor per element
-//   sum_k XA XB = sum_{p,q} 256^(10-p-q) S_pq,   S_pq = sum_k dA_p dB_q   exact in int32 while 6 K 2^14 < 2^31 (K <= 21845: the
+//   T[m, k] ~= XA[m, k] 2^(ea[m] - 48),  K[k, r] ~= XB[k, r] 2^(eb[r] - 56),   signed fixed point relative to the row / column maximum
+//   XA = sum_{p=0..5} dA_p 256^(5-p),  XB = sum_{q=0..6} dB_q 256^(6-q),  d in [-128, 127]: the bytes of X + 0x80..80 with bit 7 of
+//   the low bytes flipped ARE the digits as int8 -- one 64-bit add and one xor per element
+//   sum_k XA XB = sum_{p,q} 256^(11-p-q) S_pq,   S_pq = sum_k dA_p dB_q   exact in int32 while 6 K 2^14 < 2^31 (K <= 21845: the
 //   split-K schedule keeps a chunk below that)
-// The 26 digit pairs with p + q <= 6 are formed (relative Frobenius error 4e-14 .. 6e-14 for the operands of this path, against
-// 5e-14 .. 1e-13 for the 7-digit base-128 split with 28 products this replaced: profiles/r1_ozaki_int8_numerics.txt); all pairs of
-// equal weight p + q = t share ONE int32 accumulator in TMEM, so a 128 x 64 tile needs 7 x 64 = 448 of the 512 TMEM columns.
-// Stacking the B digit planes along N turns the 26 products of a k-step into 9 instructions:
-//   A_p (128 x 32)  x  [B_0; ..; B_{min(5, 6-p)}]  ->  accumulators t = p .. min(p + 5, 6).
+// The 27 digit pairs with p + q <= 6 are formed; all pairs of equal weight p + q = t share ONE int32 accumulator in TMEM, so a
+// 128 x 64 tile needs 7 x 64 = 448 of the 512 TMEM columns.  Stacking the B digit planes along N turns the 27 products of a k-step
+// into 9 instructions:  A_p (128 x 32)  x  [B_0; ..; B_{6-p}]  ->  accumulators t = p .. 6.
+// Accuracy (relative Frobenius, profiles/r1_ozaki_int8_numerics.txt): 2e-14 .. 3e-14 for Gaussian T, set by the 48 bits of T relative
+// to its row maxima; the Khatri-Rao operand keeps 56 bits because products of factor entries are heavy-tailed (column maximum 20 x the
+// typical entry for two factors, more for higher orders) and its planes cost next to nothing.  The first draft (7 base-128 digits
+// for both, 28 products, 7 bytes per element of T) gave 5e-14 .. 1e-13.
 // T costs 6 bytes per element as pre-packed digit planes (variant 2), so the pass is bound by that HBM stream (0.98 ms at 1024^3)
-// instead of the FP64 pipe (3.9 ms); at 4.5 POPS the 26 products take 0.80 ms.
+// instead of the FP64 pipe (3.9 ms); at 4.5 POPS the 27 products take 0.82 ms.
 //
 // Warp roles (10 warps, 1 CTA per SM, persistent over 128-row tiles):
 //   warps 0-7  converters: FP64 tile (TMA) -> 6 int8 digit planes in the canonical UMMA shared-memory layout
@@ -26,16 +29,19 @@
 
 namespace itcpd {
 
-constexpr int I8_NDIG = 6;              // base-256 digits per operand
+constexpr int I8_NDIG = 6;              // base-256 digits of the tensor operand (6 bytes per element of T)
+constexpr int I8_NDIG_B = 7;            // base-256 digits of the Khatri-Rao operand: it is small, and products of factor entries are
+                                        // heavy-tailed (column maximum >> typical entry), so it gets a digit more than T
 constexpr int I8_NACC = 7;              // int32 accumulators per output element: digit pairs with p + q = t, t = 0 .. 6
-constexpr int I8_FRAC = 47;             // fixed-point bits (one below 8 * I8_NDIG: the signed top digit keeps headroom)
+constexpr int I8_FRAC = 8 * I8_NDIG;    // fixed-point bits (48 / 56); i8_exponent keeps |x| 2^-E below 1/2 - 2^-8 so the top digit stays < 128
+constexpr int I8_FRAC_B = 8 * I8_NDIG_B;
 constexpr int I8_MAX_KCHUNK = 680;      // k-tiles one accumulator may sum: 6 pairs x 680 x 32 x 2^14 < 2^31
 constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 32;
 constexpr int I8_FSTAGES = 3, I8_DSTAGES = 2;
 constexpr int I8_F_BYTES = I8_BM * I8_BK * 8;                  // 32768: one FP64 tile
 constexpr int I8_A_PLANE = I8_BM * I8_BK;                      // 4096
 constexpr int I8_A_BYTES = I8_NDIG * I8_A_PLANE;               // 24576
-constexpr int I8_B_BYTES = I8_NDIG * I8_BN * I8_BK;            // 12288
+constexpr int I8_B_BYTES = I8_NDIG_B * I8_BN * I8_BK;          // 14336
 constexpr int I8_SMEM = I8_FSTAGES * I8_F_BYTES + I8_DSTAGES * (I8_A_BYTES + I8_B_BYTES) + 256 + 1024;
 constexpr int I8_EXP_ZERO = -100000;                           // exponent of an all-zero row / column
 constexpr int I8_EXP_NONFINITE = 100000;                       // a NaN / Inf was seen: the whole output row / column becomes NaN (as in FP64)
@@ -43,7 +49,7 @@ constexpr int I8_EXP_NONFINITE = 100000;                       // a NaN / Inf wa
 // ------------------------------------------------------------------------------------------------------------------
 // digit arithmetic (barrier-free device code: exercised on the CPU by tests/test_i8_digits_emulation_cpu.py)
 // ------------------------------------------------------------------------------------------------------------------
-// smallest E with |x| 2^-E < 1/2
+// smallest E with |x| 2^-E < 1/2 - 2^-8 (up to one binade of slack)
 // running maximum of |x| that a NaN or an infinity turns into +inf for good (fmax alone would drop a NaN)
 __device__ __forceinline__ double i8_amax(double amax, double x) {
     const double a = fabs(x);
@@ -53,34 +59,45 @@ __device__ __forceinline__ int i8_exponent(double amax) {
     if (!(amax > 0.0)) return I8_EXP_ZERO;
     const int biased = (int)((unsigned long long)__double_as_longlong(amax) >> 52) & 0x7ff;
     if (biased == 0x7ff) return I8_EXP_NONFINITE;
-    if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(47-E) representable)
-    return biased - 1022 + 1;          // amax in [2^(b-1023), 2^(b-1022))  ->  amax 2^-(b-1021) < 1/2
+    if (biased < 128) return I8_EXP_ZERO;   // < 2^-895: treated as an all-zero row (keeps 2^(48-E) representable)
+    // amax in [2^(b-1023), 2^(b-1022))  ->  amax 2^-(b-1021) < 1/2.  The digits of X + 0x8080808080 need X < 2^47 - 2^39.01 (the
+    // signed top byte must not reach +128): a maximum whose six leading mantissa bits are ones (amax 2^-E >= 1/2 - 2^-8) takes the
+    // next exponent, so that always  X < 2^47 - 2^40  and  X + 0x8080808080 < 2^47
+    const int near_top = (((unsigned long long)__double_as_longlong(amax) >> 46) & 0x3f) == 0x3f;
+    return biased - 1022 + 1 + near_top;
 }
-// 2^(47 - E) as a double (0 for an all-zero row: every digit is then 0)
-__device__ __forceinline__ double i8_scale(int E) {
+// 2^(48 - E) as a double (0 for an all-zero row: every digit is then 0)
+__device__ __forceinline__ double i8_scale(int E, int frac = I8_FRAC) {
     if (E == I8_EXP_ZERO || E == I8_EXP_NONFINITE) return 0.0;
-    return __longlong_as_double((long long)(1023 + I8_FRAC - E) << 52);
+    return __longlong_as_double((long long)(1023 + frac - E) << 52);
 }
-// X = rint(x scale), |X| <= 2^46.  The bytes of Z = (X + 0x8080808080) ^ 0x8080808080 are the balanced base-256 digits as
-// int8: byte j (j = 0 .. 4) of the sum is d + 128 for digit plane 5 - j, flipping its bit 7 gives d; byte 5 is the signed
-// top digit (plane 0).  `lo` = planes 5, 4, 3, 2 (bytes 0..3), `hi` = planes 1, 0 (bytes 0, 1).
+// X = rint(x scale), |X| < 2^(8 ND - 1) - 2^(8 ND - 8).  The bytes of Z = (X + C) ^ C, C = 0x80 in each of the ND - 1 low bytes, are
+// the balanced base-256 digits as int8: low byte j of the sum is d + 128 for digit plane ND - 1 - j, flipping its bit 7 gives
+// d; the top byte is the signed top digit (plane 0).  `lo` = the four lowest planes (bytes 0..3), `hi` = the remaining ones.
+template <int ND>
 __device__ __forceinline__ void i8_fields(double x, double scale, unsigned &lo, unsigned &hi) {
     const long long X = __double2ll_rn(x * scale);
-    const unsigned long long Z = (unsigned long long)(X + 0x8080808080ll) ^ 0x8080808080ull;
+    constexpr long long C = (ND == 6) ? 0x8080808080ll : 0x808080808080ll;
+    const unsigned long long Z = (unsigned long long)(X + C) ^ (unsigned long long)C;
     lo = (unsigned)Z;
-    hi = (unsigned)(Z >> 32) & 0xffffu;
+    hi = (unsigned)(Z >> 32) & ((ND == 6) ? 0xffffu : 0xffffffu);
 }
 // bytes of four consecutive elements -> one word per plane (byte i = element i): a 4 x 4 byte transpose with PRMT
-__device__ __forceinline__ void i8_pack4(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned (&out)[I8_NDIG]) {
+template <int ND>
+__device__ __forceinline__ void i8_pack4(const unsigned (&lo)[4], const unsigned (&hi)[4], unsigned (&out)[ND]) {
     const unsigned a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[2], lo[3], 0x5140);   // bytes 0 and 1 of the four lo words
     const unsigned c = __byte_perm(lo[0], lo[1], 0x7362), d = __byte_perm(lo[2], lo[3], 0x7362);   // bytes 2 and 3
     const unsigned e = __byte_perm(hi[0], hi[1], 0x5140), f = __byte_perm(hi[2], hi[3], 0x5140);   // bytes 0 and 1 of the four hi words
-    out[5] = __byte_perm(a, b, 0x5410);
-    out[4] = __byte_perm(a, b, 0x7632);
-    out[3] = __byte_perm(c, d, 0x5410);
-    out[2] = __byte_perm(c, d, 0x7632);
-    out[1] = __byte_perm(e, f, 0x5410);
-    out[0] = __byte_perm(e, f, 0x7632);
+    out[ND - 1] = __byte_perm(a, b, 0x5410);
+    out[ND - 2] = __byte_perm(a, b, 0x7632);
+    out[ND - 3] = __byte_perm(c, d, 0x5410);
+    out[ND - 4] = __byte_perm(c, d, 0x7632);
+    out[ND - 5] = __byte_perm(e, f, 0x5410);
+    out[ND - 6] = __byte_perm(e, f, 0x7632);
+    if (ND == 7) {
+        const unsigned g = __byte_perm(hi[0], hi[1], 0x7362), h = __byte_perm(hi[2], hi[3], 0x7362);   // byte 2 of the hi words
+        out[0] = __byte_perm(g, h, 0x5410);
+    }
 }
 
 // exponents of the rows of a strided matrix view: row r, reduction index j at  base[r * sr + j * sj]
@@ -177,7 +194,7 @@ __global__ void i8_krp_exponent_kernel(I8Krp a, int *__restrict__ E) {
     for (int64_t k = k0; k < min(a.kext, k0 + 256); ++k, it.next(a)) amax = i8_amax(amax, it.value(a, r));
     atomicMax(&E[r], i8_exponent(amax));
 }
-// digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 12288-byte block per k-tile of 32:
+// digit planes of the Khatri-Rao operand in the canonical K-major UMMA layout, one 14336-byte block per k-tile of 32:
 //   byte(q, n, kk) = ((q*64 + n) % 8) * 16 + ((q*64 + n) / 8) * 256 + (kk / 16) * 128 + (kk % 16)
 // one thread per (k-tile, n, half): 16 consecutive k of one column -> one 16-byte store per plane
 __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t ktiles, uint8_t *__restrict__ out) {
@@ -186,22 +203,22 @@ __global__ void i8_krp_pack_kernel(I8Krp a, const int *__restrict__ E, int64_t k
     const int half = (int)(idx & 1);
     const int n = (int)((idx >> 1) % I8_BN);
     const int64_t kt = (idx >> 1) / I8_BN;
-    const double scale = i8_scale(E[n]);
-    unsigned plane[I8_NDIG][4];
+    const double scale = i8_scale(E[n], I8_FRAC_B);
+    unsigned plane[I8_NDIG_B][4];
     I8KrpIter it;
     it.init(a, kt * I8_BK + 16 * half);
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        unsigned lo[4], hi[4], o[I8_NDIG];
+        unsigned lo[4], hi[4], o[I8_NDIG_B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j, it.next(a)) i8_fields(it.value(a, n), scale, lo[j], hi[j]);
-        i8_pack4(lo, hi, o);
+        for (int j = 0; j < 4; ++j, it.next(a)) i8_fields<I8_NDIG_B>(it.value(a, n), scale, lo[j], hi[j]);
+        i8_pack4<I8_NDIG_B>(lo, hi, o);
 #pragma unroll
-        for (int p = 0; p < I8_NDIG; ++p) plane[p][w] = o[p];
+        for (int p = 0; p < I8_NDIG_B; ++p) plane[p][w] = o[p];
     }
     uint8_t *blk = out + kt * (int64_t)I8_B_BYTES;
 #pragma unroll
-    for (int q = 0; q < I8_NDIG; ++q) {
+    for (int q = 0; q < I8_NDIG_B; ++q) {
         const int row = q * I8_BN + n;
         uint4 v = make_uint4(plane[q][0], plane[q][1], plane[q][2], plane[q][3]);
         *reinterpret_cast<uint4 *>(blk + (row & 7) * 16 + (row >> 3) * 256 + half * 128) = v;
@@ -228,9 +245,9 @@ __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, 
             double x, sc;
             if (KIND == 0) { x = F[(16 * (tid >> 7) + j) * I8_BM + (tid & 127)]; sc = scale0; }
             else { x = F[(16 * warp + j) * I8_BK + lane]; sc = i8_scale(ea_tile[16 * warp + j]); }
-            i8_fields(x, sc, lo[jj], hi[jj]);
+            i8_fields<I8_NDIG>(x, sc, lo[jj], hi[jj]);
         }
-        i8_pack4(lo, hi, o);
+        i8_pack4<I8_NDIG>(lo, hi, o);
 #pragma unroll
         for (int p = 0; p < I8_NDIG; ++p) plane[p][w] = o[p];
     }
@@ -242,7 +259,7 @@ __device__ __forceinline__ void i8_convert_thread(const double *__restrict__ F, 
         *reinterpret_cast<uint4 *>(A + p * I8_A_PLANE + off) = make_uint4(plane[p][0], plane[p][1], plane[p][2], plane[p][3]);
 }
 
-// C = 2^(ea + eb - 94 + 80) sum_t acc_t 2^(-8 t):  v = sum_t acc_t 2^(-8 t) is formed by the caller, smallest weights first
+// C = 2^(ea + eb - 104 + 88) sum_t acc_t 2^(-8 t):  v = sum_t acc_t 2^(-8 t) is formed by the caller, smallest weights first
 // exact int32 -> double without the (quarter-rate) I2F.F64 conversion: the double whose high word is 0x43300000 and whose low
 // word is a + 2^31 equals 2^52 + 2^31 + a; one DADD removes the offset exactly
 __device__ __forceinline__ double i8_i2d(int a) {
@@ -252,9 +269,9 @@ __device__ __forceinline__ double i8_weight(int t) { return __longlong_as_double
 __device__ __forceinline__ double i8_finish(double v, int em, int er) {
     if (em == I8_EXP_NONFINITE || er == I8_EXP_NONFINITE) return __longlong_as_double(0x7ff8000000000000ll);   // NaN, like the FP64 contraction
     if (em == I8_EXP_ZERO || er == I8_EXP_ZERO) return 0.0;
-    // v 2^e as two exact power-of-two multiplications (e = em + er - 14 lies in [-1800, 2036]: each half is a normal double);
+    // v 2^e as two exact power-of-two multiplications (e = em + er - 16 lies in [-1802, 2036]: each half is a normal double);
     // ldexp() is a ~20-instruction library routine, and this runs once per output element
-    const int e = em + er - 14, h = e >> 1;
+    const int e = em + er - I8_FRAC - I8_FRAC_B + 8 * (I8_NDIG - 1 + I8_NDIG_B - 1), h = e >> 1;   // = em + er - 16
     return v * __longlong_as_double((long long)(1023 + h) << 52) * __longlong_as_double((long long)(1023 + e - h) << 52);
 }
 
@@ -475,22 +492,15 @@ __device__ __forceinline__ void i8_mma_cols(uint32_t tmem, uint64_t adesc, uint3
         i8_mma(d, adesc, bdesc, i8_idesc(ncols, a_mn_major), acc);
     }
 }
-// the 9 tcgen05.mma of one k-step: A digit plane p (128 x 32)  x  B planes 0 .. min(5, 6 - p)  ->  accumulators p .. min(p + 5, 6).
-// On the first k-step of a unit an accumulator's FIRST product overwrites: plane 0 initialises t = 0 .. 5, and t = 6 is first
-// touched by (p = 1, q = 5), which therefore gets its own overwriting instruction there (10 instructions on that k-step).
+// the 9 tcgen05.mma of one k-step: A digit plane p (128 x 32)  x  B planes 0 .. 6 - p  ->  accumulators p .. 6 (the 27 digit pairs
+// with p + q <= 6).  Plane 0 touches every accumulator first, so it alone overwrites on the first k-step of a unit.
 template <int KIND>
 __device__ __forceinline__ void i8_issue_kstep(uint32_t tmem, uint32_t a0, uint32_t b0, bool first_kstep) {
 #pragma unroll
     for (int p = 0; p < I8_NDIG; ++p) {
         const uint64_t adesc = (KIND == 0) ? i8_smem_desc(a0 + p * I8_A_PLANE, 128, 256)    // K-major: LBO = k chunk, SBO = 8-row group
                                            : i8_smem_desc(a0 + p * I8_A_PLANE, 128, 512);   // MN-major: LBO = k group of 8, SBO = 16-row block
-        const int nq = (I8_NACC - p < I8_NDIG) ? I8_NACC - p : I8_NDIG;
-        if (first_kstep && p == 1) {
-            i8_mma_cols(tmem, adesc, b0, KIND, 1, 0, nq - 1, 1u);
-            i8_mma_cols(tmem, adesc, b0, KIND, I8_NACC - 1, nq - 1, 1, 0u);
-        } else {
-            i8_mma_cols(tmem, adesc, b0, KIND, p, 0, nq, (first_kstep && p == 0) ? 0u : 1u);
-        }
+        i8_mma_cols(tmem, adesc, b0, KIND, p, 0, I8_NACC - p, (first_kstep && p == 0) ? 0u : 1u);
     }
 }
 
@@ -633,7 +643,7 @@ partial_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *
 // plain TMA -> tcgen05.mma -> TMEM pipeline: warp 0 producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int I8P_STAGES = 4;
-constexpr int I8P_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 36864
+constexpr int I8P_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;      // 38912
 constexpr int I8P_SMEM = I8P_STAGES * I8P_STAGE_BYTES + 256 + 1024;
 
 // one CTA per (row tile, k-tile): stage the 128 x 32 FP64 tile in shared memory (zero fill outside the tensor), then the

@@ -297,8 +297,7 @@ def test_whole_i8_kernel_on_the_functional_model(sim, kind, Mrows, Ncols, R, gri
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     assert err < 1e-12, err
     ktiles, row_tiles = -(-kext // 32), -(-rows_out // 128)
-    units = row_tiles * ksplit * -(-R // 64)
-    assert nmma == 9 * ktiles * row_tiles * -(-R // 64) + units       # 26 digit products per k-step as 9 instructions, one more on a unit's first k-step
+    assert nmma == 9 * ktiles * row_tiles * -(-R // 64)       # 27 digit products per k-step and rank block as 9 instructions
 
 
 def test_split_k_schedule_policy():

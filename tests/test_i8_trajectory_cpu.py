@@ -1,45 +1,45 @@
 """Is the accuracy of the 6-digit INT8 contraction (csrc/gemm_i8.cu, experimental) enough for the north-star trajectory bar?
-A vectorised numpy statement of the same arithmetic (47-bit fixed point per row / column, balanced base-256 digits as the
+A vectorised numpy statement of the same arithmetic (48-bit fixed point per row / column, balanced base-256 digits as the
 bytes of (X + 0x8080808080) ^ 0x8080808080, the 26 digit-plane products with p + q <= 6, combination smallest weights first)
 replaces the oracle's MTTKRP inside its ALS loop; the fit trajectory over 100 sweeps must stay within 1e-9 of the plain oracle's."""
 import numpy as np
 
 from oracle import cpals
 
-NDIG, NACC, FRAC = 6, 7, 47
+NDIG, NDIG_B, NACC, FRAC, FRAC_B = 6, 7, 7, 48, 56
 
 
-def digits(X):
-    """X: int64 array, |X| <= 2^46 -> list of 6 float64 digit planes, most significant first (i8_fields in gemm_i8.cu)"""
-    Z = (X + 0x8080808080) ^ 0x8080808080
-    planes = [((Z >> (8 * j)) & 0xff).astype(np.uint8).view(np.int8).reshape(X.shape) for j in range(5)]   # planes 5 .. 1 as int8
-    planes.append(((Z >> 40) & 0xff).astype(np.uint8).view(np.int8).reshape(X.shape))                        # signed top digit
+def digits(X, nd):
+    """X: int64 array -> list of nd float64 digit planes, most significant first (i8_fields<ND> in gemm_i8.cu)"""
+    C = sum(0x80 << (8 * j) for j in range(nd - 1))
+    Z = (X + C) ^ C
+    planes = [((Z >> (8 * j)) & 0xff).astype(np.uint8).view(np.int8).reshape(X.shape) for j in range(nd)]   # lowest plane first; the top byte is signed
     out = [p.astype(np.float64) for p in planes[::-1]]
-    assert np.array_equal(sum(out[p].astype(np.int64) << (8 * (NDIG - 1 - p)) for p in range(NDIG)), X)    # the digits ARE X
+    assert np.array_equal(sum(out[p].astype(np.int64) << (8 * (nd - 1 - p)) for p in range(nd)), X)         # the digits ARE X
     return out
 
 
 def exponents(A, axis):
     amax = np.max(np.abs(A), axis=axis, keepdims=True)
-    _, e = np.frexp(np.where(amax > 0, amax, 1.0))        # amax = f 2^e, f in [0.5, 1)
-    return e + 1                                          # |a| 2^-E < 1/2
+    f, e = np.frexp(np.where(amax > 0, amax, 1.0))        # amax = f 2^e, f in [0.5, 1)
+    return e + 1 + (f >= 1.0 - 2.0 ** -7)                 # |a| 2^-E < 1/2 - 2^-8 (i8_exponent: six leading mantissa ones -> next exponent)
 
 
 def gemm_i8(A, B):
     """A (M x K) @ B (K x N) through the digit-split scheme"""
     ea, eb = exponents(A, 1), exponents(B, 0)
     XA = np.rint(np.ldexp(A, FRAC - ea)).astype(np.int64)
-    XB = np.rint(np.ldexp(B, FRAC - eb)).astype(np.int64)
-    dA, dB = digits(XA), digits(XB)
+    XB = np.rint(np.ldexp(B, FRAC_B - eb)).astype(np.int64)
+    dA, dB = digits(XA, NDIG), digits(XB, NDIG_B)
     v = np.zeros((A.shape[0], B.shape[1]))
     for t in range(NACC - 1, -1, -1):
         acc = np.zeros_like(v)
         for p in range(NDIG):
-            if 0 <= t - p < NDIG:
+            if 0 <= t - p < NDIG_B:
                 acc += dA[p] @ dB[t - p]                  # exact: |entries| < 2^53
         assert np.max(np.abs(acc)) < 2 ** 31              # what the int32 TMEM accumulators must hold
         v = acc * 2.0 ** (-8 * t) + v
-    return np.ldexp(v, ea + eb - 2 * FRAC + 8 * 2 * (NDIG - 1))
+    return np.ldexp(v, ea + eb - FRAC - FRAC_B + 8 * (NDIG - 1 + NDIG_B - 1))
 
 
 def mttkrp_i8(T, factors, n):

@@ -23,7 +23,7 @@ def one_pass(rows, kext, R):
     P = rows * kext
     rt, kt, rb = math.ceil(rows / BM), math.ceil(kext / BK), math.ceil(R / BN)
     ksteps = rt * kt * rb
-    nq = [min(NDIG, NACC - p) for p in range(NDIG)]   # B planes per A plane: the 26 digit pairs with p + q <= 6
+    nq = [NACC - p for p in range(NDIG)]              # B planes per A plane: the 27 digit pairs with p + q <= 6 (7 digits on the Khatri-Rao side)
     mma_ops = ksteps * 2 * BM * BK * BN * sum(nq)     # every rank block padded to 64 columns
     a_bytes, b_reads = NDIG * BM * BK, sum(nq) * BN * BK
     t = {
@@ -34,8 +34,8 @@ def one_pass(rows, kext, R):
         "hbm7": 6.0 * P / HBM,                        # variant 2 streams the 6 digit planes
         "mma": mma_ops / I8,
         # shared-memory traffic per k-step: operand reads of the 10 instructions (A planes once, stacked B planes re-read)
-        "smem1": ksteps * (a_bytes + b_reads + BM * BK * 8 * 2 + a_bytes + NDIG * BN * BK) / SMEM,   # + TMA FP64 in, converter read, planes written, B in
-        "smem2": ksteps * (a_bytes + b_reads + a_bytes + NDIG * BN * BK) / SMEM,                       # + bulk copies in
+        "smem1": ksteps * (a_bytes + b_reads + BM * BK * 8 * 2 + a_bytes + NACC * BN * BK) / SMEM,   # + TMA FP64 in, converter read, planes written, B in
+        "smem2": ksteps * (a_bytes + b_reads + a_bytes + NACC * BN * BK) / SMEM,                       # + bulk copies in
         # converters: ~25 integer/logic ops + 1 FP64 mul + 1 F2I per element on 128 int lanes / SM
         "conv": rb * P * 25.0 / (128 * CLK * SMS),
     }
