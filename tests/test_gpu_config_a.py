@@ -32,8 +32,6 @@ def test_config_a_fit_trajectory_100_sweeps_and_readme_rule(engine):
     assert c2.total_iter == r2.total_iter and abs(c2.final_fit - r2.final_fit) <= 1e-9
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ITCPD_EXPERIMENTAL", "0") == "0",
-                    reason="gemm_i8 / early_pass_b have not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("gemm_i8,early_b", [(1, 0), (2, 0), (0, 1), (2, 1)])
 def test_config_a_trajectory_with_the_experimental_contraction_paths(engine, gemm_i8, early_b):
     """the same north-star criterion (per-sweep fit within 1e-9 of the oracle over 100 sweeps) with the MTTKRP on the INT8

@@ -386,10 +386,6 @@ def test_team_cholesky_rank_deficient_and_nan(engine):
     assert out[0][3] == out[1][3] and out[0][3][0] == 1   # NaN: both kernels hand over to the QRCP path
 
 
-EXPERIMENTAL = os.environ.get("ITCPD_EXPERIMENTAL", "0") != "0"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="chol_alg=2 (right-looking Cholesky) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("R", [1, 5, 31, 32, 33, 50, 64, 65, 100, 128])
 def test_right_looking_cholesky_matches_team_kernel(engine, R):
     """solve.cu: pivoted_cholesky_rl_kernel (R <= 64) / pivoted_cholesky_rl2_kernel (two threads per column, R <= 128) -- same
@@ -419,7 +415,6 @@ def test_right_looking_cholesky_matches_team_kernel(engine, R):
     assert np.max(np.abs(res[2][3] - res[1][3])) / nT2 < 1e-10 and np.max(np.abs(res[2][4] - res[1][4])) / nT2 < 1e-10
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="chol_alg=2 has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 def test_right_looking_cholesky_rank_deficient(engine):
     dims, R = (30, 25, 20), 12
     T, cp = make_problem(dims, R, seed=17)
@@ -444,7 +439,6 @@ def test_right_looking_cholesky_rank_deficient(engine):
     assert relerr(out[2][3], out[1][3]) < 1e-9
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="gemm_i8 (INT8 tensor-core digit-split contraction) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("dims,R", [((128, 64, 32), 48), ((256, 32, 64), 64), ((128, 32, 32, 4), 20),
                                     ((100, 37, 45), 50), ((33, 17, 9), 20), ((64, 48, 40), 130)])   # ragged tiles, padded mode 0, 3 rank blocks
 @pytest.mark.parametrize("variant", [1, 2])   # 1: digits of T extracted on the fly, 2: pre-packed digit planes in HBM
@@ -462,7 +456,6 @@ def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R, variant):
         engine.set_option("gemm_i8", 0)
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="gemm_i8 (INT8 tensor-core digit-split contraction) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("dims,R", [((64, 40, 512), 64), ((100, 24, 700), 40)])   # pass A of the (1,1) tree: 1 row tile x 640 / 525 k-tiles
 @pytest.mark.parametrize("variant", [1, 2])
 def test_gemm_i8_split_k_matches_oracle(engine, dims, R, variant):
@@ -488,7 +481,6 @@ def test_gemm_i8_split_k_matches_oracle(engine, dims, R, variant):
         engine.set_option("split_b", 0)
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="early_pass_b (pass B on its own stream under the middle modes' updates) has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("dims,R,splits,graph", [((40, 36, 44), 20, (2, 1), 1), ((40, 36, 44), 20, (2, 1), 0), ((24, 20, 18, 16), 12, (3, 1), 1),
                                                  ((64, 48, 40), 64, (2, 1), 1)])
 def test_early_pass_b_is_bitwise_the_default_sweep(engine, dims, R, splits, graph):
@@ -525,7 +517,6 @@ def test_early_pass_b_is_bitwise_the_default_sweep(engine, dims, R, splits, grap
         engine.set_option("split_b", 0)
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="graph_single has not run on hardware yet: opt in with ITCPD_EXPERIMENTAL=1")
 def test_single_sweep_calls_through_the_graph_are_bitwise_the_plain_calls(engine):
     """option graph_single: the per-iteration loop of the reference API (itcpd_sweep(1) per iteration) replays the captured
     sweep from its third call on; trajectory, factors and lambda must be bitwise those of kernel-by-kernel launches."""
