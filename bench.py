@@ -246,8 +246,8 @@ def run_ours(args, cfg):
         eng.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
         if os.environ.get("ITCPD_PEER", "1") == "1":
             # fused all-reduce + solve over NVLink peer memory (CUDA IPC handles exchanged through torch.distributed)
-            if os.environ.get("ITCPD_PEER_GRAPH", "0") == "1":
-                eng.set_option("peer_graph", 1)  # experimental: NCCL-free sweeps with device-side epochs, replayed from a CUDA graph
+            if "ITCPD_PEER_GRAPH" in os.environ:   # default on: NCCL-free sweeps with device-side epochs, replayed from a CUDA graph
+                eng.set_option("peer_graph", int(os.environ["ITCPD_PEER_GRAPH"] != "0"))
             mine = torch.frombuffer(bytearray(eng.peer_export()), dtype=torch.uint8).cuda()
             allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)
@@ -272,9 +272,9 @@ def run_ours(args, cfg):
     # ---- timed region: exactly K sweeps, CUDA events on the library's stream (the sweep body replays a CUDA graph) ----
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()   # before the barrier: spawning nvidia-smi must not delay rank 0 inside the other ranks' timed region
+    barrier()
     eng.event_record(0)
     if flush:
         for _ in range(K):
@@ -415,6 +415,7 @@ def main():
     ap.add_argument("--config", default="B", choices=sorted(CONFIGS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (configs A, C, D, E)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: stop taking samples after this many seconds")
     args = ap.parse_args()

@@ -267,13 +267,13 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         else TRY(peer_signal(c, epoch));
         TRY(phase_mark(c, PH_SIGNAL));
         if (c->overlap_factor) CUDA_TRY(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
-        if (dev_epoch) TRY(peer_graph_wait(c));
         PeerSrc src;
         memset(&src, 0, sizeof(src));
         src.n = c->peer_n;
         for (int q = 0; q < c->peer_n; ++q) src.p[q] = reinterpret_cast<const double *>((const char *)c->peer_base[q] + slot_off);
-        src.flags = dev_epoch ? nullptr : reinterpret_cast<const volatile long long *>(c->xchg.p);  // null: the wait already happened
+        src.flags = reinterpret_cast<const volatile long long *>(c->xchg.p);
         src.epoch = epoch;
+        src.epoch_dev = dev_epoch ? c->peer_epochs.as<long long>() : nullptr;   // capturable sweeps: the signal kernel advanced it
         src.reduced_out = c->M[mode].as<double>();
         TRY(k_solve_apply_peers(c, c->Gamma.as<double>(), src, c->dims[mode], c->rank, c->X.as<double>(), status_dev));
     } else {
@@ -340,6 +340,7 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(3, std::max(0, atoi(s)));
+    if (const char *s = getenv("ITCPD_SOLVE")) c->solve_alg = std::min(1, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
@@ -422,6 +423,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
         c->peer_graph = value != 0;
     }
     else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 3, "chol_alg must be 0, 1, 2 or 3"); c->chol_alg = (int)value; }
+    else if (n == "solve_alg") { ARG_CHECK(value == 0 || value == 1, "solve_alg must be 0 (warp per row) or 1 (thread per row for R <= 64)"); c->solve_alg = (int)value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     c->graph_epoch++;
@@ -799,9 +801,24 @@ int itcpd_sweep_async(itcpd_ctx *c, int nsweeps, double chol_tol) {
             graph_key(c, chol_tol, key);          // buffers may have been (re)allocated by the plain sweep
             const int64_t l0 = c->launches;
             cudaGraph_t graph = nullptr;
+            // The capture records whatever ensure_partial decides from the host state: a partial that happens to be current now
+            // (e.g. after itcpd_mttkrp in the per-hook path) would leave its GEMM out of every replayed sweep.  Capture from the
+            // state every replay starts in -- both partials stale -- and put the host state back if the capture fails.
+            uint64_t fver0[ITCPD_MAX_ORDER];
+            bool mvalid0[ITCPD_MAX_ORDER];
+            memcpy(fver0, c->fver, sizeof(fver0));
+            memcpy(mvalid0, c->m_valid, sizeof(mvalid0));
+            const int last0 = c->last_mttkrp_mode;
+            c->PA.valid = c->PB.valid = false;
             CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
             int st = one_sweep_device(c, chol_tol);
             cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            // nothing ran: the device still holds the pre-capture factors, so the captured sweep's bookkeeping is undone either way
+            memcpy(c->fver, fver0, sizeof(fver0));
+            memcpy(c->m_valid, mvalid0, sizeof(mvalid0));
+            c->last_mttkrp_mode = last0;
+            c->PA.valid = c->PB.valid = false;
+            c->gemm_join_pending = false;
             if (st != ITCPD_OK || e != cudaSuccess || !graph) {
                 if (graph) cudaGraphDestroy(graph);
                 cudaGetLastError();

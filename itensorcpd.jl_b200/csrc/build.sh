@@ -9,7 +9,11 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 pids=()
 for f in api gemm_dmma gemm_i8 kernels solve qrcp qrcp_wide sampled sampled_sharded peer_graph comm sparse_sign; do
   src="${HERE}/${f}.cu"; obj="${HERE}/_obj/${f}.o"
-  if [[ ! -f "${obj}" || "${src}" -nt "${obj}" || "${HERE}/common.cuh" -nt "${obj}" || "${HERE}/../../include/itcpd_b200.h" -nt "${obj}" ]]; then
+  stale=0
+  for dep in "${src}" "${HERE}"/*.cuh "${HERE}/../../include/itcpd_b200.h"; do
+    [[ ! -f "${obj}" || "${dep}" -nt "${obj}" ]] && stale=1
+  done
+  if [[ "${stale}" == 1 ]]; then
     "${NVCC}" "${FLAGS[@]}" -c "${src}" -o "${obj}" &
     pids+=($!)
   fi

@@ -79,6 +79,7 @@ struct PeerSrc {
     int n;
     const volatile long long *flags;
     long long epoch;
+    const long long *epoch_dev;   // non-null: the epoch to wait for lives in device memory (capturable sweeps, peer_graph.cu)
     double *reduced_out;
 };
 
@@ -107,10 +108,14 @@ struct itcpd_ctx {
     cudaStream_t gemm_stream = nullptr;
     cudaEvent_t ev_gemm_fork = nullptr, ev_gemm_done = nullptr;
     bool gemm_join_pending = false;
-    int chol_alg = 1;  // 0: block kernel (any n), 1: team kernel for n <= 128 (same arithmetic, bitwise), 2: + right-looking for n <= 64 (experimental)
-    // chol_alg = 3 (experimental): right-looking kernels only where the factorisation is EXPOSED (no GEMM runs in that mode's update, or
-    // R > 64 where no factorisation kernel can share an SM with a GEMM CTA); the team kernel (40 registers: co-resident) where it hides
+    // chol_alg: 0 block kernel (any n); 1 team kernel for n <= 128 (same arithmetic, bitwise); 2 right-looking kernels for n <= 128;
+    // 3 (default) right-looking only where the factorisation is EXPOSED (no GEMM runs in that mode's update, or R > 64 where no
+    // factorisation kernel can share an SM with a GEMM CTA), the team kernel (40 registers: co-resident with a GEMM CTA) where it hides
+    int chol_alg = 3;
     bool chol_exposed = true;   // set by the sweep driver before every factorisation
+    // solve_alg: 0 one WARP per right-hand side (any n <= 1024); 1 (default) one THREAD per right-hand side for n <= 64, vector in
+    // registers, fully unrolled substitution (same operations in the same order: bitwise the warp kernel), rank-deficient fallback in place
+    int solve_alg = 1;
     int64_t launches = 0;
 
     // options
@@ -179,7 +184,7 @@ struct itcpd_ctx {
     // option "graph_single" (off by default, not yet run on hardware): the reference-facing loop calls itcpd_sweep(1) once per
     // iteration (optimize.jl:15-31), which never reaches the nsweeps >= 3 rule; with the option on, the second single-sweep call
     // with an unchanged configuration captures the graph and later calls replay it
-    int graph_single = 0;
+    int graph_single = 1;
     int64_t plain_sweep_key[24] = {0};
     bool plain_sweep_key_valid = false;
     int64_t sweep_graph_launches = 0;
@@ -199,7 +204,7 @@ struct itcpd_ctx {
     itcpd::DevBuf lev_gather;     // all-gathered leverage scores of the sharded factor (sampled_sharded.cu)
     // peer_graph.cu (option "peer_graph", off by default): device-side exchange epochs [0] partial-M, [1] small all-reduce;
     // small slots live behind the partial-M slots of the exchange buffer
-    int peer_graph = 0;
+    int peer_graph = 1;
     itcpd::DevBuf peer_epochs;
     size_t peer_small_off = 0;
     int64_t peer_small_doubles = 0;

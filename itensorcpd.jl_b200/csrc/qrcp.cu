@@ -8,6 +8,7 @@
 // it only runs when the pivoted Cholesky met a pivot <= tol), then one thread per right-hand side
 // applies Q^T, the triangular solve and Z^T.  The kernels exit immediately unless status[0] == QRCP.
 #include "common.cuh"
+#include "qrcp_rows.cuh"
 #include <cfloat>
 
 namespace itcpd {
@@ -242,64 +243,55 @@ __global__ void __launch_bounds__(QT) qrcp_factor_kernel(const double *__restric
     }
 }
 
-// one thread per right-hand side: b <- Q^T b; solve T11; zero tail; apply Z^T; scatter through jpvt
+// one thread per right-hand side: b <- Q^T b; solve T11; zero tail; apply Z^T; scatter through jpvt (qrcp_rows.cuh)
 __global__ void __launch_bounds__(64) qrcp_solve_rows_kernel(const double *__restrict__ ws, const int *__restrict__ jpvt,
                                                              const int *__restrict__ status, const double *__restrict__ M, int64_t rows,
                                                              int m, int n, double *__restrict__ X, double *__restrict__ bglob, int force) {
     if (!force && status[0] != ITCPD_SOLVE_QRCP) return;
     const int64_t i = blockIdx.x * 64ll + threadIdx.x;
     if (i >= rows) return;
-    const double *A = ws, *tau = A + (size_t)m * n, *tauz = tau + n;
-    const int rnk = status[1];
-    double *b = bglob + i;
-#define BV(k) b[(int64_t)(k) * rows]
-    for (int k = 0; k < m; ++k) BV(k) = M[i + rows * (int64_t)k];
-    // Q^T b = H_{n-1} ... H_0 b applied in order 0..n-1
-    for (int j = 0; j < n; ++j) {
-        double dot = BV(j);
-        for (int q = j + 1; q < m; ++q) dot = fma(A[q + (size_t)m * j], BV(q), dot);
-        const double f = tau[j] * dot;
-        BV(j) -= f;
-        for (int q = j + 1; q < m; ++q) BV(q) = fma(-f, A[q + (size_t)m * j], BV(q));
-    }
-    // T11 y = (Q^T b)(0:rnk)
-    for (int k = rnk - 1; k >= 0; --k) {
-        double s = BV(k);
-        for (int q = k + 1; q < rnk; ++q) s = fma(-A[k + (size_t)m * q], BV(q), s);
-        BV(k) = s / A[k + (size_t)m * k];
-    }
-    for (int k = rnk; k < n; ++k) BV(k) = 0.0;
-    // Z^T y: Z = Z_0 Z_1 ... Z_{rnk-1}; Z^T y applies Z_{rnk-1}^T first ... LAPACK dormrz('L','T') loops i = 0..rnk-1
-    const int l = n - rnk;
-    if (l > 0) {
-        for (int j = 0; j < rnk; ++j) {
-            double dot = BV(j);
-            for (int q = 0; q < l; ++q) dot = fma(A[j + (size_t)m * (rnk + q)], BV(rnk + q), dot);
-            const double f = tauz[j] * dot;
-            BV(j) -= f;
-            for (int q = 0; q < l; ++q) BV(rnk + q) = fma(-f, A[j + (size_t)m * (rnk + q)], BV(rnk + q));
-        }
-    }
-    for (int k = 0; k < n; ++k) X[i + rows * (int64_t)jpvt[k]] = BV(k);
-#undef BV
+    qrcp_row_solve(ws, jpvt, status[1], M, rows, m, n, X, bglob, i);
+}
+
+// workspace of the fallback: the factor behind the Cholesky factor in solve_ws, the pivots behind the Cholesky pivots
+int qrcp_workspace(itcpd_ctx *c, int m, int n, int64_t rows, QrcpWs *w) {
+    const size_t chol_doubles = (size_t)(n | 1) * n + n;            // the Cholesky factor lives in front (solve.cu)
+    const size_t ws_doubles = (size_t)m * n + 8 * (size_t)n;
+    TRY(c->solve_ws.reserve((chol_doubles + ws_doubles) * 8 + 1024));
+    TRY(c->ipiv.reserve((size_t)n * 4 * 2));
+    if (rows > 0) TRY(c->work.reserve((size_t)rows * m * 8));
+    w->ws = c->solve_ws.as<double>() + chol_doubles;
+    w->jpvt = c->ipiv.as<int>() + n;
+    w->bglob = c->work.as<double>();
+    return ITCPD_OK;
+}
+
+// the factorisation half alone: depends on A (and the status word) only, so the sweep driver runs it right behind the
+// pivoted Cholesky on the side stream; it exits immediately unless the Cholesky failed (or `force`)
+int qrcp_factor_only(itcpd_ctx *c, const double *A, int m, int n, int64_t rows, int *status_dev, int force) {
+    ARG_CHECK(m >= n && n >= 1, "pivoted-QR least squares needs a tall (m >= n) matrix");
+    QrcpWs w;
+    TRY(qrcp_workspace(c, m, n, rows, &w));
+    qrcp_factor_kernel<<<1, QT, 0, c->stream>>>(A, m, n, w.ws, w.jpvt, status_dev, force);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
+int qrcp_rows_only(itcpd_ctx *c, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force) {
+    QrcpWs w;
+    TRY(qrcp_workspace(c, m, n, rows, &w));
+    qrcp_solve_rows_kernel<<<(unsigned)ceil_div(rows, 64), 64, 0, c->stream>>>(w.ws, w.jpvt, status_dev, Bt, rows, m, n, X, w.bglob, force);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
 }
 
 // min-norm least squares  X (rows x n) = (A \\ B^T)^T  for a tall column-major A (m x n, m >= n) and the rows x m
 // matrix Bt whose row i is right-hand side i.  `force` = 0: run only when status[0] says the Cholesky failed.
 int qrcp_ls_solve(itcpd_ctx *c, const double *A, int m, int n, const double *Bt, int64_t rows, double *X, int *status_dev, int force) {
-    ARG_CHECK(m >= n && n >= 1, "pivoted-QR least squares needs a tall (m >= n) matrix");
-    const size_t chol_doubles = (size_t)(n | 1) * n + n;            // the Cholesky factor lives in front (solve.cu)
-    const size_t ws_doubles = (size_t)m * n + 8 * (size_t)n;
-    TRY(c->solve_ws.reserve((chol_doubles + ws_doubles) * 8 + 1024));
-    TRY(c->ipiv.reserve((size_t)n * 4 * 2));
-    double *ws = c->solve_ws.as<double>() + chol_doubles;
-    int *jp = c->ipiv.as<int>() + n;
-    TRY(c->work.reserve((size_t)rows * m * 8));
-    qrcp_factor_kernel<<<1, QT, 0, c->stream>>>(A, m, n, ws, jp, status_dev, force);
-    qrcp_solve_rows_kernel<<<(unsigned)ceil_div(rows, 64), 64, 0, c->stream>>>(ws, jp, status_dev, Bt, rows, m, n, X, c->work.as<double>(), force);
-    c->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    return ITCPD_OK;
+    TRY(qrcp_factor_only(c, A, m, n, rows, status_dev, force));
+    return qrcp_rows_only(c, m, n, Bt, rows, X, status_dev, force);
 }
 
 int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {

@@ -7,9 +7,35 @@
 //   * chol_solve_warp_kernel: one WARP per right-hand side (a row of M); the vector lives in registers
 //     (lane l owns entries l, l+32, ...), each substitution step is one shuffle broadcast + E FMAs.
 #include "common.cuh"
+#include "qrcp_rows.cuh"
 #include <cfloat>
 
 namespace itcpd {
+
+// fused all-reduce, first half: wait until every peer has published its partial M for this exchange (system-scope flags
+// written by the peers' signal kernels into OUR memory).  The epoch is a kernel argument (host-counted exchanges) or, for
+// sweeps that are replayed from a CUDA graph, a word in device memory that the signal kernel advanced (peer_graph.cu).
+// Bounded: a peer that died must surface as a launch failure on this rank, not as a hung box.  All threads must call.
+__device__ __forceinline__ void peer_wait_all(const PeerSrc &src) {
+    if (!src.flags) return;
+    if ((int)threadIdx.x < src.n) {
+        const long long epoch = src.epoch_dev ? *src.epoch_dev : src.epoch;
+        unsigned long long t0 = 0, spins = 0;
+        while (src.flags[threadIdx.x] < epoch) {
+            if ((++spins & 0xfffff) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > ITCPD_PEER_TIMEOUT_NS) {
+                    if (blockIdx.x == 0) printf("itcpd: peer %d never published exchange %lld\n", (int)threadIdx.x, epoch);
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
 
 constexpr int CH_THREADS = 256;
 
@@ -237,7 +263,7 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_team_kernel(cons
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
-// ---- right-looking variant for n <= 64 (chol_alg = 2, EXPERIMENTAL: not the default, not yet run on hardware) -----
+// ---- right-looking variant for n <= 64 (chol_alg = 2, and chol_alg = 3 where the factorisation is exposed) -----
 // The left-looking dot is what the team kernel's dependent chain is made of (profiles/r1_cholesky_probe.txt).  Here
 // thread k owns ORIGINAL column k of the trailing matrix in registers for the whole factorisation and nothing is ever
 // swapped: a step is  pivot search -> u_k = A[q,k] / d  (q = pivot column; a uniform dynamic register index, read
@@ -368,7 +394,7 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
     if (tid == 0) { status[0] = (rank == n) ? ITCPD_SOLVE_CHOLESKY : ITCPD_SOLVE_QRCP; status[1] = rank; status[2] = (rank == n) ? 0 : 1; }
 }
 
-// ---- right-looking variant for 64 < n <= 128 (chol_alg = 2, EXPERIMENTAL like the kernel above) --------------------------
+// ---- right-looking variant for 64 < n <= 128 (chol_alg = 2 / 3) -------------------------------------------------------
 // A 128-entry column does not fit one thread's registers, so every column is owned by TWO threads: thread (k, h) keeps rows
 // 64 h .. 64 h + 63 of original column k (k = tid & 127, h = tid >> 7: 256 threads).  The pivot search runs on the h = 0 threads
 // (they carry the running diagonals; both halves update theirs identically from the published u), the thread whose half holds
@@ -490,27 +516,7 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
                                                                          int64_t rows, int n, double *__restrict__ X, int u_in_smem,
                                                                          int fwd_only, int nn_dev_slot) {
     extern __shared__ double sm_dyn[];
-    if (src.flags) {
-        // fused all-reduce: wait until every peer has published its partial M for this exchange (system-scope flags
-        // written by peer_signal_kernel into OUR memory), then sum the peers' rows in rank order while loading them
-        if (threadIdx.x < src.n) {
-            // bounded: a peer that died must surface as a launch failure on this rank, not as a hung box
-            unsigned long long t0 = 0, spins = 0;
-            while (src.flags[threadIdx.x] < src.epoch) {
-                if ((++spins & 0xfffff) == 0) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > ITCPD_PEER_TIMEOUT_NS) {
-                        if (blockIdx.x == 0) printf("itcpd: peer %d never published exchange %lld\n", (int)threadIdx.x, src.epoch);
-                        __trap();
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        __threadfence_system();
-    }
+    peer_wait_all(src);
     const bool chol_ok = fwd_only || status[0] == ITCPD_SOLVE_CHOLESKY;
     if (!chol_ok && !src.reduced_out) return;  // the QRCP path handles this system
     const int ldw = n | 1;
@@ -604,6 +610,99 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
     }
 }
 
+// ---- one THREAD per right-hand side (n <= NMAX <= 64; solve_alg = 1, the default) -----------------------------------------
+// The warp kernel above pays a shuffle + a dependent multiply per substitution step (2 n steps, ~190 ns each: 24-29 us per
+// launch whatever the row count).  Here thread i owns right-hand side i with the whole vector in registers, the loops are
+// fully unrolled (static register indices), every factor entry is a broadcast shared-memory read, and the dependent chain of
+// a step is one multiply + one fma.  Loads and stores are coalesced across the threads of a warp (consecutive rows of a
+// column-major matrix) for any pivot order.  Every element sees the operations of the warp kernel in the same order:
+// the results are bitwise identical (tests/test_gpu_dense.py::test_thread_solve_is_bitwise_the_warp_kernel).
+// The rank-deficient fallback (qrcp_rows.cuh; its factorisation ran behind the Cholesky) is taken in place, so a
+// mode update needs no extra no-op launches on its critical path.
+constexpr int TSR_THREADS = 64;   // 64 x 216 registers and 34 KB of shared memory: a CTA fits next to a persistent GEMM CTA (early_pass_b)
+constexpr int TSR_ROWS = 64;
+
+template <int NMAX>
+__global__ void __launch_bounds__(TSR_THREADS, 1) chol_solve_thread_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
+                                                                        const int *__restrict__ status, PeerSrc src, int64_t rows, int n,
+                                                                        double *__restrict__ X, QrcpWs qr) {
+    constexpr int LDU = NMAX + 1;
+    __shared__ double s_U[NMAX * LDU];   // s_U[k * LDU + l] = U[k, l] (k <= l < n), 0 elsewhere
+    __shared__ double s_rd[NMAX];        // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
+    __shared__ int s_pv[NMAX];
+    peer_wait_all(src);
+    const bool chol_ok = status[0] == ITCPD_SOLVE_CHOLESKY;
+    const int ldw = n | 1;
+    const int tid = threadIdx.x;
+    if (chol_ok) {
+#pragma unroll 16
+        for (int e = tid; e < NMAX * NMAX; e += TSR_THREADS) {
+            const int l = e / NMAX, k = e - l * NMAX;   // consecutive threads read consecutive k of column l
+            s_U[k * LDU + l] = (k <= l && l < n) ? Wg[k + (size_t)ldw * l] : 0.0;
+        }
+        for (int e = tid; e < NMAX; e += TSR_THREADS) s_rd[e] = (e < n) ? 1.0 / Wg[e + (size_t)ldw * e] : 0.0;
+    }
+    for (int e = tid; e < NMAX; e += TSR_THREADS) s_pv[e] = (e < n) ? piv[e] : 0;
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)TSR_ROWS + tid;
+    if (tid >= TSR_ROWS || i >= rows) return;
+    if (!chol_ok) {
+        // rank deficient: reduce the peers' rows (unpermuted) into M, then the pivoted-QR min-norm solve of this row
+        const double *Mrow = src.p[0];
+        if (src.reduced_out) {
+            for (int k = 0; k < n; ++k) {
+                const int64_t off = i + rows * (int64_t)k;
+                double v = 0.0;
+                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
+                src.reduced_out[off] = v;
+            }
+            Mrow = src.reduced_out;
+        }
+        qrcp_row_solve(qr.ws, qr.jpvt, status[1], Mrow, rows, n, n, X, qr.bglob, i);
+        return;
+    }
+    double b[NMAX];
+    if (src.reduced_out) {
+#pragma unroll
+        for (int k = 0; k < NMAX; ++k) {
+            b[k] = 0.0;
+            if (k < n) {
+                const int64_t off = i + rows * (int64_t)s_pv[k];
+                double v = 0.0;
+                for (int q = 0; q < src.n; ++q) v += src.p[q][off];   // fixed rank order: identical bits on every rank
+                src.reduced_out[off] = v;
+                b[k] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NMAX; ++k) b[k] = (k < n) ? src.p[0][i + rows * (int64_t)s_pv[k]] : 0.0;
+    }
+    // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+        if (k < n) {
+            const double yk = b[k] * s_rd[k];
+            b[k] = yk;
+#pragma unroll
+            for (int l = k + 1; l < NMAX; ++l) b[l] = fma(-s_U[k * LDU + l], yk, b[l]);
+        }
+    }
+    // backward: U x = y  (after x_k is known, y_l -= U[l,k] x_k for l < k)
+#pragma unroll
+    for (int k = NMAX - 1; k >= 0; --k) {
+        if (k < n) {
+            const double xk = b[k] * s_rd[k];
+            b[k] = xk;
+#pragma unroll
+            for (int l = 0; l < k; ++l) b[l] = fma(-s_U[l * LDU + k], xk, b[l]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+        if (k < n) X[i + rows * (int64_t)s_pv[k]] = b[k];
+}
+
 // dynamic shared memory budget: 227 KB per CTA minus the static arrays of these kernels (pivots, reciprocal diagonal)
 static int smem_limit(itcpd_ctx *) { return 208 * 1024; }
 
@@ -688,14 +787,6 @@ static int run_tri_solves(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, d
     return ITCPD_ERR_UNSUPPORTED;
 }
 
-int qrcp_minnorm_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev);  // qrcp.cu
-
-// The factorisation only needs Gamma (the Gram-Hadamard), not the MTTKRP, so the sweep driver runs it on a
-// side stream underneath the GEMM pass; k_solve_apply then joins and applies it to the rows of M.
-int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
-    return run_cholesky(c, Gamma, R, tol, status_dev);
-}
-
 static PeerSrc single_src(const double *M) {
     PeerSrc s;
     memset(&s, 0, sizeof(s));
@@ -704,27 +795,52 @@ static PeerSrc single_src(const double *M) {
     return s;
 }
 
-int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
-    TRY(run_tri_solves(c, single_src(M), rows, R, X, status_dev, 0, 1));
-    TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
+static bool thread_solve_ok(const itcpd_ctx *c, int R) { return c->solve_alg == 1 && R <= 64; }
+
+static int run_thread_solves(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev) {
+    QrcpWs w;
+    TRY(qrcp_workspace(c, R, R, rows, &w));
+    const unsigned grid = (unsigned)ceil_div(rows, TSR_ROWS);
+    if (R <= 16) chol_solve_thread_kernel<16><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
+    else if (R <= 32) chol_solve_thread_kernel<32><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
+    else chol_solve_thread_kernel<64><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
+}
+
+// The factorisation only needs Gamma (the Gram-Hadamard), not the MTTKRP, so the sweep driver runs it on a side stream
+// underneath the GEMM pass; k_solve_apply then joins and applies it to the rows of M.  The factorisation half of the
+// rank-deficient fallback (pivoted QR; a device-side early exit unless the Cholesky stopped at a pivot <= tol) rides along,
+// so that the apply step is a single launch.
+int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
+    TRY(run_cholesky(c, Gamma, R, tol, status_dev));
+    return qrcp_factor_only(c, Gamma, R, R, 0, status_dev, 0);
+}
+
+static int apply_rows(itcpd_ctx *c, const PeerSrc &src, const double *Mreduced, int64_t rows, int R, double *X, int *status_dev) {
+    if (thread_solve_ok(c, R)) return run_thread_solves(c, src, rows, R, X, status_dev);
+    TRY(run_tri_solves(c, src, rows, R, X, status_dev, 0, 1));
+    // rank-deficient systems are re-solved by the pivoted-QR min-norm path (a device-side early exit on status[0] when
+    // the Cholesky succeeded, so no host round trip is needed)
+    return qrcp_rows_only(c, R, R, Mreduced, rows, X, status_dev, 0);
+}
+
+int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
+    (void)Gamma;
+    return apply_rows(c, single_src(M), M, rows, R, X, status_dev);
 }
 
 // fused all-reduce + solve: the right-hand sides are the sum of the peers' partial MTTKRPs (read over NVLink while
 // loading); src.reduced_out (this rank's M buffer) receives the reduced matrix for the rank-deficient fallback
 int k_solve_apply_peers(itcpd_ctx *c, const double *Gamma, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev) {
-    TRY(run_tri_solves(c, src, rows, R, X, status_dev, 0, 1));
-    TRY(qrcp_minnorm_solve(c, Gamma, src.reduced_out, rows, R, X, status_dev));
-    return ITCPD_OK;
+    (void)Gamma;
+    return apply_rows(c, src, src.reduced_out, rows, R, X, status_dev);
 }
 
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev) {
-    TRY(run_cholesky(c, Gamma, R, tol, status_dev));
-    TRY(run_tri_solves(c, single_src(M), rows, R, X, status_dev, 0, 1));
-    // rank-deficient systems are re-solved by the pivoted-QR min-norm path; it is a no-op (device-side
-    // early exit on status[0]) when the Cholesky succeeded, so no host round trip is needed here.
-    TRY(qrcp_minnorm_solve(c, Gamma, M, rows, R, X, status_dev));
-    return ITCPD_OK;
+    TRY(k_solve_factor(c, Gamma, R, tol, status_dev));
+    return k_solve_apply(c, Gamma, M, rows, R, X, status_dev);
 }
 
 // leverage scores (math_tools/probability.jl:3-10): p_i = ||Q[i,:]||^2 / min(I,R) with A = QR.
