@@ -332,7 +332,12 @@ int itcpd_create(itcpd_ctx **out, int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->gemm_stream, cudaStreamNonBlocking));
+    {   // early_pass_b: the pass-B GEMM must win the SMs over the small, many-CTA kernels of the modes updated underneath it,
+        // or it only starts once they have drained (measured: no gain without the priority)
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->gemm_stream, cudaStreamNonBlocking, hi));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gemm_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_gemm_done, cudaEventDisableTiming));
     if (const char *s = getenv("ITCPD_EARLY_B")) c->early_pass_b = atoi(s) != 0;   // experimental
@@ -340,7 +345,6 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(3, std::max(0, atoi(s)));
-    if (const char *s = getenv("ITCPD_SOLVE")) c->solve_alg = std::min(1, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
@@ -423,7 +427,6 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
         c->peer_graph = value != 0;
     }
     else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 3, "chol_alg must be 0, 1, 2 or 3"); c->chol_alg = (int)value; }
-    else if (n == "solve_alg") { ARG_CHECK(value == 0 || value == 1, "solve_alg must be 0 (warp per row) or 1 (thread per row for R <= 64)"); c->solve_alg = (int)value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     c->graph_epoch++;

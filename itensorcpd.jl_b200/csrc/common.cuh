@@ -113,9 +113,6 @@ struct itcpd_ctx {
     // factorisation kernel can share an SM with a GEMM CTA), the team kernel (40 registers: co-resident with a GEMM CTA) where it hides
     int chol_alg = 3;
     bool chol_exposed = true;   // set by the sweep driver before every factorisation
-    // solve_alg: 0 one WARP per right-hand side (any n <= 1024); 1 (default) one THREAD per right-hand side for n <= 64, vector in
-    // registers, fully unrolled substitution (same operations in the same order: bitwise the warp kernel), rank-deficient fallback in place
-    int solve_alg = 1;
     int64_t launches = 0;
 
     // options

@@ -514,29 +514,57 @@ template <int E>
 __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
                                                                          const int *__restrict__ status, PeerSrc src,
                                                                          int64_t rows, int n, double *__restrict__ X, int u_in_smem,
-                                                                         int fwd_only, int nn_dev_slot) {
+                                                                         int fwd_only, int nn_dev_slot, QrcpWs qr) {
     extern __shared__ double sm_dyn[];
     peer_wait_all(src);
     const bool chol_ok = fwd_only || status[0] == ITCPD_SOLVE_CHOLESKY;
-    if (!chol_ok && !src.reduced_out) return;  // the QRCP path handles this system
     const int ldw = n | 1;
     const double *U = Wg;
     __shared__ double s_rd[1024];  // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
-    double *s_rows = sm_dyn + (u_in_smem ? (size_t)ldw * n : 0);  // TSW_WARPS x 1024 doubles, only when src.reduced_out
-    for (int e = threadIdx.x; e < n; e += TSW_WARPS * 32) s_rd[e] = 1.0 / Wg[e + (size_t)ldw * e];
-    if (u_in_smem) {
-        for (int e = threadIdx.x; e < ldw * n; e += TSW_WARPS * 32) sm_dyn[e] = Wg[e];
-        U = sm_dyn;
+    __shared__ int s_pv[1024];
+    double *s_rows = sm_dyn + (u_in_smem ? (((size_t)ldw * n + 1) & ~(size_t)1) : 0);  // TSW_WARPS x 1024 doubles, only when src.reduced_out
+    if (chol_ok) {
+        for (int e = threadIdx.x; e < n; e += TSW_WARPS * 32) { s_rd[e] = 1.0 / Wg[e + (size_t)ldw * e]; s_pv[e] = piv[e]; }
+        if (u_in_smem) {
+            // the workspace is 16-byte aligned and holds ldw * n + n doubles: stage it with 16-byte loads, a batch in flight per thread
+            if (((reinterpret_cast<uintptr_t>(Wg) | reinterpret_cast<uintptr_t>(sm_dyn)) & 15) == 0) {
+                const int n2 = (ldw * n + 1) >> 1;
+                const double2 *g2 = reinterpret_cast<const double2 *>(Wg);
+                double2 *s2 = reinterpret_cast<double2 *>(sm_dyn);
+#pragma unroll 4
+                for (int e = threadIdx.x; e < n2; e += TSW_WARPS * 32) s2[e] = g2[e];
+            } else {
+                for (int e = threadIdx.x; e < ldw * n; e += TSW_WARPS * 32) sm_dyn[e] = Wg[e];
+            }
+            U = sm_dyn;
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t i = blockIdx.x * (int64_t)TSW_WARPS + (threadIdx.x >> 5);
     if (i >= rows) return;
+    if (!chol_ok) {
+        // rank deficient (the pivoted Cholesky met a pivot <= tol): reduce the peers' rows if any, then lane 0 runs the pivoted-QR
+        // min-norm solve of this row (qrcp_rows.cuh; its factorisation ran right behind the Cholesky).  Rare path: one lane per row.
+        const double *Mrow = src.p[0];
+        if (src.reduced_out) {
+            for (int k = lane; k < n; k += 32) {
+                const int64_t off = i + rows * (int64_t)k;
+                double v = 0.0;
+                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
+                src.reduced_out[off] = v;
+            }
+            __syncwarp();
+            Mrow = src.reduced_out;
+        }
+        if (lane == 0) qrcp_row_solve(qr.ws, qr.jpvt, status[1], Mrow, rows, n, n, X, qr.bglob, i);
+        return;
+    }
     const int nn = fwd_only ? status[nn_dev_slot] : n;
     double b[E];
     if (src.reduced_out) {
         // fused all-reduce: every peer's row is read ONCE (unpermuted, coalesced, fixed rank order: identical bits on
-        // every rank), stored as the reduced matrix (rank-deficient fallback / later readers) and permuted through a
+        // every rank), stored as the reduced matrix (later readers: the fit) and permuted through a
         // per-warp shared-memory row
         double *rowbuf = s_rows + (size_t)(threadIdx.x >> 5) * 1024;
 #pragma unroll
@@ -550,18 +578,17 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
                 rowbuf[k] = v;
             }
         }
-        if (!chol_ok) return;
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = lane + 32 * e;
-            b[e] = (k < n) ? rowbuf[piv[k]] : 0.0;
+            b[e] = (k < n) ? rowbuf[s_pv[k]] : 0.0;
         }
     } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int k = lane + 32 * e;
-            b[e] = (k < n) ? src.p[0][i + rows * (int64_t)piv[k]] : 0.0;
+            b[e] = (k < n) ? src.p[0][i + rows * (int64_t)s_pv[k]] : 0.0;
         }
     }
     // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
@@ -606,101 +633,8 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int k = lane + 32 * e;
-        if (k < n) X[i + rows * (int64_t)piv[k]] = b[e];
+        if (k < n) X[i + rows * (int64_t)s_pv[k]] = b[e];
     }
-}
-
-// ---- one THREAD per right-hand side (n <= NMAX <= 64; solve_alg = 1, the default) -----------------------------------------
-// The warp kernel above pays a shuffle + a dependent multiply per substitution step (2 n steps, ~190 ns each: 24-29 us per
-// launch whatever the row count).  Here thread i owns right-hand side i with the whole vector in registers, the loops are
-// fully unrolled (static register indices), every factor entry is a broadcast shared-memory read, and the dependent chain of
-// a step is one multiply + one fma.  Loads and stores are coalesced across the threads of a warp (consecutive rows of a
-// column-major matrix) for any pivot order.  Every element sees the operations of the warp kernel in the same order:
-// the results are bitwise identical (tests/test_gpu_dense.py::test_thread_solve_is_bitwise_the_warp_kernel).
-// The rank-deficient fallback (qrcp_rows.cuh; its factorisation ran behind the Cholesky) is taken in place, so a
-// mode update needs no extra no-op launches on its critical path.
-constexpr int TSR_THREADS = 64;   // 64 x 216 registers and 34 KB of shared memory: a CTA fits next to a persistent GEMM CTA (early_pass_b)
-constexpr int TSR_ROWS = 64;
-
-template <int NMAX>
-__global__ void __launch_bounds__(TSR_THREADS, 1) chol_solve_thread_kernel(const double *__restrict__ Wg, const int *__restrict__ piv,
-                                                                        const int *__restrict__ status, PeerSrc src, int64_t rows, int n,
-                                                                        double *__restrict__ X, QrcpWs qr) {
-    constexpr int LDU = NMAX + 1;
-    __shared__ double s_U[NMAX * LDU];   // s_U[k * LDU + l] = U[k, l] (k <= l < n), 0 elsewhere
-    __shared__ double s_rd[NMAX];        // reciprocal diagonal (what OpenBLAS' trsm kernels multiply by)
-    __shared__ int s_pv[NMAX];
-    peer_wait_all(src);
-    const bool chol_ok = status[0] == ITCPD_SOLVE_CHOLESKY;
-    const int ldw = n | 1;
-    const int tid = threadIdx.x;
-    if (chol_ok) {
-#pragma unroll 16
-        for (int e = tid; e < NMAX * NMAX; e += TSR_THREADS) {
-            const int l = e / NMAX, k = e - l * NMAX;   // consecutive threads read consecutive k of column l
-            s_U[k * LDU + l] = (k <= l && l < n) ? Wg[k + (size_t)ldw * l] : 0.0;
-        }
-        for (int e = tid; e < NMAX; e += TSR_THREADS) s_rd[e] = (e < n) ? 1.0 / Wg[e + (size_t)ldw * e] : 0.0;
-    }
-    for (int e = tid; e < NMAX; e += TSR_THREADS) s_pv[e] = (e < n) ? piv[e] : 0;
-    __syncthreads();
-    const int64_t i = blockIdx.x * (int64_t)TSR_ROWS + tid;
-    if (tid >= TSR_ROWS || i >= rows) return;
-    if (!chol_ok) {
-        // rank deficient: reduce the peers' rows (unpermuted) into M, then the pivoted-QR min-norm solve of this row
-        const double *Mrow = src.p[0];
-        if (src.reduced_out) {
-            for (int k = 0; k < n; ++k) {
-                const int64_t off = i + rows * (int64_t)k;
-                double v = 0.0;
-                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
-                src.reduced_out[off] = v;
-            }
-            Mrow = src.reduced_out;
-        }
-        qrcp_row_solve(qr.ws, qr.jpvt, status[1], Mrow, rows, n, n, X, qr.bglob, i);
-        return;
-    }
-    double b[NMAX];
-    if (src.reduced_out) {
-#pragma unroll
-        for (int k = 0; k < NMAX; ++k) {
-            b[k] = 0.0;
-            if (k < n) {
-                const int64_t off = i + rows * (int64_t)s_pv[k];
-                double v = 0.0;
-                for (int q = 0; q < src.n; ++q) v += src.p[q][off];   // fixed rank order: identical bits on every rank
-                src.reduced_out[off] = v;
-                b[k] = v;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < NMAX; ++k) b[k] = (k < n) ? src.p[0][i + rows * (int64_t)s_pv[k]] : 0.0;
-    }
-    // forward: U^T y = P^T b  (column-oriented: after y_k is known, b_l -= U[k,l] y_k for l > k)
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k) {
-        if (k < n) {
-            const double yk = b[k] * s_rd[k];
-            b[k] = yk;
-#pragma unroll
-            for (int l = k + 1; l < NMAX; ++l) b[l] = fma(-s_U[k * LDU + l], yk, b[l]);
-        }
-    }
-    // backward: U x = y  (after x_k is known, y_l -= U[l,k] x_k for l < k)
-#pragma unroll
-    for (int k = NMAX - 1; k >= 0; --k) {
-        if (k < n) {
-            const double xk = b[k] * s_rd[k];
-            b[k] = xk;
-#pragma unroll
-            for (int l = 0; l < k; ++l) b[l] = fma(-s_U[l * LDU + k], xk, b[l]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k)
-        if (k < n) X[i + rows * (int64_t)s_pv[k]] = b[k];
 }
 
 // dynamic shared memory budget: 227 KB per CTA minus the static arrays of these kernels (pivots, reciprocal diagonal)
@@ -759,7 +693,7 @@ static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, in
 
 template <int E>
 static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
-    const size_t u_bytes = (size_t)(R | 1) * R * 8;
+    const size_t u_bytes = (((size_t)(R | 1) * R + 1) & ~(size_t)1) * 8;   // rounded up to 16 bytes (staged with 16-byte loads)
     const int u_in = u_bytes + (size_t)TSW_WARPS * 1024 * 8 <= (size_t)smem_limit(c);
     auto kern = chol_solve_warp_kernel<E>;
     static bool attr[64] = {false};  // function attributes are per device
@@ -768,8 +702,11 @@ static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, doubl
         attr[c->device & 63] = true;
     }
     const size_t row_bytes = M.reduced_out ? (size_t)TSW_WARPS * 1024 * 8 : 0;
+    QrcpWs w;
+    memset(&w, 0, sizeof(w));
+    if (!fwd_only) TRY(qrcp_workspace(c, R, R, rows, &w));
     kern<<<(unsigned)ceil_div(rows, TSW_WARPS), TSW_WARPS * 32, (u_in ? u_bytes : 0) + row_bytes, c->stream>>>(
-        c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, u_in, fwd_only, slot);
+        c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, u_in, fwd_only, slot, w);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
@@ -795,20 +732,6 @@ static PeerSrc single_src(const double *M) {
     return s;
 }
 
-static bool thread_solve_ok(const itcpd_ctx *c, int R) { return c->solve_alg == 1 && R <= 64; }
-
-static int run_thread_solves(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev) {
-    QrcpWs w;
-    TRY(qrcp_workspace(c, R, R, rows, &w));
-    const unsigned grid = (unsigned)ceil_div(rows, TSR_ROWS);
-    if (R <= 16) chol_solve_thread_kernel<16><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
-    else if (R <= 32) chol_solve_thread_kernel<32><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
-    else chol_solve_thread_kernel<64><<<grid, TSR_THREADS, 0, c->stream>>>(c->solve_ws.as<double>(), c->ipiv.as<int>(), status_dev, M, rows, R, X, w);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return ITCPD_OK;
-}
-
 // The factorisation only needs Gamma (the Gram-Hadamard), not the MTTKRP, so the sweep driver runs it on a side stream
 // underneath the GEMM pass; k_solve_apply then joins and applies it to the rows of M.  The factorisation half of the
 // rank-deficient fallback (pivoted QR; a device-side early exit unless the Cholesky stopped at a pivot <= tol) rides along,
@@ -818,24 +741,22 @@ int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *st
     return qrcp_factor_only(c, Gamma, R, R, 0, status_dev, 0);
 }
 
-static int apply_rows(itcpd_ctx *c, const PeerSrc &src, const double *Mreduced, int64_t rows, int R, double *X, int *status_dev) {
-    if (thread_solve_ok(c, R)) return run_thread_solves(c, src, rows, R, X, status_dev);
-    TRY(run_tri_solves(c, src, rows, R, X, status_dev, 0, 1));
-    // rank-deficient systems are re-solved by the pivoted-QR min-norm path (a device-side early exit on status[0] when
-    // the Cholesky succeeded, so no host round trip is needed)
-    return qrcp_rows_only(c, R, R, Mreduced, rows, X, status_dev, 0);
+// rank-deficient systems take the pivoted-QR min-norm path INSIDE the row-solve kernel (lane 0 of the row's warp runs
+// qrcp_row_solve; the factorisation half ran behind the Cholesky), so a mode update has no no-op launches on its critical path
+static int apply_rows(itcpd_ctx *c, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev) {
+    return run_tri_solves(c, src, rows, R, X, status_dev, 0, 1);
 }
 
 int k_solve_apply(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double *X, int *status_dev) {
     (void)Gamma;
-    return apply_rows(c, single_src(M), M, rows, R, X, status_dev);
+    return apply_rows(c, single_src(M), rows, R, X, status_dev);
 }
 
 // fused all-reduce + solve: the right-hand sides are the sum of the peers' partial MTTKRPs (read over NVLink while
 // loading); src.reduced_out (this rank's M buffer) receives the reduced matrix for the rank-deficient fallback
 int k_solve_apply_peers(itcpd_ctx *c, const double *Gamma, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev) {
     (void)Gamma;
-    return apply_rows(c, src, src.reduced_out, rows, R, X, status_dev);
+    return apply_rows(c, src, rows, R, X, status_dev);
 }
 
 int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, int R, double tol, double *X, int *status_dev) {

@@ -340,6 +340,15 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
     *s = reinterpret_cast<cudaStream_t>(st);
     return cudaSuccess;
 }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned flags, int priority) {
+    if (priority > 0 || priority < -5) violation("cudaStreamCreateWithPriority: priority %d outside the device's range [-5, 0]", priority);
+    return cudaStreamCreateWithFlags(s, flags);
+}
+cudaError_t cudaDeviceGetStreamPriorityRange(int *least, int *greatest) {
+    if (least) *least = 0;
+    if (greatest) *greatest = -5;
+    return cudaSuccess;
+}
 cudaError_t cudaStreamDestroy(cudaStream_t s) {
     std::lock_guard<std::mutex> g(g_mu);
     Stream *st = as_stream(s, "cudaStreamDestroy");

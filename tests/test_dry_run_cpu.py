@@ -141,7 +141,14 @@ def test_bench_line_contract_in_the_dry_run(dry_results, env_extra, args):
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
               "clocks", "gpu_launches", "roofline", "e2e"):
         assert k in line, k
-    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] >= 3 and line["dtype"] == "f64" and line["unit"] == "sweeps/s"
+    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] >= 3 and line["unit"] == "sweeps/s"
+    assert line["dtype"].startswith("i8 digits") if env_extra.get("ITCPD_GEMM_I8") else line["dtype"] == "f64"   # the arithmetic the path computes in
+    assert set(line["config"]) == {"workload", "l2"}   # the keys the reference arm prints too; everything else lives in config_detail
+    assert "parity" in line and "config_detail" in line
+    if not args:   # the default workload carries the other BASELINE.json configurations as compact records
+        assert [r["config"] for r in line["extra"]] == ["D", "C", "A", "E"], line["extra"]
+        for r in line["extra"]:   # (E draws its samples on the device: no kernel runs here, so its host-side pivot check refuses the zeros)
+            assert "error" not in r or r["config"] == "E", r
     assert "workload" in line["config"] and "model" not in line["config"]
     assert line["gpu_launches"] > 0
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):

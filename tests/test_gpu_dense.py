@@ -556,48 +556,6 @@ def test_single_sweep_calls_through_the_graph_are_bitwise_the_plain_calls(engine
         engine.set_option("graph_single", 1)
 
 
-@pytest.mark.parametrize("R", [1, 5, 16, 17, 32, 33, 50, 64])
-def test_thread_solve_is_bitwise_the_warp_kernel(engine, R):
-    """solve.cu: chol_solve_thread_kernel (one thread per right-hand side, vector in registers, fully unrolled) performs the
-    warp kernel's operations in the same order: X must be bitwise identical, on the Cholesky path and on the rank-deficient
-    fallback that the thread kernel takes in place."""
-    dims = (70, 45, 20)
-    T, cp = make_problem(dims, R, seed=211 + R)
-    f = [x.copy() for x in cp.factors]
-    cases = [("full rank", f)]
-    if R >= 5:
-        g = [x.copy() for x in f]
-        for m in range(3):
-            g[m][:, 3] = g[m][:, 1]
-        cases.append(("rank deficient", g))
-    engine.set_option("chol_alg", 1)
-    try:
-        for name, facs in cases:
-            out = {}
-            for alg in (0, 1):
-                engine.set_option("solve_alg", alg)
-                engine.set_tensor(T)
-                engine.set_cpd(facs, cp.lam)
-                engine.compute_grams()
-                res = []
-                for n in range(3):
-                    engine.gram_hadamard(n, fetch=False)
-                    engine.mttkrp(n, fetch=False)
-                    pr = engine.solve(n, 1e-6)
-                    engine.normalize(n)
-                    res.append((pr, engine.get_factor(n), engine.get_lambda()))
-                    engine.set_factor(n, facs[n])
-                out[alg] = res
-            for a, b in zip(out[0], out[1]):
-                assert a[0] == b[0], name
-                assert np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2], equal_nan=True), name
-            if name == "rank deficient":
-                assert out[1][1][0][0] == 1   # the fallback path was taken
-    finally:
-        engine.set_option("solve_alg", 1)
-        engine.set_option("chol_alg", CHOL_DEFAULT)
-
-
 def test_generator_matches_cpu_restatement(engine):
     """oracle/synth.py restates the device's counter-based generator (Philox4x32-10 + Box-Muller on the logical element index):
     the full-size parity trajectories under tests/golden/ were computed by the oracle on tensors regenerated that way."""

@@ -1,6 +1,6 @@
 """The DEFAULT multi-GPU exchange, executed on the host: api.cu's peer_signal_kernel and solve.cu's row-solve kernels -- the
-warp-per-row chol_solve_warp_kernel and the thread-per-row chol_solve_thread_kernel (fused all-reduce + row solve behind the
-bounded flag wait peer_wait_all) -- are compiled verbatim behind
+warp-per-row chol_solve_warp_kernel (fused all-reduce + row solve behind the bounded flag wait peer_wait_all) -- are compiled
+verbatim behind
 tests/simt_emu.h and run as forked "ranks" over a MAP_SHARED exchange buffer.  Every rank must end with
 X = (sum of the ranks' partial M) Gamma^{-1} and with the reduced M stored locally, for several consecutive exchanges
 (epoch parity slots)."""
@@ -30,7 +30,7 @@ HARNESS = r"""
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __trap() { abort(); }
 static unsigned long long emu_globaltimer() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ull + ts.tv_nsec; }
-double sm_dyn[(65 * 64) + 8 * 1024 + 64];
+double sm_dyn[(65 * 64) + 8 * 1024 + 64] __attribute__((aligned(16)));
 namespace itcpd_emu {
 %(peersrc)s
 %(signal)s
@@ -90,15 +90,10 @@ int main(int argc, char **argv) {
                 src.flags = (const volatile long long *)(shared + r * xchg_bytes);
                 src.epoch = epoch;
                 src.reduced_out = Mred.data();
-#if %(THREAD)d
-                const int ctas = (rows + TSR_ROWS - 1) / TSR_ROWS;
-                for (int b = 0; b < ctas; ++b)
-                    emu_launch(TSR_THREADS, 0, [&] { blockIdx.x = b; chol_solve_thread_kernel<%(NMAX)d>(W.data(), piv.data(), status, src, rows, n, X.data(), QrcpWs{nullptr, nullptr, nullptr}); });
-#else
                 const int ctas = (rows + TSW_WARPS - 1) / TSW_WARPS;
                 for (int b = 0; b < ctas; ++b)
-                    emu_launch(TSW_WARPS * 32, 0, [&] { blockIdx.x = b; chol_solve_warp_kernel<%(E)d>(W.data(), piv.data(), status, src, rows, n, X.data(), 1, 0, 1); });
-#endif
+                    emu_launch(TSW_WARPS * 32, 0, [&] { blockIdx.x = b; chol_solve_warp_kernel<%(E)d>(W.data(), piv.data(), status, src, rows, n, X.data(), 1, 0, 1, QrcpWs{nullptr, nullptr, nullptr}); });
+
                 snprintf(path, sizeof(path), "%%s/X_%%d_%%d.bin", dir, x, r);
                 FILE *f = fopen(path, "wb"); fwrite(X.data(), 8, X.size(), f); fclose(f);
                 snprintf(path, sizeof(path), "%%s/R_%%d_%%d.bin", dir, x, r);
@@ -142,15 +137,13 @@ def _extract():
     return peersrc, signal, helper + rows_h[q0:q1] + body
 
 
-@pytest.mark.parametrize("thread_kernel", [0, 1])
-@pytest.mark.parametrize("G,n,rows", [(2, 12, 20), (3, 40, 70)])
-def test_default_peer_exchange_and_fused_solve_emulated(tmp_path, G, n, rows, thread_kernel):
+@pytest.mark.parametrize("G,n,rows", [(2, 12, 20), (3, 40, 17)])
+def test_default_peer_exchange_and_fused_solve_emulated(tmp_path, G, n, rows):
     peersrc, signal, body = _extract()
     os.makedirs(BUILD, exist_ok=True)
     E = (n + 31) // 32
-    NMAX = 16 if n <= 16 else (32 if n <= 32 else 64)
-    cpp, exe = os.path.join(BUILD, f"peer_solve_emu_{E}_{thread_kernel}.cpp"), os.path.join(BUILD, f"peer_solve_emu_{E}_{thread_kernel}")
-    open(cpp, "w").write(HARNESS % {"peersrc": peersrc, "signal": signal, "solve": body, "E": E, "THREAD": thread_kernel, "NMAX": NMAX})
+    cpp, exe = os.path.join(BUILD, f"peer_solve_emu_{E}.cpp"), os.path.join(BUILD, f"peer_solve_emu_{E}")
+    open(cpp, "w").write(HARNESS % {"peersrc": peersrc, "signal": signal, "solve": body, "E": E})
     subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(ROOT, "tests"), "-o", exe, cpp, "-lpthread"], check=True,
                    capture_output=True)
     rng = np.random.default_rng(n)
