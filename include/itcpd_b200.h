@@ -78,6 +78,10 @@ int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);
 
 /* ---- target tensor (ALS.target, als_optimizer.jl:5-10; decompose.jl:5-7 wraps without copy) - */
 int itcpd_set_tensor(itcpd_ctx *ctx, int order, const int64_t *dims, const double *host_colmajor);
+/* Shape only: tells the handle the extents of the target without allocating or touching any tensor storage (the
+ * handle then serves reconstruct / CPD-only calls; every call that reads T fails with ITCPD_ERR_ARG).  Replaces the
+ * `ITensor(inds(target))` shape carrier of the reference (optimizers/.../randomized/qr_lev_score_sampled.jl:77). */
+int itcpd_set_shape(itcpd_ctx *ctx, int order, const int64_t *dims);
 /* i.i.d. N(0,1) entries from a counter-based generator (Philox4x32-10 + Box-Muller); element with
  * global column-major linear index e gets the value of counter (seed, e + elem_offset), so slabs of
  * one big tensor can be generated independently on several GPUs. */

@@ -34,6 +34,7 @@ _SIGS = {
     "itcpd_launch_count": (C.c_int64, [C.c_void_p]),
     "itcpd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "itcpd_set_tensor": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_dp]),
+    "itcpd_set_shape": (C.c_int, [C.c_void_p, C.c_int, c_i64p]),
     "itcpd_generate_tensor": (C.c_int, [C.c_void_p, C.c_int, c_i64p, C.c_uint64, C.c_int64]),
     "itcpd_generate_lowrank_tensor": (C.c_int, [C.c_void_p, C.c_int, c_i64p, C.c_int, C.c_uint64, C.c_double]),
     "itcpd_get_tensor": (C.c_int, [C.c_void_p, c_dp]),

@@ -114,7 +114,7 @@ static void invalidate_all(itcpd_ctx *c) {
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { c->m_valid[n] = false; c->fver[n]++; }
 }
 
-static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
+static int set_shape(itcpd_ctx *c, int order, const int64_t *dims, bool allocate = true) {
     ARG_CHECK(order >= 2 && order <= ITCPD_MAX_ORDER, "tensor order must be in [2,8]");
     int64_t n = 1;
     for (int i = 0; i < order; ++i) {
@@ -126,9 +126,9 @@ static int set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
     c->ld0 = dims[0] + (dims[0] & 1);
     c->nelem = n;
     c->nstore = n / dims[0] * c->ld0;
-    TRY(c->T.reserve((size_t)c->nstore * 8 + 256));
+    if (allocate) TRY(c->T.reserve((size_t)c->nstore * 8 + 256));
     c->has_tensor = true;
-    c->has_tensor_data = true;
+    c->has_tensor_data = allocate;
     for (int n = 0; n < ITCPD_MAX_ORDER; ++n) c->proj_n[n] = 0;  // cached projectors belong to the previous tensor
     choose_splits(c);
     invalidate_all(c);
@@ -449,6 +449,13 @@ int itcpd_set_tensor(itcpd_ctx *c, int order, const int64_t *dims, const double 
     CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ITCPD_OK;
+}
+
+int itcpd_set_shape(itcpd_ctx *c, int order, const int64_t *dims) {
+    CHECK_CTX(c);
+    ARG_CHECK(dims != nullptr, "null dims");
+    USE_DEVICE(c);
+    return set_shape(c, order, dims, false);
 }
 
 int itcpd_generate_tensor(itcpd_ctx *c, int order, const int64_t *dims, uint64_t seed, int64_t elem_offset) {

@@ -83,6 +83,11 @@ class Engine:
         self.dims = tuple(int(d) for d in dims)
         check(self._L.itcpd_set_tensor(self._h, len(self.dims), self._dims_arg(self.dims), _addr(T)))
 
+    def set_shape(self, dims):
+        """extents only: no tensor storage is allocated or touched (reconstruct / CPD-only use of a handle)"""
+        self.dims = tuple(int(d) for d in dims)
+        check(self._L.itcpd_set_shape(self._h, len(self.dims), self._dims_arg(self.dims)))
+
     def generate_tensor(self, dims, seed: int = 0, elem_offset: int = 0):
         self.dims = tuple(int(d) for d in dims)
         check(self._L.itcpd_generate_tensor(self._h, len(self.dims), self._dims_arg(self.dims), int(seed), int(elem_offset)))

@@ -439,7 +439,7 @@ def _proj_range(alg, n, dRis):
 
 
 def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed,
-                       guess_num_levs=None, prelim_niter=10) -> "ALS":
+                       guess_num_levs=None, prelim_niter=10, owns_tensor=True) -> "ALS":
     """optimizers/.../randomized/qr_lev_score_sampled.jl:1-78 (QRPivProjected), :80-176 (SEQRCSPivProjected) and
     :178-282 (KSEQRCSPivProjected)."""
     from .engine import column_to_multi_coords
@@ -490,8 +490,12 @@ def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots,
         projectors.append(proj)
         eng.set_projector(n, proj)   # gathers + caches target_transform[n] on the device
     extra = dict(ref_projectors=ref_pivs, projects=pivots, projects_tensors=projectors, effective_ranks=eff,
-                 normal=True if normal is None else normal, dims=tuple(dims))
-    eng.drop_tensor()  # ALS(ITensor(inds(target)), ...): only the samples are needed from here on (:77, :175)
+                 normal=True if normal is None else normal, dims=tuple(dims), owns_tensor=owns_tensor)
+    if owns_tensor:
+        # ALS(ITensor(inds(target)), ...): only the samples are needed from here on (:77, :175).  The reference drops ITS reference to
+        # the tensor, not the caller's: a tensor that lives in an Engine the caller passed in (rank-adaptive decompose keeps it
+        # resident across rank steps, decompose.jl:51-66) stays where it is.
+        eng.drop_tensor()
     return ALS(eng, alg, extra, check)
 
 
@@ -506,8 +510,12 @@ def update_samples(target, als: "ALS", new_num_end, reshuffle=False, new_num_sta
     _PivotBased.__init__(alg, old.Start if new_num_start == 0 else new_num_start, old.End if new_num_end == 0 else new_num_end,
                          old.random_modes, old.rank_vect)
     eng = als.engine
-    eng.set_tensor(target)  # the setup dropped the dense tensor; the reference also re-reads `target` here (:135)
     ai = als.additional_items
+    owns = not isinstance(target, Engine)
+    if owns:
+        eng.set_tensor(target)  # the setup dropped the dense tensor; the reference also re-reads `target` here (:135)
+    else:
+        assert target is eng, "update_samples: pass the host tensor or the Engine the ALS object was set up on"
     dims = eng.dims
     N = len(dims)
     pivots = [p.copy() for p in ai["projects"]]
@@ -522,7 +530,8 @@ def update_samples(target, als: "ALS", new_num_end, reshuffle=False, new_num_sta
         proj = np.asfortranarray(pivots[pos][int_start - 1: int_end, :])
         projectors.append(proj)
         eng.set_projector(pos, proj)
-    eng.drop_tensor()
+    if owns:
+        eng.drop_tensor()
     extra = dict(ai)
     extra.update(projects=pivots, projects_tensors=projectors)
     return ALS(eng, alg, extra, als.check)
@@ -549,7 +558,8 @@ _default_engines = {}
 
 
 def _engine_for(target, device=0) -> Engine:
-    """`target` is a host array (uploaded) or an Engine that already holds the tensor."""
+    """`target` is a host array (uploaded into the per-device default engine, which this module then owns) or an Engine
+    that already holds the tensor (owned by the caller: never dropped or overwritten here)."""
     if isinstance(target, Engine):
         return target
     eng = _default_engines.get(device)
@@ -578,7 +588,7 @@ def compute_als(target, cp: CPD, alg=None, check=None, maxiter=None, normal=None
             eng.leverage_scores(n)  # :factor_weights
     elif isinstance(alg, _PivotBased):
         return _setup_pivot_based(alg, eng, cp, check, normal, shuffle_pivots, trunc_tol, injective, rng, seed,
-                                  guess_num_levs=guess_num_levs, prelim_niter=prelim_niter)
+                                  guess_num_levs=guess_num_levs, prelim_niter=prelim_niter, owns_tensor=not isinstance(target, Engine))
     else:
         raise TypeError(f"unsupported algorithm {type(alg).__name__}")
     return ALS(eng, alg, extra, check)
@@ -670,10 +680,13 @@ def _decompose_adaptive(A, epsilon, max_rank, rng=None, alg=None, check=None, ma
         cp = increase_cpd_rank(cp, current, rng)
 
 
+_recon_engines = {}
+
+
 def reconstruct(cp: CPD, device=0) -> np.ndarray:
-    """reconstruct.jl:2-9 on the device (no P x R intermediate)."""
-    eng = _default_engines.get(device) or _default_engines.setdefault(device, Engine(device))
-    if tuple(eng.dims) != tuple(cp.dims):
-        eng.generate_tensor(cp.dims, seed=0)  # shape carrier only
+    """reconstruct.jl:2-9 on the device (no P x R intermediate).  Runs on a handle of its own that only knows the SHAPE
+    (itcpd_set_shape allocates no tensor), so a tensor resident in the decomposition engine is never disturbed."""
+    eng = _recon_engines.get(device) or _recon_engines.setdefault(device, Engine(device))
+    eng.set_shape(cp.dims)
     eng.set_cpd(cp.factors, cp.lam)
     return eng.reconstruct()

@@ -6,27 +6,45 @@
 #   [extensions]  ITCPDB200Ext = ["Libdl"]
 #
 # No CUDA.jl, no ITensors GPU backend: every numeric step is a `ccall` into the shared library, which owns all
-# device memory behind an opaque handle.  The public API is untouched:
+# device memory behind an opaque handle.  The public API is untouched; the user wraps the algorithm object:
 #
 #   using ITensorCPD, Libdl
-#   cp = ITensorCPD.decompose(T, 64; alg = ITensorCPD.B200Normal(), check = ITensorCPD.FitCheck(1e-3, 100, norm(T)))
+#   check = ITensorCPD.FitCheck(1e-3, 100, norm(T))
+#   cp = ITensorCPD.decompose(T, 64; alg = ITensorCPD.B200(), check)                                   # dense ALS (KRPFreeNormal semantics)
+#   cp = ITensorCPD.decompose(T, 64; alg = ITensorCPD.B200(ITensorCPD.LevScoreSampled(640)), check = ITensorCPD.CPDiffCheck(1e-5, 50))
+#   cp = ITensorCPD.decompose(T, 64; alg = ITensorCPD.B200(ITensorCPD.SEQRCSPivProjected(1, 4096, (1, 2, 3), (128, 128, 128))), maxiter = 20)
+#   cp = ITensorCPD.decompose(T, 1e-3, 90; alg = ITensorCPD.B200(), start_rank = 45, rank_step = 45)   # rank adaptive: T is uploaded ONCE
+#   That = ITensorCPD.reconstruct(cp, ITensorCPD.B200())                                               # no P x R intermediate
 #
-# NOTE: Julia is not installed in the build image, so this file could not be executed there; the same control
-# flow is exercised through the Python ctypes mirror (itensorcpd.jl_b200/host.py), symbol for symbol.
+# The wrapper type lives in the package (extensions cannot add names; INTEGRATION.md patch 1):
+#     struct B200{A} <: ProjectionAlgorithm      # (any supertype works: dispatch below is on B200 itself)
+#         alg::A
+#         device::Int
+#     end
+#     B200() = B200(KRPFreeNormal(), 0);  B200(alg) = B200(alg, 0)
+#
+# NOTE: Julia is not installed in the build image, so this file has not been executed there.  The same control flow is
+# exercised through the Python ctypes mirror (itensorcpd.jl_b200/host.py) symbol for symbol, and
+# tests/test_julia_binding_cpu.py checks every `ccall` below against the C header (symbol, argument count, argument types).
 module ITCPDB200Ext
 
 using ITensorCPD
-using ITensorCPD: CPD, ALS, CPDOptimizer, MttkrpAlgorithm, ConvergeAlg, FitCheck, NoCheck, cp_rank, cholesky_epsilon
-using ITensors: ITensor, Index, inds, ind, dim, dims, array, itensor, order
+using ITensorCPD: CPD, CPDOptimizer, ConvergeAlg, FitCheck, NoCheck, CPDiffCheck, CPAngleCheck, cp_rank, cholesky_epsilon, B200,
+                  KRPFreeNormal, KRPNormal, LevScoreSampled, QRPivProjected, SEQRCSPivProjected, KSEQRCSPivProjected,
+                  column_to_multi_coords
+using ITensors: ITensor, Index, inds, ind, dim, dims, array, itensor, order, prime
+using Random: randperm, AbstractRNG, default_rng
 using Libdl
 
-# same idiom as the reference's own native helper (src/ITensorCPD.jl:25-36, src/algebra/SEQRCS.jl:41-60): a module global
-# holding the library path, assigned in __init__, named directly in the (symbol, library) tuple of every ccall
+# One definition of where the library lives and how it is built, shared with deps/build_b200.jl (ADVICE r1: the two files
+# disagreed by one directory level).  Same idiom as the reference's own native helper (src/ITensorCPD.jl:25-36,
+# src/algebra/SEQRCS.jl:41-60): a module global holding the path, assigned in __init__, named in every ccall.
+include(joinpath(@__DIR__, "..", "..", "deps", "b200_paths.jl"))
 libitcpd = ""
 
 function __init__()
-    lib = joinpath(@__DIR__, "..", "..", "lib", "libitcpd_b200.so")
-    isfile(lib) || include(joinpath(@__DIR__, "..", "..", "deps", "build_b200.jl"))
+    lib = B200Paths.library_path()
+    isfile(lib) || B200Paths.build()
     global libitcpd = lib
 end
 
@@ -37,222 +55,471 @@ end
 lasterr() = unsafe_string(ccall((:itcpd_last_error, libitcpd), Cstring, ()))
 chk(code) = code == 0 ? nothing : throw(B200Error(code, lasterr()))
 
+## ---------------------------------------------------------------------------------------------------------------
+## Handles.  ONE handle (and therefore at most one resident tensor) per device, cached: the rank-adaptive loop
+## (src/decompose.jl:51-66) calls als_optimize once per rank step with the SAME target, and re-uploading 8.6 GB per step would
+## dominate (SURVEY 8f-1).  A handle is re-used when the host array is the same object with the same content fingerprint;
+## otherwise the tensor is uploaded again into the same handle (its device buffers are recycled, never duplicated).
+## ---------------------------------------------------------------------------------------------------------------
 mutable struct Handle
     ptr::Ptr{Cvoid}
     function Handle(device::Integer = 0)
         p = Ref{Ptr{Cvoid}}(C_NULL)
         chk(ccall((:itcpd_create, libitcpd), Cint, (Ref{Ptr{Cvoid}}, Cint), p, device))
         h = new(p[])
-        finalizer(x -> ccall((:itcpd_destroy, libitcpd), Cint, (Ptr{Cvoid},), x.ptr), h)
+        finalizer(destroy!, h)
         return h
     end
 end
+function destroy!(h::Handle)
+    h.ptr == C_NULL && return nothing
+    ccall((:itcpd_destroy, libitcpd), Cint, (Ptr{Cvoid},), h.ptr)
+    h.ptr = C_NULL
+    return nothing
+end
 
-## The algorithm object users select: `alg = ITensorCPD.B200Normal()` (normal-equation ALS, like KRPFreeNormal).
-## Extensions cannot add names to the parent module, so the 4-line type definition lives in the package itself
-## (INTEGRATION.md, patch 1: src/algorithms/als_algorithms/standard/tensor.jl):
-##     struct B200Normal <: MttkrpAlgorithm
-##         device::Int
-##     end
-##     B200Normal() = B200Normal(0)
-using ITensorCPD: B200Normal
-
-## A CPDOptimizer whose `optimize` drives the library one sweep at a time (als_optimizer.jl:23-24 is duck typed).
-struct B200ALS <: CPDOptimizer
-    target::ITensor
-    mttkrp_alg::B200Normal
+mutable struct Resident
     handle::Handle
-    check::ConvergeAlg
+    host_ptr::Ptr{Float64}
+    dims::Vector{Int64}
+    fingerprint::UInt64
+    comm::Bool
+end
+const RESIDENT = Dict{Int,Resident}()
+
+## cheap content fingerprint (<= 4096 strided samples + the corners): catches in-place edits of the host array between calls
+function fingerprint(T::Array{Float64})
+    n = length(T)
+    step = max(1, n ÷ 4096)
+    h = hash(n)
+    @inbounds for i in 1:step:n
+        h = hash(T[i], h)
+    end
+    return hash(T[n], h)
 end
 
-## compute_als hook (optimizers/als_optimizers/standard/tensor.jl:3-14): upload T and the factors, Grams on device.
-function ITensorCPD.compute_als(alg::B200Normal, target::ITensor, cp::CPD{<:ITensor};
-                                extra_args = Dict(), check = nothing, kwargs...)
-    h = Handle(alg.device)
-    T = array(target)                       # dense column-major Array{Float64,N}, wrapped without copy
+## the handle holding `target` on `device`; uploads only when the tensor is not already resident there
+function handle_for(target::ITensor, device::Int)
+    T = array(target)                       # dense column-major Array{Float64,N}, wrapped without copy (decompose.jl:5-7)
+    T isa Array{Float64} || throw(ArgumentError("libitcpd_b200 works on dense Float64 targets"))
     ds = collect(Int64, size(T))
-    chk(ccall((:itcpd_set_tensor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}), h.ptr, length(ds), ds, T))
-    chk(ccall((:itcpd_set_rank, libitcpd), Cint, (Ptr{Cvoid}, Cint), h.ptr, dim(cp_rank(cp))))
-    for (n, f) in enumerate(cp.factors)     # ITensor (i_n, r): I_n x R column-major
-        chk(ccall((:itcpd_set_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, array(f)))
+    fp = fingerprint(T)
+    r = get(RESIDENT, device, nothing)
+    if r !== nothing && r.handle.ptr != C_NULL && r.host_ptr == pointer(T) && r.dims == ds && r.fingerprint == fp
+        return r.handle
     end
-    chk(ccall((:itcpd_set_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, array(cp.λ)))
-    chk(ccall((:itcpd_compute_grams, libitcpd), Cint, (Ptr{Cvoid},), h.ptr))
-    return B200ALS(target, alg, h, check)
+    h = (r === nothing || r.handle.ptr == C_NULL) ? Handle(device) : r.handle
+    chk(ccall((:itcpd_set_tensor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}), h.ptr, length(ds), ds, T))
+    RESIDENT[device] = Resident(h, pointer(T), ds, fp, r === nothing ? false : r.comm)
+    return h
 end
 
-## optimize hook (optimizers/als_optimizers/optimize.jl:6-35): the while loop and the convergence state machine stay
-## in Julia, each sweep body is one `itcpd_sweep` call returning <T,T̂> and ‖T̂‖² for FitCheck (fit_check.jl:28-29).
-function ITensorCPD.optimize(cp::CPD, als::B200ALS; verbose = false)
-    h = als.handle.ptr
-    rank = cp_rank(cp)
-    iter = als.check.iter
-    converge = als.check
-    inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
-    while iter < converge.max_counter
-        chk(ccall((:itcpd_sweep, libitcpd), Cint, (Ptr{Cvoid}, Cint, Float64, Ref{Float64}, Ref{Float64}),
-                  h, 1, cholesky_epsilon, inner, nrm2))
-        b200_check_converge(converge, dim(rank), inner[], nrm2[], verbose) && break
-        iter += 1
+## release the device copy explicitly (otherwise it lives until the next target replaces it or the process ends)
+function b200_release!(device::Int = 0)
+    r = pop!(RESIDENT, device, nothing)
+    r === nothing || destroy!(r.handle)
+    return nothing
+end
+
+function upload_cpd!(h::Handle, cp::CPD)
+    R = dim(cp_rank(cp))
+    chk(ccall((:itcpd_set_rank, libitcpd), Cint, (Ptr{Cvoid}, Cint), h.ptr, R))
+    for (n, f) in enumerate(cp.factors)     # I_n x R column-major, whatever index order the ITensor stores
+        A = Array{Float64}(array(f, inds(cp)[n], cp_rank(cp)))
+        chk(ccall((:itcpd_set_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, A))
     end
+    chk(ccall((:itcpd_set_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, Array{Float64}(array(cp.λ))))
+    return R
+end
+
+function fetch_cpd(h::Handle, cp::CPD, target)
+    rank = cp_rank(cp)
     factors = Vector{ITensor}()
     for (n, i) in enumerate(inds(cp))
         A = Matrix{Float64}(undef, dim(i), dim(rank))
-        chk(ccall((:itcpd_get_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
+        chk(ccall((:itcpd_get_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, A))
         push!(factors, itensor(A, i, rank))
     end
     lam = Vector{Float64}(undef, dim(rank))
-    chk(ccall((:itcpd_get_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
-    return CPD{typeof(als.target)}(factors, itensor(lam, rank))
+    chk(ccall((:itcpd_get_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, lam))
+    return CPD{typeof(target)}(factors, itensor(lam, rank))
 end
 
-## FitCheck fed with the two device scalars: verbatim fit_check.jl:25-65 minus the tensor algebra of :28-29.
-function b200_check_converge(check::FitCheck, R, inner_prod, fact_square, verbose)
+## ---------------------------------------------------------------------------------------------------------------
+## Convergence checks.  FitCheck / NoCheck run the REFERENCE's own check_converge methods (fit_check.jl:24-66,
+## no_check.jl:9-20), unchanged: the two device scalars <T,That> and ||That||^2 are handed over as the smallest ITensors for
+## which the reference's formulas (fit_check.jl:28-29, converge_checks.jl:5-11) return exactly those numbers:
+##     MttKRP = [inner, 0, ...] on (i1, r), factors[end] = [1, 0, ...] on (i1, r), lambda = e_1 on r
+##        => sum(hadamard_product(MttKRP, had_contract(factor, lambda, r))) = inner
+##     partial_gram = [G] with G[1,1] = ||That||^2 on (r, r')       => norm_factors = G[1,1] * lambda_1^2 = ||That||^2
+## so the state machine (counters, lastfit, the "Error NAN" throw, verbose printing with dim(rank)) is the package's own code.
+## ---------------------------------------------------------------------------------------------------------------
+function feed_reference_check!(check::FitCheck, rank::Index, inner::Float64, fact_square::Float64, verbose)
+    i1 = Index(1, "b200")
+    R = dim(rank)
+    m = zeros(Float64, 1, R); m[1, 1] = inner
+    f = zeros(Float64, 1, R); f[1, 1] = 1.0
+    l = zeros(Float64, R); l[1] = 1.0
+    g = zeros(Float64, R, R); g[1, 1] = fact_square
+    ITensorCPD.save_mttkrp(check, itensor(m, i1, rank))
+    return ITensorCPD.check_converge(check, [itensor(f, i1, rank)], itensor(l, rank), [itensor(g, rank, prime(rank))]; verbose)
+end
+function feed_reference_check!(check::NoCheck, rank::Index, ::Float64, ::Float64, verbose)
+    l = zeros(Float64, dim(rank))
+    return ITensorCPD.check_converge(check, ITensor[], itensor(l, rank), ITensor[]; verbose)   # only reads ind(lambda, 1)
+end
+
+## CPDiffCheck / CPAngleCheck compare consecutive CPDs through their factor matrices (cp_diff_check.jl:20-71,
+## cp_angle_check.jl:20-73).  The library keeps the previous CPD on the device (itcpd_cpd_snapshot) and returns
+## <That_prev, That_curr> and ||That_curr||^2 (itcpd_cpd_diff_terms); the counters below are those files' state machines
+## restated on the two scalars (their tensor algebra is what moved to the device; PrevCP only serves as the "has a snapshot" flag).
+function diff_scalars(h::Handle)
+    inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
+    chk(ccall((:itcpd_cpd_diff_terms, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h.ptr, inner, nrm2))
+    return inner[], nrm2[]
+end
+snapshot!(h::Handle) = chk(ccall((:itcpd_cpd_snapshot, libitcpd), Cint, (Ptr{Cvoid},), h.ptr))
+
+function finish!(check, value)
+    check.total_iter = check.iter; check.iter = 0; check.counter = 0
+    check.final_fit = value; check.PrevCP = nothing
+end
+function device_check!(check::CPDiffCheck, h::Handle, rank::Index, verbose)
     check.iter += 1
-    normResidual = sqrt(abs(check.ref_norm * check.ref_norm + fact_square - 2 * abs(inner_prod)))
-    curr_fit = one(normResidual) - (normResidual / check.ref_norm)
+    if isnothing(check.PrevCP)
+        snapshot!(h)
+        _, nrm2 = diff_scalars(h)
+        check.PrevCP = true
+        check.norm_prev_iter = nrm2
+        return false
+    end
+    inner, nrm2 = diff_scalars(h)
+    normResidual = sqrt(abs(check.norm_prev_iter + nrm2 - 2 * abs(inner)))
+    curr_fit = 1.0 - normResidual / sqrt(abs(check.norm_prev_iter))
     Δfit = abs(check.lastfit - curr_fit)
     check.lastfit = curr_fit
-    verbose && println("$(R)\t $(check.iter) \t $(curr_fit) \t $(Δfit)")
-    isnan(curr_fit) && throw("Error NAN")
+    check.norm_prev_iter = nrm2
+    snapshot!(h)
+    verbose && println("$(dim(rank))\t $(check.iter) \t $(curr_fit) \t $(Δfit)")
     if Δfit < check.tolerance
         check.counter += 1
         if check.counter >= 2
-            check.total_iter = check.iter; check.iter = 0; check.counter = 0
-            check.final_fit = check.lastfit; check.lastfit = 0
+            finish!(check, check.lastfit); check.lastfit = 0
             return true
         end
     else
         check.counter = 0
     end
     if check.iter >= check.max_counter
-        check.total_iter = check.iter; check.iter = 0; check.counter = 0
-        check.final_fit = check.lastfit; check.lastfit = 0
+        finish!(check, check.lastfit); check.lastfit = 0
     end
     return false
 end
-## NoCheck never looks at the factors: no_check.jl:9-20 restated on the rank dimension alone.
-function b200_check_converge(check::NoCheck, R, _, __, verbose)
+function device_check!(check::CPAngleCheck, h::Handle, rank::Index, verbose)
     check.iter += 1
-    verbose && println("$(R)\t $(check.iter)")
-    if check.iter == check.max_counter
-        check.iter = 0
-        return true
+    if isnothing(check.PrevCP)
+        snapshot!(h)
+        _, nrm2 = diff_scalars(h)
+        check.PrevCP = true
+        check.norm_prev_iter = sqrt(nrm2)
+        return false
+    end
+    inner, nrm2 = diff_scalars(h)
+    norm_curr = sqrt(nrm2)
+    theta = min(1.0, inner / (norm_curr * check.norm_prev_iter))
+    curr_angle = acos(theta)
+    Δangle = abs(check.lastangle - curr_angle)
+    check.lastangle = curr_angle
+    check.norm_prev_iter = norm_curr
+    snapshot!(h)
+    verbose && println("$(dim(rank))\t $(check.iter) \t $(curr_angle) \t $(Δangle)")
+    if Δangle < check.tolerance
+        check.counter += 1
+        if check.counter >= 2
+            finish!(check, check.lastangle); check.lastangle = 0
+            return true
+        end
+    else
+        check.counter = 0
+    end
+    if check.iter >= check.max_counter
+        finish!(check, check.lastangle); check.lastangle = 0
     end
     return false
 end
+## FitCheck is not available to the sampled solvers: it only counts sweeps (ProjectionAlgorithm.jl:30-51)
+function device_check!(check::FitCheck, h::Handle, rank::Index, verbose)
+    check.iter == 0 && println("Warning: FitCheck is not enabled for sampled B200 solvers, will run $(check.max_counter) iterations.")
+    check.iter += 1
+    check.iter >= check.max_counter && (check.iter = 0)
+    return false
+end
+device_check!(check::NoCheck, h::Handle, rank::Index, verbose) = feed_reference_check!(check, rank, 0.0, 0.0, verbose)
 
 ## ---------------------------------------------------------------------------------------------------------------
-## Sampled path: leverage-score sampled ALS with the whole per-mode update on the device.
-## Package-side type (INTEGRATION.md patch 1b, next to LevScoreSampled in
-## src/algorithms/als_algorithms/randomized/krp_lev_score_sampled.jl:9-17):
-##     struct B200LevScoreSampled <: ProjectionAlgorithm
-##         NSamples::Tuple
-##         device::Int
-##     end
-##     B200LevScoreSampled(n::Int) = B200LevScoreSampled((n,), 0)
+## Dense normal-equation ALS: B200(KRPFreeNormal()) / B200(KRPNormal())  (both reference formulations give the same M_n;
+## on the device one dimension-tree GEMM pass serves them)
 ## ---------------------------------------------------------------------------------------------------------------
-using ITensorCPD: B200LevScoreSampled, CPDiffCheck, CPAngleCheck
-
-struct B200SampledALS <: CPDOptimizer
+struct B200ALS{A} <: CPDOptimizer
     target::ITensor
-    mttkrp_alg::B200LevScoreSampled
+    mttkrp_alg::B200{A}
     handle::Handle
     check::ConvergeAlg
-    normal::Bool
-    stop_resample::Int
-    seed::UInt64
+    additional_items::Dict
 end
 
-## compute_als(::LevScoreSampled) (optimizers/als_optimizers/randomized/krp_lev_score_sampled.jl:1-40): factor weights on device
-function ITensorCPD.compute_als(alg::B200LevScoreSampled, target::ITensor, cp::CPD{<:ITensor};
-                                extra_args = Dict(), check = nothing, normal = false, stop_resample = -1, seed = 0, kwargs...)
-    dense = ITensorCPD.compute_als(B200Normal(alg.device), target, cp; check)   # uploads T, factors, lambda
-    h = dense.handle
-    for n in 1:length(cp)
-        chk(ccall((:itcpd_leverage_scores, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, C_NULL))
-    end
-    return B200SampledALS(target, alg, h, check, normal, stop_resample, UInt64(seed))
+## compute_als hook (optimizers/als_optimizers/standard/tensor.jl:3-14): T resident (uploaded at most once), factors, Grams on device
+function ITensorCPD.compute_als(alg::B200{<:Union{KRPFreeNormal,KRPNormal}}, target::ITensor, cp::CPD{<:ITensor};
+                                extra_args = Dict(), check = nothing, kwargs...)
+    h = handle_for(target, alg.device)
+    upload_cpd!(h, cp)
+    chk(ccall((:itcpd_compute_grams, libitcpd), Cint, (Ptr{Cvoid},), h.ptr))
+    return B200ALS(target, alg, h, check, extra_args)
 end
 
-## optimize (optimize.jl:6-35) with the ProjectionAlgorithm hooks (ProjectionAlgorithm.jl:7-68) collapsed into two calls per mode
-function ITensorCPD.optimize(cp::CPD, als::B200SampledALS; verbose = false)
-    h = als.handle.ptr
-    N = length(cp)
+## optimize hook (optimizers/als_optimizers/optimize.jl:6-35): the while loop and the convergence state machine stay in Julia,
+## each sweep body is one `itcpd_sweep` call (a CUDA-graph replay from the second iteration on) returning <T,That> and ||That||^2
+function ITensorCPD.optimize(cp::CPD, als::B200ALS{<:Union{KRPFreeNormal,KRPNormal}}; verbose = false)
+    h = als.handle
+    rank = cp_rank(cp)
     iter = als.check.iter
-    pivs = [Matrix{Int64}(undef, (length(als.mttkrp_alg.NSamples) == 1 ? als.mttkrp_alg.NSamples[1] : als.mttkrp_alg.NSamples[n]), N - 1) for n in 1:N]
-    drawn = falses(N)
-    seed = als.seed
-    while iter < als.check.max_counter
-        for fact in 1:N
-            resample = als.stop_resample < 0 || als.stop_resample > als.check.iter || !drawn[fact]   # krp_lev...:24-27
-            if resample
-                seed += 1
-                chk(ccall((:itcpd_sample_factor_matrices, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, UInt64, Ptr{Int64}),
-                          h, fact - 1, size(pivs[fact], 1), seed, pivs[fact]))
-                drawn[fact] = true
-            end
-            chk(ccall((:itcpd_sampled_update, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Float64, Cint),
-                      h, fact - 1, size(pivs[fact], 1), pivs[fact], cholesky_epsilon, als.normal ? 1 : 0))
-        end
-        b200_sampled_converged(als.check, h, dim(cp_rank(cp)), verbose) && break
+    converge = als.check
+    inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
+    while iter < converge.max_counter
+        chk(ccall((:itcpd_sweep, libitcpd), Cint, (Ptr{Cvoid}, Cint, Float64, Ref{Float64}, Ref{Float64}),
+                  h.ptr, 1, cholesky_epsilon, inner, nrm2))
+        feed_reference_check!(converge, rank, inner[], nrm2[], verbose) && break
         iter += 1
     end
     return fetch_cpd(h, cp, als.target)
 end
 
-## CPDiffCheck from the two device scalars (cp_diff_check.jl:20-71); FitCheck is not supported for sampled solvers
-## (ProjectionAlgorithm.jl:30-51): it only counts sweeps.
-function b200_sampled_converged(check::CPDiffCheck, h, R, verbose)
-    check.iter += 1
-    inner = Ref{Float64}(0.0); nrm2 = Ref{Float64}(0.0)
-    if isnothing(check.PrevCP)
-        chk(ccall((:itcpd_cpd_snapshot, libitcpd), Cint, (Ptr{Cvoid},), h))
-        chk(ccall((:itcpd_cpd_diff_terms, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
-        check.PrevCP = true
-        check.norm_prev_iter = nrm2[]
-        return false
+## ---------------------------------------------------------------------------------------------------------------
+## Leverage-score sampled ALS: B200(LevScoreSampled(n))  (algorithms/.../randomized/krp_lev_score_sampled.jl:9-58 with the
+## leverage scores, the weighted sampling, both gathers and the sampled solve on the device)
+## ---------------------------------------------------------------------------------------------------------------
+function ITensorCPD.compute_als(alg::B200{<:LevScoreSampled}, target::ITensor, cp::CPD{<:ITensor};
+                                extra_args = Dict(), check = nothing, normal = false, stop_resample = -1, seed = 0, kwargs...)
+    h = handle_for(target, alg.device)
+    upload_cpd!(h, cp)
+    for n in 1:length(cp)     # :factor_weights (optimizers/.../krp_lev_score_sampled.jl:18-24)
+        chk(ccall((:itcpd_leverage_scores, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, n - 1, C_NULL))
     end
-    chk(ccall((:itcpd_cpd_diff_terms, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h, inner, nrm2))
-    normResidual = sqrt(abs(check.norm_prev_iter + nrm2[] - 2 * abs(inner[])))
-    curr_fit = 1.0 - normResidual / sqrt(abs(check.norm_prev_iter))
-    Δfit = abs(check.lastfit - curr_fit)
-    check.lastfit = curr_fit
-    check.norm_prev_iter = nrm2[]
-    chk(ccall((:itcpd_cpd_snapshot, libitcpd), Cint, (Ptr{Cvoid},), h))
-    verbose && println("$(check.iter) \t $(curr_fit) \t $(Δfit)")
-    done = false
-    if Δfit < check.tolerance
-        check.counter += 1
-        done = check.counter >= 2
-    else
-        check.counter = 0
-    end
-    if done || check.iter >= check.max_counter
-        check.total_iter = check.iter; check.iter = 0; check.counter = 0
-        check.final_fit = check.lastfit; check.lastfit = 0; check.PrevCP = nothing
-    end
-    return done
+    extra_args[:normal] = normal; extra_args[:stop_resample] = stop_resample; extra_args[:seed] = UInt64(seed) * UInt64(1000003)
+    return B200ALS(target, alg, h, check, extra_args)
 end
-function b200_sampled_converged(check::FitCheck, h, R, verbose)
-    check.iter == 0 && println("Warning: FitCheck is not enabled for B200LevScoreSampled will run $(check.max_counter) iterations.")
-    check.iter += 1
-    check.iter >= check.max_counter && (check.iter = 0)
-    return false
-end
-b200_sampled_converged(check::NoCheck, h, R, verbose) = b200_check_converge(check, R, 0.0, 0.0, verbose)
 
-function fetch_cpd(h, cp::CPD, target)
+nsamples(a::LevScoreSampled, n) = length(a.NSamples) == 1 ? a.NSamples[1] : a.NSamples[n]
+
+## optimize (optimize.jl:6-35) with the ProjectionAlgorithm hooks (ProjectionAlgorithm.jl:7-68) collapsed into two calls per mode
+function ITensorCPD.optimize(cp::CPD, als::B200ALS{<:LevScoreSampled}; verbose = false)
+    h = als.handle
+    N = length(cp)
     rank = cp_rank(cp)
-    factors = Vector{ITensor}()
-    for (n, i) in enumerate(inds(cp))
-        A = Matrix{Float64}(undef, dim(i), dim(rank))
-        chk(ccall((:itcpd_get_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h, n - 1, A))
-        push!(factors, itensor(A, i, rank))
+    iter = als.check.iter
+    ai = als.additional_items
+    pivs = [Matrix{Int64}(undef, nsamples(als.mttkrp_alg.alg, n), N - 1) for n in 1:N]
+    drawn = falses(N)
+    seed = ai[:seed]
+    while iter < als.check.max_counter
+        for fact in 1:N
+            if ai[:stop_resample] < 0 || ai[:stop_resample] > als.check.iter || !drawn[fact]   # krp_lev...:24-27
+                seed += 1
+                chk(ccall((:itcpd_sample_factor_matrices, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, UInt64, Ptr{Int64}),
+                          h.ptr, fact - 1, size(pivs[fact], 1), seed, pivs[fact]))
+                drawn[fact] = true
+            end
+            chk(ccall((:itcpd_sampled_update, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Float64, Cint),
+                      h.ptr, fact - 1, size(pivs[fact], 1), pivs[fact], cholesky_epsilon, ai[:normal] ? 1 : 0))
+        end
+        device_check!(als.check, h, rank, verbose) && break
+        iter += 1
     end
-    lam = Vector{Float64}(undef, dim(rank))
-    chk(ccall((:itcpd_get_lambda, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, lam))
-    return CPD{typeof(target)}(factors, itensor(lam, rank))
+    return fetch_cpd(h, cp, als.target)
+end
+
+## ---------------------------------------------------------------------------------------------------------------
+## Pivot-projected solvers: B200(QRPivProjected(...)), B200(SEQRCSPivProjected(...)), B200(KSEQRCSPivProjected(...))
+## (algorithms/.../randomized/qr_lev_score_sampled.jl:10-168; setups optimizers/.../randomized/qr_lev_score_sampled.jl:1-282).
+## The column-pivoted QR / SE-QRCS of every unfolding, the fibre gathers (target_transform) and the per-sweep sampled solves run
+## on the device; the pivot bookkeeping (effective rank, shuffling, column -> coordinates) is the reference's own host code.
+## ---------------------------------------------------------------------------------------------------------------
+const PivotAlg = Union{QRPivProjected,SEQRCSPivProjected,KSEQRCSPivProjected}
+pick(v, n) = v isa Tuple ? (length(v) == 1 ? v[1] : v[n]) : v
+
+function proj_range(alg, n, dRis)    # optimizers/.../qr_lev_score_sampled.jl:52-60
+    int_end = pick(alg.End, n)
+    int_end = iszero(int_end) ? dRis : int_end
+    int_end = min(dRis, int_end)
+    int_start = pick(alg.Start, n)
+    @assert int_start > 0 && int_start ≤ int_end
+    return int_start, int_end
+end
+
+function ITensorCPD.compute_als(alg::B200{<:PivotAlg}, target::ITensor, cp::CPD{<:ITensor};
+                                extra_args = Dict(), check = nothing, shuffle_pivots = true, trunc_tol = 0.01, normal = true,
+                                injective = false, rng::AbstractRNG = default_rng(), kwargs...)
+    h = handle_for(target, alg.device)
+    inner = alg.alg
+    N = length(cp)
+    ds = collect(Int, dims(target))
+    lst = inner isa QRPivProjected || isnothing(inner.random_modes) ? () : inner.random_modes
+    krp_mode = inner isa KSEQRCSPivProjected
+    if krp_mode
+        # preliminary leverage-score sampled ALS (optimizers/.../qr_lev...:193-202); its factors' KRP stands in for the unfoldings
+        pre = ITensorCPD.als_optimize(target, cp; alg = B200(LevScoreSampled(10 * dim(cp_rank(cp))), alg.device), check = NoCheck(10),
+                                      normal = true, stop_resample = 0)
+        upload_cpd!(h, pre)
+    else
+        upload_cpd!(h, cp)
+    end
+    ref_pivs = Vector{Vector{Int}}(); pivots = Vector{Matrix{Int}}(); projectors = Vector{Matrix{Int64}}(); effective_ranks = Int[]
+    for n in 1:N
+        rdims = Tuple(ds[m] for m in 1:N if m != n)
+        dRis = prod(rdims)
+        int_start, int_end = proj_range(inner, n, dRis)
+        m = ds[n]
+        p = Vector{Int64}(undef, dRis)
+        dr = Vector{Float64}(undef, krp_mode ? dim(cp_rank(cp)) : min(m, dRis))
+        if n in lst
+            k_sk = isnothing(inner.rank_vect) ? int_end : inner.rank_vect[n]
+            l = Int(round(3 * m * log(m)))            # optimizers/.../qr_lev...:122 / :234
+            s = Int(round(log(m)))                    # :123 / :236
+            nrd = Ref{Int64}(0); ncand = Ref{Int64}(0)
+            if krp_mode     # SE-QRCS of the Khatri-Rao product of the preliminary factors (SEQRCS.jl:184-241)
+                chk(ccall((:itcpd_seqrcs_krp, libitcpd), Cint,
+                          (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+                          h.ptr, n - 1, l, s, min(k_sk, l), injective ? 1 : 0, p, dr, nrd, ncand))
+            else            # SE-QRCS of the unfolding itself (SEQRCS.jl:139-182)
+                chk(ccall((:itcpd_seqrcs, libitcpd), Cint,
+                          (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+                          h.ptr, n - 1, l, s, min(k_sk, l), injective ? 1 : 0, p, dr, nrd, ncand))
+            end
+            dr = dr[1:nrd[]]
+        elseif krp_mode
+            throw(ArgumentError("B200(KSEQRCSPivProjected): list every mode in random_modes (the exact KRP QRCP is a host matrix; use itcpd_qrcp_matrix)"))
+        else
+            chk(ccall((:itcpd_qrcp_unfolding, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Float64}), h.ptr, n - 1, p, dr))
+        end
+        push!(ref_pivs, Vector{Int}(p))
+        meff = sum(abs.(dr) ./ maximum(abs.(dr)) .> trunc_tol)                              # :28 / :137
+        push!(effective_ranks, meff)
+        p_rest = p[meff+1:end]
+        p = vcat(p[1:meff], shuffle_pivots ? p_rest[randperm(rng, length(p_rest))] : p_rest)
+        coords = column_to_multi_coords(Vector{Int}(p), rdims)                               # the reference's own index map (pivot_mapping.jl:17-30)
+        push!(pivots, coords)
+        proj = Matrix{Int64}(coords[int_start:int_end, :])
+        push!(projectors, proj)
+        chk(ccall((:itcpd_set_projector, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}), h.ptr, n - 1, size(proj, 1), proj))   # gathers target_transform[n]
+    end
+    krp_mode && upload_cpd!(h, cp)       # the decomposition itself starts from the caller's CPD
+    extra_args[:ref_projectors] = ref_pivs; extra_args[:projects] = pivots; extra_args[:projects_tensors] = projectors
+    extra_args[:effective_ranks] = effective_ranks; extra_args[:normal] = normal
+    # the reference replaces the target by an empty ITensor here (:77, :175, :281); the device copy stays with the per-device
+    # cache instead, so that update_samples and the rank-adaptive loop do not upload it again
+    return B200ALS(target, alg, h, check, extra_args)
+end
+
+function ITensorCPD.optimize(cp::CPD, als::B200ALS{<:PivotAlg}; verbose = false)
+    h = als.handle
+    N = length(cp)
+    rank = cp_rank(cp)
+    upload_cpd!(h, cp)                  # an ALS object can be re-used with another starting CPD (update_samples)
+    iter = als.check.iter
+    normal = als.additional_items[:normal] ? 1 : 0
+    while iter < als.check.max_counter
+        for fact in 1:N                 # pivot_hadamard + cached target_transform + sampled solve + row_norm (qr_lev...:151-168)
+            chk(ccall((:itcpd_projected_update, libitcpd), Cint, (Ptr{Cvoid}, Cint, Float64, Cint), h.ptr, fact - 1, cholesky_epsilon, normal))
+        end
+        device_check!(als.check, h, rank, verbose) && break
+        iter += 1
+    end
+    return fetch_cpd(h, cp, als.target)
+end
+
+## update_samples (algorithms/.../qr_lev_score_sampled.jl:95-149): a new sample range without redoing the QR; re-gathers T_s
+function ITensorCPD.update_samples(target::ITensor, als::B200ALS{<:PivotAlg}, new_num_end; reshuffle = false, new_num_start = 0,
+                                   rng::AbstractRNG = default_rng())
+    old = als.mttkrp_alg.alg
+    inner = ITensorCPD.copy_alg(old, new_num_start, new_num_end)
+    h = handle_for(target, als.mttkrp_alg.device)
+    ai = copy(als.additional_items)
+    ds = collect(Int, dims(target)); N = length(ds)
+    pivots = deepcopy(ai[:projects]); projectors = Vector{Matrix{Int64}}()
+    for n in 1:N
+        rdims = Tuple(ds[m] for m in 1:N if m != n)
+        if reshuffle
+            p = ai[:ref_projectors][n]; meff = ai[:effective_ranks][n]
+            p_rest = p[meff+1:end]
+            pivots[n] = column_to_multi_coords(vcat(p[1:meff], p_rest[randperm(rng, length(p_rest))]), rdims)
+        end
+        int_start, int_end = proj_range(inner, n, prod(rdims))
+        proj = Matrix{Int64}(pivots[n][int_start:int_end, :])
+        push!(projectors, proj)
+        chk(ccall((:itcpd_set_projector, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}), h.ptr, n - 1, size(proj, 1), proj))
+    end
+    ai[:projects] = pivots; ai[:projects_tensors] = projectors
+    return B200ALS(target, B200(inner, als.mttkrp_alg.device), h, als.check, ai)
+end
+
+## ---------------------------------------------------------------------------------------------------------------
+## reconstruct (src/algebra/reconstruct.jl:2-9) on the device: no P x R intermediate.  Uses a scratch handle that only knows
+## the SHAPE (itcpd_set_shape allocates no tensor), so a resident target is never disturbed.
+## ---------------------------------------------------------------------------------------------------------------
+function ITensorCPD.reconstruct(cp::CPD, alg::B200)
+    h = Handle(alg.device)
+    try
+        is = inds(cp)
+        ds = collect(Int64, dim.(is))
+        chk(ccall((:itcpd_set_shape, libitcpd), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}), h.ptr, length(ds), ds))
+        upload_cpd!(h, cp)
+        out = Array{Float64}(undef, ds...)
+        chk(ccall((:itcpd_reconstruct, libitcpd), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, out))
+        return itensor(out, is...)
+    finally
+        destroy!(h)
+    end
+end
+
+## ||T - That||_F without materialising That (what every reference test computes through norm(reconstruct(cpd) - T))
+function b200_residual_norm(target::ITensor, cp::CPD, alg::B200 = B200())
+    h = handle_for(target, alg.device)
+    upload_cpd!(h, cp)
+    r = Ref{Float64}(0.0)
+    chk(ccall((:itcpd_residual_norm, libitcpd), Cint, (Ptr{Cvoid}, Ref{Float64}), h.ptr, r))
+    return r[]
+end
+
+## ---------------------------------------------------------------------------------------------------------------
+## Multi-GPU: one Julia process per GPU (MPI.jl, Distributed, ...).  Each rank passes its slab T[.., slab_g] of the last mode as
+## `target` and the slab's rows of the last factor; everything else is replicated.  The launcher supplies two collectives over
+## raw bytes: bcast(bytes_from_rank0) -> bytes and allgather(my_bytes) -> concatenation in rank order.
+## After this call every collective of a sweep happens inside the library (NCCL for the small last-mode sums, NVLink peer
+## memory for the M_n all-reduce, which is fused into the row-solve kernel; sweeps replay one CUDA graph).
+## ---------------------------------------------------------------------------------------------------------------
+function b200_init_multi_gpu!(target::ITensor, R::Int, nranks::Int, rank::Int; device::Int = rank, bcast::Function, allgather::Function,
+                              peer_memory::Bool = true)
+    h = handle_for(target, device)
+    chk(ccall((:itcpd_set_rank, libitcpd), Cint, (Ptr{Cvoid}, Cint), h.ptr, R))
+    uid = zeros(UInt8, 128)
+    rank == 0 && chk(ccall((:itcpd_comm_unique_id, libitcpd), Cint, (Ptr{UInt8},), uid))
+    uid = bcast(uid)
+    chk(ccall((:itcpd_comm_init, libitcpd), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h.ptr, nranks, rank, uid))
+    if peer_memory
+        mine = zeros(UInt8, 64)
+        chk(ccall((:itcpd_peer_export, libitcpd), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h.ptr, mine))
+        all = allgather(mine)
+        chk(ccall((:itcpd_peer_import, libitcpd), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h.ptr, nranks, rank, all))
+    end
+    RESIDENT[device].comm = true
+    return h
+end
+
+## the sharded last factor, assembled on every rank (rows_total = the global extent of the last mode)
+function b200_allgather_factor(h::Handle, mode::Int, rows_total::Int, R::Int)
+    A = Matrix{Float64}(undef, rows_total, R)
+    chk(ccall((:itcpd_allgather_factor, libitcpd), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}), h.ptr, mode - 1, rows_total, A))
+    return A
 end
 
 ## Seam 3: the sparse-sign generators keep the C ABI of libsparse_sign (SEQRCS.jl:41-60); pointing the module
