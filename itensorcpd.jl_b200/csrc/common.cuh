@@ -101,6 +101,9 @@ struct itcpd_ctx {
     cudaStream_t side_stream = nullptr;   // Gram-Hadamard + factorisation run here underneath the MTTKRP
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_factor = 1;
+    // option "fused_tail" (default on): normalise + Gram + fit + log of a mode update as three launches (mode_tail.cu) and one small
+    // all-reduce for the sharded mode; off = the hook-by-hook kernels (colsumsq, scale, Gram from the normalised factor, fit, log)
+    int fused_tail = 1;
     // option "early_pass_b" (off by default, not yet run on hardware): pass B of the dimension tree only depends on the factors
     // of modes < split_b, so it is launched on its own stream as soon as they are updated and the updates of the modes in
     // [split_b, split_a) (second-level contraction from P_A, solve, normalise, Gram) run underneath it
@@ -230,6 +233,7 @@ int probe_dfma(itcpd_ctx *c, double *tflops);
 
 // ---- kernels.cu ---------------------------------------------------------------------------
 int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G);
+int k_sum_slices(itcpd_ctx *c, const double *part, int64_t n, int slices, double *out);
 int k_cross_gram(itcpd_ctx *c, const double *A, const double *B, int64_t rows, int R, double *C);
 int k_cpd_diff_terms(itcpd_ctx *c, double *out2);
 int k_gram_hadamard(itcpd_ctx *c, int skip_mode, double *Gamma);
@@ -244,6 +248,11 @@ int k_sumsq(itcpd_ctx *c, const double *x, int64_t n, double *out_dev);
 int k_pad_copy_in(itcpd_ctx *c, const double *src_dense, double *dst_padded);   // dims[0] -> ld0
 int k_pad_copy_out(itcpd_ctx *c, const double *src_padded, double *dst_dense);
 int k_reconstruct(itcpd_ctx *c, double *out_dense_or_null, double *resid_sumsq_dev_or_null);
+
+// ---- mode_tail.cu -------------------------------------------------------------------------
+// fused tail of a mode update inside the sweep: X -> lambda, A[mode], G[mode] (+ fit scalars and the sweep-log entry for the last mode)
+bool mode_tail_supported(const itcpd_ctx *c);
+int k_mode_tail(itcpd_ctx *c, int mode, bool with_fit, const int *status_dev, int nmodes);
 
 // ---- solve.cu -----------------------------------------------------------------------------
 // X (rows x R) = (Gamma \ M^T)^T with the ldiv_solve.jl semantics. status_dev[0]=path, [1]=rank.

@@ -72,6 +72,13 @@ __global__ void sum_slices_kernel(const double *__restrict__ part, int64_t n, in
     out[i] = s;
 }
 
+int k_sum_slices(itcpd_ctx *c, const double *part, int64_t n, int slices, double *out) {
+    sum_slices_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>(part, n, slices, out);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ITCPD_OK;
+}
+
 int k_gram(itcpd_ctx *c, const double *A, int64_t rows, int R, double *G) {
     const int slices = (int)std::max<int64_t>(1, ceil_div(rows, GSLICE));
     TRY(c->redux.reserve((size_t)slices * R * R * 8));

@@ -97,8 +97,8 @@ def small_shapes_default_options():
 @scenario
 def small_shapes_every_option():
     opts = [("tile_warps", 4), ("stream_k", 0), ("stream_k", 2), ("tma3d", 0), ("swizzle", 0), ("overlap_factor", 0), ("use_graph", 0), ("chol_alg", 0),
-            ("chol_alg", 1), ("chol_alg", 2), ("graph_single", 0), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
-    defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 3, "graph_single": 1, "mttkrp_alg": 0, "early_pass_b": 0,
+            ("chol_alg", 1), ("chol_alg", 2), ("graph_single", 0), ("fused_tail", 0), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
+    defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 3, "graph_single": 1, "fused_tail": 1, "mttkrp_alg": 0, "early_pass_b": 0,
                 "gemm_i8": 0, "time_gemm": 0, "time_phases": 0}
     with itcpd.Engine(0) as eng:
         for name, val in opts:

@@ -147,9 +147,28 @@ def test_build_recipes_cover_every_translation_unit():
     sh = open(os.path.join(csrc, "build.sh")).read()
     listed = re.search(r"for f in ([a-z0-9_ ]+); do", sh).group(1).split()
     assert sorted(listed) == units
-    jl = open(os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "deps", "build_b200.jl")).read()
+    jl = open(os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "deps", "b200_paths.jl")).read()   # the one build recipe both Julia files use
     assert 'readdir(csrc)' in jl and 'endswith(".cu")' in jl
     ext = open(os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "ext", "ITCPDB200Ext", "ITCPDB200Ext.jl")).read()
     # every entry point the extension ccalls is declared in the header
     called = set(re.findall(r"ccall\(\(:(itcpd_[a-z0-9_]+), libitcpd\)", ext))
     assert len(called) >= 12 and called <= set(header_symbols()), called - set(header_symbols())
+
+
+def test_c99_program_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/cabi_smoke.c is the ABI exercised from C (dlopen + plain pointers).  Here (no GPU) it must compile as strict C99
+    against include/itcpd_b200.h, resolve every symbol it uses, and stop at itcpd_create with ITCPD_ERR_NO_DEVICE -- there is
+    no CPU fallback to fall into.  The GPU suite runs the same program to completion (tests/test_gpu_cabi_c.py)."""
+    exe = str(tmp_path / "cabi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi_smoke.c"),
+                    "-o", exe, "-ldl", "-lm"], check=True, capture_output=True)
+    out = subprocess.run([exe, os.path.join(ROOT, "itensorcpd.jl_b200", "lib", "libitcpd_b200.so")], capture_output=True, text=True, timeout=120)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert out.returncode == 0 and "CABI_SMOKE_OK" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 77 and "no CPU fallback" in out.stderr, (out.returncode, out.stdout, out.stderr)

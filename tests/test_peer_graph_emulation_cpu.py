@@ -97,11 +97,13 @@ int main(int argc, char **argv) {
 
 @pytest.fixture(scope="module")
 def harness():
+    hdr = open(os.path.join(os.path.dirname(SRC), "peer.cuh")).read()      # PeerPtrs + bounded_wait (shared with mode_tail.cu)
+    hdr = hdr[hdr.index("struct PeerPtrs"):hdr.rindex("}  // namespace itcpd")]
     text = open(SRC).read()
-    start = text.index("struct PeerPtrs")
+    start = text.index("__global__ void peer_signal_dev_kernel")
     end = text.index("bool peer_graph_active")
-    body = text[start:end]
-    body, n = re.subn(r"static PeerPtrs peer_ptrs\(const itcpd_ctx \*c\) \{.*?\n\}\n", "", body, flags=re.S)
+    body = hdr + text[start:end]
+    body, n = re.subn(r"static inline PeerPtrs peer_ptrs\(const itcpd_ctx \*c\) \{.*?\n\}\n", "", body, flags=re.S)
     assert n == 1
     body, n = re.subn(r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\(now\)\);', "now = emu_globaltimer();", body)
     assert n == 1

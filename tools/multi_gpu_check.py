@@ -34,8 +34,8 @@ def main():
     eng.comm_init(world, rank, uid.cpu().numpy().tobytes())
     if os.environ.get("ITCPD_PEER", "1") == "1":
         # fused all-reduce + solve over NVLink peer memory: exchange the CUDA IPC handles of the exchange buffers
-        if os.environ.get("ITCPD_PEER_GRAPH", "0") == "1":
-            eng.set_option("peer_graph", 1)  # experimental: NCCL-free sweeps (device-side epochs), CUDA-graph replay
+        if "ITCPD_PEER_GRAPH" in os.environ:  # default on: NCCL-free sweeps (device-side epochs), CUDA-graph replay
+            eng.set_option("peer_graph", int(os.environ["ITCPD_PEER_GRAPH"] != "0"))
         mine = torch.frombuffer(bytearray(eng.peer_export()), dtype=torch.uint8).cuda()
         allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
         dist.all_gather(allh, mine)
