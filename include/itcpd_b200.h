@@ -186,6 +186,14 @@ int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *ro
  * the LOCAL rows of the sharded factor, itcpd_sample_factor_matrices draws from the all-gathered scores. */
 int itcpd_sampled_update(itcpd_ctx *ctx, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol, int normal);
 
+/* Device-resident sweeps of the leverage-score sampled solver: for every mode a weighted draw of nsamp[mode] samples, the sampled
+ * least-squares update, row_norm and the leverage refresh -- optimize.jl:17-28 with the ProjectionAlgorithm hooks of LevScoreSampled
+ * (algorithms/als_algorithms/randomized/krp_lev_score_sampled.jl:9-58, ProjectionAlgorithm.jl:57-68) and no host round trip.
+ * The k-th draw of the call is seeded with draw_counter + k, exactly the seeds a host loop of itcpd_sample_factor_matrices(seed) +
+ * itcpd_sampled_update passes (the two drivers are bitwise equal); the sweep body is replayed from a CUDA graph.  Asynchronous:
+ * returns once the sweeps are enqueued.  Single-GPU handles only. */
+int itcpd_sampled_sweep_async(itcpd_ctx *ctx, int nsweeps, const int64_t *nsamp, uint64_t draw_counter, double chol_tol, int normal);
+
 /* qr(T_(mode), ColumnNorm()) of the pivot-projected setup (optimizers/.../randomized/qr_lev_score_sampled.jl:22-23,126-127):
  * column-pivoted Householder QR of the mode unfolding on the device.  piv_out: the full pivot order, n = P / I_mode
  * int64 entries, 1-based; rdiag_out: diag(R), min(I_mode, n) doubles. */

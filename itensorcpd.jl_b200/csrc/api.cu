@@ -382,6 +382,9 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->sweep_graph_exec) { cudaGraphExecDestroy(c->sweep_graph_exec); c->sweep_graph_exec = nullptr; }
+    if (c->sampled_graph_exec) { cudaGraphExecDestroy(c->sampled_graph_exec); c->sampled_graph_exec = nullptr; }
+    c->draw_counter.release();
+    c->lev_q.release();
     cudaStreamSynchronize(c->side_stream);
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
@@ -997,16 +1000,18 @@ int itcpd_sample_factor_matrices(itcpd_ctx *c, int skip_mode, int64_t nsamp, uin
 }
 
 // the sampled least-squares problem of one mode (ProjectionAlgorithm.jl:57-68): K is nsamp x R, Ts is I x nsamp
-static int sampled_ls(itcpd_ctx *c, int mode, const double *K, const double *Ts, int64_t nsamp, double chol_tol, int normal) {
+// Ts == null (normal equations only): the fibres are read straight from the tensor through the device pivots `piv`
+static int sampled_ls(itcpd_ctx *c, int mode, const double *K, const double *Ts, const int64_t *piv, int64_t nsamp, double chol_tol, int normal) {
     const int R = c->rank;
     const int64_t I = c->dims[mode];
     c->m_valid[mode] = false;  // M[mode] is reused for the *sampled* MTTKRP
     if (normal) {
         // (K'K) X' = (T_s K)'
         TRY(k_gram(c, K, nsamp, R, c->Gamma.as<double>()));
-        TRY(k_small_gemm_nn(c, Ts, K, I, nsamp, R, c->M[mode].as<double>()));
+        TRY(k_sampled_mttkrp(c, mode, nsamp, piv, Ts, K, c->M[mode].as<double>()));
         return k_solve(c, c->Gamma.as<double>(), c->M[mode].as<double>(), I, R, chol_tol, c->X.as<double>(), c->status.as<int>());
     }
+    ARG_CHECK(Ts != nullptr, "normal=false needs the gathered unfolding");
     ARG_CHECK(nsamp >= R && nsamp < ((int64_t)1 << 31), "normal=false needs at least R samples");
     return qrcp_ls_solve(c, K, (int)nsamp, R, Ts, I, c->X.as<double>(), c->status.as<int>(), 1);
 }
@@ -1354,7 +1359,7 @@ int itcpd_projected_update(itcpd_ctx *c, int mode, double chol_tol, int normal) 
     }
     TRY(c->samp_K.reserve((size_t)ns * R * 8));
     TRY(k_pivot_hadamard(c, mode, ns, c->proj_piv[mode].as<int64_t>(), c->samp_K.as<double>()));
-    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->proj_T[mode].as<double>(), ns, chol_tol, normal));
+    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->proj_T[mode].as<double>(), c->proj_piv[mode].as<int64_t>(), ns, chol_tol, normal));
     TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
     c->fver[mode]++;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1376,6 +1381,24 @@ int itcpd_drop_tensor(itcpd_ctx *c) {
     return ITCPD_OK;
 }
 
+// one mode of the leverage-score sampled solver from DEVICE pivots: sampled KRP rows, sampled least squares, row_norm, leverage refresh
+static int sampled_mode_update_device(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv, double chol_tol, int normal) {
+    const int R = c->rank;
+    const int64_t I = c->dims[mode];
+    TRY(c->samp_K.reserve((size_t)nsamp * R * 8));
+    TRY(k_pivot_hadamard(c, mode, nsamp, piv, c->samp_K.as<double>()));
+    const double *Ts = nullptr;
+    if (!normal) {   // the QR least squares works on the gathered unfolding itself
+        TRY(c->samp_T.reserve((size_t)nsamp * I * 8));
+        TRY(k_gather_fibers(c, mode, nsamp, piv, c->samp_T.as<double>()));
+        Ts = c->samp_T.as<double>();
+    }
+    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), Ts, piv, nsamp, chol_tol, normal));
+    TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
+    c->fver[mode]++;
+    return ensure_leverage(c, mode);  // also refreshes G[mode] (post_solve of LevScoreSampled, krp_lev...:55-58)
+}
+
 int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *host_pivots, double chol_tol, int normal) {
     CHECK_CTX(c);
     NEED_T(c);
@@ -1383,23 +1406,118 @@ int itcpd_sampled_update(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *h
     ARG_CHECK(nsamp >= 1 && host_pivots && c->has_tensor, "bad nsamp / null pointer / no tensor");
     USE_DEVICE(c);
     TRY(ensure_cpd_buffers(c));
-    const int R = c->rank;
-    const int64_t I = c->dims[mode];
     TRY(upload_pivots(c, mode, nsamp, host_pivots));
     if (comm_active(c)) {
         TRY(sharded_sampled_update(c, mode, nsamp, c->samp_piv.as<int64_t>(), nullptr, chol_tol, normal, true));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         return ITCPD_OK;
     }
-    TRY(c->samp_K.reserve((size_t)nsamp * R * 8));
-    TRY(c->samp_T.reserve((size_t)nsamp * I * 8));
-    TRY(k_pivot_hadamard(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_K.as<double>()));
-    TRY(k_gather_fibers(c, mode, nsamp, c->samp_piv.as<int64_t>(), c->samp_T.as<double>()));
-    TRY(sampled_ls(c, mode, c->samp_K.as<double>(), c->samp_T.as<double>(), nsamp, chol_tol, normal));
-    TRY(k_colnorm_scale(c, c->X.as<double>(), I, R, c->A[mode].as<double>(), c->lambda.as<double>(), false));
-    c->fver[mode]++;
-    TRY(ensure_leverage(c, mode));  // also refreshes G[mode] (post_solve of LevScoreSampled, krp_lev...:55-58)
+    TRY(sampled_mode_update_device(c, mode, nsamp, c->samp_piv.as<int64_t>(), chol_tol, normal));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITCPD_OK;
+}
+
+// ---- device-resident sweeps of the leverage-score sampled solver -----------------------------------------------------------
+// One sweep = for every mode: weighted draw (seeded by the device-side draw counter), sampled Khatri-Rao rows, sampled normal
+// equations or QR least squares, row_norm, leverage refresh -- the ProjectionAlgorithm hooks of optimize.jl:17-28 for
+// LevScoreSampled (krp_lev_score_sampled.jl:9-58) with no host round trip.  Same kernels and seeds as the per-mode entry points
+// (itcpd_sample_factor_matrices + itcpd_sampled_update): the two drivers are bitwise equal.  After one plain sweep has sized every
+// buffer the sweep body is captured into a CUDA graph; the draw counter lives in device memory, so a replay draws fresh samples.
+__global__ void set_counter_kernel(unsigned long long *ctr, unsigned long long v) { *ctr = v; }
+
+static int one_sampled_sweep_device(itcpd_ctx *c, const int64_t *nsamp, double chol_tol, int normal) {
+    for (int mode = 0; mode < c->order; ++mode) {
+        TRY(k_sample_rows(c, mode, nsamp[mode], 0, c->samp_piv.as<int64_t>(), c->draw_counter.as<unsigned long long>()));
+        TRY(sampled_mode_update_device(c, mode, nsamp[mode], c->samp_piv.as<int64_t>(), chol_tol, normal));
+    }
+    return ITCPD_OK;
+}
+
+int itcpd_sampled_sweep_async(itcpd_ctx *c, int nsweeps, const int64_t *nsamp, uint64_t draw_counter, double chol_tol, int normal) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    ARG_CHECK(nsweeps >= 1 && nsamp != nullptr, "bad nsweeps / null nsamp");
+    ARG_CHECK(!comm_active(c), "the device-resident sampled sweep is single-GPU; a sharded handle goes through itcpd_sampled_update per mode");
+    USE_DEVICE(c);
+    TRY(ensure_cpd_buffers(c));
+    const int N = c->order, R = c->rank;
+    int64_t ns_max = 0, it_max = 0;
+    for (int m = 0; m < N; ++m) {
+        ARG_CHECK(nsamp[m] >= 1, "nsamp must be positive for every mode");
+        ARG_CHECK(normal || nsamp[m] >= R, "normal=false needs at least R samples");
+        ns_max = std::max(ns_max, nsamp[m]);
+        it_max = std::max(it_max, nsamp[m] * c->dims[m]);
+    }
+    TRY(c->samp_piv.reserve((size_t)ns_max * (N - 1) * 8));
+    TRY(c->samp_K.reserve((size_t)ns_max * R * 8));
+    if (!normal) TRY(c->samp_T.reserve((size_t)it_max * 8));
+    TRY(c->draw_counter.reserve(64));
+    for (int m = 0; m < N; ++m) TRY(ensure_leverage(c, m));
+    set_counter_kernel<<<1, 1, 0, c->stream>>>(c->draw_counter.as<unsigned long long>(), (unsigned long long)draw_counter);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+
+    auto make_key = [&](int64_t key[32]) {
+        int k = 0;
+        memset(key, 0, 32 * sizeof(int64_t));
+        key[k++] = (int64_t)(intptr_t)c->T.p; key[k++] = (int64_t)(intptr_t)c->A[0].p; key[k++] = (int64_t)(intptr_t)c->samp_K.p;
+        key[k++] = (int64_t)(intptr_t)c->samp_piv.p; key[k++] = (int64_t)(intptr_t)c->work2.p; key[k++] = (int64_t)(intptr_t)c->work.p;
+        key[k++] = (int64_t)(intptr_t)c->redux.p; key[k++] = (int64_t)(intptr_t)c->samp_T.p;
+        key[k++] = N; key[k++] = R; key[k++] = normal; key[k++] = c->chol_alg; key[k++] = c->graph_epoch;
+        memcpy(&key[k++], &chol_tol, 8);
+        for (int n = 0; n < ITCPD_MAX_ORDER; ++n) { key[k++] = n < N ? c->dims[n] : 0; key[k++] = n < N ? nsamp[n] : 0; }
+    };
+    auto host_bookkeeping = [&]() {   // what one_sampled_sweep_device does to the host state
+        for (int n = 0; n < N; ++n) { c->fver[n]++; c->lev_ver[n] = c->fver[n]; c->m_valid[n] = false; }
+    };
+    int done = 0;
+    int64_t key[32];
+    make_key(key);
+    const bool have_exec = c->sampled_graph_exec && memcmp(key, c->sampled_graph_key, sizeof(key)) == 0;
+    const bool warm = c->sampled_plain_key_valid && memcmp(key, c->sampled_plain_key, sizeof(key)) == 0;
+    if (c->use_graph && (nsweeps >= 3 || have_exec || warm)) {
+        if (!have_exec) {
+            if (c->sampled_graph_exec) { cudaGraphExecDestroy(c->sampled_graph_exec); c->sampled_graph_exec = nullptr; }
+            if (!warm) {
+                TRY(one_sampled_sweep_device(c, nsamp, chol_tol, normal));   // plain sweep: sizes every scratch buffer
+                done = 1;
+            }
+            make_key(key);
+            const int64_t l0 = c->launches;
+            uint64_t fver0[ITCPD_MAX_ORDER], lev0[ITCPD_MAX_ORDER];
+            memcpy(fver0, c->fver, sizeof(fver0));
+            memcpy(lev0, c->lev_ver, sizeof(lev0));
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            const int st = one_sampled_sweep_device(c, nsamp, chol_tol, normal);
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            memcpy(c->fver, fver0, sizeof(fver0));     // nothing ran during the capture
+            memcpy(c->lev_ver, lev0, sizeof(lev0));
+            c->sampled_graph_launches = c->launches - l0;
+            c->launches = l0;
+            if (st != ITCPD_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (st != ITCPD_OK) return st;
+                set_error("CUDA graph capture of the sampled sweep failed: %s", cudaGetErrorString(e));
+                return ITCPD_ERR_CUDA;
+            }
+            const cudaError_t e2 = cudaGraphInstantiate(&c->sampled_graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) { c->sampled_graph_exec = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e2)); return ITCPD_ERR_CUDA; }
+            memcpy(c->sampled_graph_key, key, sizeof(key));
+        }
+        for (; done < nsweeps; ++done) {
+            CUDA_TRY(cudaGraphLaunch(c->sampled_graph_exec, c->stream));
+            c->launches += c->sampled_graph_launches;
+            host_bookkeeping();
+        }
+    }
+    if (done < nsweeps) {
+        for (; done < nsweeps; ++done) TRY(one_sampled_sweep_device(c, nsamp, chol_tol, normal));
+        make_key(c->sampled_plain_key);
+        c->sampled_plain_key_valid = true;
+    }
     return ITCPD_OK;
 }
 

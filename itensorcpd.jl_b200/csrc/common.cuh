@@ -181,6 +181,15 @@ struct itcpd_ctx {
     int64_t graph_epoch = 0;
     cudaGraphExec_t sweep_graph_exec = nullptr;
     int64_t sweep_graph_key[24] = {0};
+    // device-resident sweeps of the leverage-score sampled solver (itcpd_sampled_sweep_async): their own captured graph, and the
+    // device-side draw counter that seeds every weighted draw (so that a replayed graph draws fresh samples)
+    cudaGraphExec_t sampled_graph_exec = nullptr;
+    int64_t sampled_graph_key[32] = {0};
+    int64_t sampled_graph_launches = 0;
+    int64_t sampled_plain_key[32] = {0};
+    bool sampled_plain_key_valid = false;
+    itcpd::DevBuf draw_counter;
+    itcpd::DevBuf lev_q;   // leverage scores: Q_1 = A P U^{-1} (rows x R), G_2 = Q_1^T Q_1 and the Neumann correction W (solve.cu)
     // option "graph_single" (off by default, not yet run on hardware): the reference-facing loop calls itcpd_sweep(1) once per
     // iteration (optimize.jl:15-31), which never reaches the nsweeps >= 3 rule; with the option on, the second single-sweep call
     // with an unchanged configuration captures the graph and later calls replay it
@@ -265,7 +274,8 @@ int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int
 int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows_local, int64_t rows_total, int R, double *lev_out);
 
 // ---- sampled.cu ---------------------------------------------------------------------------
-int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev);
+int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev, unsigned long long *draw_counter_dev = nullptr);
+int k_sampled_mttkrp(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, const double *Ts_dev, const double *K_dev, double *M_dev);  // T_s K
 int k_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *K_dev);
 int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
 int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);

@@ -72,6 +72,106 @@ int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_de
     return ITCPD_OK;
 }
 
+// ---- sampled MTTKRP in one pass: M_s[i, r] = sum_s T[fibre(s)][i] * K[s, r]   (= T_s K of ProjectionAlgorithm.jl:60-62) ----
+// The gathered unfolding T_s (I x nsamp) is never materialised: a CTA owns 64 rows x 64 rank columns and a chunk of the samples,
+// stages 16 fibres' segments and 16 rows of K per step in shared memory and accumulates a 4 x 4 register tile per thread.  The
+// sample chunks (split-K: with I / 64 row blocks alone only a handful of SMs would have work) write partial tiles that are added
+// in chunk order (fixed order: bitwise reproducible).  Bytes: 8 per gathered element (a 32-byte sector per element for modes
+// other than the first: inherent to a strided fibre) + 8 R per sample for K.
+constexpr int SM_BI = 64, SM_BR = 64, SM_SB = 16;
+
+__global__ void __launch_bounds__(256) sampled_mttkrp_kernel(const double *__restrict__ T, const double *__restrict__ Ts, SDims d, int mode, int64_t nsamp,
+                                                             int64_t chunk, const int64_t *__restrict__ piv, const double *__restrict__ K, int R,
+                                                             double *__restrict__ part) {
+    __shared__ double st[SM_SB][SM_BI + 1], sk[SM_SB][SM_BR + 1];
+    __shared__ int64_t s_off[SM_SB];
+    const int64_t I = d.dim[mode];
+    const int64_t i0 = (int64_t)blockIdx.x * SM_BI;
+    const int r0 = blockIdx.y * SM_BR;
+    const int64_t s_begin = (int64_t)blockIdx.z * chunk, s_end = min(nsamp, s_begin + chunk);
+    int64_t stride_mode = 1;
+    for (int m = 0; m < mode; ++m) stride_mode *= d.ext[m];
+    const int ti = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int64_t sb = s_begin; sb < s_end; sb += SM_SB) {
+        if (threadIdx.x < SM_SB) {   // fibre start offsets of this batch (Ts given: the fibres were gathered before, column s of Ts)
+            const int64_t s = sb + threadIdx.x;
+            int64_t off = 0, str = 1;
+            if (Ts) off = I * s;
+            else if (s < s_end) {
+                int col = 0;
+                for (int m = 0; m < d.n; ++m) {
+                    if (m != mode) { off += (piv[s + nsamp * col] - 1) * str; ++col; }
+                    str *= d.ext[m];
+                }
+            }
+            s_off[threadIdx.x] = off;
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < SM_SB * SM_BI; q += 256) {
+            const int ss = q / SM_BI, ii = q % SM_BI;   // consecutive threads walk along one fibre
+            const int64_t s = sb + ss, i = i0 + ii;
+            st[ss][ii] = (s < s_end && i < I) ? (Ts ? Ts[s_off[ss] + i] : T[s_off[ss] + i * stride_mode]) : 0.0;
+        }
+        for (int q = threadIdx.x; q < SM_SB * SM_BR; q += 256) {
+            const int rr = q / SM_SB, ss = q % SM_SB;   // consecutive threads read consecutive samples of one column of K
+            const int64_t s = sb + ss;
+            const int r = r0 + rr;
+            sk[ss][rr] = (s < s_end && r < R) ? K[s + nsamp * (int64_t)r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ss = 0; ss < SM_SB; ++ss) {
+            double tv[4], kv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) tv[a] = st[ss][ti + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) kv[b] = sk[ss][tr + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(tv[a], kv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+    double *dst = part + (size_t)blockIdx.z * (size_t)I * R;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t i = i0 + ti + 16 * a;
+            const int r = r0 + tr + 16 * b;
+            if (i < I && r < R) dst[i + I * (int64_t)r] = acc[a][b];
+        }
+}
+
+// M (I x R) = T_s K.  Ts_dev == null: the fibres are read from the tensor through the pivots (T_s is never materialised);
+// otherwise Ts_dev is the cached gathered unfolding (pivot-projected solvers: the tensor may be gone).  Scratch: c->work2.
+int k_sampled_mttkrp(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, const double *Ts_dev, const double *K_dev, double *M_dev) {
+    const int R = c->rank;
+    const int64_t I = c->dims[mode];
+    const int64_t rowb = ceil_div(I, SM_BI), colb = ceil_div(R, SM_BR);
+    // enough (row block, column block, sample chunk) CTAs for two per SM, chunks a multiple of the 16-sample batch
+    int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * (int64_t)c->sm_count, rowb * colb), ceil_div(nsamp, 4 * SM_SB)));
+    const int64_t chunk = ceil_div(ceil_div(nsamp, nchunks), SM_SB) * SM_SB;
+    nchunks = ceil_div(nsamp, chunk);
+    double *part = M_dev;
+    if (nchunks > 1) {
+        TRY(c->work2.reserve((size_t)nchunks * (size_t)I * R * 8));
+        part = c->work2.as<double>();
+    }
+    dim3 grid((unsigned)rowb, (unsigned)colb, (unsigned)nchunks);
+    sampled_mttkrp_kernel<<<grid, 256, 0, c->stream>>>(c->T.as<double>(), Ts_dev, sdims(c), mode, nsamp, chunk, piv_dev, K_dev, R, part);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (nchunks > 1) TRY(k_sum_slices(c, part, I * R, (int)nchunks, M_dev));
+    return ITCPD_OK;
+}
+
 // ---- sparse-sign sketch of the unfolding: out[i, j] = sum_{e in row j} val[e] T_(mode)[i, col[e]] ----
 // (row_ptr, col, val) is the sketch in CSR-by-sketch-row order, entries of a row in increasing
 // non-zero order (the order the reference's dict_rows visits them, pivot_mapping.jl:127-137).
@@ -189,10 +289,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-__global__ void sample_kernel(const double *__restrict__ cdf, int64_t n, int64_t nsamp, uint64_t seed, uint64_t stream,
-                              int64_t *__restrict__ out) {
+// seed_dev != null: the draw's seed is seed + *seed_dev (a device-side draw counter, so that a captured sweep draws fresh samples
+// at every replay); the host-driven entry points pass the seed by value
+__global__ void sample_kernel(const double *__restrict__ cdf, int64_t n, int64_t nsamp, uint64_t seed, const unsigned long long *__restrict__ seed_dev,
+                              uint64_t stream, int64_t *__restrict__ out) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= nsamp) return;
+    if (seed_dev) seed += (uint64_t)*seed_dev;
     const uint64_t bits = splitmix64(splitmix64(seed ^ (stream * 0xD1B54A32D192ED03ull)) + (uint64_t)s);
     const double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0) * cdf[n - 1];
     int64_t lo = 0, hi = n - 1;
@@ -203,14 +306,20 @@ __global__ void sample_kernel(const double *__restrict__ cdf, int64_t n, int64_t
     out[s] = lo + 1;  // 1-based
 }
 
-int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev) {
+__global__ void bump_counter_kernel(unsigned long long *ctr) { *ctr += 1ull; }
+
+int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int64_t *piv_dev, unsigned long long *draw_counter_dev) {
+    if (draw_counter_dev) {   // one draw = one seed: advance the device-side draw counter first (host loop: `seed += 1` before every draw)
+        bump_counter_kernel<<<1, 1, 0, c->stream>>>(draw_counter_dev);
+        c->launches++;
+    }
     int col = 0;
     for (int m = 0; m < c->order; ++m) {
         if (m == skip_mode) continue;
         const int64_t n = mode_rows(c, m);
         TRY(c->work.reserve((size_t)n * 8));
         cdf_kernel<<<1, 1024, 0, c->stream>>>(c->lev[m].as<double>(), n, c->work.as<double>());
-        sample_kernel<<<(unsigned)ceil_div(nsamp, 256), 256, 0, c->stream>>>(c->work.as<double>(), n, nsamp, seed, (uint64_t)m,
+        sample_kernel<<<(unsigned)ceil_div(nsamp, 256), 256, 0, c->stream>>>(c->work.as<double>(), n, nsamp, seed, draw_counter_dev, (uint64_t)m,
                                                                            piv_dev + nsamp * col);
         c->launches += 2;
         ++col;
@@ -223,7 +332,7 @@ int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int
 int k_cdf_sample(itcpd_ctx *c, const double *weights_dev, int64_t n, int64_t nsamp, uint64_t seed, uint64_t stream_id, int64_t *out_dev) {
     TRY(c->work.reserve((size_t)n * 8));
     cdf_kernel<<<1, 1024, 0, c->stream>>>(weights_dev, n, c->work.as<double>());
-    sample_kernel<<<(unsigned)ceil_div(nsamp, 256), 256, 0, c->stream>>>(c->work.as<double>(), n, nsamp, seed, stream_id, out_dev);
+    sample_kernel<<<(unsigned)ceil_div(nsamp, 256), 256, 0, c->stream>>>(c->work.as<double>(), n, nsamp, seed, nullptr, stream_id, out_dev);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;

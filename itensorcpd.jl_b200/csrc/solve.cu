@@ -606,6 +606,15 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
             else if (l > k && l < nn) b[e] = fma(-U[k + (size_t)ldw * l], yk, b[e]);
         }
     }
+    if (fwd_only == 2) {
+        // y = U^{-T} P^T a_i is row i of Q_1 = A P U^{-1} (Cholesky-QR): store it, zero beyond the numerical rank
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            if (k < n) X[i + rows * (int64_t)k] = (k < nn) ? b[e] : 0.0;
+        }
+        return;
+    }
     if (fwd_only) {
         double s = 0.0;
 #pragma unroll
@@ -764,37 +773,73 @@ int k_solve(itcpd_ctx *c, const double *Gamma, const double *M, int64_t rows, in
     return k_solve_apply(c, Gamma, M, rows, R, X, status_dev);
 }
 
-// leverage scores (math_tools/probability.jl:3-10): p_i = ||Q[i,:]||^2 / min(I,R) with A = QR.
-// Q = A U^{-1} for the Cholesky factor of the Gram matrix, so ||Q[i,:]||^2 = ||U^{-T} a_i||^2
-// (restricted to the numerical rank found by the pivoted factorisation).
+// leverage scores (math_tools/probability.jl:3-10): p_i = ||Q[i,:]||^2 / min(I,R) with A = QR  (the reference takes a Householder QR).
+// Cholesky-QR with a correction: U = chol(A^T A) (pivoted: a numerically rank-deficient factor is truncated at its rank), Q_1 = A P U^{-1}
+// by forward substitution.  In floating point Q_1^T Q_1 = G_2 = I + E with |E| ~ cond(A)^2 eps, and EXACTLY
+//     ||Q[i,:]||^2 = a_i^T (A^T A)^{-1} a_i = q_i^T G_2^{-1} q_i        (q_i = row i of Q_1),
+// so the scores are the quadratic form with G_2^{-1} ~ I - E + E^2 = 3 I - 3 G_2 + G_2^2 (error |E|^3): the accuracy of a second
+// Cholesky-QR pass without a second factorisation.  Plain ||q_i||^2 (round 1) was off by cond(A)^2 eps -- 1e-4 for the nearly collinear
+// factors of late ALS sweeps; with the correction the error is ~ cond(A) eps + (cond(A)^2 eps)^3
+// (tests/test_gpu_sampled.py::test_leverage_scores_ill_conditioned: cond 1e6, scores within 1e-9 of a Householder QR).
 __global__ void fill_kernel(double *x, int64_t n, double v) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
 }
-__global__ void scale_kernel(double *x, int64_t n, double v) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= v;
+
+// W = 3 I - 3 G2 + G2 G2   (R x R; G2 symmetric)
+__global__ void __launch_bounds__(256) neumann_kernel(const double *__restrict__ G2, int R, double *__restrict__ W) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= R * R) return;
+    const int r1 = e % R, r2 = e / R;
+    double s = 0.0;
+    for (int k = 0; k < R; ++k) s = fma(G2[r1 + (size_t)R * k], G2[k + (size_t)R * r2], s);
+    W[e] = s - 3.0 * G2[e] + (r1 == r2 ? 3.0 : 0.0);
 }
 
-int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out) {
-    if (rows <= R) {  // square/wide factor: Q is orthogonal, every row has unit norm
-        fill_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)rows);
-        c->launches++;
-        return ITCPD_OK;
+// lev[i] = scale * q_i^T W q_i, one warp per row (lane l holds columns l, l + 32, ...; W read through the L1/L2)
+template <int E>
+__global__ void __launch_bounds__(256) quadform_rows_kernel(const double *__restrict__ Q, const double *__restrict__ W, int64_t rows, int R,
+                                                            double scale, double *__restrict__ lev) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    if (i >= rows) return;
+    double q[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const int k = lane + 32 * e; q[e] = (k < R) ? Q[i + rows * (int64_t)k] : 0.0; }
+    double acc = 0.0;
+    for (int k = 0; k < R; ++k) {   // t_k = sum_l W[l, k] q_l  (lanes over l), acc += q_k t_k
+        double t = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const int l = lane + 32 * e; if (l < R) t = fma(W[l + (size_t)R * k], q[e], t); }
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        double qk = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) if (e == (k >> 5)) qk = q[e];
+        qk = __shfl_sync(0xffffffffu, qk, k & 31);
+        acc = fma(qk, t, acc);
     }
-    TRY(c->status.reserve(256));
-    int *st = c->status.as<int>() + 32;
-    TRY(run_cholesky(c, G, R, -1.0, st));
-    TRY(run_tri_solves(c, single_src(A), rows, R, lev_out, st, 1, 1));
-    scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)std::min<int64_t>(rows, R));
+    if (lane == 0) lev[i] = scale * acc;
+}
+
+static int run_quadform(itcpd_ctx *c, const double *Q, const double *W, int64_t rows, int R, double scale, double *lev) {
+    const unsigned grid = (unsigned)ceil_div(rows, 8);
+    const int E = (int)ceil_div(R, 32);
+    if (E <= 1) quadform_rows_kernel<1><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else if (E <= 2) quadform_rows_kernel<2><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else if (E <= 4) quadform_rows_kernel<4><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else if (E <= 8) quadform_rows_kernel<8><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else if (E <= 16) quadform_rows_kernel<16><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else if (E <= 32) quadform_rows_kernel<32><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
+    else { set_error("rank %d is above the 1024 limit of the leverage kernels", R); return ITCPD_ERR_UNSUPPORTED; }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
 }
 
-// the same for `rows` local rows of a factor with rows_total rows overall (slab-sharded factor; G is the global Gram)
-int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int64_t rows_total, int R, double *lev_out) {
-    if (rows_total <= R) {
+// `rows` local rows of a factor with rows_total rows overall (rows_total == rows unless the factor is slab-sharded; G is the
+// GLOBAL Gram then, and G2 is all-reduced by the caller-supplied hook so that every rank applies the same correction)
+static int leverage_impl(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int64_t rows_total, int R, double *lev_out) {
+    if (rows_total <= R) {  // square/wide factor: Q is orthogonal, every row has unit norm
         fill_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)rows_total);
         c->launches++;
         return ITCPD_OK;
@@ -802,11 +847,24 @@ int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows
     TRY(c->status.reserve(256));
     int *st = c->status.as<int>() + 32;
     TRY(run_cholesky(c, G, R, -1.0, st));
-    TRY(run_tri_solves(c, single_src(A), rows, R, lev_out, st, 1, 1));
-    scale_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, c->stream>>>(lev_out, rows, 1.0 / (double)std::min<int64_t>(rows_total, R));
+    TRY(c->lev_q.reserve(((size_t)rows * R + 2 * (size_t)R * R) * 8));
+    double *Q1 = c->lev_q.as<double>(), *G2 = Q1 + (size_t)rows * R, *W = G2 + (size_t)R * R;
+    TRY(run_tri_solves(c, single_src(A), rows, R, Q1, st, 2, 1));            // Q_1 = A P U^{-1}, zero beyond the numerical rank
+    TRY(k_gram(c, Q1, rows, R, G2));
+    if (comm_active(c) && rows != rows_total) TRY(comm_allreduce_sum(c, G2, (int64_t)R * R));
+    neumann_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, c->stream>>>(G2, R, W);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    return ITCPD_OK;
+    return run_quadform(c, Q1, W, rows, R, 1.0 / (double)std::min<int64_t>(rows_total, R), lev_out);
+}
+
+int k_leverage(itcpd_ctx *c, const double *A, const double *G, int64_t rows, int R, double *lev_out) {
+    return leverage_impl(c, A, G, rows, rows, R, lev_out);
+}
+
+// the same for `rows` local rows of a factor with rows_total rows overall (slab-sharded factor; G is the global Gram)
+int k_leverage_rows(itcpd_ctx *c, const double *A, const double *G, int64_t rows_local, int64_t rows_total, int R, double *lev_out) {
+    return leverage_impl(c, A, G, rows_local, rows_total, R, lev_out);
 }
 
 }  // namespace itcpd

@@ -270,6 +270,11 @@ class Engine:
         check(self._L.itcpd_sampled_update(self._h, mode, p.shape[0], _addr(p), float(chol_tol), int(bool(normal))))
 
     # -- pivot-projected solvers ------------------------------------------------------------
+    def sampled_sweep_async(self, nsweeps: int, nsamps, draw_counter: int, chol_tol: float = 1e-6, normal: bool = True):
+        """device-resident sweeps of the leverage-score sampled solver; the k-th draw is seeded with draw_counter + k"""
+        ns = (C.c_int64 * len(self.dims))(*[int(n) for n in nsamps])
+        check(self._L.itcpd_sampled_sweep_async(self._h, int(nsweeps), ns, int(draw_counter), float(chol_tol), int(bool(normal))))
+
     def qrcp_unfolding(self, mode: int):
         """qr(T_(mode), ColumnNorm()): (p 1-based int64 over all unfolding columns, diag(R))."""
         m = self.dims[mode]

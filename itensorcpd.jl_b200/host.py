@@ -603,8 +603,17 @@ def optimize(cp: CPD, als: ALS, verbose=False) -> CPD:
     if isinstance(alg, _PivotBased):
         eng.set_cpd(cp.factors, cp.lam)  # an ALS object can be re-used with another starting CPD (update_samples)
     fused = isinstance(alg, MttkrpAlgorithm) and isinstance(als.check, (NoCheck, FitCheck)) and not als.additional_items.get("per_hook")
+    # leverage-score sampling that redraws every iteration: the whole sweep (draws, gathers, sampled solves, leverage refresh) stays on
+    # the device; same seeds and kernels as the hook-by-hook path below (bitwise equal), no host round trip per mode
+    fused_sampled = (type(alg) is LevScoreSampled and als.additional_items.get("stop_resample", -1) < 0
+                     and not als.additional_items.get("per_hook") and not getattr(eng, "sharded", False))
     while it < als.check.max_counter:
-        if fused:
+        if fused_sampled:
+            ai = als.additional_items
+            eng.sampled_sweep_async(1, [alg.nsamples(f) for f in range(N)], ai["seed"], CHOLESKY_EPSILON, normal=ai["normal"])
+            ai["seed"] += N
+            done = alg.check_converge(als, verbose)
+        elif fused:
             # one device-resident sweep (itcpd_sweep == the five hooks for every mode + fit scalars)
             inner, norm2 = eng.sweep(1, CHOLESKY_EPSILON)
             if isinstance(als.check, FitCheck):

@@ -137,6 +137,14 @@ class FakeEngine(itcpd.Engine):
         K = sampled.pivot_hadamard([x for m, x in enumerate(self.f) if m != mode], pivots)
         self._ls(mode, K, sampled.fused_flatten_sample(self.T, mode, pivots), normal)
 
+    def sampled_sweep_async(self, nsweeps, nsamps, draw_counter, chol_tol=1e-6, normal=True):
+        """the device-resident sampled sweep: the k-th draw is seeded with draw_counter + k (same seeds as the per-mode calls)"""
+        d = int(draw_counter)
+        for _ in range(nsweeps):
+            for mode in range(len(self.dims)):
+                d += 1
+                self.sampled_update(mode, self.sample_factor_matrices(mode, nsamps[mode], d), chol_tol, normal)
+
     def qrcp_unfolding(self, mode):
         _, R, p = sampled.qrcp(cpals.unfold(self.T, mode), want_q=False)
         return p, np.diag(R).copy()

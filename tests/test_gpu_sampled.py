@@ -88,6 +88,26 @@ def test_leverage_scores(engine, rows, R):  # probability.jl:3-10
     assert abs(p.sum() - 1.0) < 1e-10 or rows < R
 
 
+@pytest.mark.parametrize("cond", [1e3, 1e6])
+def test_leverage_scores_ill_conditioned(engine, cond):
+    """Late ALS sweeps produce nearly collinear factor columns.  The reference takes a Householder QR (probability.jl:6); the device
+    route is Cholesky-QR with a second-order Neumann correction (solve.cu: leverage_impl), accurate to ~ cond * eps where the plain
+    Gram + Cholesky route of round 1 lost cond^2 * eps (1e-4 at cond 1e6)."""
+    rng = np.random.default_rng(17)
+    rows, R = 300, 20
+    U, _ = np.linalg.qr(rng.standard_normal((rows, R)))
+    V, _ = np.linalg.qr(rng.standard_normal((R, R)))
+    A = np.asfortranarray((U * np.logspace(0, -np.log10(cond), R)[None, :]) @ V.T)
+    assert abs(np.linalg.cond(A) / cond - 1) < 1e-6
+    engine.set_tensor(np.zeros((rows, 3, 2), order="F"))
+    engine.set_cpd([A, np.ones((3, R), order="F"), np.ones((2, R), order="F")], np.ones(R))
+    p = engine.leverage_scores(0)
+    q, _ = np.linalg.qr(A)
+    po = np.sum(q * q, axis=1) / R
+    assert np.max(np.abs(p - po)) < 1e-9 * np.max(po), (np.max(np.abs(p - po)) / np.max(po))
+    assert abs(p.sum() - 1.0) < 1e-9
+
+
 def test_weighted_sampling_distribution(engine):  # probability.jl:12-33 (statistical)
     rng = np.random.default_rng(6)
     dims = (30, 20, 10)
@@ -410,3 +430,52 @@ def test_block_lev_score_sampled_als(engine):
     assert piv.shape == (20, 2) and piv.min() >= 1 and piv[:, 0].max() <= 8 and piv[:, 1].max() <= 5
     # rows of a block are consecutive in the blocked (first non-skipped) mode
     assert np.all(np.diff(piv[:4, 0]) == 1) and len(set(piv[:4, 1].tolist())) == 1
+
+
+@pytest.mark.parametrize("normal", [True, False])
+@pytest.mark.parametrize("dims,R,ns", [((30, 26, 22), 6, 120), ((40, 18, 12, 9), 5, (90, 64, 77, 100))])
+def test_device_sampled_sweeps_equal_the_per_mode_calls(engine, dims, R, ns, normal):
+    """itcpd_sampled_sweep_async (draws, gathers, sampled solves and leverage refresh with no host round trip, replayed from a CUDA
+    graph, seeds from a device-side draw counter) against the hook-by-hook driver (itcpd_sample_factor_matrices + itcpd_sampled_update
+    per mode): same seeds, same kernels -> bitwise equal factors, also across the plain-sweep -> graph-replay transition."""
+    import itcpd
+
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(cpals.reconstruct(cpals.random_CPD(dims, R, rng)) + 0.01 * rng.standard_normal(dims))
+    cp0 = cpals.random_CPD(dims, R, rng)
+    out = {}
+    for per_hook in (True, False):
+        engine.set_tensor(A)
+        als = itcpd.compute_als(engine, itcpd.CPD(cp0.factors, cp0.lam), alg=itcpd.LevScoreSampled(ns), normal=normal, check=itcpd.NoCheck(7), seed=4)
+        als.additional_items["per_hook"] = per_hook
+        launches0 = engine.launch_count
+        o = itcpd.optimize(itcpd.CPD(cp0.factors, cp0.lam), als)
+        out[per_hook] = (o, engine.launch_count - launches0, [engine.leverage_scores(n) for n in range(len(dims))])
+    for a, b in zip(out[True][0].factors, out[False][0].factors):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[True][0].lam, out[False][0].lam)
+    for a, b in zip(out[True][2], out[False][2]):
+        assert np.array_equal(a, b)
+    assert out[False][1] > 0
+    # and the sampled solver still does its job: the fit of the sampled solution is close to the noise floor
+    e = np.linalg.norm(A - itcpd.reconstruct(out[False][0])) / np.linalg.norm(A)
+    assert e < 0.2, e
+
+
+def test_sampled_mttkrp_kernel_matches_gather_then_multiply(engine):
+    """sampled.cu: sampled_mttkrp_kernel (fibres read through the pivots, 64 x 64 register-tiled, split over sample chunks) against
+    numpy on the gathered unfolding, for every mode, ragged sizes, more samples than one chunk"""
+    T, cp, rng = problem((70, 33, 21), 37, 11)
+    engine.set_tensor(T)
+    engine.set_cpd(cp.factors, cp.lam)
+    for mode in range(3):
+        others = [m for m in range(3) if m != mode]
+        nsamp = 1500 + 17 * mode
+        piv = np.asfortranarray(np.stack([rng.integers(1, T.shape[m] + 1, size=nsamp) for m in others], axis=1).astype(np.int64))
+        engine.sampled_update(mode, piv)
+        K = sampled.pivot_hadamard([cp.factors[m] for m in others], piv)
+        Ts = sampled.fused_flatten_sample(T, mode, piv)
+        X = cpals.ldiv_solve(K.T @ K, np.asfortranarray((Ts @ K).T)).T
+        Ao, lo = cpals.row_norm(X)
+        assert np.linalg.norm(engine.get_factor(mode) - Ao) / np.linalg.norm(Ao) < 1e-9, mode
+        engine.set_factor(mode, cp.factors[mode])

@@ -119,7 +119,12 @@ def test_sampled_solvers_control_flow():
         o = itcpd.als_optimize(e, start, alg=alg, check=itcpd.CPDiffCheck(1e-6, 60), rng=np.random.default_rng(9), **kw)
         assert np.linalg.norm(A - cpals.reconstruct(cpals.CPD(o.factors, o.lam))) / nA < 0.2, type(alg).__name__
         if isinstance(alg, (itcpd.QRPivProjected, itcpd.SEQRCSPivProjected, itcpd.KSEQRCSPivProjected)):
-            assert e.T is None  # ALS(ITensor(inds(target)), ...): the dense tensor is released after the setup
+            # ALS(ITensor(inds(target)), ...) drops the ALS object's reference to the tensor, not the caller's: a tensor that lives in an
+            # engine the CALLER passed in stays resident, so that a second set-up on the same engine (the rank-adaptive loop,
+            # decompose.jl:51-66) finds it again (it used to be dropped, and the second rank step failed)
+            assert e.T is not None
+            o2 = itcpd.als_optimize(e, start, alg=alg, check=itcpd.NoCheck(3), rng=np.random.default_rng(9), **kw)
+            assert np.all(np.isfinite(o2.factors[0]))
 
 
 def test_update_samples_bookkeeping():  # test/rand_cp_als.jl:28-36
