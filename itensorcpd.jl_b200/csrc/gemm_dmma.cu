@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(256) streamk_fixup_kernel(const int *__restric
         const int r = rb * BN + lc;
         if (row < rows_out && r < R) {
             double v = 0.0;
-            for (int p = p0; p < p1; ++p) v += slots[(size_t)slot_list[p] * (size_t)(BM * BN) + e];
+#pragma unroll 4
+            for (int p = p0; p < p1; ++p) v += slots[(size_t)slot_list[p] * (size_t)(BM * BN) + e];   // ascending k: fixed order, loads in flight together
             out[row + rows_out * (int64_t)r] = v;
         }
     }
@@ -502,7 +503,10 @@ static int launch_cfg(itcpd_ctx *c, const CUtensorMap &map, const double *Kp, do
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     if (tb.nsplit > 0) {
-        streamk_fixup_kernel<<<dim3((unsigned)tb.nsplit, (unsigned)std::max(1, std::min(BM * BN / 1024, 4 * c->sm_count / tb.nsplit))), 256, 0, c->stream>>>(tb.dev.as<int>(), tb.dev.as<int>() + tb.off_ptr, tb.dev.as<int>() + tb.off_list,
+        // few split tiles with many parts each (the short-and-wide pass A of a slab: 8 tiles x 37 parts) need one element per thread to
+        // cover the SMs; many split tiles (the last wave of pass B) are parallel enough at 4 elements per thread
+        const int per_tile = tb.nsplit * 4 <= c->sm_count ? BM * BN / 256 : BM * BN / 1024;
+        streamk_fixup_kernel<<<dim3((unsigned)tb.nsplit, (unsigned)std::max(1, std::min(per_tile, 16 * c->sm_count / tb.nsplit))), 256, 0, c->stream>>>(tb.dev.as<int>(), tb.dev.as<int>() + tb.off_ptr, tb.dev.as<int>() + tb.off_list,
                                                               c->sk_slots.as<double>(), out, rows_out, R, num_rblocks, BM, BN);
         c->launches++;
         CUDA_TRY(cudaGetLastError());

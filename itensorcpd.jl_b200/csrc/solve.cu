@@ -796,41 +796,50 @@ __global__ void __launch_bounds__(256) neumann_kernel(const double *__restrict__
     W[e] = s - 3.0 * G2[e] + (r1 == r2 ? 3.0 : 0.0);
 }
 
-// lev[i] = scale * q_i^T W q_i, one warp per row (lane l holds columns l, l + 32, ...; W read through the L1/L2)
-template <int E>
-__global__ void __launch_bounds__(256) quadform_rows_kernel(const double *__restrict__ Q, const double *__restrict__ W, int64_t rows, int R,
-                                                            double scale, double *__restrict__ lev) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = blockIdx.x * 8ll + (threadIdx.x >> 5);
-    if (i >= rows) return;
-    double q[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) { const int k = lane + 32 * e; q[e] = (k < R) ? Q[i + rows * (int64_t)k] : 0.0; }
-    double acc = 0.0;
-    for (int k = 0; k < R; ++k) {   // t_k = sum_l W[l, k] q_l  (lanes over l), acc += q_k t_k
-        double t = 0.0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) { const int l = lane + 32 * e; if (l < R) t = fma(W[l + (size_t)R * k], q[e], t); }
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        double qk = 0.0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) if (e == (k >> 5)) qk = q[e];
-        qk = __shfl_sync(0xffffffffu, qk, k & 31);
-        acc = fma(qk, t, acc);
+// lev[i] = scale * q_i^T W q_i.  R <= 128: W staged in shared memory, one warp per row with the row broadcast from shared memory
+// and lane l owning the outputs t_k = sum_j W[k,j] q_j for k = l, l + 32, ... (no shuffle inside the j loop: one reduction per row).
+// Larger R: W read through the L1/L2, same arithmetic order.
+constexpr int QF_WARPS = 8, QF_ROWS = 4;   // rows per warp
+
+__global__ void __launch_bounds__(QF_WARPS * 32) quadform_rows_kernel(const double *__restrict__ Q, const double *__restrict__ W, int64_t rows, int R,
+                                                                       double scale, double *__restrict__ lev, int w_in_smem) {
+    extern __shared__ double sm_q[];          // [W: R x R when staged] [q rows: QF_WARPS x R]
+    const double *Wp = W;
+    if (w_in_smem) {
+        for (int e = threadIdx.x; e < R * R; e += QF_WARPS * 32) sm_q[e] = W[e];
+        Wp = sm_q;
     }
-    if (lane == 0) lev[i] = scale * acc;
+    double *qrow = sm_q + (w_in_smem ? (size_t)R * R : 0) + (size_t)(threadIdx.x >> 5) * R;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int rr = 0; rr < QF_ROWS; ++rr) {
+        const int64_t i = ((int64_t)blockIdx.x * QF_WARPS + (threadIdx.x >> 5)) * QF_ROWS + rr;
+        if (i >= rows) break;   // uniform over the warp
+        for (int k = lane; k < R; k += 32) qrow[k] = Q[i + rows * (int64_t)k];
+        __syncwarp();
+        double acc = 0.0;
+        for (int k = lane; k < R; k += 32) {
+            double t = 0.0;
+            for (int j = 0; j < R; ++j) t = fma(Wp[k + (size_t)R * j], qrow[j], t);   // W is symmetric: lanes read consecutive words
+            acc = fma(qrow[k], t, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) lev[i] = scale * acc;
+        __syncwarp();
+    }
 }
 
 static int run_quadform(itcpd_ctx *c, const double *Q, const double *W, int64_t rows, int R, double scale, double *lev) {
-    const unsigned grid = (unsigned)ceil_div(rows, 8);
-    const int E = (int)ceil_div(R, 32);
-    if (E <= 1) quadform_rows_kernel<1><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else if (E <= 2) quadform_rows_kernel<2><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else if (E <= 4) quadform_rows_kernel<4><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else if (E <= 8) quadform_rows_kernel<8><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else if (E <= 16) quadform_rows_kernel<16><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else if (E <= 32) quadform_rows_kernel<32><<<grid, 256, 0, c->stream>>>(Q, W, rows, R, scale, lev);
-    else { set_error("rank %d is above the 1024 limit of the leverage kernels", R); return ITCPD_ERR_UNSUPPORTED; }
+    const unsigned grid = (unsigned)ceil_div(rows, QF_WARPS * QF_ROWS);
+    const int w_in = R <= 128;
+    const size_t smem = ((w_in ? (size_t)R * R : 0) + (size_t)QF_WARPS * R) * 8;
+    static bool attr[64] = {false};
+    if (!attr[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(quadform_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit(c)));
+        attr[c->device & 63] = true;
+    }
+    ARG_CHECK(smem <= (size_t)smem_limit(c), "rank too large for the leverage kernels");
+    quadform_rows_kernel<<<grid, QF_WARPS * 32, smem, c->stream>>>(Q, W, rows, R, scale, lev, w_in);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;

@@ -146,7 +146,7 @@ def test_bench_line_contract_in_the_dry_run(dry_results, env_extra, args):
     assert set(line["config"]) == {"workload", "l2"}   # the keys the reference arm prints too; everything else lives in config_detail
     assert "parity" in line and "config_detail" in line
     if not args:   # the default workload carries the other BASELINE.json configurations as compact records
-        assert [r["config"] for r in line["extra"]] == ["D", "C", "A", "E"], line["extra"]
+        assert [r["config"] for r in line["extra"]] == ["D", "C", "A", "E", "B+gemm_i8=2"], line["extra"]
         for r in line["extra"]:   # (E draws its samples on the device: no kernel runs here, so its host-side pivot check refuses the zeros)
             assert "error" not in r or r["config"] == "E", r
     assert "workload" in line["config"] and "model" not in line["config"]

@@ -473,6 +473,34 @@ def test_gemm_i8_mttkrp_matches_oracle(engine, dims, R, variant):
         engine.set_option("gemm_i8", 0)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("kind", ["lognormal", "spiky rows", "tiny rows"])
+def test_gemm_i8_wide_dynamic_range(engine, kind, variant):
+    """The INT8 path represents every row of the unfolding in 48-bit fixed point relative to the row's maximum, so entries far
+    below the row maximum lose relative precision.  The bar is the north star's (1e-12 relative Frobenius on the MTTKRP), checked
+    here on inputs whose magnitudes span many decades inside a row and from row to row -- against the FP64 oracle."""
+    rng = np.random.default_rng(7)
+    dims, R = (96, 80, 64), 40
+    T = rng.standard_normal(dims)
+    if kind == "lognormal":
+        T = np.sign(T) * np.exp(4.0 * rng.standard_normal(dims))           # ~ 7 decades inside every row
+    elif kind == "spiky rows":
+        T[::7] *= 1e9                                                       # a few huge entries dominate their rows
+        T[3::11, 5::13] *= 1e-9
+    else:
+        T *= np.exp(20.0 * rng.standard_normal((dims[0], 1, 1)))            # rows differ by ~ 17 decades (per-row exponents)
+    T = np.asfortranarray(T)
+    cp = cpals.random_CPD(T, R, np.random.default_rng(8))
+    engine.set_option("gemm_i8", variant)
+    try:
+        engine.set_tensor(T)
+        engine.set_cpd(cp.factors, cp.lam)
+        for n in range(3):
+            assert relerr(engine.mttkrp(n), cpals.mttkrp_krp_normal(T, cp.factors, n)) < 1e-12, (kind, n)
+    finally:
+        engine.set_option("gemm_i8", 0)
+
+
 @pytest.mark.parametrize("dims,R", [((64, 40, 512), 64), ((100, 24, 700), 40)])   # pass A of the (1,1) tree: 1 row tile x 640 / 525 k-tiles
 @pytest.mark.parametrize("variant", [1, 2])
 def test_gemm_i8_split_k_matches_oracle(engine, dims, R, variant):
