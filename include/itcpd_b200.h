@@ -119,6 +119,10 @@ int itcpd_mttkrp(itcpd_ctx *ctx, int mode, double *host_out);
  * deficiency the column-pivoted-QR min-norm solve (dgelsy semantics, rcond = R*eps).
  * Operates on the device-resident Gamma and M_mode; path_out/rank_out may be NULL. */
 int itcpd_solve(itcpd_ctx *ctx, int mode, double chol_tol, int *path_out, int *rank_out);
+/* (path, rank) of the most recent R x R solve on this handle, whichever entry point ran it (itcpd_solve, the sampled / projected
+ * updates, the last mode of a sweep): ITCPD_SOLVE_CHOLESKY, or ITCPD_SOLVE_QRCP when the pivoted Cholesky met a pivot <= tol and
+ * the pivoted-QR min-norm fallback of ldiv_solve.jl:19-21 was taken. */
+int itcpd_last_solve_status(itcpd_ctx *ctx, int mode_slot, int *path_out, int *rank_out);
 /* row_norm (math_tools/row_norm.jl:4-24): lambda_r = ||X[:,r]||, A_mode = X ./ lambda */
 int itcpd_normalize(itcpd_ctx *ctx, int mode);
 /* post_solve (tensor.jl:46-49): G_mode = A_mode' A_mode */

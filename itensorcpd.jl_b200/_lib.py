@@ -50,6 +50,7 @@ _SIGS = {
     "itcpd_gram_hadamard": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "itcpd_mttkrp": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "itcpd_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "itcpd_last_solve_status": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "itcpd_normalize": (C.c_int, [C.c_void_p, C.c_int]),
     "itcpd_post_solve": (C.c_int, [C.c_void_p, C.c_int]),
     "itcpd_fit_terms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -663,6 +663,18 @@ int itcpd_solve(itcpd_ctx *c, int mode, double chol_tol, int *path_out, int *ran
     return ITCPD_OK;
 }
 
+int itcpd_last_solve_status(itcpd_ctx *c, int mode_slot, int *path_out, int *rank_out) {
+    CHECK_CTX(c);
+    ARG_CHECK(mode_slot >= 0 && mode_slot < ITCPD_MAX_ORDER && c->status.p, "bad slot / no solve has run (slot 0 outside whole sweeps, the mode index after a sweep)");
+    USE_DEVICE(c);
+    int *h = reinterpret_cast<int *>(c->pinned);
+    CUDA_TRY(cudaMemcpyAsync(h, c->status.as<int>() + 3 * mode_slot, 12, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (path_out) *path_out = h[0];
+    if (rank_out) *rank_out = h[1];
+    return ITCPD_OK;
+}
+
 int itcpd_normalize(itcpd_ctx *c, int mode) {
     CHECK_CTX(c);
     CHECK_MODE(c, mode);

@@ -166,6 +166,12 @@ class Engine:
         check(self._L.itcpd_solve(self._h, mode, float(chol_tol), C.byref(path), C.byref(rk)))
         return path.value, rk.value
 
+    def last_solve_status(self, slot: int = 0):
+        """(path, rank) of the most recent R x R solve (slot 0; after whole sweeps slot = mode index)"""
+        path, rank = C.c_int(0), C.c_int(0)
+        check(self._L.itcpd_last_solve_status(self._h, int(slot), C.byref(path), C.byref(rank)))
+        return path.value, rank.value
+
     def normalize(self, mode: int):
         check(self._L.itcpd_normalize(self._h, mode))
 

@@ -26,6 +26,9 @@ def timed(fn):
 
 for ns in (10 * R, 64 * R):
     for per_hook in (False, True):
+        warm = itcpd.compute_als(eng, cp0, alg=itcpd.LevScoreSampled(ns), normal=True, check=itcpd.NoCheck(3), seed=4)   # untimed: buffers + graph
+        warm.additional_items["per_hook"] = per_hook
+        itcpd.optimize(cp0, warm)
         als = itcpd.compute_als(eng, cp0, alg=itcpd.LevScoreSampled(ns), normal=True, check=itcpd.NoCheck(sweeps), seed=5)
         als.additional_items["per_hook"] = per_hook
         cp, dt = timed(lambda: itcpd.optimize(cp0, als))
