@@ -241,7 +241,9 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         c->stream = c->side_stream;
     }
     // chol_alg = 3: the factorisation hides under a GEMM if one runs in this mode's update (or pass B is in flight: early_pass_b)
-    c->chol_exposed = !(c->overlap_factor && (c->gemm_join_pending ||
+    // a factorisation that would hide under a SHORT pass is treated as exposed: 2 R P_local flops at ~35 TFLOP/s below ~1.4 ms
+    const bool short_pass = 2.0 * (double)c->rank * (double)c->nstore < 1e9 * (double)c->chol_short_gflop;
+    c->chol_exposed = short_pass || !(c->overlap_factor && (c->gemm_join_pending ||
                                               (c->mttkrp_alg != ITCPD_MTTKRP_DIRECT && !partial_is_current(c, mode < c->split_a ? 0 : 1))));
     int st = k_gram_hadamard(c, mode, c->Gamma.as<double>());
     if (st == ITCPD_OK) st = k_solve_factor(c, c->Gamma.as<double>(), c->rank, tol, status_dev);
@@ -283,13 +285,6 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
         TRY(k_solve_apply(c, c->Gamma.as<double>(), c->M[mode].as<double>(), c->dims[mode], c->rank, c->X.as<double>(), status_dev));
     }
     TRY(phase_mark(c, PH_SOLVE));
-    if (mode_tail_supported(c)) {
-        // lambda, A_mode and G_mode from the Gram of the solve output; the last mode's call also leaves the fit scalars and the log entry
-        TRY(k_mode_tail(c, mode, mode == c->order - 1, c->status.as<int>(), c->order));
-        c->fver[mode]++;
-        TRY(phase_mark(c, PH_GRAM));
-        return ITCPD_OK;
-    }
     TRY(k_colnorm_scale(c, c->X.as<double>(), c->dims[mode], c->rank, c->A[mode].as<double>(), c->lambda.as<double>(), mode == c->order - 1));
     TRY(phase_mark(c, PH_NORMALIZE));
     c->fver[mode]++;
@@ -352,7 +347,6 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(3, std::max(0, atoi(s)));
-    if (const char *s = getenv("ITCPD_FUSED_TAIL")) c->fused_tail = atoi(s) != 0;
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
@@ -428,7 +422,6 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "time_phases") { c->time_phases = value != 0; c->phase_used = 0; }
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
-    else if (n == "fused_tail") c->fused_tail = value != 0;
     else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "graph_single") c->graph_single = value != 0;
     else if (n == "i8_spare_sms") { ARG_CHECK(value >= 0 && value < 64, "i8_spare_sms must be in [0, 64)"); c->i8_spare_sms = (int)value; }
@@ -439,6 +432,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
         c->peer_graph = value != 0;
     }
     else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 3, "chol_alg must be 0, 1, 2 or 3"); c->chol_alg = (int)value; }
+    else if (n == "chol_short_gflop") { ARG_CHECK(value >= 0, "chol_short_gflop must be non-negative"); c->chol_short_gflop = value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }
     c->graph_epoch++;
@@ -778,7 +772,6 @@ static int one_sweep_device(itcpd_ctx *c, double chol_tol) {
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_gemm_done, 0));
         c->gemm_join_pending = false;
     }
-    if (mode_tail_supported(c)) return ITCPD_OK;   // the last mode's fused tail wrote the fit scalars and the log entry
     TRY(k_fit_terms(c, c->fit2.as<double>(), false));
     TRY(phase_mark(c, PH_FIT));
     log_sweep_kernel<<<1, 1, 0, c->stream>>>(c->fit2.as<double>(), c->status.as<int>(), N, c->sweep_log.as<double>() + 1,

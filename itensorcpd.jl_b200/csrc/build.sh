@@ -7,7 +7,7 @@ mkdir -p "${OUT}" "${HERE}/_obj"
 NVCC="${NVCC:-nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
 pids=()
-for f in api gemm_dmma gemm_i8 kernels mode_tail solve qrcp qrcp_wide sampled sampled_sharded peer_graph comm sparse_sign; do
+for f in api gemm_dmma gemm_i8 kernels solve qrcp qrcp_wide sampled sampled_sharded peer_graph comm sparse_sign; do
   src="${HERE}/${f}.cu"; obj="${HERE}/_obj/${f}.o"
   stale=0
   for dep in "${src}" "${HERE}"/*.cuh "${HERE}/../../include/itcpd_b200.h"; do

@@ -101,9 +101,6 @@ struct itcpd_ctx {
     cudaStream_t side_stream = nullptr;   // Gram-Hadamard + factorisation run here underneath the MTTKRP
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_factor = 1;
-    // option "fused_tail" (default on): normalise + Gram + fit + log of a mode update as three launches (mode_tail.cu) and one small
-    // all-reduce for the sharded mode; off = the hook-by-hook kernels (colsumsq, scale, Gram from the normalised factor, fit, log)
-    int fused_tail = 1;
     // option "early_pass_b" (off by default, not yet run on hardware): pass B of the dimension tree only depends on the factors
     // of modes < split_b, so it is launched on its own stream as soon as they are updated and the updates of the modes in
     // [split_b, split_a) (second-level contraction from P_A, solve, normalise, Gram) run underneath it
@@ -112,9 +109,11 @@ struct itcpd_ctx {
     cudaEvent_t ev_gemm_fork = nullptr, ev_gemm_done = nullptr;
     bool gemm_join_pending = false;
     // chol_alg: 0 block kernel (any n); 1 team kernel for n <= 128 (same arithmetic, bitwise); 2 right-looking kernels for n <= 128;
-    // 3 (default) right-looking only where the factorisation is EXPOSED (no GEMM runs in that mode's update, or R > 64 where no
-    // factorisation kernel can share an SM with a GEMM CTA), the team kernel (40 registers: co-resident with a GEMM CTA) where it hides
+    // 3 (default) right-looking where the factorisation is EXPOSED (no GEMM runs in that mode's update), where R > 64 (no factorisation
+    // kernel can share an SM with a GEMM CTA) and where the GEMM pass is short (< ~1.4 ms: a co-resident team kernel then costs the
+    // GEMM more than the 56 us it hides -- measured on the 8-GPU slabs); the team kernel (40 registers: co-resident) under long passes
     int chol_alg = 3;
+    int64_t chol_short_gflop = 50;   // option "chol_short_gflop": passes below this many GFLOP count as short (0: never)
     bool chol_exposed = true;   // set by the sweep driver before every factorisation
     int64_t launches = 0;
 
@@ -257,11 +256,6 @@ int k_sumsq(itcpd_ctx *c, const double *x, int64_t n, double *out_dev);
 int k_pad_copy_in(itcpd_ctx *c, const double *src_dense, double *dst_padded);   // dims[0] -> ld0
 int k_pad_copy_out(itcpd_ctx *c, const double *src_padded, double *dst_dense);
 int k_reconstruct(itcpd_ctx *c, double *out_dense_or_null, double *resid_sumsq_dev_or_null);
-
-// ---- mode_tail.cu -------------------------------------------------------------------------
-// fused tail of a mode update inside the sweep: X -> lambda, A[mode], G[mode] (+ fit scalars and the sweep-log entry for the last mode)
-bool mode_tail_supported(const itcpd_ctx *c);
-int k_mode_tail(itcpd_ctx *c, int mode, bool with_fit, const int *status_dev, int nmodes);
 
 // ---- solve.cu -----------------------------------------------------------------------------
 // X (rows x R) = (Gamma \ M^T)^T with the ldiv_solve.jl semantics. status_dev[0]=path, [1]=rank.

@@ -1,4 +1,4 @@
-// Peer-memory helpers shared by peer_graph.cu and mode_tail.cu: the table of peer-mapped exchange buffers and the bounded
+// Peer-memory helpers of peer_graph.cu: the table of peer-mapped exchange buffers and the bounded
 // system-scope flag wait (a peer that died must surface as a launch failure on this rank, not as a hung box).
 #pragma once
 #include "common.cuh"

@@ -97,8 +97,8 @@ def small_shapes_default_options():
 @scenario
 def small_shapes_every_option():
     opts = [("tile_warps", 4), ("stream_k", 0), ("stream_k", 2), ("tma3d", 0), ("swizzle", 0), ("overlap_factor", 0), ("use_graph", 0), ("chol_alg", 0),
-            ("chol_alg", 1), ("chol_alg", 2), ("graph_single", 0), ("fused_tail", 0), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
-    defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 3, "graph_single": 1, "fused_tail": 1, "mttkrp_alg": 0, "early_pass_b": 0,
+            ("chol_alg", 1), ("chol_alg", 2), ("graph_single", 0), ("mttkrp_alg", 1), ("early_pass_b", 1), ("gemm_i8", 1), ("gemm_i8", 2), ("time_gemm", 1), ("time_phases", 1)]
+    defaults = {"tile_warps": 8, "stream_k": 1, "tma3d": 1, "swizzle": 1, "overlap_factor": 1, "use_graph": 1, "chol_alg": 3, "graph_single": 1, "mttkrp_alg": 0, "early_pass_b": 0,
                 "gemm_i8": 0, "time_gemm": 0, "time_phases": 0}
     with itcpd.Engine(0) as eng:
         for name, val in opts:
@@ -367,6 +367,7 @@ def chol_alg_3_uses_the_right_looking_kernel_only_where_the_factorisation_is_exp
         fake.fakecuda_clear()
         with itcpd.Engine(0) as eng:
             eng.set_option("chol_alg", 3)
+            eng.set_option("chol_short_gflop", 0)   # this scenario is about the per-mode schedule, not about the short-pass rule (below)
             eng.set_option("split_a", 2)
             eng.set_option("split_b", 1)
             eng.set_option("use_graph", 0)
@@ -390,7 +391,16 @@ def chol_alg_3_uses_the_right_looking_kernel_only_where_the_factorisation_is_exp
         eng.synchronize()
         big = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl2"))
     assert big == (0, 6), big
-    return {"team_rl_counts": out, "rank_100": big}
+    with itcpd.Engine(0) as eng:          # default threshold: a pass this short never hides a team kernel profitably -> right-looking everywhere
+        fake.fakecuda_clear()
+        eng.set_tensor(np.zeros(dims, order="F"))
+        eng.set_cpd(factors(dims, R), np.ones(R))
+        eng.compute_grams()
+        eng.sweep_async(2)
+        eng.synchronize()
+        short = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl"))
+    assert short == (0, 6), short
+    return {"team_rl_counts": out, "rank_100": big, "short_pass": short}
 
 
 @scenario

@@ -97,7 +97,7 @@ int main(int argc, char **argv) {
 
 @pytest.fixture(scope="module")
 def harness():
-    hdr = open(os.path.join(os.path.dirname(SRC), "peer.cuh")).read()      # PeerPtrs + bounded_wait (shared with mode_tail.cu)
+    hdr = open(os.path.join(os.path.dirname(SRC), "peer.cuh")).read()      # PeerPtrs + bounded_wait (csrc/peer.cuh)
     hdr = hdr[hdr.index("struct PeerPtrs"):hdr.rindex("}  // namespace itcpd")]
     text = open(SRC).read()
     start = text.index("__global__ void peer_signal_dev_kernel")
