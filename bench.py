@@ -633,6 +633,17 @@ def run_ours(args, cfg):
     # ---- the other BASELINE.json configurations, as compact records (each with its own roofline) ----
     if not args.no_extras and args.config == "B":
         extras = []
+        watchdog = None
+        if rank == 0:
+            # the headline must survive a hang in an extra record (a peer that never answers spins for 60 s before it traps): after
+            # --extras-timeout seconds rank 0 prints the line it has and leaves
+            def bail():
+                line["extra"] = extras + [{"config": "watchdog", "error": f"extra records did not finish within {args.extras_timeout} s"}]
+                print(json.dumps(line), flush=True)
+                os._exit(0)
+            watchdog = threading.Timer(args.extras_timeout, bail)
+            watchdog.daemon = True
+            watchdog.start()
 
         def attempt(fn, label):
             try:
@@ -650,6 +661,7 @@ def run_ours(args, cfg):
             attempt(lambda: config_e_record(eng, itcpd), "E")
             attempt(lambda: dense_record(job, eng, itcpd, "B", 20, 3, peak, i8="2"), "B+gemm_i8=2")
         if rank == 0:
+            watchdog.cancel()
             line["extra"] = extras
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -669,6 +681,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra records (configs D, C, A, E)")
+    ap.add_argument("--extras-timeout", type=float, default=240.0, help="give up on the extra records after this many seconds and print the headline line")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: stop taking sweeps after this many seconds")
     ap.add_argument("--ref-slab", action="store_true", help="reference arm: time a 1/8 last-mode slab and extrapolate (small hosts)")
