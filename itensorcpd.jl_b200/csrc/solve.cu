@@ -266,21 +266,36 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_team_kernel(cons
 // ---- right-looking variant for n <= 64 (chol_alg = 2, and chol_alg = 3 where the factorisation is exposed) -----
 // The left-looking dot is what the team kernel's dependent chain is made of (profiles/r1_cholesky_probe.txt).  Here
 // thread k owns ORIGINAL column k of the trailing matrix in registers for the whole factorisation and nothing is ever
-// swapped.  A step is:  pivot search -> the pivot column's OWNER scales its whole register column by 1 / d and publishes it as
-// the row u of the factor (the trailing matrix is symmetric, bit for bit: A[q,k] = A[k,q], and both copies see the same fma) ->
-// one barrier -> every thread applies the rank-1 update to its register column (64 independent FMAs).  Static register indices
-// only (round 1 fetched A[q,k] from each thread's own column through a 64-way switch and divided per thread: 56 us at n = 64;
-// the owner-publishes form measured on hardware in round 2: see DESIGN.md 5.3).
+// swapped: a step is  pivot search -> u_k = A[q,k] / d  (q = pivot column; a uniform dynamic register index, read
+// through a jump table) -> publish u through shared memory -> rank-1 update of the register column (independent FMAs).
 // Positions follow LAPACK's interchange bookkeeping (the column at position j moves to the pivot's position), so pivots,
 // tie-breaking (first maximum in POSITION order) and the output layout equal the other kernels'; the rounding differs
-// (multiplication by the reciprocal pivot, sequential fma down-dates instead of a 4-way split dot), so parity is by tolerance.
-// Like LAPACK's dpstrf('U') only the upper triangle of the input is read.
+// (sequential fma down-dates instead of a 4-way split dot), so parity is by tolerance, not bitwise.
+template <int NMAX>
+__device__ __forceinline__ double rl_fetch(const double (&col)[NMAX], int q) {
+    double a = 0.0;
+#define RL_CASE(i) case i: a = col[(i) < NMAX ? (i) : 0]; break;
+    switch (q) {
+        RL_CASE(0) RL_CASE(1) RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7)
+        RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(11) RL_CASE(12) RL_CASE(13) RL_CASE(14) RL_CASE(15)
+        RL_CASE(16) RL_CASE(17) RL_CASE(18) RL_CASE(19) RL_CASE(20) RL_CASE(21) RL_CASE(22) RL_CASE(23)
+        RL_CASE(24) RL_CASE(25) RL_CASE(26) RL_CASE(27) RL_CASE(28) RL_CASE(29) RL_CASE(30) RL_CASE(31)
+        RL_CASE(32) RL_CASE(33) RL_CASE(34) RL_CASE(35) RL_CASE(36) RL_CASE(37) RL_CASE(38) RL_CASE(39)
+        RL_CASE(40) RL_CASE(41) RL_CASE(42) RL_CASE(43) RL_CASE(44) RL_CASE(45) RL_CASE(46) RL_CASE(47)
+        RL_CASE(48) RL_CASE(49) RL_CASE(50) RL_CASE(51) RL_CASE(52) RL_CASE(53) RL_CASE(54) RL_CASE(55)
+        RL_CASE(56) RL_CASE(57) RL_CASE(58) RL_CASE(59) RL_CASE(60) RL_CASE(61) RL_CASE(62) RL_CASE(63)
+        default: break;
+    }
+#undef RL_CASE
+    return a;
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const double *__restrict__ Gin, int n, double tol,
                                                                           double *__restrict__ Wg, int *__restrict__ piv,
                                                                           int *__restrict__ status) {
     extern __shared__ double sm_dyn[];            // Gamma staging, then Uo[l + ldw * original column] = row l of the factor
-    __shared__ __align__(16) double s_u[NMAX];    // u of the current step by original column; 0 for eliminated columns
+    __shared__ __align__(16) double s_u[NMAX];    // u of the current step by original column; 0 once a column is eliminated
     __shared__ unsigned long long s_key[2];
     __shared__ int s_idx[2], s_bad[2];
     __shared__ int s_orig[NMAX];                  // position -> original column
@@ -289,10 +304,7 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
     const int tid = threadIdx.x;
     constexpr int team = NMAX, nw = NMAX / 32;
     double *W = sm_dyn;
-    for (int e = tid; e < n * n; e += CHT_THREADS) {
-        const int r = e % n, c = e / n;
-        W[r + (size_t)ldw * c] = (r <= c) ? Gin[e] : Gin[c + (size_t)n * r];   // symmetric from the upper triangle
-    }
+    for (int e = tid; e < n * n; e += CHT_THREADS) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
     if (tid < NMAX) { s_orig[tid] = tid; s_u[tid] = 0.0; }
     if (tid == 0) s_rank = n;
     __syncthreads();
@@ -307,7 +319,6 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
         int posk = k;
         double stop = 0.0;
         int rank = n;
-        unsigned long long elim = 0ull;   // bit i: original column i has been eliminated (uniform over the team)
         team_sync(nw, team);  // every column is in registers: the staging area becomes Uo
         for (int j = 0; j < n; ++j) {
             // ---- pivot: first maximum of the running diagonal in position order ----
@@ -339,32 +350,29 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
             }
             if (fail) { rank = j; break; }  // uniform over the team
             const int q = bi & 0xff, p = bi >> 8;
+            const double d = sqrt(bv);
             // ---- interchange bookkeeping only: the pivot goes to position j, the column that sat there to position p ----
             if (mine) {
                 if (k == q) { posk = j; s_orig[j] = k; }
                 else if (posk == j) { posk = p; s_orig[p] = k; }
             }
-            elim |= 1ull << q;
-            // ---- row j of the factor: the owner of the pivot column scales its column and publishes it ----
-            if (k == q) {
-                const double d = sqrt(bv);
-                const double rinv = 1.0 / d;
-#pragma unroll
-                for (int i = 0; i < NMAX; i += 2) {
-                    double2 uu;
-                    uu.x = ((elim >> i) & 1ull) ? 0.0 : col[i] * rinv;
-                    uu.y = ((elim >> (i + 1)) & 1ull) ? 0.0 : col[i + 1] * rinv;
-                    *reinterpret_cast<double2 *>(&s_u[i]) = uu;
+            // ---- row j of the factor ----
+            double u = 0.0;
+            if (alive) {
+                if (k == q) {
+                    W[j + (size_t)ldw * k] = d;
+                    s_u[k] = 0.0;
+                    alive = false;
+                } else {
+                    u = rl_fetch<NMAX>(col, q) / d;
+                    W[j + (size_t)ldw * k] = u;
+                    s_u[k] = u;
+                    ddk = fma(-u, u, ddk);
                 }
-                W[j + (size_t)ldw * k] = d;
-                alive = false;
             }
             team_sync(nw, team);
             // ---- rank-1 update of my column (rows of eliminated columns see u = 0) ----
             if (alive) {
-                const double u = s_u[k];
-                W[j + (size_t)ldw * k] = u;
-                ddk = fma(-u, u, ddk);
 #pragma unroll
                 for (int i = 0; i < NMAX; i += 2) {
                     const double2 uu = *reinterpret_cast<const double2 *>(&s_u[i]);
@@ -389,12 +397,12 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl_kernel(const 
 // ---- right-looking variant for 64 < n <= 128 (chol_alg = 2 / 3) -------------------------------------------------------
 // A 128-entry column does not fit one thread's registers, so every column is owned by TWO threads: thread (k, h) keeps rows
 // 64 h .. 64 h + 63 of original column k (k = tid & 127, h = tid >> 7: 256 threads).  The pivot search runs on the h = 0 threads
-// (they carry the running diagonals; both halves update theirs identically from the published u), the two owners of the pivot
-// column scale their halves by 1 / d and publish them as the row u of the factor, and after one block barrier both halves of every
-// column apply the rank-1 update to their 64 rows.  Two block barriers per step; every element sees exactly the operations of
-// pivoted_cholesky_rl_kernel, so for n <= 64 the two kernels are bitwise identical (tests/test_cholesky_emulation_cpu.py) and
-// pivots / tie-breaking are LAPACK's.  The team kernel needs 268 us at n = 128 (profiles/r1_cholesky_probe.txt) and, at 132 KB of
-// shared memory, cannot share an SM with a GEMM CTA: this is the factorisation the rank-128 sweeps wait for.
+// (they carry the running diagonals; both halves update theirs identically from the published u), the thread whose half holds
+// the pivot row fetches u_k = A[q, k] / d and publishes it, and after one block barrier both halves apply the rank-1 update to
+// their 64 rows.  Two block barriers per step; every element sees exactly the operations of pivoted_cholesky_rl_kernel, so for
+// n <= 64 the two kernels are bitwise identical (tests/test_cholesky_emulation_cpu.py) and pivots / tie-breaking are LAPACK's.
+// The team kernel needs 268 us at n = 128 (profiles/r1_cholesky_probe.txt) and, at 132 KB of shared memory, cannot share an SM
+// with a GEMM CTA: this is the factorisation the rank-128 sweeps wait for.
 __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl2_kernel(const double *__restrict__ Gin, int n, double tol,
                                                                            double *__restrict__ Wg, int *__restrict__ piv,
                                                                            int *__restrict__ status) {
@@ -408,15 +416,11 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl2_kernel(const
     const int tid = threadIdx.x;
     const int k = tid & 127, h = tid >> 7, lane = tid & 31, w = (tid >> 5) & 3;
     double *W = sm_dyn;
-    for (int e = tid; e < n * n; e += CHT_THREADS) {
-        const int r = e % n, c = e / n;
-        W[r + (size_t)ldw * c] = (r <= c) ? Gin[e] : Gin[c + (size_t)n * r];   // symmetric from the upper triangle
-    }
+    for (int e = tid; e < n * n; e += CHT_THREADS) W[(e % n) + (size_t)ldw * (e / n)] = Gin[e];
     if (tid < 128) { s_orig[tid] = tid; s_u[tid] = 0.0; }
     if (tid == 0) s_rank = n;
     __syncthreads();
     const bool mine = k < n;
-    unsigned long long elim = 0ull;   // bit i: original column 64 h + i has been eliminated
     double col[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) col[i] = (mine && 64 * h + i < n) ? W[(64 * h + i) + (size_t)ldw * k] : 0.0;
@@ -465,26 +469,22 @@ __global__ void __launch_bounds__(CHT_THREADS) pivoted_cholesky_rl2_kernel(const
             if (k == q) { posk = j; s_orig[j] = k; }
             else if (posk == j) { posk = p; s_orig[p] = k; }
         }
-        if ((q >> 6) == h) elim |= 1ull << (q & 63);
-        // ---- row j of the factor: the two owners of the pivot column scale their halves and publish them ----
-        if (alive && k == q) {
-            const double rinv = 1.0 / d;
-#pragma unroll
-            for (int i = 0; i < 64; i += 2) {
-                double2 uu;
-                uu.x = ((elim >> i) & 1ull) ? 0.0 : col[i] * rinv;
-                uu.y = ((elim >> (i + 1)) & 1ull) ? 0.0 : col[i + 1] * rinv;
-                *reinterpret_cast<double2 *>(&s_u[64 * h + i]) = uu;
+        // ---- row j of the factor: the half that holds row q of my column fetches it ----
+        if (alive) {
+            if (k == q) {
+                if (h == 0) { W[j + (size_t)ldw * k] = d; s_u[k] = 0.0; }
+                alive = false;
+            } else if (h == (q >> 6)) {
+                const double u = rl_fetch<64>(col, q & 63) / d;
+                W[j + (size_t)ldw * k] = u;
+                s_u[k] = u;
             }
-            if (h == 0) W[j + (size_t)ldw * k] = d;
-            alive = false;
         }
         __syncthreads();
         // ---- rank-1 update of my 64 rows (rows of eliminated columns see u = 0); the next step's first barrier orders these
         // reads of s_u before its next writes ----
         if (alive) {
             const double u = s_u[k];
-            if (h == 0) W[j + (size_t)ldw * k] = u;
             ddk = fma(-u, u, ddk);
 #pragma unroll
             for (int i = 0; i < 64; i += 2) {
