@@ -347,7 +347,6 @@ int itcpd_create(itcpd_ctx **out, int device) {
     if (const char *s = getenv("ITCPD_I8_SPARE_SMS")) c->i8_spare_sms = std::min(63, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_SWIZZLE")) c->swizzle = (atoi(s) != 0) ? 0 : 1;
     if (const char *s = getenv("ITCPD_CHOL")) c->chol_alg = std::min(3, std::max(0, atoi(s)));
-    if (const char *s = getenv("ITCPD_SOLVE")) c->solve_alg = std::min(1, std::max(0, atoi(s)));
     if (const char *s = getenv("ITCPD_NO_GRAPH")) c->use_graph = atoi(s) == 0;
     if (const char *s = getenv("ITCPD_GEMM_I8")) c->gemm_i8 = std::min(2, std::max(0, atoi(s)));   // experimental (csrc/gemm_i8.cu)
     int st = ensure_pinned(c, 4096);
@@ -433,7 +432,6 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
         c->peer_graph = value != 0;
     }
     else if (n == "chol_alg") { ARG_CHECK(value >= 0 && value <= 3, "chol_alg must be 0, 1, 2 or 3"); c->chol_alg = (int)value; }
-    else if (n == "solve_alg") { ARG_CHECK(value == 0 || value == 1, "solve_alg must be 0 (substitution) or 1 (explicit inverse + dense products, R <= 64)"); c->solve_alg = (int)value; }
     else if (n == "chol_short_gflop") { ARG_CHECK(value >= 0, "chol_short_gflop must be non-negative"); c->chol_short_gflop = value; }
     else if (n == "stream_k") { ARG_CHECK(value >= 0 && value <= 2, "stream_k must be 0, 1 or 2"); c->stream_k = (int)value; }
     else { set_error("unknown option '%s'", name); return ITCPD_ERR_ARG; }

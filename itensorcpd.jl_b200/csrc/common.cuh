@@ -115,9 +115,6 @@ struct itcpd_ctx {
     int chol_alg = 3;
     int64_t chol_short_gflop = 50;   // option "chol_short_gflop": passes below this many GFLOP count as short (0: never)
     bool chol_exposed = true;   // set by the sweep driver before every factorisation
-    // solve_alg: 0 substitution, one warp per right-hand side (any n <= 1024); 1 for n <= 64 the explicit inverse of the Cholesky factor
-    // (one small CTA behind the factorisation) + two dense 64-deep products per 32-row tile (no dependent chain on the critical path)
-    int solve_alg = 1;
     int64_t launches = 0;
 
     // options

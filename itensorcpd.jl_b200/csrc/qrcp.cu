@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(64) qrcp_solve_rows_kernel(const double *__res
 int qrcp_workspace(itcpd_ctx *c, int m, int n, int64_t rows, QrcpWs *w) {
     const size_t chol_doubles = (size_t)(n | 1) * n + n;            // the Cholesky factor lives in front (solve.cu)
     const size_t ws_doubles = (size_t)m * n + 8 * (size_t)n;
-    TRY(c->solve_ws.reserve((chol_doubles + ws_doubles + (size_t)n * n) * 8 + 1024));   // + the explicit inverse of the factor (solve.cu, solve_alg = 1)
+    TRY(c->solve_ws.reserve((chol_doubles + ws_doubles) * 8 + 1024));
     TRY(c->ipiv.reserve((size_t)n * 4 * 2));
     if (rows > 0) TRY(c->work.reserve((size_t)rows * m * 8));
     w->ws = c->solve_ws.as<double>() + chol_doubles;

@@ -646,147 +646,12 @@ __global__ void __launch_bounds__(TSW_WARPS * 32) chol_solve_warp_kernel(const d
     }
 }
 
-// ---- solve_alg = 1 (n <= 64): explicit inverse of the Cholesky factor + two small dense products --------------------------------
-// The substitution kernel above is a chain of 2 n dependent steps per right-hand side (shuffle + multiply + fma): ~29 us per launch
-// whatever the row count, three times per sweep ON the critical path.  Here the triangular inverse V = U^{-1} is computed once per
-// factorisation by one small CTA (right behind the Cholesky on the side stream: hidden wherever the Cholesky is), and the rows are
-// solved as  X P = ((M P) V) V^T  -- two 64-deep products with independent FMAs, 32 rows per CTA.  Forward error ~ cond(U) eps per
-// product, the same class as the substitutions'; fixed summation order (bitwise reproducible, identical on replicated ranks).
-// The rank-deficient fallback and the fused peer all-reduce are those of the substitution kernel.
-constexpr int TI_N = 64;
-
-// V = U^{-1} (nn x nn leading block, upper triangular), stored dense n x n column-major with zeros elsewhere.  One thread per
-// column k: x = e_k; for i = k .. 0: x_i /= U_ii, x_l -= U[l,i] x_i (l < i) -- column-oriented, the updates of a step are independent.
-__global__ void __launch_bounds__(TI_N) tri_inverse_kernel(const double *__restrict__ Wg, int n, const int *__restrict__ status, int nn_slot, int need_chol,
-                                                           double *__restrict__ V) {
-    __shared__ double sx[TI_N][TI_N + 1];   // sx[l][k]: entry l of column k
-    if (need_chol && status[0] != ITCPD_SOLVE_CHOLESKY) return;
-    const int nn = nn_slot >= 0 ? status[nn_slot] : n;
-    const int ldw = n | 1;
-    const int k = threadIdx.x;
-    for (int l = 0; l < n; ++l) sx[l][k] = (l == k && k < nn) ? 1.0 : 0.0;
-    if (k < nn) {
-        for (int i = k; i >= 0; --i) {
-            const double xi = sx[i][k] / Wg[i + (size_t)ldw * i];
-            sx[i][k] = xi;
-            const double *ui = Wg + (size_t)ldw * i;   // column i of U: U[l,i], l < i (uniform address per step: broadcast loads)
-#pragma unroll 4
-            for (int l = 0; l < i; ++l) sx[l][k] = fma(-ui[l], xi, sx[l][k]);
-        }
-    }
-    for (int l = 0; l < n; ++l)
-        if (k < n) V[l + (size_t)n * k] = sx[l][k];
-}
-
-constexpr int SI_ROWS = 16, SI_THREADS = 128;   // 16 rows x 64 columns per CTA, 4 x 2 outputs per thread; 42 KB of static shared memory
-
-// rows_mode 0: X = ((M P) V) V^T P^T (full solve); 2: X = (M P) V (row i of Q_1 = A P U^{-1}: leverage scores)
-__global__ void __launch_bounds__(SI_THREADS) solve_inverse_kernel(const double *__restrict__ V, const int *__restrict__ piv, const int *__restrict__ status,
-                                                                   PeerSrc src, int64_t rows, int n, double *__restrict__ X, int rows_mode, QrcpWs qr) {
-    __shared__ double sV[TI_N][TI_N + 1];          // sV[l][k] = V[l,k]
-    __shared__ double sB[TI_N][SI_ROWS + 1];       // sB[l][i]: permuted right-hand sides, then Z
-    __shared__ int s_pv[TI_N];
-    peer_wait_all(src);
-    const bool chol_ok = rows_mode == 2 || status[0] == ITCPD_SOLVE_CHOLESKY;
-    const int tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * SI_ROWS;
-    if (!chol_ok) {
-        // rank deficient: reduce the peers' rows if any, then the pivoted-QR min-norm solve of the row (qrcp_rows.cuh), one thread per row
-        const int64_t i = i0 + tid;
-        if (tid >= SI_ROWS || i >= rows) return;
-        const double *Mrow = src.p[0];
-        if (src.reduced_out) {
-            for (int k = 0; k < n; ++k) {
-                const int64_t off = i + rows * (int64_t)k;
-                double v = 0.0;
-                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
-                src.reduced_out[off] = v;
-            }
-            Mrow = src.reduced_out;
-        }
-        qrcp_row_solve(qr.ws, qr.jpvt, status[1], Mrow, rows, n, n, X, qr.bglob, i);
-        return;
-    }
-    for (int e = tid; e < TI_N * TI_N; e += SI_THREADS) {
-        const int k = e / TI_N, l = e % TI_N;   // consecutive threads read consecutive l of column k
-        sV[l][k] = (l < n && k < n) ? V[l + (size_t)n * k] : 0.0;
-    }
-    for (int e = tid; e < TI_N; e += SI_THREADS) s_pv[e] = (e < n) ? piv[e] : 0;
-    __syncthreads();
-    // permuted right-hand sides: B[i, l] = M[i, piv[l]] (summed over the peers in rank order; the reduced matrix is stored unpermuted)
-    for (int e = tid; e < TI_N * SI_ROWS; e += SI_THREADS) {
-        const int l = e / SI_ROWS, ii = e % SI_ROWS;   // consecutive threads read consecutive rows of one column
-        const int64_t i = i0 + ii;
-        double v = 0.0;
-        if (l < n && i < rows) {
-            const int64_t off = i + rows * (int64_t)s_pv[l];
-            if (src.reduced_out) {
-                for (int q = 0; q < src.n; ++q) v += src.p[q][off];
-                src.reduced_out[off] = v;
-            } else {
-                v = src.p[0][off];
-            }
-        }
-        sB[l][ii] = v;
-    }
-    __syncthreads();
-    const int ti = tid & 3, tr = tid >> 2;   // rows ti + 4 a (a < 4), columns tr + 32 b (b < 2)
-    double acc[4][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = 0.0;
-    // Z = B V   (V upper triangular: zeros below the diagonal are stored, the loop is dense)
-#pragma unroll 4
-    for (int l = 0; l < TI_N; ++l) {
-        double bv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bv[a] = sB[l][ti + 4 * a];
-        const double v0 = sV[l][tr], v1 = sV[l][tr + 32];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { acc[a][0] = fma(bv[a], v0, acc[a][0]); acc[a][1] = fma(bv[a], v1, acc[a][1]); }
-    }
-    if (rows_mode == 2) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int64_t i = i0 + ti + 4 * a;
-                const int k = tr + 32 * b;
-                if (i < rows && k < n) X[i + rows * (int64_t)k] = acc[a][b];
-            }
-        return;
-    }
-    __syncthreads();   // every thread is done reading B: the buffer becomes Z
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) { sB[tr + 32 * b][ti + 4 * a] = acc[a][b]; acc[a][b] = 0.0; }
-    __syncthreads();
-    // X' = Z V^T : X'[i, l] = sum_k Z[i, k] V[l, k]
-#pragma unroll 4
-    for (int k = 0; k < TI_N; ++k) {
-        double zv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) zv[a] = sB[k][ti + 4 * a];
-        const double v0 = sV[tr][k], v1 = sV[tr + 32][k];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { acc[a][0] = fma(zv[a], v0, acc[a][0]); acc[a][1] = fma(zv[a], v1, acc[a][1]); }
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int64_t i = i0 + ti + 4 * a;
-            const int l = tr + 32 * b;
-            if (i < rows && l < n) X[i + rows * (int64_t)s_pv[l]] = acc[a][b];
-        }
-}
-
 // dynamic shared memory budget: 227 KB per CTA minus the static arrays of these kernels (pivots, reciprocal diagonal)
 static int smem_limit(itcpd_ctx *) { return 208 * 1024; }
 
 static int run_cholesky(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
     const int ldw = R | 1;
-    TRY(c->solve_ws.reserve(((size_t)ldw * R + R) * 8 + ((size_t)R * R + 8 * (size_t)R) * 8 + (size_t)R * R * 8 + 1024));
+    TRY(c->solve_ws.reserve(((size_t)ldw * R + R) * 8 + ((size_t)R * R + 8 * (size_t)R) * 8 + 1024));
     TRY(c->ipiv.reserve((size_t)R * 4 * 2));
     const size_t need = ((size_t)ldw * R + R) * 8;
     const int use_smem = need <= (size_t)smem_limit(c);
@@ -856,31 +721,6 @@ static int launch_tsw(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, doubl
     return ITCPD_OK;
 }
 
-static bool inverse_solve_ok(const itcpd_ctx *c, int R) { return c->solve_alg == 1 && R <= TI_N; }
-
-static double *inverse_ws(itcpd_ctx *c, int R) {   // behind the Cholesky factor and the QRCP workspace (run_cholesky sized it)
-    return c->solve_ws.as<double>() + ((size_t)(R | 1) * R + R) + ((size_t)R * R + 8 * (size_t)R);
-}
-
-// V = U^{-1} right behind the factorisation (same stream); nn_slot >= 0: only the leading status[nn_slot] rows / columns (leverage)
-static int run_tri_inverse(itcpd_ctx *c, int R, const int *status_dev, int nn_slot, int need_chol) {
-    tri_inverse_kernel<<<1, TI_N, 0, c->stream>>>(c->solve_ws.as<double>(), R, status_dev, nn_slot, need_chol, inverse_ws(c, R));
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return ITCPD_OK;
-}
-
-static int run_inverse_rows(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int rows_mode) {
-    QrcpWs w;
-    memset(&w, 0, sizeof(w));
-    if (rows_mode == 0) TRY(qrcp_workspace(c, R, R, rows, &w));
-    solve_inverse_kernel<<<(unsigned)ceil_div(rows, SI_ROWS), SI_THREADS, 0, c->stream>>>(inverse_ws(c, R), c->ipiv.as<int>(), status_dev, M, rows, R, X,
-                                                                                           rows_mode, w);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return ITCPD_OK;
-}
-
 static int run_tri_solves(itcpd_ctx *c, const PeerSrc &M, int64_t rows, int R, double *X, const int *status_dev, int fwd_only, int slot) {
     const int E = (int)ceil_div(R, 32);
     if (E <= 1) return launch_tsw<1>(c, M, rows, R, X, status_dev, fwd_only, slot);
@@ -907,14 +747,12 @@ static PeerSrc single_src(const double *M) {
 // so that the apply step is a single launch.
 int k_solve_factor(itcpd_ctx *c, const double *Gamma, int R, double tol, int *status_dev) {
     TRY(run_cholesky(c, Gamma, R, tol, status_dev));
-    if (inverse_solve_ok(c, R)) TRY(run_tri_inverse(c, R, status_dev, -1, 1));
     return qrcp_factor_only(c, Gamma, R, R, 0, status_dev, 0);
 }
 
 // rank-deficient systems take the pivoted-QR min-norm path INSIDE the row-solve kernel (lane 0 of the row's warp runs
 // qrcp_row_solve; the factorisation half ran behind the Cholesky), so a mode update has no no-op launches on its critical path
 static int apply_rows(itcpd_ctx *c, const PeerSrc &src, int64_t rows, int R, double *X, int *status_dev) {
-    if (inverse_solve_ok(c, R)) return run_inverse_rows(c, src, rows, R, X, status_dev, 0);
     return run_tri_solves(c, src, rows, R, X, status_dev, 0, 1);
 }
 
@@ -1020,12 +858,7 @@ static int leverage_impl(itcpd_ctx *c, const double *A, const double *G, int64_t
     TRY(run_cholesky(c, G, R, -1.0, st));
     TRY(c->lev_q.reserve(((size_t)rows * R + 2 * (size_t)R * R) * 8));
     double *Q1 = c->lev_q.as<double>(), *G2 = Q1 + (size_t)rows * R, *W = G2 + (size_t)R * R;
-    if (inverse_solve_ok(c, R)) {                                             // Q_1 = A P U^{-1}, zero beyond the numerical rank
-        TRY(run_tri_inverse(c, R, st, 1, 0));
-        TRY(run_inverse_rows(c, single_src(A), rows, R, Q1, st, 2));
-    } else {
-        TRY(run_tri_solves(c, single_src(A), rows, R, Q1, st, 2, 1));
-    }
+    TRY(run_tri_solves(c, single_src(A), rows, R, Q1, st, 2, 1));            // Q_1 = A P U^{-1}, zero beyond the numerical rank
     TRY(k_gram(c, Q1, rows, R, G2));
     if (comm_active(c) && rows != rows_total) TRY(comm_allreduce_sum(c, G2, (int64_t)R * R));
     neumann_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, c->stream>>>(G2, R, W);
