@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 namespace itcpd {
 
@@ -104,6 +106,50 @@ int ensure_cpd_buffers(itcpd_ctx *c) {
     TRY(c->Gamma.reserve((size_t)R * R * 8));
     TRY(c->status.reserve(256));
     TRY(c->fit2.reserve(64));
+    return ITCPD_OK;
+}
+
+
+// Host -> device upload of the tensor.  A pinned source (itcpd_host_alloc, cudaHostRegister'ed memory) is one DMA; a PAGEABLE source
+// -- what a Julia Array or a numpy array is -- would make the driver stage it through its own small bounce buffer at ~12 GB/s.
+// Here UPLOAD_THREADS host threads copy 32 MB chunks into their own pair of pinned staging buffers while the DMA engine drains the
+// previous chunks, so the upload runs at min(parallel memcpy, PCIe) instead (bench.py `e2e.pageable`).  The copies are enqueued on the
+// handle's stream (stream order protects every later kernel); the call returns when the last chunk has been ENQUEUED and staged.
+constexpr size_t UPLOAD_CHUNK = (size_t)32 << 20;
+constexpr int UPLOAD_THREADS = 4;
+
+static int upload_to_device(itcpd_ctx *c, void *dst, const void *host, size_t bytes) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (pinned || !c->staged_upload || bytes < 4 * UPLOAD_CHUNK) {
+        CUDA_TRY(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return ITCPD_OK;
+    }
+    const int nslots = 2 * UPLOAD_THREADS;
+    if (!c->upload_stage) {
+        CUDA_TRY(cudaHostAlloc(&c->upload_stage, (size_t)nslots * UPLOAD_CHUNK, cudaHostAllocDefault));
+        for (int i = 0; i < nslots; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->upload_events[i], cudaEventDisableTiming));
+    }
+    const size_t nchunks = (bytes + UPLOAD_CHUNK - 1) / UPLOAD_CHUNK;
+    std::atomic<int> failed{0};
+    auto worker = [&](int t) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { failed = 1; return; }
+        int use = 0;
+        for (size_t ch = (size_t)t; ch < nchunks && !failed; ch += UPLOAD_THREADS, ++use) {
+            const int slot = 2 * t + (use & 1);
+            char *stage = (char *)c->upload_stage + (size_t)slot * UPLOAD_CHUNK;
+            if (use >= 2 && cudaEventSynchronize(c->upload_events[slot]) != cudaSuccess) { failed = 1; return; }   // the slot's previous DMA is done
+            const size_t off = ch * UPLOAD_CHUNK, n = std::min(UPLOAD_CHUNK, bytes - off);
+            memcpy(stage, (const char *)host + off, n);
+            if (cudaMemcpyAsync((char *)dst + off, stage, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                cudaEventRecord(c->upload_events[slot], c->stream) != cudaSuccess) { failed = 1; return; }
+        }
+    };
+    std::thread th[UPLOAD_THREADS];
+    for (int t = 0; t < UPLOAD_THREADS; ++t) th[t] = std::thread(worker, t);
+    for (int t = 0; t < UPLOAD_THREADS; ++t) th[t].join();
+    if (failed) { set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return ITCPD_ERR_CUDA; }
     return ITCPD_OK;
 }
 
@@ -375,6 +421,10 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (auto &ev : c->phase_events) cudaEventDestroy(ev);
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->upload_stage) {
+        cudaFreeHost(c->upload_stage);
+        for (auto &ev : c->upload_events) if (ev) cudaEventDestroy(ev);
+    }
     if (c->sweep_graph_exec) { cudaGraphExecDestroy(c->sweep_graph_exec); c->sweep_graph_exec = nullptr; }
     if (c->sampled_graph_exec) { cudaGraphExecDestroy(c->sampled_graph_exec); c->sampled_graph_exec = nullptr; }
     c->draw_counter.release();
@@ -422,6 +472,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "time_phases") { c->time_phases = value != 0; c->phase_used = 0; }
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
+    else if (n == "staged_upload") c->staged_upload = value != 0;
     else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "graph_single") c->graph_single = value != 0;
     else if (n == "i8_spare_sms") { ARG_CHECK(value >= 0 && value < 64, "i8_spare_sms must be in [0, 64)"); c->i8_spare_sms = (int)value; }
@@ -446,10 +497,10 @@ int itcpd_set_tensor(itcpd_ctx *c, int order, const int64_t *dims, const double 
     USE_DEVICE(c);
     TRY(set_shape(c, order, dims));
     if (c->ld0 == c->dims[0]) {
-        CUDA_TRY(cudaMemcpyAsync(c->T.p, host, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(upload_to_device(c, c->T.p, host, (size_t)c->nelem * 8));
     } else {
         TRY(c->work.reserve((size_t)c->nelem * 8));
-        CUDA_TRY(cudaMemcpyAsync(c->work.p, host, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(upload_to_device(c, c->work.p, host, (size_t)c->nelem * 8));
         TRY(k_pad_copy_in(c, c->work.as<double>(), c->T.as<double>()));
     }
     CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));
@@ -921,10 +972,10 @@ int itcpd_als_from_host(itcpd_ctx *c, int order, const int64_t *dims, const doub
     TRY(ensure_cpd_buffers(c));
     // uploads are enqueued back to back on the handle's stream; no host sync until the results are read
     if (c->ld0 == c->dims[0]) {
-        CUDA_TRY(cudaMemcpyAsync(c->T.p, host_T, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(upload_to_device(c, c->T.p, host_T, (size_t)c->nelem * 8));
     } else {
         TRY(c->work.reserve((size_t)c->nelem * 8));
-        CUDA_TRY(cudaMemcpyAsync(c->work.p, host_T, (size_t)c->nelem * 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(upload_to_device(c, c->work.p, host_T, (size_t)c->nelem * 8));
         TRY(k_pad_copy_in(c, c->work.as<double>(), c->T.as<double>()));
     }
     CUDA_TRY(cudaMemsetAsync((char *)c->T.p + (size_t)c->nstore * 8, 0, 256, c->stream));

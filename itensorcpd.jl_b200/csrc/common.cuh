@@ -162,6 +162,10 @@ struct itcpd_ctx {
     // pivot-projected solvers: cached projector (1-based int64, nsamp x (N-1)) and sampled target (I_n x nsamp) per mode
     itcpd::DevBuf proj_piv[ITCPD_MAX_ORDER], proj_T[ITCPD_MAX_ORDER], qr_A, qr_piv, qr_rdiag;
     int64_t proj_n[ITCPD_MAX_ORDER] = {0};
+    // option "staged_upload" (default on): a pageable host tensor is uploaded through pinned staging buffers filled by host threads
+    int staged_upload = 1;
+    void *upload_stage = nullptr;
+    cudaEvent_t upload_events[8] = {nullptr};
     double *pinned = nullptr;   // pinned host staging (fit scalars, status words)
     size_t pinned_doubles = 0;
 

@@ -408,6 +408,17 @@ def end_to_end_call_from_host_buffers():
     dims, R = (64, 48, 40), 16
     with itcpd.Engine(0) as eng:
         eng.als_from_host(np.zeros(dims, order="F"), factors(dims, R), 6)
+    # a PAGEABLE host tensor above the staging threshold: four host threads fill pinned staging chunks and enqueue the copies
+    # (every chunk's device range and staging source is checked by the runtime); even and odd leading dimension
+    out = {}
+    for dims in ((256, 256, 330), (255, 256, 331)):
+        fake.fakecuda_clear()
+        with itcpd.Engine(0) as eng:
+            eng.als_from_host(np.zeros(dims, order="F"), factors(dims, R), 3)
+            eng.set_option("staged_upload", 0)
+            eng.set_tensor(np.zeros(dims, order="F"))
+        out["x".join(map(str, dims))] = len(violations())
+    return out
 
 
 @scenario

@@ -66,6 +66,7 @@ bool check_device_range(const void *p, size_t n, const char *what) {
     return true;
 }
 bool is_device_ptr(const void *p) { auto *al = find_alloc(p); return al && !al->second.host; }
+bool is_pinned_ptr(const void *p) { auto *al = find_alloc(p); return al && al->second.host; }
 
 // ---- kernels -------------------------------------------------------------------------------------------------------
 struct KernelInfo { std::string name; int regs = 0, static_smem = 0; int max_dyn_smem = 48 * 1024; };
@@ -288,6 +289,13 @@ cudaError_t cudaMalloc(void **p, size_t n) { return alloc_common(p, n, false); }
 cudaError_t cudaFree(void *p) { return free_common(p, false, "cudaFree"); }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return alloc_common(p, n, true); }
 cudaError_t cudaFreeHost(void *p) { return free_common(p, true, "cudaFreeHost"); }
+
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
+    std::lock_guard<std::mutex> g(g_mu);
+    memset(a, 0, sizeof(*a));
+    a->type = is_device_ptr(p) ? cudaMemoryTypeDevice : (is_pinned_ptr(p) ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered);
+    return cudaSuccess;
+}
 
 static cudaError_t copy_common(void *dst, const void *src, size_t n, cudaMemcpyKind kind, Stream *st, bool sync, const char *what) {
     bool ok = true;

@@ -122,3 +122,27 @@ def test_nan_fit_raises_on_host_like_reference(engine):
     chk = itcpd.FitCheck(1e-9, 30, 1.0)
     with pytest.raises(RuntimeError, match="Error NAN"):
         itcpd.als_optimize(T, itcpd.CPD(f, cp.lam), check=chk)
+
+
+@pytest.mark.parametrize("dims", [(256, 250, 330), (255, 250, 331)])   # 169 / 168 MB: above the staging threshold; even and odd leading dimension
+def test_pageable_tensor_upload_is_staged_and_exact(dims):
+    """api.cu: upload_to_device -- a pageable host tensor (what a Julia Array is) goes through pinned staging buffers filled by four host
+    threads; the device copy must be bit-for-bit the host array, for itcpd_set_tensor and for itcpd_als_from_host, and equal to what the
+    single cudaMemcpyAsync path (staged_upload = 0) leaves."""
+    import itcpd
+
+    rng = np.random.default_rng(12)
+    T = np.asfortranarray(rng.standard_normal(dims))
+    with itcpd.Engine(0) as eng:
+        eng.set_tensor(T)
+        assert np.array_equal(eng.get_tensor(), T)
+        n1 = eng.tensor_norm()
+        eng.set_option("staged_upload", 0)
+        eng.set_tensor(T)
+        assert np.array_equal(eng.get_tensor(), T) and eng.tensor_norm() == n1
+        eng.set_option("staged_upload", 1)
+        f = [np.asfortranarray(x / np.linalg.norm(x, axis=0)) for x in (rng.standard_normal((d, 8)) for d in dims)]
+        a = eng.als_from_host(T, f, 3)
+        eng.set_option("staged_upload", 0)
+        b = eng.als_from_host(T, f, 3)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
