@@ -32,7 +32,7 @@ __global__ void peer_wait_dev_kernel(const volatile long long *flags, int n, con
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(256) peer_allreduce_small_kernel(PeerPtrs f, long long *epoch_dev, size_t small_off, int64_t slot_doubles,
+__global__ void __launch_bounds__(1024) peer_allreduce_small_kernel(PeerPtrs f, long long *epoch_dev, size_t small_off, int64_t slot_doubles,
                                                                    double *buf, int n) {
     __shared__ long long s_e;
     if (threadIdx.x == 0) { s_e = *epoch_dev + 1; *epoch_dev = s_e; }
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_small_kernel(PeerPtrs f, l
     const long long e = s_e;
     const size_t off = small_off + (size_t)(e & 1) * (size_t)slot_doubles * 8;
     double *mine = reinterpret_cast<double *>(f.base[f.rank] + off);
-    for (int i = threadIdx.x; i < n; i += 256) mine[i] = buf[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < f.n) {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_small_kernel(PeerPtrs f, l
     }
     __syncthreads();
     __threadfence_system();
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // 1024 threads: a handful of remote elements per thread (was 16 x G at 256)
         double v = 0.0;
         for (int q = 0; q < f.n; ++q) v += reinterpret_cast<const volatile double *>(f.base[q] + off)[i];
         buf[i] = v;
@@ -75,7 +75,7 @@ int peer_graph_wait(itcpd_ctx *c) {
 
 int peer_allreduce_small(itcpd_ctx *c, double *buf, int64_t n) {
     ARG_CHECK(n <= c->peer_small_doubles, "small all-reduce larger than the exchange buffer's small slots");
-    peer_allreduce_small_kernel<<<1, 256, 0, c->stream>>>(peer_ptrs(c), c->peer_epochs.as<long long>() + 1, c->peer_small_off, c->peer_small_doubles, buf, (int)n);
+    peer_allreduce_small_kernel<<<1, 1024, 0, c->stream>>>(peer_ptrs(c), c->peer_epochs.as<long long>() + 1, c->peer_small_off, c->peer_small_doubles, buf, (int)n);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;
