@@ -57,23 +57,29 @@ int itcpd_device_info(itcpd_ctx *ctx, int *sm_count, int *cc_major, int *cc_mino
 int itcpd_synchronize(itcpd_ctx *ctx);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t itcpd_launch_count(itcpd_ctx *ctx);
-/* runtime options (name, values; * = default):
+/* runtime options (name, values; * = default).  Every path below has run on B200 hardware:
  *   "mttkrp_alg"     0* dimension tree (KRPFreeNormal / KRPNormal results), 1 direct one-pass-per-mode MTTKRP
  *   "split_a","split_b"  force the dimension-tree split points (0* = traffic cost model)
  *   "tile_warps"     4 | 8*  warps per GEMM CTA;  "swizzle" 1* | 0 (debug);  "tma3d" 1* | 0;  "stream_k" 0 | 1* | 2
  *   "overlap_factor" 1* Gram-Hadamard + Cholesky on a side stream under the GEMM;  "use_graph" 1* CUDA-graph replay of sweeps
- *   "early_pass_b" 0* | 1: EXPERIMENTAL (not yet run on hardware): pass B of the dimension tree is launched on its own stream as soon
- *                    as the modes it contracts are updated; the modes in [split_b, split_a) are updated underneath it (env ITCPD_EARLY_B)
- *   "graph_single"  0* | 1: EXPERIMENTAL (not yet run on hardware): repeated itcpd_sweep(1) calls -- the per-iteration loop of the
- *                    reference API -- capture the sweep graph on the second call and replay it afterwards (env ITCPD_GRAPH_SINGLE)
- *   "chol_alg"       0 block kernel, 1* team kernel (R <= 128, bitwise equal to 0), 2 right-looking (R <= 128, experimental), 3 right-looking only where the factorisation is exposed (experimental)
+ *   "graph_single"   1* | 0: repeated itcpd_sweep(1) calls -- the per-iteration loop of the reference API -- capture the sweep graph
+ *                    on the second call and replay it afterwards (env ITCPD_GRAPH_SINGLE)
+ *   "chol_alg"       0 block kernel (any R), 1 team kernel (R <= 128, bitwise equal to 0), 2 right-looking kernels (R <= 128),
+ *                    3* right-looking where the factorisation is exposed, where R > 64 and under short GEMM passes, team kernel elsewhere
+ *   "chol_short_gflop" 50*: GEMM passes below this many GFLOP count as short for "chol_alg" = 3 (0: never)
+ *   "staged_upload"  1* | 0: a pageable host tensor is uploaded through pinned staging buffers filled by host threads
+ *   "peer_graph"     1* | 0: sharded sweeps without an NCCL call inside (device-side exchange epochs, small all-reduces over the
+ *                    peer-mapped buffer), so that they are captured like single-GPU sweeps; set before itcpd_peer_export
+ *   "early_pass_b"   0* | 1: pass B of the dimension tree on its own stream as soon as the modes it contracts are updated (bitwise the
+ *                    default schedule; measured: no gain) (env ITCPD_EARLY_B)
+ *   "gemm_i8"        0* | 1 | 2: OPT-IN contraction on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) on 6 / 7 base-256
+ *                    digits per operand -- 48/56-bit fixed point per row, NOT the FP64 arithmetic of the default path; 1 converts T on the
+ *                    fly, 2 keeps T's digit planes pre-packed in HBM (6 B / element / unfolding) (csrc/gemm_i8.cu)
+ *   "i8_spare_sms"   0* .. 63: SMs the persistent INT8 GEMM leaves to the side-stream factorisation
  *   "time_gemm"      1: CUDA events around every GEMM launch (itcpd_gemm_timing); disables the graph
  *   "time_phases"    1: CUDA events after every phase of a mode update (itcpd_phase_timing); disables the graph
- *   "gemm_i8"        0* | 1 | 2 (experimental, not yet run on hardware) INT8 tensor-core digit-split contraction
- *                    (csrc/gemm_i8.cu): 1 converts T on the fly, 2 keeps T's digit planes pre-packed in HBM (6 B / element / unfolding)
- *   "i8_spare_sms"   0* .. 63: SMs the persistent INT8 GEMM leaves to the side-stream factorisation (R = 128: its 132 KB Cholesky cannot co-reside)
- *   "peer_graph"     0* | 1 (experimental) NCCL-free sharded sweeps with device-side exchange epochs; set before itcpd_peer_export
- * environment at itcpd_create: ITCPD_CHOL=0|1|2, ITCPD_NO_GRAPH=1, ITCPD_NO_SWIZZLE=1, ITCPD_GEMM_I8=1 */
+ * environment at itcpd_create: ITCPD_CHOL=0|1|2|3, ITCPD_NO_GRAPH=1, ITCPD_NO_SWIZZLE=1, ITCPD_GEMM_I8=1|2, ITCPD_EARLY_B=1,
+ * ITCPD_GRAPH_SINGLE=0|1, ITCPD_I8_SPARE_SMS=n */
 int itcpd_set_option(itcpd_ctx *ctx, const char *name, int64_t value);
 
 /* ---- target tensor (ALS.target, als_optimizer.jl:5-10; decompose.jl:5-7 wraps without copy) - */
