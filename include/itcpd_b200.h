@@ -186,6 +186,11 @@ void itcpd_sparsestack(int l, int n, int s, double *vals, int *rows, int *colsta
 /* sketched_matricization (pivot_mapping.jl:111-140): A_sk = T_(mode) * Omega' (I_mode x l) from the
  * (rows 0-based, vals) arrays the generators above fill; s non-zeros per column. */
 int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *rows0, const double *vals, double *host_out);
+/* The sparse-matrix variant of the same sketch (src/algebra/pivot_mapping.jl:90-104; what SEQRCS(...; use_omega = true) calls,
+ * src/algebra/SEQRCS.jl:89-134): Omega (l x ncols) as Julia's SparseMatrixCSC stores it -- colptr (ncols + 1), rowval, both 1-based
+ * Int64, and nzval.  Same kernel, same summation order as the matrix-free variant. */
+int itcpd_sketch_unfolding_csc(itcpd_ctx *ctx, int mode, int l, int64_t ncols, const int64_t *colptr, const int64_t *rowval,
+                               const double *nzval, double *host_out);
 /* one sampled ALS mode update (ProjectionAlgorithm.jl:57-68): given 1-based pivots for `mode`, gathers T_s and K on
  * the device and solves  normal != 0: (K'K) \ (T_s K)'  (pivoted Cholesky, QRCP fallback)
  *                        normal == 0: qr(K, ColumnNorm()) \ T_s'  (pivoted-QR min-norm least squares, nsamp >= R);

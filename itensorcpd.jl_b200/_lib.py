@@ -72,6 +72,7 @@ _SIGS = {
     "itcpd_sparse_sign": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itcpd_sparsestack": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itcpd_sketch_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_dp]),
+    "itcpd_sketch_unfolding_csc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_dp]),
     "itcpd_sampled_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int]),
     "itcpd_sampled_sweep_async": (C.c_int, [C.c_void_p, C.c_int, c_i64p, C.c_uint64, C.c_double, C.c_int]),
     "itcpd_qrcp_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_dp]),

@@ -1204,6 +1204,52 @@ int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows
     return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
 }
 
+// sparse-matrix variant of the sketch (pivot_mapping.jl:90-104): Omega (l x ncols) in compressed-sparse-column form exactly as Julia's
+// SparseMatrixCSC stores it (colptr: ncols + 1 entries, rowval, both 1-based; nzval).  A_sk = T_(mode) Omega^T, entries of a sketch row
+// visited in increasing column order (the order of `omega[j, :].nzind`), so the result is bitwise the matrix-free variant's when Omega
+// came from sparse_sign_matrix(...; omega = true).
+int itcpd_sketch_unfolding_csc(itcpd_ctx *c, int mode, int l, int64_t ncols, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                               double *host_out) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    CHECK_MODE(c, mode);
+    ARG_CHECK(l >= 1 && colptr && rowval && nzval && host_out, "bad argument");
+    ARG_CHECK(!comm_active(c), "itcpd_sketch_unfolding_csc needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
+    ARG_CHECK(ncols == c->nelem / c->dims[mode], "Omega must have one column per column of the mode's unfolding");
+    USE_DEVICE(c);
+    const int64_t nnz = colptr[ncols] - 1;
+    ARG_CHECK(colptr[0] == 1 && nnz >= 0, "colptr must be 1-based (SparseMatrixCSC)");
+    for (int64_t col = 0; col < ncols; ++col) ARG_CHECK(colptr[col + 1] >= colptr[col], "colptr must be non-decreasing");
+    SketchCsr k;
+    k.row_ptr.assign((size_t)l + 1, 0);
+    k.col.resize((size_t)nnz);
+    k.val.resize((size_t)nnz);
+    for (int64_t q = 0; q < nnz; ++q) {
+        ARG_CHECK(rowval[q] >= 1 && rowval[q] <= l, "sketch row index out of range");
+        k.row_ptr[(size_t)rowval[q]]++;
+    }
+    for (int j = 0; j < l; ++j) k.row_ptr[(size_t)j + 1] += k.row_ptr[j];
+    {
+        std::vector<int64_t> fill(k.row_ptr.begin(), k.row_ptr.end() - 1);
+        for (int64_t col = 0; col < ncols; ++col) {   // increasing column order inside every sketch row
+            for (int64_t q = colptr[col] - 1; q < colptr[col + 1] - 1; ++q) {
+                const int64_t pos = fill[(size_t)rowval[q] - 1]++;
+                k.col[(size_t)pos] = col;
+                k.val[(size_t)pos] = nzval[q];
+            }
+        }
+    }
+    const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)nnz * 8;
+    TRY(c->work.reserve(b_ptr + 2 * b_col + 64));
+    char *base = (char *)c->work.p;
+    CUDA_TRY(cudaMemcpyAsync(base, k.row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, k.col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, k.val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    TRY(c->samp_T.reserve((size_t)l * c->dims[mode] * 8));
+    TRY(k_sketch_csr(c, mode, l, (const int64_t *)base, (const int64_t *)(base + b_ptr), (const double *)(base + b_ptr + b_col), c->samp_T.as<double>()));
+    return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+}
+
 // ---- column-pivoted QR on the device (pivot-projected setup) ----------------------------------------
 static int qrcp_fetch(itcpd_ctx *c, int64_t n, int64_t nr, int64_t *piv_out, double *rdiag_out) {
     std::vector<int64_t> tmp((size_t)n);

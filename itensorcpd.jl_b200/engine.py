@@ -271,6 +271,19 @@ class Engine:
         check(self._L.itcpd_sketch_unfolding(self._h, mode, int(l), int(s), _addr(rows0), _addr(vals), _addr(out)))
         return out
 
+    def sketch_unfolding_omega(self, mode: int, omega) -> np.ndarray:
+        """sparse-matrix variant (pivot_mapping.jl:90-104): `omega` is a scipy.sparse matrix (l x ncols); handed over in Julia's
+        SparseMatrixCSC convention (1-based colptr / rowval)"""
+        om = omega.tocsc()
+        om.sort_indices()
+        colptr = np.ascontiguousarray(om.indptr, dtype=np.int64) + 1
+        rowval = np.ascontiguousarray(om.indices, dtype=np.int64) + 1
+        nzval = np.ascontiguousarray(om.data, dtype=np.float64)
+        l, ncols = om.shape
+        out = np.empty((self.dims[mode], l), order="F")
+        check(self._L.itcpd_sketch_unfolding_csc(self._h, mode, int(l), int(ncols), _addr(colptr), _addr(rowval), _addr(nzval), _addr(out)))
+        return out
+
     def sampled_update(self, mode: int, pivots, chol_tol: float = 1e-6, normal: bool = True):
         p = self._piv(pivots)
         check(self._L.itcpd_sampled_update(self._h, mode, p.shape[0], _addr(p), float(chol_tol), int(bool(normal))))

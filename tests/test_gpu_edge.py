@@ -108,6 +108,31 @@ def test_cholesky_tolerance_boundary_matches_lapack_decision(engine):
     assert {d[1] for d in decisions} == {0, 1}, decisions  # both branches were exercised
 
 
+def test_last_solve_status_reports_the_path_taken(engine):
+    """itcpd_last_solve_status: (path, rank) of the most recent R x R solve -- Cholesky for a full-rank Gram-Hadamard, the pivoted-QR
+    fallback of ldiv_solve.jl:19-21 with the numerical rank when two columns are duplicated; after whole sweeps one slot per mode."""
+    rng = np.random.default_rng(21)
+    T = np.asfortranarray(rng.standard_normal((30, 25, 20)))
+    cp = cpals.random_CPD(T, 12, rng)
+    engine.set_tensor(T)
+    engine.set_cpd(cp.factors, cp.lam)
+    engine.compute_grams()
+    engine.gram_hadamard(1, fetch=False); engine.mttkrp(1, fetch=False)
+    assert engine.solve(1, 1e-6) == (0, 12) and engine.last_solve_status(0) == (0, 12)
+    f = [x.copy() for x in cp.factors]
+    for m in range(3):
+        f[m][:, 7] = f[m][:, 2]
+        f[m][:, 11] = f[m][:, 5]
+    engine.set_cpd(f, cp.lam)
+    engine.compute_grams()
+    engine.gram_hadamard(1, fetch=False); engine.mttkrp(1, fetch=False)
+    assert engine.solve(1, 1e-6) == (1, 10) and engine.last_solve_status(0) == (1, 10)
+    engine.set_cpd(cp.factors, cp.lam)
+    engine.compute_grams()
+    engine.sweep(2)
+    assert [engine.last_solve_status(m) for m in range(3)] == [(0, 12)] * 3
+
+
 def test_nan_fit_raises_on_host_like_reference(engine):
     """row_norm has no zero guard (row_norm.jl:19-21): a zero column -> NaN -> throw("Error NAN") (fit_check.jl:40-42)."""
     import itcpd

@@ -72,6 +72,10 @@ def test_sketch_unfolding_matches_dense(engine, inj):  # test/pivot_mapping.jl:1
         import scipy.sparse as sp
         om = sp.csc_matrix((vals, (rows0, np.repeat(np.arange(n), s))), shape=(l, n))
         assert np.linalg.norm(A_sk - cpals.unfold(T, mode) @ om.toarray().T) < 1e-12
+        # the sparse-matrix variant (pivot_mapping.jl:90-104; SEQRCS(...; use_omega = true)): same kernel, same summation order
+        A_om = engine.sketch_unfolding_omega(mode, om)
+        assert np.array_equal(A_om, A_sk)
+        assert np.linalg.norm(A_om - sampled.sketched_matricization_omega(T, mode, om)) < 1e-12
 
 
 @pytest.mark.parametrize("rows,R", [(40, 6), (300, 50), (5, 9), (64, 64)])
