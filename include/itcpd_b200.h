@@ -67,6 +67,9 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "chol_alg"       0 block kernel (any R), 1 team kernel (R <= 128, bitwise equal to 0), 2 right-looking kernels (R <= 128),
  *                    3* right-looking where the factorisation is exposed, where R > 64 and under short GEMM passes, team kernel elsewhere
  *   "chol_short_gflop" 50*: GEMM passes below this many GFLOP count as short for "chol_alg" = 3 (0: never)
+ *   "seqrcs_use_omega" 0* | 1: itcpd_seqrcs lists its candidate columns in increasing order, the order SEQRCS(...; use_omega = true)
+ *                    produces (SEQRCS.jl:109-113; the sketch itself is bitwise the same either way, see itcpd_sketch_unfolding_csc);
+ *                    0 = the matrix-free variant's order (:159), the reference's default
  *   "staged_upload"  1* | 0: a pageable host tensor is uploaded through pinned staging buffers filled by host threads
  *   "peer_graph"     1* | 0: sharded sweeps without an NCCL call inside (device-side exchange epochs, small all-reduces over the
  *                    peer-mapped buffer), so that they are captured like single-GPU sweeps; set before itcpd_peer_export

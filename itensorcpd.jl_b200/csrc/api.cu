@@ -473,6 +473,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "tma3d") c->tma3d = value != 0;
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "staged_upload") c->staged_upload = value != 0;
+    else if (n == "seqrcs_use_omega") c->seqrcs_use_omega = value != 0;
     else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "graph_single") c->graph_single = value != 0;
     else if (n == "i8_spare_sms") { ARG_CHECK(value >= 0 && value < 64, "i8_spare_sms must be in [0, 64)"); c->i8_spare_sms = (int)value; }
@@ -1328,6 +1329,8 @@ int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int
             if (!seen[(size_t)col]) { seen[(size_t)col] = 1; cand.push_back(col); }
         }
     }
+    // SEQRCS(Val(true), ...) (SEQRCS.jl:109-113) finds the same columns with findall over eachcol(omega[p_sk, :]): increasing column order
+    if (c->seqrcs_use_omega) std::sort(cand.begin(), cand.end());
     const int64_t nc = (int64_t)cand.size();
     ARG_CHECK(nc >= 1, "SE-QRCS selected no candidate column");
     // 5. gather the candidate columns (fused_flatten_sample, SEQRCS.jl:166) and QRCP them

@@ -164,6 +164,9 @@ struct itcpd_ctx {
     int64_t proj_n[ITCPD_MAX_ORDER] = {0};
     // option "staged_upload" (default on): a pageable host tensor is uploaded through pinned staging buffers filled by host threads
     int staged_upload = 1;
+    // option "seqrcs_use_omega": candidate columns of itcpd_seqrcs in increasing order, as SEQRCS(...; use_omega = true) lists them
+    // (SEQRCS.jl:109-113); off = the order of the matrix-free variant (:159), the reference's default
+    int seqrcs_use_omega = 0;
     void *upload_stage = nullptr;
     cudaEvent_t upload_events[8] = {nullptr};
     double *pinned = nullptr;   // pinned host staging (fit scalars, status words)

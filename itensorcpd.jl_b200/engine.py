@@ -312,8 +312,10 @@ class Engine:
         check(self._L.itcpd_qrcp_matrix(self._h, m, n, _addr(A), steps, _addr(piv), _addr(rd)))
         return piv, rd
 
-    def seqrcs(self, mode: int, l: int, s: int, t: int, injective: bool = False, seed: Optional[int] = None):
-        """SEQRCS (SEQRCS.jl:139-182, compute_r=false): (p 1-based, diag(R) of the candidate QR, #candidates)."""
+    def seqrcs(self, mode: int, l: int, s: int, t: int, injective: bool = False, seed: Optional[int] = None, use_omega: bool = False):
+        """SEQRCS (SEQRCS.jl:139-182, compute_r=false): (p 1-based, diag(R) of the candidate QR, #candidates).
+        use_omega=True: the candidate order of the sparse-matrix variant (SEQRCS.jl:89-134)."""
+        self.set_option("seqrcs_use_omega", int(bool(use_omega)))
         m = self.dims[mode]
         n = int(np.prod(self.dims)) // m
         piv = np.empty(n, dtype=np.int64)

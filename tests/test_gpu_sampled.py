@@ -242,6 +242,12 @@ def test_device_seqrcs_matches_oracle_and_qrcp_quality(engine, inj):
     assert np.array_equal(piv[:k], p[:k])                             # same leading pivots
     _, _, p_act = sampled.qrcp(A)
     assert abs(_rank_k_error(A, piv, k) - _rank_k_error(A, p_act, k)) <= 1e-2
+    # the sparse-matrix variant (SEQRCS.jl:89-134, use_omega = true): same sketch, candidates listed in increasing column order
+    piv_o, _, ncand_o = engine.seqrcs(0, l, s, t, injective=inj, seed=17, use_omega=True)
+    _, _, p_o = sampled.seqrcs_tensor(A, 0, l, s, t, use_omega=True, injective=inj, which="ref", seed=17)
+    assert ncand_o == ncand and set(piv_o[:ncand].tolist()) == set(piv[:ncand].tolist())
+    assert np.array_equal(piv_o[:k], p_o[:k]) and np.array_equal(piv_o[ncand:], p_o[ncand:])
+    engine.set_option("seqrcs_use_omega", 0)
 
 
 def test_projected_update_matches_oracle(engine):
