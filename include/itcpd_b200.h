@@ -70,6 +70,10 @@ int64_t itcpd_launch_count(itcpd_ctx *ctx);
  *   "seqrcs_use_omega" 0* | 1: itcpd_seqrcs lists its candidate columns in increasing order, the order SEQRCS(...; use_omega = true)
  *                    produces (SEQRCS.jl:109-113; the sketch itself is bitwise the same either way, see itcpd_sketch_unfolding_csc);
  *                    0 = the matrix-free variant's order (:159), the reference's default
+ *   "sketch_unfold"  1* | 0: the SE-QRCS set-up sketches every mode but the first from an explicit unfolding (a second copy of the tensor
+ *                    for the duration of the call, made by a tiled transpose; skipped when HBM has no room) instead of gathering
+ *                    its strided columns in place; bitwise the same sketch, 10x faster.  2 = also in itcpd_sketch_unfolding[_csc]
+ *                    (how the tests compare the two paths)
  *   "staged_upload"  1* | 0: a pageable host tensor is uploaded through pinned staging buffers filled by host threads
  *   "peer_graph"     1* | 0: sharded sweeps without an NCCL call inside (device-side exchange epochs, small all-reduces over the
  *                    peer-mapped buffer), so that they are captured like single-GPU sweeps; set before itcpd_peer_export
@@ -186,6 +190,10 @@ int itcpd_multi_coords_to_column(int64_t ncols, const int64_t *coords, int ndims
  * (algebra/sparse_sign.c:25-70, algebra/sparsestack.c:24-79; bound at SEQRCS.jl:41-60). */
 void itcpd_sparse_sign(int l, int n, int s, double *vals, int *rows, int *colstarts);
 void itcpd_sparsestack(int l, int n, int s, double *vals, int *rows, int *colstarts);
+/* 1 if the two generators above read libc's rand() stream without its per-call lock (glibc: the state array is borrowed through
+ * initstate()/setstate(), advanced in place and handed back, after a self-test on private state; 2.3x faster, the same numbers and
+ * the same continuation of the stream), 0 if they call rand() (any other libc, or ITCPD_PLAIN_RAND set in the environment). */
+int itcpd_sparse_sign_fast_stream(void);
 /* sketched_matricization (pivot_mapping.jl:111-140): A_sk = T_(mode) * Omega' (I_mode x l) from the
  * (rows 0-based, vals) arrays the generators above fill; s non-zeros per column. */
 int itcpd_sketch_unfolding(itcpd_ctx *ctx, int mode, int l, int s, const int *rows0, const double *vals, double *host_out);
@@ -224,6 +232,14 @@ int itcpd_qrcp_matrix(itcpd_ctx *ctx, int64_t m, int64_t n, const double *host_A
  * rdiag_out: diag(R) of the candidate QR (nrdiag_out values, caller provides I_mode doubles). */
 int itcpd_seqrcs(itcpd_ctx *ctx, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
                  int64_t *nrdiag_out, int64_t *ncand_out);
+/* The same for several modes in one call -- the loop of optimizers/.../randomized/qr_lev_score_sampled.jl:80-176 over its random
+ * modes.  Embeddings are generated in the order of `modes`, so the libc rand() stream is consumed exactly as by per-mode calls in
+ * that order; the host half of mode i+1 (the reference's generator, the sort of the sketch by row) runs on a helper thread while
+ * the device factorises mode i.  seeds: NULL, or one value per mode -- >= 0: srand(seed) right before that mode's generator
+ * (tests / reproducible runs), < 0: the stream continues.  piv_out[i]: P / I_modes[i] int64; rdiag_out: NULL or one pointer per mode
+ * (NULL entries allowed); nrdiag_out / ncand_out: NULL or nmodes values. */
+int itcpd_seqrcs_modes(itcpd_ctx *ctx, int nmodes, const int *modes, const int *l, const int *s, const int *t, int injective,
+                       const int64_t *seeds, int64_t *const *piv_out, double *const *rdiag_out, int64_t *nrdiag_out, int64_t *ncand_out);
 /* KRP-structured SE-QRCS (algebra/SEQRCS.jl:184-241, compute_r = false): the same procedure applied to the Khatri-Rao
  * product of the handle's CURRENT factors of every mode != `mode` (R x n, never formed): the sketch is
  * omega_hadamard (algebra/had_contract.jl:300-329), candidates are gathered with pivot_hadamard.  Outputs as itcpd_seqrcs. */

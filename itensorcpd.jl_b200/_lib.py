@@ -71,6 +71,7 @@ _SIGS = {
     "itcpd_multi_coords_to_column": (C.c_int, [C.c_int64, C.c_void_p, C.c_int, c_i64p, C.c_void_p]),
     "itcpd_sparse_sign": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "itcpd_sparsestack": (None, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "itcpd_sparse_sign_fast_stream": (C.c_int, []),
     "itcpd_sketch_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_dp]),
     "itcpd_sketch_unfolding_csc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_dp]),
     "itcpd_sampled_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int]),
@@ -78,6 +79,8 @@ _SIGS = {
     "itcpd_qrcp_unfolding": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_dp]),
     "itcpd_qrcp_matrix": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp, C.c_int64, C.c_void_p, c_dp]),
     "itcpd_seqrcs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "itcpd_seqrcs_modes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "itcpd_seqrcs_krp": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "itcpd_set_projector": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "itcpd_projected_update": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),

@@ -1,7 +1,9 @@
 // extern "C" entry points of libitcpd_b200 (see include/itcpd_b200.h for the contract and the
 // reference interfaces each one replaces).
 #include "common.cuh"
+#include <chrono>
 #include <cmath>
+#include <functional>
 #include <cstdarg>
 #include <cstdlib>
 #include <algorithm>
@@ -421,6 +423,8 @@ int itcpd_destroy(itcpd_ctx *c) {
     for (auto &ev : c->phase_events) cudaEventDestroy(ev);
     for (auto &ev : c->user_events) if (ev) cudaEventDestroy(ev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto &pin : c->sketch_pin) if (pin) cudaFreeHost(pin);
+    c->unfolded.release();
     if (c->upload_stage) {
         cudaFreeHost(c->upload_stage);
         for (auto &ev : c->upload_events) if (ev) cudaEventDestroy(ev);
@@ -474,6 +478,7 @@ int itcpd_set_option(itcpd_ctx *c, const char *name, int64_t value) {
     else if (n == "overlap_factor") c->overlap_factor = value != 0;
     else if (n == "staged_upload") c->staged_upload = value != 0;
     else if (n == "seqrcs_use_omega") c->seqrcs_use_omega = value != 0;
+    else if (n == "sketch_unfold") { ARG_CHECK(value >= 0 && value <= 2, "sketch_unfold must be 0, 1 or 2"); c->sketch_unfold = (int)value; }
     else if (n == "early_pass_b") c->early_pass_b = value != 0;
     else if (n == "graph_single") c->graph_single = value != 0;
     else if (n == "i8_spare_sms") { ARG_CHECK(value >= 0 && value < 64, "i8_spare_sms must be in [0, 64)"); c->i8_spare_sms = (int)value; }
@@ -1153,39 +1158,109 @@ int itcpd_multi_coords_to_column(int64_t ncols, const int64_t *coords, int ndims
 // CSR by sketch row with a stable counting sort: entries of a row stay in increasing non-zero order
 // (the order the reference's dict_rows visits them, pivot_mapping.jl:127-137); uploaded into c->work.
 struct SketchCsr {
-    std::vector<int64_t> row_ptr, col;
-    std::vector<double> val;
-    const int64_t *d_ptr = nullptr, *d_col = nullptr;
+    std::vector<int64_t> row_ptr;
+    std::vector<int64_t> col_own;   // pageable storage of the single-shot entry points; the SE-QRCS set-up points col / val at the
+    std::vector<double> val_own;    // handle's pinned slots instead (c->sketch_pin)
+    int64_t *col = nullptr;
+    double *val = nullptr;
+    int64_t nnz = 0;
+    const int64_t *d_ptr = nullptr;
+    int64_t *d_col = nullptr;       // the sketch kernel turns the column numbers into element offsets in place
     const double *d_val = nullptr;
 };
 
-static int build_sketch_csr(itcpd_ctx *c, int l, int s_eff, int64_t ncols, const int *rows0, const double *vals, SketchCsr &k) {
+// Pure host work (no CUDA calls: it also runs on the set-up's helper thread).  Stable and parallel: the non-zeros are cut into one
+// chunk per thread, every thread counts its chunk per sketch row, a serial pass over (row, thread) hands each thread its first slot
+// in every row, and the threads place their chunks -- thread w's entries of a row land behind those of threads < w, in order.
+static int sketch_csr_fill(int l, int s_eff, int64_t ncols, const int *rows0, const double *vals, SketchCsr &k) {
     const int64_t nnz = ncols * s_eff;
+    k.nnz = nnz;
     k.row_ptr.assign((size_t)l + 1, 0);
-    k.col.resize((size_t)nnz);
-    k.val.resize((size_t)nnz);
-    for (int64_t q = 0; q < nnz; ++q) {
-        ARG_CHECK(rows0[q] >= 0 && rows0[q] < l, "sketch row index out of range");
-        k.row_ptr[(size_t)rows0[q] + 1]++;
-    }
-    for (int j = 0; j < l; ++j) k.row_ptr[(size_t)j + 1] += k.row_ptr[j];
-    {
-        std::vector<int64_t> fill(k.row_ptr.begin(), k.row_ptr.end() - 1);
-        for (int64_t q = 0; q < nnz; ++q) {
-            const int64_t pos = fill[rows0[q]]++;
-            k.col[(size_t)pos] = q / s_eff;
-            k.val[(size_t)pos] = vals[q];
+    const int hw = (int)std::thread::hardware_concurrency();
+    int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(8, hw > 0 ? hw : 1), nnz / 262144));
+    if (const char *f = getenv("ITCPD_SKETCH_THREADS")) nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(64, atoi(f)), ncols));   // tests: threads on small inputs
+    std::vector<int64_t> first((size_t)nt * l, 0);          // counts, then first slots: first[w * l + row]
+    std::atomic<int> bad(0);
+    auto chunk_lo = [&](int w) { return (nnz * w / nt) / s_eff * s_eff; };   // chunk borders on column borders
+    auto count = [&](int w) {
+        int64_t *cnt = first.data() + (size_t)w * l;
+        const int64_t hi = w + 1 == nt ? nnz : chunk_lo(w + 1);
+        for (int64_t q = chunk_lo(w); q < hi; ++q) {
+            const int r = rows0[q];
+            if (r < 0 || r >= l) { bad = 1; return; }
+            cnt[r]++;
         }
+    };
+    auto place = [&](int w) {
+        int64_t *slot = first.data() + (size_t)w * l;
+        const int64_t lo = chunk_lo(w), hi = w + 1 == nt ? nnz : chunk_lo(w + 1);
+        int64_t column = lo / s_eff;
+        int within = 0;
+        for (int64_t q = lo; q < hi; ++q) {
+            const int64_t pos = slot[rows0[q]]++;
+            k.col[pos] = column;
+            k.val[pos] = vals[q];
+            if (++within == s_eff) { within = 0; ++column; }
+        }
+    };
+    auto run = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (int w = 1; w < nt; ++w) th.emplace_back(fn, w);
+        fn(0);
+        for (auto &t : th) t.join();
+    };
+    run(count);
+    if (bad) return ITCPD_ERR_ARG;
+    int64_t running = 0;
+    for (int r = 0; r < l; ++r) {
+        for (int w = 0; w < nt; ++w) {
+            const int64_t n_here = first[(size_t)w * l + r];
+            first[(size_t)w * l + r] = running;
+            running += n_here;
+        }
+        k.row_ptr[(size_t)r + 1] = running;
     }
-    const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)nnz * 8;
+    run(place);
+    return ITCPD_OK;
+}
+
+static int sketch_csr_upload(itcpd_ctx *c, int l, SketchCsr &k) {
+    const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)k.nnz * 8;
     TRY(c->work.reserve(b_ptr + 2 * b_col + 64));
     char *base = (char *)c->work.p;
     CUDA_TRY(cudaMemcpyAsync(base, k.row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, k.col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, k.val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, k.col, b_col, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, k.val, b_col, cudaMemcpyHostToDevice, c->stream));
     k.d_ptr = (const int64_t *)base;
-    k.d_col = (const int64_t *)(base + b_ptr);
+    k.d_col = (int64_t *)(base + b_ptr);
     k.d_val = (const double *)(base + b_ptr + b_col);
+    return ITCPD_OK;
+}
+
+static int build_sketch_csr(itcpd_ctx *c, int l, int s_eff, int64_t ncols, const int *rows0, const double *vals, SketchCsr &k) {
+    k.col_own.resize((size_t)(ncols * s_eff));
+    k.val_own.resize((size_t)(ncols * s_eff));
+    k.col = k.col_own.data();
+    k.val = k.val_own.data();
+    if (sketch_csr_fill(l, s_eff, ncols, rows0, vals, k) != ITCPD_OK) {
+        set_error("sketch row index out of range");
+        return ITCPD_ERR_ARG;
+    }
+    return sketch_csr_upload(c, l, k);
+}
+
+// every mode but the first reads its unfolding's columns with a stride: make the unfolding explicit once (one read + one write of
+// the tensor) when HBM has room for a second copy, and sketch from contiguous columns.  *out stays nullptr when it does not apply.
+static int unfold_for_sketch(itcpd_ctx *c, int mode, const double **out) {
+    *out = nullptr;
+    if (mode == 0 || !c->sketch_unfold) return ITCPD_OK;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (size_t)c->nelem * 8;
+    if (c->unfolded.bytes < need && free_b < need + ((size_t)4 << 30)) return ITCPD_OK;
+    TRY(c->unfolded.reserve(need));
+    TRY(k_unfold(c, mode, c->unfolded.as<double>()));
+    *out = c->unfolded.as<double>();
     return ITCPD_OK;
 }
 
@@ -1201,8 +1276,12 @@ int itcpd_sketch_unfolding(itcpd_ctx *c, int mode, int l, int s, const int *rows
     SketchCsr k;
     TRY(build_sketch_csr(c, l, s_eff, ncols, rows0, vals, k));
     TRY(c->samp_T.reserve((size_t)l * c->dims[mode] * 8));
-    TRY(k_sketch_csr(c, mode, l, k.d_ptr, k.d_col, k.d_val, c->samp_T.as<double>()));
-    return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+    const double *unfolded = nullptr;
+    if (c->sketch_unfold == 2) TRY(unfold_for_sketch(c, mode, &unfolded));   // the set-up's path, reachable for the parity tests
+    TRY(k_sketch_csr(c, mode, l, k.nnz, k.d_ptr, k.d_col, k.d_val, c->samp_T.as<double>(), unfolded));
+    const int rc = d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+    c->unfolded.release();
+    return rc;
 }
 
 // sparse-matrix variant of the sketch (pivot_mapping.jl:90-104): Omega (l x ncols) in compressed-sparse-column form exactly as Julia's
@@ -1222,9 +1301,12 @@ int itcpd_sketch_unfolding_csc(itcpd_ctx *c, int mode, int l, int64_t ncols, con
     ARG_CHECK(colptr[0] == 1 && nnz >= 0, "colptr must be 1-based (SparseMatrixCSC)");
     for (int64_t col = 0; col < ncols; ++col) ARG_CHECK(colptr[col + 1] >= colptr[col], "colptr must be non-decreasing");
     SketchCsr k;
+    k.nnz = nnz;
     k.row_ptr.assign((size_t)l + 1, 0);
-    k.col.resize((size_t)nnz);
-    k.val.resize((size_t)nnz);
+    k.col_own.resize((size_t)nnz);
+    k.val_own.resize((size_t)nnz);
+    k.col = k.col_own.data();
+    k.val = k.val_own.data();
     for (int64_t q = 0; q < nnz; ++q) {
         ARG_CHECK(rowval[q] >= 1 && rowval[q] <= l, "sketch row index out of range");
         k.row_ptr[(size_t)rowval[q]]++;
@@ -1235,20 +1317,19 @@ int itcpd_sketch_unfolding_csc(itcpd_ctx *c, int mode, int l, int64_t ncols, con
         for (int64_t col = 0; col < ncols; ++col) {   // increasing column order inside every sketch row
             for (int64_t q = colptr[col] - 1; q < colptr[col + 1] - 1; ++q) {
                 const int64_t pos = fill[(size_t)rowval[q] - 1]++;
-                k.col[(size_t)pos] = col;
-                k.val[(size_t)pos] = nzval[q];
+                k.col[pos] = col;
+                k.val[pos] = nzval[q];
             }
         }
     }
-    const size_t b_ptr = ((size_t)l + 1) * 8, b_col = (size_t)nnz * 8;
-    TRY(c->work.reserve(b_ptr + 2 * b_col + 64));
-    char *base = (char *)c->work.p;
-    CUDA_TRY(cudaMemcpyAsync(base, k.row_ptr.data(), b_ptr, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr, k.col.data(), b_col, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + b_ptr + b_col, k.val.data(), b_col, cudaMemcpyHostToDevice, c->stream));
+    TRY(sketch_csr_upload(c, l, k));
     TRY(c->samp_T.reserve((size_t)l * c->dims[mode] * 8));
-    TRY(k_sketch_csr(c, mode, l, (const int64_t *)base, (const int64_t *)(base + b_ptr), (const double *)(base + b_ptr + b_col), c->samp_T.as<double>()));
-    return d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+    const double *unfolded = nullptr;
+    if (c->sketch_unfold == 2) TRY(unfold_for_sketch(c, mode, &unfolded));   // the set-up's path, reachable for the parity tests
+    TRY(k_sketch_csr(c, mode, l, k.nnz, k.d_ptr, k.d_col, k.d_val, c->samp_T.as<double>(), unfolded));
+    const int rc = d2h(c, host_out, c->samp_T.p, (size_t)l * c->dims[mode] * 8);
+    c->unfolded.release();
+    return rc;
 }
 
 // ---- column-pivoted QR on the device (pivot-projected setup) ----------------------------------------
@@ -1290,28 +1371,82 @@ int itcpd_qrcp_unfolding(itcpd_ctx *c, int mode, int64_t *piv_out, double *rdiag
     return qrcp_fetch(c, n, nr, piv_out, rdiag_out);
 }
 
-int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
-                 int64_t *nrdiag_out, int64_t *ncand_out) {
-    CHECK_CTX(c);
-    NEED_T(c);
-    CHECK_MODE(c, mode);
-    ARG_CHECK(l >= 1 && s >= 1 && t >= 1 && t <= l && piv_out && c->has_tensor, "bad argument (need 1 <= t <= l)");
-    ARG_CHECK(!comm_active(c), "itcpd_seqrcs needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
-    USE_DEVICE(c);
-    const int N = c->order;
-    const int64_t m = c->dims[mode], n = c->nelem / m;
-    ARG_CHECK(n < (int64_t)1 << 31 && (int64_t)n * std::min(s, l) < (int64_t)1 << 31, "the reference's C generators index with 32-bit ints");
-    const int s_eff = std::min(s, l);
-    // 1. sparse-sign embedding (SEQRCS.jl:144-146) -- same libc rand() stream as the reference's generators
-    std::vector<double> vals((size_t)n * s_eff);
-    std::vector<int> rows((size_t)n * s_eff), colstarts((size_t)n + 1);
-    if (injective) itcpd_sparsestack(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
-    else itcpd_sparse_sign(l, (int)n, s, vals.data(), rows.data(), colstarts.data());
-    // 2. sketch A_sk = T_(mode) Omega^T (I x l) (SEQRCS.jl:149)
+// One SE-QRCS embedding on the host: the reference's generator (same libc rand() stream, SEQRCS.jl:144-146) and the sketch in
+// CSR-by-sketch-row order.  No CUDA calls: the set-up runs it for mode n+1 on a helper thread while the device factorises mode n.
+struct Embedding {
+    std::vector<double> vals;
+    std::vector<int> rows, colstarts;
     SketchCsr k;
-    TRY(build_sketch_csr(c, l, s_eff, n, rows.data(), vals.data(), k));
+    int l = 0, s_eff = 0;
+    int64_t ncols = 0;
+    int status = ITCPD_OK;
+    double gen_ms = 0.0, csr_ms = 0.0;
+};
+
+static void host_embedding(int l, int s, int64_t ncols, int injective, int64_t seed, Embedding &e) {
+    const auto t0 = std::chrono::steady_clock::now();
+    e.l = l;
+    e.s_eff = std::min(s, l);
+    e.ncols = ncols;
+    const size_t nnz = (size_t)ncols * e.s_eff;
+    if (e.vals.size() < nnz) { e.vals.resize(nnz); e.rows.resize(nnz); }
+    if (e.colstarts.size() < (size_t)ncols + 1) e.colstarts.resize((size_t)ncols + 1);
+    if (seed >= 0) srand((unsigned)seed);
+    if (injective) itcpd_sparsestack(l, (int)ncols, s, e.vals.data(), e.rows.data(), e.colstarts.data());
+    else itcpd_sparse_sign(l, (int)ncols, s, e.vals.data(), e.rows.data(), e.colstarts.data());
+    const auto t1 = std::chrono::steady_clock::now();
+    e.status = sketch_csr_fill(l, e.s_eff, ncols, e.rows.data(), e.vals.data(), e.k);
+    const auto t2 = std::chrono::steady_clock::now();
+    e.gen_ms = 1e3 * std::chrono::duration<double>(t1 - t0).count();
+    e.csr_ms = 1e3 * std::chrono::duration<double>(t2 - t1).count();
+}
+
+// pinned home of an embedding's CSR entries (slot 0 / 1 alternate between consecutive modes); grows, never shrinks
+static int sketch_pin_reserve(itcpd_ctx *c, int slot, int64_t nnz, SketchCsr &k) {
+    const size_t need = (size_t)nnz * 16;
+    if (c->sketch_pin_bytes[slot] < need) {
+        if (c->sketch_pin[slot]) cudaFreeHost(c->sketch_pin[slot]);
+        c->sketch_pin[slot] = nullptr;
+        c->sketch_pin_bytes[slot] = 0;
+        CUDA_TRY(cudaHostAlloc(&c->sketch_pin[slot], need, cudaHostAllocDefault));
+        c->sketch_pin_bytes[slot] = need;
+    }
+    k.col = (int64_t *)c->sketch_pin[slot];
+    k.val = (double *)((char *)c->sketch_pin[slot] + (size_t)nnz * 8);
+    return ITCPD_OK;
+}
+
+// ITCPD_TRACE_SETUP=1: host wall-clock marks (after a stream synchronize) between the steps of the SE-QRCS set-up, to stderr
+struct SetupTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit SetupTrace(cudaStream_t s) : on(getenv("ITCPD_TRACE_SETUP") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[itcpd setup] %-28s %8.2f ms\n", what, 1e3 * std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+// device half of SE-QRCS for one mode, given its embedding (SEQRCS.jl:149-168)
+static int seqrcs_device_part(itcpd_ctx *c, int mode, int t, Embedding &e, int64_t *piv_out, double *rdiag_out, int64_t *nrdiag_out,
+                              int64_t *ncand_out) {
+    const int N = c->order, l = e.l;
+    const int64_t m = c->dims[mode], n = e.ncols;
+    SketchCsr &k = e.k;
+    SetupTrace tr(c->stream);
+    // 2. sketch A_sk = T_(mode) Omega^T (I x l) (SEQRCS.jl:149)
+    TRY(sketch_csr_upload(c, l, k));
     TRY(c->qr_A.reserve((size_t)m * std::max<int64_t>(l, 1) * 8));
-    TRY(k_sketch_csr(c, mode, l, k.d_ptr, k.d_col, k.d_val, c->qr_A.as<double>()));
+    tr.mark("csr upload");
+    const double *unfolded = nullptr;
+    TRY(unfold_for_sketch(c, mode, &unfolded));
+    if (unfolded) tr.mark("explicit unfolding");
+    TRY(k_sketch_csr(c, mode, l, k.nnz, k.d_ptr, k.d_col, k.d_val, c->qr_A.as<double>(), unfolded));
+    tr.mark("sketch kernel");
     // 3. QRCP of the sketch, first t pivots (SEQRCS.jl:152-158)
     TRY(c->qr_piv.reserve((size_t)std::max<int64_t>(n, l) * 8));
     TRY(c->qr_rdiag.reserve((size_t)std::max<int64_t>(m, 1) * 8 + (size_t)std::min<int64_t>(m, l) * 8));
@@ -1319,13 +1454,14 @@ int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int
     std::vector<int64_t> p_sk((size_t)t);
     CUDA_TRY(cudaMemcpyAsync(p_sk.data(), c->qr_piv.p, (size_t)t * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    tr.mark("qrcp of the sketch");
     // 4. candidate columns: for each selected sketch row (pivot order) the columns hashed to it, unique'd (SEQRCS.jl:159)
     std::vector<char> seen((size_t)n, 0);
     std::vector<int64_t> cand;
     for (int64_t q = 0; q < t; ++q) {
         const int64_t r = p_sk[(size_t)q];
-        for (int64_t e = k.row_ptr[(size_t)r]; e < k.row_ptr[(size_t)r + 1]; ++e) {
-            const int64_t col = k.col[(size_t)e];
+        for (int64_t en = k.row_ptr[(size_t)r]; en < k.row_ptr[(size_t)r + 1]; ++en) {
+            const int64_t col = k.col[en];
             if (!seen[(size_t)col]) { seen[(size_t)col] = 1; cand.push_back(col); }
         }
     }
@@ -1346,22 +1482,75 @@ int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int
     }
     TRY(c->samp_piv.reserve((size_t)nc * (N - 1) * 8));
     CUDA_TRY(cudaMemcpyAsync(c->samp_piv.p, coords.data(), (size_t)nc * (N - 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    tr.mark("candidates + coords");
     TRY(c->qr_A.reserve((size_t)m * nc * 8));
     TRY(k_gather_fibers(c, mode, nc, c->samp_piv.as<int64_t>(), c->qr_A.as<double>()));
+    tr.mark("gather candidates");
     const int64_t nr = std::min(m, nc);
     TRY(k_qrcp_wide(c, c->qr_A.as<double>(), m, nc, nr, c->qr_piv.as<int64_t>(), c->qr_rdiag.as<double>()));
     std::vector<int64_t> p_sub((size_t)nc);
     CUDA_TRY(cudaMemcpyAsync(p_sub.data(), c->qr_piv.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
     if (rdiag_out) CUDA_TRY(cudaMemcpyAsync(rdiag_out, c->qr_rdiag.p, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    tr.mark("qrcp of the candidates");
     // 6. p = [candidates[p_subset]; setdiff(1:n, candidates)] (SEQRCS.jl:167-168), 1-based
     int64_t w = 0;
     for (int64_t i = 0; i < nc; ++i) piv_out[w++] = cand[(size_t)p_sub[(size_t)i]] + 1;
     for (int64_t col = 0; col < n; ++col)
         if (!seen[(size_t)col]) piv_out[w++] = col + 1;
+    tr.mark("pivot list");
     if (nrdiag_out) *nrdiag_out = nr;
     if (ncand_out) *ncand_out = nc;
     return ITCPD_OK;
+}
+
+// SE-QRCS of several modes in one call (the loop of optimizers/.../qr_lev_score_sampled.jl:80-176 over its random modes).  The
+// embeddings are generated in the order of `modes`, so the libc rand() stream is consumed exactly as by the per-mode calls; the
+// host half of mode i+1 (generator + CSR) runs on a helper thread while the device works on mode i.
+int itcpd_seqrcs_modes(itcpd_ctx *c, int nmodes, const int *modes, const int *l, const int *s, const int *t, int injective,
+                       const int64_t *seeds, int64_t *const *piv_out, double *const *rdiag_out, int64_t *nrdiag_out, int64_t *ncand_out) {
+    CHECK_CTX(c);
+    NEED_T(c);
+    ARG_CHECK(nmodes >= 1 && modes && l && s && t && piv_out && c->has_tensor, "bad argument");
+    ARG_CHECK(!comm_active(c), "itcpd_seqrcs needs the whole unfolding: run the pivot setup on an unsharded handle (replicas), then shard");
+    for (int i = 0; i < nmodes; ++i) {
+        CHECK_MODE(c, modes[i]);
+        ARG_CHECK(l[i] >= 1 && s[i] >= 1 && t[i] >= 1 && t[i] <= l[i] && piv_out[i], "bad argument (need 1 <= t <= l)");
+        const int64_t n = c->nelem / c->dims[modes[i]];
+        ARG_CHECK(n < (int64_t)1 << 31 && (int64_t)n * std::min(s[i], l[i]) < (int64_t)1 << 31, "the reference's C generators index with 32-bit ints");
+    }
+    USE_DEVICE(c);
+    Embedding emb[2];
+    auto ncols_of = [&](int i) { return c->nelem / c->dims[modes[i]]; };
+    auto start_host = [&](int i, std::thread &th) -> int {
+        Embedding &e = emb[i & 1];
+        TRY(sketch_pin_reserve(c, i & 1, ncols_of(i) * std::min(s[i], l[i]), e.k));   // pinned slots are allocated on the calling thread
+        th = std::thread(host_embedding, l[i], s[i], ncols_of(i), injective, seeds ? seeds[i] : (int64_t)-1, std::ref(e));
+        return ITCPD_OK;
+    };
+    std::thread th;
+    TRY(start_host(0, th));
+    int rc = ITCPD_OK;
+    for (int i = 0; i < nmodes && rc == ITCPD_OK; ++i) {
+        th.join();
+        Embedding &e = emb[i & 1];
+        if (getenv("ITCPD_TRACE_SETUP")) fprintf(stderr, "[itcpd setup] mode %d: generator %.2f ms, csr %.2f ms (host%s)\n", modes[i], e.gen_ms, e.csr_ms, i ? ", overlapped" : "");
+        if (e.status != ITCPD_OK) { set_error("sketch row index out of range"); rc = e.status; break; }
+        if (i + 1 < nmodes) rc = start_host(i + 1, th);
+        if (rc == ITCPD_OK)
+            rc = seqrcs_device_part(c, modes[i], t[i], e, piv_out[i], rdiag_out ? rdiag_out[i] : nullptr, nrdiag_out ? nrdiag_out + i : nullptr,
+                                    ncand_out ? ncand_out + i : nullptr);
+    }
+    if (th.joinable()) th.join();
+    c->unfolded.release();
+    return rc;
+}
+
+int itcpd_seqrcs(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
+                 int64_t *nrdiag_out, int64_t *ncand_out) {
+    int64_t *pivs[1] = {piv_out};
+    double *rds[1] = {rdiag_out};
+    return itcpd_seqrcs_modes(c, 1, &mode, &l, &s, &t, injective, nullptr, pivs, rds, nrdiag_out, ncand_out);
 }
 
 int itcpd_seqrcs_krp(itcpd_ctx *c, int mode, int l, int s, int t, int injective, int64_t *piv_out, double *rdiag_out,
@@ -1396,7 +1585,7 @@ int itcpd_seqrcs_krp(itcpd_ctx *c, int mode, int l, int s, int t, int injective,
     std::vector<char> seen((size_t)n, 0);
     for (int64_t q = 0; q < t; ++q) {
         const int64_t r = p_sk[(size_t)q];
-        for (int64_t e = k.row_ptr[(size_t)r]; e < k.row_ptr[(size_t)r + 1]; ++e) seen[(size_t)k.col[(size_t)e]] = 1;
+        for (int64_t e = k.row_ptr[(size_t)r]; e < k.row_ptr[(size_t)r + 1]; ++e) seen[(size_t)k.col[e]] = 1;
     }
     std::vector<int64_t> cand;
     for (int64_t col = 0; col < n; ++col) if (seen[(size_t)col]) cand.push_back(col);

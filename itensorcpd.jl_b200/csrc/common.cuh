@@ -167,8 +167,14 @@ struct itcpd_ctx {
     // option "seqrcs_use_omega": candidate columns of itcpd_seqrcs in increasing order, as SEQRCS(...; use_omega = true) lists them
     // (SEQRCS.jl:109-113); off = the order of the matrix-free variant (:159), the reference's default
     int seqrcs_use_omega = 0;
+    // option "sketch_unfold" (default on): the SE-QRCS set-up sketches modes >= 1 from an explicit unfolding when HBM has room for it
+    int sketch_unfold = 1;
     void *upload_stage = nullptr;
     cudaEvent_t upload_events[8] = {nullptr};
+    itcpd::DevBuf unfolded;   // explicit unfolding of the mode being sketched (SE-QRCS set-up, modes >= 1; released when the set-up returns)
+    // pinned homes of the SE-QRCS embeddings' CSR entries (two: the helper thread fills one while the other is in use)
+    void *sketch_pin[2] = {nullptr, nullptr};
+    size_t sketch_pin_bytes[2] = {0, 0};
     double *pinned = nullptr;   // pinned host staging (fit scalars, status words)
     size_t pinned_doubles = 0;
 
@@ -279,7 +285,8 @@ int k_sample_rows(itcpd_ctx *c, int skip_mode, int64_t nsamp, uint64_t seed, int
 int k_sampled_mttkrp(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, const double *Ts_dev, const double *K_dev, double *M_dev);  // T_s K
 int k_pivot_hadamard(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *K_dev);
 int k_gather_fibers(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_dev, double *out_dev);
-int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);
+int k_sketch_csr(itcpd_ctx *c, int mode, int l, int64_t nnz, const int64_t *row_ptr_dev, int64_t *col_dev, const double *val_dev, double *out_dev,
+                 const double *unfolded_dev = nullptr);   // col_dev is overwritten (element offsets)
 int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, int64_t *jpvt_dev, double *rdiag_dev);  // qrcp_wide.cu
 int k_unfold(itcpd_ctx *c, int mode, double *out);
 int k_omega_hadamard(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev);

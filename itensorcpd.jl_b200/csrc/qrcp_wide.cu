@@ -178,6 +178,7 @@ int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, in
 // Explicit unfolding T_(mode): I_mode x prod(others), others in original order, first fastest.
 struct UDims { int n; int64_t ext[ITCPD_MAX_ORDER], dim[ITCPD_MAX_ORDER]; };
 
+// mode 0: the unfolding is the tensor itself up to the padding of the leading dimension -- a coalesced copy
 __global__ void unfold_kernel(const double *__restrict__ T, UDims d, int mode, int64_t ncols, double *__restrict__ out) {
     const int64_t I = d.dim[mode];
     int64_t stride_mode = 1;
@@ -194,12 +195,58 @@ __global__ void unfold_kernel(const double *__restrict__ T, UDims d, int mode, i
     }
 }
 
+// mode >= 1: T is [a (the modes before, fastest) | i (the mode) | b (the modes after)], the unfolding is [i | a | b]: a batch of
+// 2-D transposes, 32 x 32 tiles through shared memory so that both the read (along a) and the write (along i) are coalesced.
+// One read and one write of the tensor (HBM-bound); the strided gathers of the sketch then run on contiguous columns.
+__global__ void __launch_bounds__(256) unfold_tiled_kernel(const double *__restrict__ T, UDims d, int mode, int64_t A, int64_t I, int64_t tiles_a,
+                                                           int64_t tiles_i, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    int64_t blk = blockIdx.x;
+    const int64_t ta = blk % tiles_a; blk /= tiles_a;
+    const int64_t ti = blk % tiles_i;
+    const int64_t b = blk / tiles_i;
+    int64_t stride_mode = 1;
+    for (int q = 0; q < mode; ++q) stride_mode *= d.ext[q];
+    const int64_t stride_b = stride_mode * d.ext[mode];
+    {
+        const int64_t a = ta * 32 + tx;
+        if (a < A) {
+            int64_t rem = a, off = 0, str = 1;
+            for (int q = 0; q < mode; ++q) { off += (rem % d.dim[q]) * str; rem /= d.dim[q]; str *= d.ext[q]; }
+            const double *src = T + off + b * stride_b;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t i = ti * 32 + ty + 8 * r;
+                if (i < I) tile[ty + 8 * r][tx] = src[i * stride_mode];
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t i = ti * 32 + tx;
+    if (i < I) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t a = ta * 32 + ty + 8 * r;
+            if (a < A) out[i + I * (a + A * b)] = tile[tx][ty + 8 * r];
+        }
+    }
+}
+
 int k_unfold(itcpd_ctx *c, int mode, double *out) {
     UDims d;
     d.n = c->order;
     for (int i = 0; i < c->order; ++i) { d.ext[i] = (i == 0) ? c->ld0 : c->dims[i]; d.dim[i] = c->dims[i]; }
-    const int64_t ncols = c->nelem / c->dims[mode];
-    unfold_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(c->T.as<double>(), d, mode, ncols, out);
+    const int64_t I = c->dims[mode], ncols = c->nelem / I;
+    if (mode == 0) {
+        unfold_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(c->T.as<double>(), d, mode, ncols, out);
+    } else {
+        int64_t A = 1;
+        for (int q = 0; q < mode; ++q) A *= c->dims[q];
+        const int64_t B = ncols / A, tiles_a = ceil_div(A, 32), tiles_i = ceil_div(I, 32);
+        ARG_CHECK(tiles_a * tiles_i * B < ((int64_t)1 << 31), "unfolding: too many tiles for one grid");
+        unfold_tiled_kernel<<<(unsigned)(tiles_a * tiles_i * B), 256, 0, c->stream>>>(c->T.as<double>(), d, mode, A, I, tiles_a, tiles_i, out);
+    }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;

@@ -175,30 +175,54 @@ int k_sampled_mttkrp(itcpd_ctx *c, int mode, int64_t nsamp, const int64_t *piv_d
 // ---- sparse-sign sketch of the unfolding: out[i, j] = sum_{e in row j} val[e] T_(mode)[i, col[e]] ----
 // (row_ptr, col, val) is the sketch in CSR-by-sketch-row order, entries of a row in increasing
 // non-zero order (the order the reference's dict_rows visits them, pivot_mapping.jl:127-137).
-__global__ void __launch_bounds__(128) sketch_kernel(const double *__restrict__ T, SDims d, int mode, const int64_t *__restrict__ row_ptr,
-                                                     const int64_t *__restrict__ col, const double *__restrict__ val,
+// The column number of every non-zero is decoded ONCE into the element offset of that column's first entry (sketch_offsets_kernel,
+// in place); the gather loop is then one broadcast load of (offset, value) and one load of T per non-zero -- the 64-bit
+// divisions of the decode used to be repeated by every thread of every CTA and bounded the kernel.
+__global__ void __launch_bounds__(256) sketch_offsets_kernel(SDims d, int mode, int64_t nnz, int64_t *__restrict__ col) {
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < nnz; e += 256ll * gridDim.x) {
+        int64_t rem = col[e], off = 0, str = 1;
+        for (int m = 0; m < d.n; ++m) {
+            if (m != mode) { off += (rem % d.dim[m]) * str; rem /= d.dim[m]; }
+            str *= d.ext[m];
+        }
+        col[e] = off;
+    }
+}
+
+__global__ void __launch_bounds__(128) sketch_kernel(const double *__restrict__ T, int64_t I, int64_t stride_mode, const int64_t *__restrict__ row_ptr,
+                                                     const int64_t *__restrict__ off, const double *__restrict__ val,
                                                      double *__restrict__ out) {
     const int64_t j = blockIdx.x;
-    const int64_t I = d.dim[mode];
-    int64_t stride_mode = 1;
-    for (int m = 0; m < mode; ++m) stride_mode *= d.ext[m];
+    const int64_t e0 = row_ptr[j], e1 = row_ptr[j + 1];
     for (int64_t i = threadIdx.x + 128ll * blockIdx.y; i < I; i += 128ll * gridDim.y) {
+        const double *Ti = T + i * stride_mode;
         double acc = 0.0;
-        for (int64_t e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
-            int64_t rem = col[e], off = 0, str = 1;
-            for (int m = 0; m < d.n; ++m) {
-                if (m != mode) { off += (rem % d.dim[m]) * str; rem /= d.dim[m]; }
-                str *= d.ext[m];
-            }
-            acc = fma(val[e], T[off + i * stride_mode], acc);
-        }
+        for (int64_t e = e0; e < e1; ++e) acc = fma(val[e], Ti[off[e]], acc);
         out[i + I * j] = acc;
     }
 }
 
-int k_sketch_csr(itcpd_ctx *c, int mode, int l, const int64_t *row_ptr_dev, const int64_t *col_dev, const double *val_dev, double *out_dev) {
+// col -> col * I: the same decode for a sketch that reads the explicit unfolding (I x ncols, the mode's index fastest)
+__global__ void __launch_bounds__(256) sketch_offsets_unfolded_kernel(int64_t I, int64_t nnz, int64_t *__restrict__ col) {
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < nnz; e += 256ll * gridDim.x) col[e] *= I;
+}
+
+// unfolded_dev: nullptr = gather from the tensor in place (strided for every mode but the first: one 8-byte element per 32-byte
+// sector); else the explicit unfolding of `mode` (k_unfold), whose columns are contiguous.  Same products, same order: bitwise equal.
+int k_sketch_csr(itcpd_ctx *c, int mode, int l, int64_t nnz, const int64_t *row_ptr_dev, int64_t *col_dev, const double *val_dev, double *out_dev,
+                 const double *unfolded_dev) {
+    const SDims d = sdims(c);
+    int64_t stride_mode = 1;
+    for (int m = 0; m < mode; ++m) stride_mode *= d.ext[m];
+    if (nnz > 0) {
+        const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(nnz, 256), c->sm_count * 16);
+        if (unfolded_dev) sketch_offsets_unfolded_kernel<<<nb, 256, 0, c->stream>>>(c->dims[mode], nnz, col_dev);
+        else sketch_offsets_kernel<<<nb, 256, 0, c->stream>>>(d, mode, nnz, col_dev);
+        c->launches++;
+    }
     dim3 grid((unsigned)l, (unsigned)std::min<int64_t>(ceil_div(c->dims[mode], 128), 8));
-    sketch_kernel<<<grid, 128, 0, c->stream>>>(c->T.as<double>(), sdims(c), mode, row_ptr_dev, col_dev, val_dev, out_dev);
+    sketch_kernel<<<grid, 128, 0, c->stream>>>(unfolded_dev ? unfolded_dev : c->T.as<double>(), c->dims[mode], unfolded_dev ? 1 : stride_mode, row_ptr_dev,
+                                               col_dev, val_dev, out_dev);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return ITCPD_OK;

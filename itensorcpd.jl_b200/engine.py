@@ -327,6 +327,26 @@ class Engine:
                                    C.byref(nr), C.byref(nc)))
         return piv, rd[: nr.value].copy(), nc.value
 
+    def seqrcs_modes(self, modes, ls, ss, ts, injective: bool = False, seeds=None, use_omega: bool = False):
+        """SE-QRCS of several modes in one call (the set-up loop of optimizers/.../qr_lev_score_sampled.jl:80-176): same results and same
+        rand() stream as seqrcs() mode by mode, with the host half of the next mode overlapped with the device half of this one.
+        Returns [(p, diag R, #candidates)] in the order of `modes`."""
+        self.set_option("seqrcs_use_omega", int(bool(use_omega)))
+        nm = len(modes)
+        total = int(np.prod(self.dims))
+        pivs = [np.empty(total // self.dims[m], dtype=np.int64) for m in modes]
+        rds = [np.empty(self.dims[m]) for m in modes]
+        as_i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        modes_a, l_a, s_a, t_a = as_i32(modes), as_i32(ls), as_i32(ss), as_i32(ts)
+        seeds_a = None if seeds is None else np.ascontiguousarray([-1 if x is None else int(x) for x in seeds], dtype=np.int64)
+        piv_ptrs = (C.c_void_p * nm)(*[_addr(p) for p in pivs])
+        rd_ptrs = (C.c_void_p * nm)(*[_addr(r) for r in rds])
+        nr, nc = np.zeros(nm, dtype=np.int64), np.zeros(nm, dtype=np.int64)
+        check(self._L.itcpd_seqrcs_modes(self._h, nm, _addr(modes_a), _addr(l_a), _addr(s_a), _addr(t_a), int(bool(injective)),
+                                         None if seeds_a is None else _addr(seeds_a), C.cast(piv_ptrs, C.c_void_p), C.cast(rd_ptrs, C.c_void_p),
+                                         _addr(nr), _addr(nc)))
+        return [(pivs[i], rds[i][: int(nr[i])].copy(), int(nc[i])) for i in range(nm)]
+
     def seqrcs_krp(self, mode: int, l: int, s: int, t: int, injective: bool = False, seed: Optional[int] = None):
         """KRP-structured SE-QRCS of the handle's current factors != mode (SEQRCS.jl:184-241, compute_r=false)."""
         n = int(np.prod([d for m, d in enumerate(self.dims) if m != mode]))

@@ -457,20 +457,35 @@ def _setup_pivot_based(alg, eng: Engine, cp: CPD, check, normal, shuffle_pivots,
         updated = als_optimize(eng, start_cp, alg=LevScoreSampled(prelim), check=NoCheck(prelim_niter), normal=True,
                                stop_resample=0, seed=0 if seed is None else seed)
         eng.set_cpd(updated.factors, updated.lam)  # the device holds the preliminary factors during the pivot search
+    def sketch_params(n):
+        m = dims[n]
+        int_end = _proj_range(alg, n, int(np.prod([dims[q] for q in range(N) if q != n])))[1]
+        k_sk = int_end if alg.rank_vect is None else alg.rank_vect[n + 1]
+        l = int(round(3 * m * math.log(m)))   # qr_lev...:122 / :234
+        s = int(round(math.log(m)))           # :123 / :236
+        return l, s, min(k_sk, l), (None if seed is None else seed + n)
+
+    # SE-QRCS of the tensor's unfoldings: every random mode in ONE call, in mode order -- the reference's generators draw from one
+    # global rand() stream and only these modes consume it, so the stream is the same as in the reference's loop, and the library
+    # overlaps the host half of mode n+1 with the device half of mode n
+    sketched = {}
+    if not krp_mode and not isinstance(alg, QRPivProjected):
+        ms = [n for n in range(N) if (n + 1) in lst]
+        if ms:
+            prm = [sketch_params(n) for n in ms]
+            res = eng.seqrcs_modes(ms, [q[0] for q in prm], [q[1] for q in prm], [q[2] for q in prm], injective=injective,
+                                   seeds=None if seed is None else [q[3] for q in prm])
+            sketched = {n: (r[0], r[1]) for n, r in zip(ms, res)}
     for n in range(N):
         rdims = [dims[m] for m in range(N) if m != n]
         dRis = int(np.prod(rdims))
         int_start, int_end = _proj_range(alg, n, dRis)
         m = dims[n]
-        if (n + 1) in lst and not isinstance(alg, QRPivProjected):
-            k_sk = int_end if alg.rank_vect is None else alg.rank_vect[n + 1]
-            l = int(round(3 * m * math.log(m)))   # qr_lev...:122 / :234
-            s = int(round(math.log(m)))           # :123 / :236
-            sd = None if seed is None else seed + n
-            if krp_mode:
-                p, dr, _ = eng.seqrcs_krp(n, l, s, min(k_sk, l), injective=injective, seed=sd)
-            else:
-                p, dr, _ = eng.seqrcs(n, l, s, min(k_sk, l), injective=injective, seed=sd)
+        if n in sketched:
+            p, dr = sketched[n]
+        elif (n + 1) in lst and not isinstance(alg, QRPivProjected):
+            l, s, t, sd = sketch_params(n)
+            p, dr, _ = eng.seqrcs_krp(n, l, s, t, injective=injective, seed=sd)
         elif krp_mode:
             # exact QRCP of the (cprank x dRis) Khatri-Rao matrix of the preliminary factors (:241-243)
             K = np.ones((1, updated.rank))

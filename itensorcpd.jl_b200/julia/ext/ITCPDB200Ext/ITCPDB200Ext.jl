@@ -374,27 +374,49 @@ function ITensorCPD.compute_als(alg::B200{<:PivotAlg}, target::ITensor, cp::CPD{
         upload_cpd!(h, cp)
     end
     ref_pivs = Vector{Vector{Int}}(); pivots = Vector{Matrix{Int}}(); projectors = Vector{Matrix{Int64}}(); effective_ranks = Int[]
+    # sketch parameters of a random mode (optimizers/.../qr_lev...:122-123 / :234-236)
+    function sketch_params(n)
+        m = ds[n]
+        int_end = proj_range(inner, n, prod(ds[q] for q in 1:N if q != n))[2]
+        k_sk = isnothing(inner.rank_vect) ? int_end : inner.rank_vect[n]
+        l = Int(round(3 * m * log(m)))
+        return l, Int(round(log(m))), min(k_sk, l)
+    end
+    # SE-QRCS of the unfoldings (SEQRCS.jl:139-182): every random mode in ONE call, in mode order -- only these modes draw from the
+    # generators' global rand() stream, so it is consumed as in the reference's loop; the library overlaps the host half of mode n+1
+    # with the device half of mode n
+    sketched = Dict{Int,Tuple{Vector{Int64},Vector{Float64}}}()
+    if !krp_mode && !isempty(lst)
+        ms = [n for n in 1:N if n in lst]
+        prm = [sketch_params(n) for n in ms]
+        ps = [Vector{Int64}(undef, prod(ds[q] for q in 1:N if q != n)) for n in ms]
+        drs = [Vector{Float64}(undef, ds[n]) for n in ms]
+        nrd = zeros(Int64, length(ms)); ncand = zeros(Int64, length(ms))
+        GC.@preserve ps drs begin
+            chk(ccall((:itcpd_seqrcs_modes, libitcpd), Cint,
+                      (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Int64}, Ptr{Ptr{Int64}}, Ptr{Ptr{Float64}}, Ptr{Int64}, Ptr{Int64}),
+                      h.ptr, length(ms), Cint[n - 1 for n in ms], Cint[q[1] for q in prm], Cint[q[2] for q in prm], Cint[q[3] for q in prm],
+                      injective ? 1 : 0, C_NULL, [pointer(p) for p in ps], [pointer(d) for d in drs], nrd, ncand))
+        end
+        for (i, n) in enumerate(ms)
+            sketched[n] = (ps[i], drs[i][1:nrd[i]])
+        end
+    end
     for n in 1:N
         rdims = Tuple(ds[m] for m in 1:N if m != n)
         dRis = prod(rdims)
         int_start, int_end = proj_range(inner, n, dRis)
         m = ds[n]
-        p = Vector{Int64}(undef, dRis)
+        p = Vector{Int64}(undef, haskey(sketched, n) ? 0 : dRis)
         dr = Vector{Float64}(undef, krp_mode ? dim(cp_rank(cp)) : min(m, dRis))
-        if n in lst
-            k_sk = isnothing(inner.rank_vect) ? int_end : inner.rank_vect[n]
-            l = Int(round(3 * m * log(m)))            # optimizers/.../qr_lev...:122 / :234
-            s = Int(round(log(m)))                    # :123 / :236
+        if haskey(sketched, n)
+            p, dr = sketched[n]
+        elseif n in lst      # SE-QRCS of the Khatri-Rao product of the preliminary factors (SEQRCS.jl:184-241)
+            l, s, t = sketch_params(n)
             nrd = Ref{Int64}(0); ncand = Ref{Int64}(0)
-            if krp_mode     # SE-QRCS of the Khatri-Rao product of the preliminary factors (SEQRCS.jl:184-241)
-                chk(ccall((:itcpd_seqrcs_krp, libitcpd), Cint,
-                          (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
-                          h.ptr, n - 1, l, s, min(k_sk, l), injective ? 1 : 0, p, dr, nrd, ncand))
-            else            # SE-QRCS of the unfolding itself (SEQRCS.jl:139-182)
-                chk(ccall((:itcpd_seqrcs, libitcpd), Cint,
-                          (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
-                          h.ptr, n - 1, l, s, min(k_sk, l), injective ? 1 : 0, p, dr, nrd, ncand))
-            end
+            chk(ccall((:itcpd_seqrcs_krp, libitcpd), Cint,
+                      (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+                      h.ptr, n - 1, l, s, t, injective ? 1 : 0, p, dr, nrd, ncand))
             dr = dr[1:nrd[]]
         elseif krp_mode
             throw(ArgumentError("B200(KSEQRCSPivProjected): list every mode in random_modes (the exact KRP QRCP is a host matrix; use itcpd_qrcp_matrix)"))

@@ -158,6 +158,10 @@ class FakeEngine(itcpd.Engine):
         _, R, p = sampled.seqrcs_tensor(self.T, mode, l, s, t, injective=injective, seed=seed, info=info)
         return p, np.diag(R).copy(), info["subset"]
 
+    def seqrcs_modes(self, modes, ls, ss, ts, injective=False, seeds=None, use_omega=False):
+        return [self.seqrcs(m, l, s, t, injective=injective, seed=None if seeds is None else seeds[i])
+                for i, (m, l, s, t) in enumerate(zip(modes, ls, ss, ts))]
+
     def seqrcs_krp(self, mode, l, s, t, injective=False, seed=None):
         _, R, p = sampled.seqrcs_krp([x for m, x in enumerate(self.f) if m != mode], l, s, t, injective=injective, seed=seed)
         return p, np.diag(R).copy(), 0

@@ -94,9 +94,36 @@ def test_library_sparse_sign_bit_exact_vs_reference_c(inj, l, n, s):
     import itcpd
     from oracle import sampled
 
+    libc = ctypes.CDLL(None)
     rows, vals, cs = itcpd.sparse_sign_matrix(l, n, s, injective=inj, seed=99)
+    after = [libc.rand() for _ in range(40)]
     rv, rr, rc = sampled.sparse_sign_call(l, n, s, inj, "ref", seed=99)
+    after_ref = [libc.rand() for _ in range(40)]
     assert np.array_equal(rows, rr) and np.array_equal(cs, rc) and np.array_equal(vals, rv, equal_nan=True)
+    assert after == after_ref      # the global stream continues exactly where the reference's C would have left it
+
+
+def test_lock_free_rand_stream_is_in_use_and_equals_plain_rand(tmp_path):
+    """The generators borrow glibc's state array instead of calling rand() per draw (sparse_sign.cu: GlibcStream).  On this image's
+    glibc the self-test must accept it (else the set-up timings in DESIGN.md are not what runs), and a process forced onto plain
+    rand() (ITCPD_PLAIN_RAND) must produce the same arrays and leave the same stream behind, across consecutive calls."""
+    import itcpd
+
+    assert itcpd.load().itcpd_sparse_sign_fast_stream() == 1
+    prog = (
+        "import sys, ctypes, hashlib, numpy as np; sys.path.insert(0, %r); import itcpd\n"
+        "libc = ctypes.CDLL(None); libc.srand(2026); h = hashlib.sha256()\n"
+        "for inj, l, n, s in [(False, 300, 5000, 4), (True, 300, 5000, 4), (False, 9, 700, 9), (True, 64, 3, 5), (False, 31, 31 * 31, 1)]:\n"
+        "    rows, vals, cs = itcpd.sparse_sign_matrix(l, n, s, injective=inj)\n"
+        "    h.update(rows.tobytes()); h.update(np.nan_to_num(vals).tobytes()); h.update(str(libc.rand()).encode())\n"
+        "print(itcpd.load().itcpd_sparse_sign_fast_stream(), h.hexdigest())\n" % ROOT)
+    outs = []
+    for env_extra in ({}, {"ITCPD_PLAIN_RAND": "1"}):
+        env = dict(os.environ, **env_extra)
+        out = subprocess.run(["python", "-c", prog], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(out.stdout.split())
+    assert outs[0][0] == "1" and outs[1][0] == "0" and outs[0][1] == outs[1][1]
 
 
 def test_host_fitcheck_matches_oracle_state_machine():

@@ -250,6 +250,62 @@ def test_device_seqrcs_matches_oracle_and_qrcp_quality(engine, inj):
     engine.set_option("seqrcs_use_omega", 0)
 
 
+def test_seqrcs_modes_equals_per_mode_calls_and_threaded_sort(engine, monkeypatch):
+    """itcpd_seqrcs_modes (generator + row sort of mode n+1 on a helper thread while the device factorises mode n) against one
+    itcpd_seqrcs per mode under the same seeds: identical pivot lists, with the stable counting sort forced onto 5 threads."""
+    rng = np.random.default_rng(41)
+    T = np.asfortranarray(rng.standard_normal((24, 30, 20)))
+    engine.set_tensor(T)
+    modes, ls, ss, ts = [0, 1, 2], [90, 110, 70], [2, 3, 1], [12, 10, 9]
+    single = [engine.seqrcs(m, l, s, t, seed=50 + m) for m, l, s, t in zip(modes, ls, ss, ts)]
+    monkeypatch.setenv("ITCPD_SKETCH_THREADS", "5")
+    both = engine.seqrcs_modes(modes, ls, ss, ts, seeds=[50, 51, 52])
+    for (p1, r1, c1), (p2, r2, c2) in zip(single, both):
+        assert c1 == c2 and np.array_equal(p1, p2) and np.array_equal(r1, r2)
+    # one stream across the call (seed only the first mode) == per-mode calls that let the stream run on
+    import ctypes
+    ctypes.CDLL(None).srand(77)
+    cont = [engine.seqrcs(m, l, s, t) for m, l, s, t in zip(modes, ls, ss, ts)]
+    both = engine.seqrcs_modes(modes, ls, ss, ts, seeds=[77, None, None])
+    for (p1, r1, c1), (p2, r2, c2) in zip(cont, both):
+        assert c1 == c2 and np.array_equal(p1, p2) and np.array_equal(r1, r2)
+    # the explicit-unfolding path of the set-up (tiled transpose, then contiguous columns) against the in-place strided gather
+    engine.set_option("sketch_unfold", 0)
+    inplace = engine.seqrcs_modes(modes, ls, ss, ts, seeds=[50, 51, 52])
+    engine.set_option("sketch_unfold", 1)
+    for (p1, r1, c1), (p2, r2, c2) in zip(single, inplace):
+        assert c1 == c2 and np.array_equal(p1, p2) and np.array_equal(r1, r2)
+    # the sketch itself under the threaded sort, against the oracle
+    import itcpd
+    rows0, vals, cs = itcpd.sparse_sign_matrix(110, 24 * 20, 3, seed=3)
+    A_sk = engine.sketch_unfolding(1, 110, 3, rows0, vals)
+    Ao = sampled.sketched_matricization(T, 1, 110, rows0 + 1, vals, 3)
+    assert np.linalg.norm(A_sk - Ao) <= 1e-12 * np.linalg.norm(Ao)
+
+
+@pytest.mark.parametrize("dims", [(23, 37, 41), (64, 32, 96), (7, 5, 3, 9), (33, 65)])
+def test_sketch_from_explicit_unfolding_is_bitwise_the_inplace_sketch(engine, dims):
+    """option sketch_unfold: the tiled transpose (partial tiles, a padded leading dimension, order 2 and 4) followed by the sketch on
+    contiguous columns must give exactly the numbers of the strided in-place gather, for every mode."""
+    import itcpd
+    rng = np.random.default_rng(sum(dims))
+    T = np.asfortranarray(rng.standard_normal(dims))
+    engine.set_tensor(T)
+    try:
+        for mode in range(len(dims)):
+            n = T.size // dims[mode]
+            l, s = 3 * dims[mode] + 1, 2
+            rows0, vals, cs = itcpd.sparse_sign_matrix(l, n, s, seed=9 + mode)
+            engine.set_option("sketch_unfold", 0)
+            a = engine.sketch_unfolding(mode, l, s, rows0, vals)
+            engine.set_option("sketch_unfold", 2)
+            b = engine.sketch_unfolding(mode, l, s, rows0, vals)
+            assert np.array_equal(a, b), mode
+            assert np.linalg.norm(a - sampled.sketched_matricization(T, mode, l, rows0 + 1, vals, s)) <= 1e-12 * np.linalg.norm(a)
+    finally:
+        engine.set_option("sketch_unfold", 1)
+
+
 def test_projected_update_matches_oracle(engine):
     T, cp, rng = problem((14, 12, 10), 5, 23)
     engine.set_tensor(T)

@@ -14,7 +14,7 @@ EXT = os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "ext", "ITCPDB200Ext", "
 DEPS = os.path.join(ROOT, "itensorcpd.jl_b200", "julia", "deps")
 
 JL_KIND = {"Ptr{Cvoid}": "ptr", "Ref{Ptr{Cvoid}}": "ptr", "Ptr{Float64}": "ptr", "Ref{Float64}": "ptr", "Ptr{Int64}": "ptr", "Ref{Int64}": "ptr",
-           "Ptr{UInt8}": "ptr", "Ptr{Int32}": "ptr", "Ref{Cint}": "ptr", "Ptr{Ptr{Float64}}": "ptr", "Cstring": "ptr",
+           "Ptr{UInt8}": "ptr", "Ptr{Int32}": "ptr", "Ptr{Cint}": "ptr", "Ptr{Ptr{Int64}}": "ptr", "Ref{Cint}": "ptr", "Ptr{Ptr{Float64}}": "ptr", "Cstring": "ptr",
            "Cint": "i32", "Int64": "i64", "UInt64": "i64", "Float64": "f64", "Cvoid": "void"}
 
 
@@ -60,7 +60,7 @@ def test_extension_covers_the_entry_points_the_verdict_asked_for():
             "itcpd_get_lambda", "itcpd_compute_grams", "itcpd_sweep", "itcpd_leverage_scores", "itcpd_sample_factor_matrices", "itcpd_sampled_update",
             "itcpd_cpd_snapshot", "itcpd_cpd_diff_terms",
             # pivot-projected solvers (qr_lev_score_sampled.jl), reconstruct, multi-GPU init
-            "itcpd_qrcp_unfolding", "itcpd_seqrcs", "itcpd_seqrcs_krp", "itcpd_set_projector", "itcpd_projected_update",
+            "itcpd_qrcp_unfolding", "itcpd_seqrcs_modes", "itcpd_seqrcs_krp", "itcpd_set_projector", "itcpd_projected_update",
             "itcpd_set_shape", "itcpd_reconstruct", "itcpd_residual_norm",
             "itcpd_comm_unique_id", "itcpd_comm_init", "itcpd_peer_export", "itcpd_peer_import", "itcpd_allgather_factor",
             "itcpd_sparse_sign", "itcpd_sparsestack"}
