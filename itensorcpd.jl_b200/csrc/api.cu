@@ -1443,6 +1443,12 @@ static int seqrcs_device_part(itcpd_ctx *c, int mode, int t, Embedding &e, int64
     TRY(c->qr_A.reserve((size_t)m * std::max<int64_t>(l, 1) * 8));
     tr.mark("csr upload");
     const double *unfolded = nullptr;
+    if (mode > 0 && c->sketch_unfold && tr.on) {   // trace only: time the allocation apart from the transpose
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        tr.mark("cudaMemGetInfo");
+        if (free_b > (size_t)c->nelem * 8 + ((size_t)4 << 30)) { TRY(c->unfolded.reserve((size_t)c->nelem * 8)); tr.mark("allocate the unfolding"); }
+    }
     TRY(unfold_for_sketch(c, mode, &unfolded));
     if (unfolded) tr.mark("explicit unfolding");
     TRY(k_sketch_csr(c, mode, l, k.nnz, k.d_ptr, k.d_col, k.d_val, c->qr_A.as<double>(), unfolded));
@@ -1542,7 +1548,11 @@ int itcpd_seqrcs_modes(itcpd_ctx *c, int nmodes, const int *modes, const int *l,
                                     ncand_out ? ncand_out + i : nullptr);
     }
     if (th.joinable()) th.join();
-    c->unfolded.release();
+    {
+        SetupTrace tr(c->stream);
+        c->unfolded.release();
+        tr.mark("release the unfolding");
+    }
     return rc;
 }
 
