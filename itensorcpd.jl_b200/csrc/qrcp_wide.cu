@@ -10,6 +10,7 @@
 //                                       (no dlaqp2 down-dating needed: the column is in flight anyway), per-CTA maxima
 #include "common.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace itcpd {
 
@@ -136,6 +137,68 @@ __global__ void __launch_bounds__(256) qrw_apply_kernel(double *__restrict__ A, 
     }
 }
 
+// The same update with the column held in registers: one DRAM read and one write per element (the kernel above walks the column twice
+// and takes the second pass from L1/L2, 40 % / 62 % hit rates in the ncu capture).  A lane owns rows j0 + lane + 32 q, q < NR, where
+// j0 = j rounded down to a multiple of 4 so that a warp's 256-byte row segments stay 32-byte aligned as j advances; all NR loads
+// are in flight before the first use.  Chosen when m - j0 <= 32 * NR for an instantiated NR.  1024 x 44032, all 1024 steps: 83.9 ms
+// against 99.5 ms for the two-pass kernel (first 128 steps 5.2 TB/s against 4.0); NR = 32 runs two CTAs per SM at 128 registers with
+// 180 bytes of spills -- one CTA per SM without spills measured 89.4 ms (profiles/r2_qrcp_wide_ncu.txt).
+template <int NR, int MINB>
+__global__ void __launch_bounds__(256, MINB) qrw_apply_reg_kernel(double *__restrict__ A, int64_t m, int64_t n, int64_t j,
+                                                                              const double *__restrict__ vbuf, const double *__restrict__ scal,
+                                                                              double *__restrict__ vn, double *__restrict__ bmax_v,
+                                                                              int64_t *__restrict__ bmax_i) {
+    __shared__ double sh_v[32 * NR];   // v on rows [j0, j0 + 32 NR): zero before row j and past row m
+    __shared__ double sv[QW_WARPS];
+    __shared__ int64_t si[QW_WARPS];
+    const int64_t j0 = j & ~(int64_t)3;
+    const int pre = (int)(j - j0), len = (int)(m - j0);
+    for (int i = threadIdx.x; i < 32 * NR; i += 256) sh_v[i] = (i >= pre && i < len) ? vbuf[i - pre] : 0.0;
+    __syncthreads();
+    const double tau = scal[0];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = j + 1 + blockIdx.x * (int64_t)QW_WARPS + w;
+    double nr = -1.0;
+    if (k < n) {
+        double *a = A + m * k + j0;
+        double x[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const int i = lane + 32 * q;
+            x[q] = (i >= pre && i < len) ? a[i] : 0.0;
+        }
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) dot = fma(sh_v[lane + 32 * q], x[q], dot);
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const double f = tau * dot;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const int i = lane + 32 * q;
+            const double y = fma(-f, sh_v[i], x[q]);
+            if (i >= pre && i < len) a[i] = y;
+            if (i > pre) s = fma(y, y, s);      // rows below the pivot row (y is 0 past row m)
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        nr = sqrt(s);
+        if (lane == 0) vn[k] = nr;
+    }
+    if (lane == 0) { sv[w] = nr; si[w] = k; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bv = sv[0]; int64_t bi = si[0];
+        for (int q = 1; q < QW_WARPS; ++q) if (sv[q] > bv) { bv = sv[q]; bi = si[q]; }
+        bmax_v[blockIdx.x] = bv; bmax_i[blockIdx.x] = bi;
+    }
+}
+
+template <int NR, int MINB = 2>
+static void launch_apply_reg(itcpd_ctx *c, unsigned nblocks, double *A, int64_t m, int64_t n, int64_t j, const double *vbuf, const double *scal,
+                             double *vn, double *bmax_v, int64_t *bmax_i) {
+    qrw_apply_reg_kernel<NR, MINB><<<nblocks, 256, 0, c->stream>>>(A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+}
+
 __global__ void iota_kernel(int64_t *x, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] = i;
@@ -161,13 +224,22 @@ int k_qrcp_wide(itcpd_ctx *c, double *A, int64_t m, int64_t n, int64_t steps, in
     }
     ARG_CHECK((size_t)m * 8 <= 200 * 1024, "QRCP supports at most 25600 rows");
     int64_t nblocks = nb0;
+    const bool reg_path = getenv("ITCPD_QRCP_TWO_PASS") == nullptr;   // the two-pass kernel stays for m > 2048 (and for A/B comparisons)
     for (int64_t j = 0; j < kmax; ++j) {
         qrw_pivot_house_kernel<<<1, 1024, 0, c->stream>>>(A, m, n, j, vn, bmax_v, bmax_i, nblocks, jpvt_dev, vbuf, scal, rdiag_dev);
         c->launches++;
         const int64_t trailing = n - j - 1;
         nblocks = ceil_div(std::max<int64_t>(trailing, 0), QW_WARPS);
         if (trailing > 0) {
-            qrw_apply_kernel<<<(unsigned)nblocks, 256, (size_t)(m - j) * 8, c->stream>>>(A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            const int64_t span = m - (j & ~(int64_t)3);   // rows a warp covers, from the aligned start
+            const unsigned nb = (unsigned)nblocks;
+            if (!reg_path || span > 2048) qrw_apply_kernel<<<nb, 256, (size_t)(m - j) * 8, c->stream>>>(A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else if (span > 1024) launch_apply_reg<64, 1>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else if (span > 512) launch_apply_reg<32, 2>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else if (span > 256) launch_apply_reg<16>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else if (span > 128) launch_apply_reg<8>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else if (span > 64) launch_apply_reg<4>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
+            else launch_apply_reg<2>(c, nb, A, m, n, j, vbuf, scal, vn, bmax_v, bmax_i);
             c->launches++;
         }
     }

@@ -199,9 +199,11 @@ def _rank_k_error(A, p, k):
     return np.linalg.norm(Ap - Q @ (Q.T @ Ap), 2) / np.linalg.norm(A, 2)
 
 
-@pytest.mark.parametrize("m,n", [(12, 40), (50, 3000), (40, 25), (64, 64)])
+@pytest.mark.parametrize("m,n", [(12, 40), (50, 3000), (40, 25), (64, 64), (131, 500), (259, 400), (515, 700), (1029, 1200), (2053, 300), (2200, 2300)])
 def test_device_qrcp_matches_lapack(engine, m, n):
-    """qr(A, ColumnNorm()): same pivot order and |diag(R)| as LAPACK dgeqp3 on generic matrices."""
+    """qr(A, ColumnNorm()): same pivot order and |diag(R)| as LAPACK dgeqp3 on generic matrices.  The row counts walk through every
+    register-resident instantiation of the apply kernel (2 ... 64 values per lane, odd sizes: unaligned column starts) and past it
+    (more than 2048 rows: the two-pass kernel)."""
     rng = np.random.default_rng(20)
     A = np.asfortranarray(rng.standard_normal((m, n)) * np.exp(rng.standard_normal(n))[None, :])
     piv, rd = engine.qrcp_matrix(A)

@@ -22,5 +22,5 @@ if os.environ.get("QR_CHECK"):
     import scipy.linalg
     R, p = scipy.linalg.qr(A[:, :4096], mode="r", pivoting=True)
     piv, rd = eng.qrcp_matrix(np.asfortranarray(A[:, :4096]))
-    print("pivots equal lapack:", int(np.sum(piv[:1024] == p[:1024])), "of 1024; rdiag rel", float(np.max(np.abs(np.abs(rd) - np.abs(np.diag(R))) / np.abs(R[0, 0]))))
+    print("pivots equal lapack:", int(np.sum(piv[:1024] - 1 == p[:1024])), "of 1024; rdiag rel", float(np.max(np.abs(np.abs(rd) - np.abs(np.diag(R))) / np.abs(R[0, 0]))))
 eng.close()
