@@ -799,7 +799,8 @@ __global__ void __launch_bounds__(256) neumann_kernel(const double *__restrict__
 // lev[i] = scale * q_i^T W q_i.  R <= 128: W staged in shared memory, one warp per row with the row broadcast from shared memory
 // and lane l owning the outputs t_k = sum_j W[k,j] q_j for k = l, l + 32, ... (no shuffle inside the j loop: one reduction per row).
 // Larger R: W read through the L1/L2, same arithmetic order.
-constexpr int QF_WARPS = 8, QF_ROWS = 4;   // rows per warp
+constexpr int QF_WARPS = 8, QF_ROWS = 1;   // rows per warp: one -- a factor of 1024 rows then fills 128 CTAs instead of 32 (33 -> 10 us)
+constexpr int QF_KPL = 4;                  // outputs per lane kept as independent accumulation chains (R <= 128)
 
 __global__ void __launch_bounds__(QF_WARPS * 32) quadform_rows_kernel(const double *__restrict__ Q, const double *__restrict__ W, int64_t rows, int R,
                                                                        double scale, double *__restrict__ lev, int w_in_smem) {
@@ -818,10 +819,20 @@ __global__ void __launch_bounds__(QF_WARPS * 32) quadform_rows_kernel(const doub
         for (int k = lane; k < R; k += 32) qrow[k] = Q[i + rows * (int64_t)k];
         __syncwarp();
         double acc = 0.0;
-        for (int k = lane; k < R; k += 32) {
-            double t = 0.0;
-            for (int j = 0; j < R; ++j) t = fma(Wp[k + (size_t)R * j], qrow[j], t);   // W is symmetric: lanes read consecutive words
-            acc = fma(qrow[k], t, acc);
+        for (int k0 = lane; k0 < R; k0 += 32 * QF_KPL) {
+            // t_k = sum_j W[k, j] q_j for up to QF_KPL values of k at once: the chains are independent, each sums j in ascending order
+            double t[QF_KPL];
+            int kk[QF_KPL];
+#pragma unroll
+            for (int u = 0; u < QF_KPL; ++u) { t[u] = 0.0; kk[u] = min(k0 + 32 * u, R - 1); }   // clamped rows are computed and dropped
+            for (int j = 0; j < R; ++j) {
+                const double qj = qrow[j];
+#pragma unroll
+                for (int u = 0; u < QF_KPL; ++u) t[u] = fma(Wp[kk[u] + (size_t)R * j], qj, t[u]);   // W is symmetric: lanes read consecutive words
+            }
+#pragma unroll
+            for (int u = 0; u < QF_KPL; ++u)
+                if (k0 + 32 * u < R) acc = fma(qrow[k0 + 32 * u], t[u], acc);
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) lev[i] = scale * acc;
