@@ -295,6 +295,10 @@ static int mode_update_device(itcpd_ctx *c, int mode, double tol, int *status_de
                                               (c->mttkrp_alg != ITCPD_MTTKRP_DIRECT && !partial_is_current(c, mode < c->split_a ? 0 : 1))));
     int st = k_gram_hadamard(c, mode, c->Gamma.as<double>());
     if (st == ITCPD_OK) st = k_solve_factor(c, c->Gamma.as<double>(), c->rank, tol, status_dev);
+    // every factorisation outside this driver (itcpd_solve, the sampled solves, the leverage refresh) has nothing to hide under: leave
+    // the flag at its default, or those callers inherit whatever the last mode of the last dense sweep decided (after a full-size
+    // sweep: "hidden" -> the 96 us team kernel instead of the 56 us right-looking one, 0.26 ms per sampled sweep)
+    c->chol_exposed = true;
     c->stream = main_stream;
     TRY(st);
     if (c->overlap_factor) CUDA_TRY(cudaEventRecord(c->ev_join, c->side_stream));
