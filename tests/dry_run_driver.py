@@ -400,7 +400,27 @@ def chol_alg_3_uses_the_right_looking_kernel_only_where_the_factorisation_is_exp
         eng.synchronize()
         short = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl"))
     assert short == (0, 6), short
-    return {"team_rl_counts": out, "rank_100": big, "short_pass": short}
+    # outside the dense sweep driver nothing can hide a factorisation: after sweeps whose LAST mode hid its own (team kernel), a
+    # stand-alone solve and a leverage refresh must still take the right-looking kernel (the flag is not inherited)
+    with itcpd.Engine(0) as eng:
+        eng.set_option("chol_alg", 3)
+        eng.set_option("chol_short_gflop", 0)
+        eng.set_option("split_a", 2)
+        eng.set_option("split_b", 1)
+        eng.set_option("use_graph", 0)
+        eng.set_tensor(np.zeros(dims, order="F"))
+        eng.set_cpd(factors(dims, R), np.ones(R))
+        eng.compute_grams()
+        eng.sweep_async(1)
+        eng.synchronize()
+        fake.fakecuda_clear()
+        eng.gram_hadamard(0, fetch=False)
+        eng.mttkrp(0, fetch=False)
+        eng.solve(0, 1e-6)
+        eng.leverage_scores(1)
+        after = (launches("pivoted_cholesky_team"), launches("pivoted_cholesky_rl"))
+    assert after == (0, 2), after
+    return {"team_rl_counts": out, "rank_100": big, "short_pass": short, "after_dense": after}
 
 
 @scenario
