@@ -192,7 +192,10 @@ void itcpd_sparse_sign(int l, int n, int s, double *vals, int *rows, int *colsta
 void itcpd_sparsestack(int l, int n, int s, double *vals, int *rows, int *colstarts);
 /* 1 if the two generators above read libc's rand() stream without its per-call lock (glibc: the state array is borrowed through
  * initstate()/setstate(), advanced in place and handed back, after a self-test on private state; 2.3x faster, the same numbers and
- * the same continuation of the stream), 0 if they call rand() (any other libc, or ITCPD_PLAIN_RAND set in the environment). */
+ * the same continuation of the stream), 0 if they call rand() (any other libc, or ITCPD_PLAIN_RAND set in the environment).
+ * While a generator call is in progress libc sits on a scratch state: a rand() call made by ANOTHER thread during that window draws
+ * from the scratch state instead of interleaving with the generator (with plain rand() the two would interleave; neither is
+ * reproducible, and the reference's generators have the same single-stream assumption). */
 int itcpd_sparse_sign_fast_stream(void);
 /* sketched_matricization (pivot_mapping.jl:111-140): A_sk = T_(mode) * Omega' (I_mode x l) from the
  * (rows 0-based, vals) arrays the generators above fill; s non-zeros per column. */
